@@ -1,0 +1,612 @@
+/*
+ * mm_capi.cu -- implementation of the C ABI declared in include/mashmap_b200.h.
+ *
+ * Owns the device context: the index blob (one arena, see mm_internal.h), the per-batch buffers,
+ * the stream and the stage timers, and drives K1 (mm_sketch.cu) -> K2 (mm_l1.cu) -> K3 (mm_l2.cu).
+ * There is no CPU implementation behind any entry point: without a usable sm_100 device every call
+ * fails with MM_ENODEVICE.
+ */
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "mm_internal.h"
+
+static thread_local std::string g_create_error;
+
+struct mm_ctx {
+  int device = -1;
+  int sm_count = 0;
+  mm_params params{};
+  cudaStream_t stream = nullptr;
+  std::string error;
+  uint64_t launches = 0;
+
+  /* index blob */
+  unsigned char *blob = nullptr;
+  uint64_t blob_bytes = 0;
+  bool blob_owned = false;
+  bool blob_ready = false;
+  mm_blob_header hdr{};
+  mm_dev_index ix{};
+  std::vector<int32_t> cutoffs, min_hits;
+
+  /* batch */
+  uint8_t *d_bases = nullptr; uint64_t bases_cap = 0; uint64_t n_bases = 0;
+  mm_segment *d_segs = nullptr; uint64_t segs_cap = 0; uint64_t n_segs = 0;
+  uint64_t *d_sk_hash = nullptr; int2 *d_sk_pos = nullptr; int8_t *d_sk_strand = nullptr; uint64_t sk_cap = 0;
+  mm_segment_result *d_seg_res = nullptr;
+  mm_l1_candidate *d_cands = nullptr; uint64_t cand_cap = 0;
+  mm_l2_locus *d_loci = nullptr; uint64_t loci_cap = 0;
+  uint32_t *d_counters = nullptr;
+  uint64_t *d_scratch = nullptr; uint64_t scratch_cap = 0; uint64_t scratch_slice = 0; uint64_t scratch_pool = 0;
+  uint32_t l1_grid = 0;
+  uint64_t n_cands = 0, n_loci = 0;
+  bool batch_mapped = false;
+
+  cudaEvent_t ev[8]{};
+  float stage_ms[8]{};
+};
+
+namespace {
+
+int fail(mm_ctx *c, int code, const char *fmt, ...)
+{
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->error = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CU(c, call)                                                                              \
+  do {                                                                                           \
+    cudaError_t e_ = (call);                                                                     \
+    if (e_ != cudaSuccess)                                                                       \
+      return fail(c, e_ == cudaErrorMemoryAllocation ? MM_ENOMEM : MM_ECUDA, "%s: %s", #call,    \
+                  cudaGetErrorString(e_));                                                       \
+  } while (0)
+
+template <typename T>
+int grow(mm_ctx *c, T *&ptr, uint64_t &cap, uint64_t need, uint64_t pad = 0)
+{
+  if (need + pad <= cap && ptr) return MM_OK;
+  if (ptr) { cudaFree(ptr); ptr = nullptr; cap = 0; }
+  uint64_t n = need + pad;
+  CU(c, cudaMalloc((void **)&ptr, n * sizeof(T)));
+  cap = n;
+  return MM_OK;
+}
+
+uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
+
+void resolve_index(mm_ctx *c)
+{
+  const mm_blob_header &h = c->hdr;
+  unsigned char *b = c->blob;
+  mm_dev_index &ix = c->ix;
+  ix.idx_hash = (const uint64_t *)(b + h.off_idx_hash);
+  ix.idx_wpos = (const int32_t *)(b + h.off_idx_wpos);
+  ix.idx_wend = (const int32_t *)(b + h.off_idx_wend);
+  ix.idx_strand = (const int8_t *)(b + h.off_idx_strand);
+  ix.contig_start = (const uint64_t *)(b + h.off_contig_start);
+  ix.tab = (const mm_tab_slot *)(b + h.off_tab);
+  ix.pts = (const uint64_t *)(b + h.off_pts);
+  ix.contig_len = (const int32_t *)(b + h.off_contig_len);
+  ix.contig_name_id = (const int32_t *)(b + h.off_contig_name_id);
+  ix.contig_group = (const int32_t *)(b + h.off_contig_group);
+  ix.cutoffs = (const int32_t *)(b + h.off_cutoffs);
+  ix.min_hits = (const int32_t *)(b + h.off_min_hits);
+  ix.n_minmers = h.n_minmers;
+  ix.n_contigs = h.n_contigs;
+  ix.tab_log2 = h.tab_log2;
+  ix.n_cutoffs = h.n_cutoffs;
+  ix.n_min_hits = h.n_min_hits;
+}
+
+constexpr uint64_t TABLE_REGION_BYTES = 64 * 1024; /* room reserved for each of cutoffs / min_hits */
+
+int write_tables(mm_ctx *c)
+{
+  if (!c->blob || c->cutoffs.empty() || c->min_hits.empty()) return MM_OK;
+  if (c->cutoffs.size() * 4 > TABLE_REGION_BYTES || c->min_hits.size() * 4 > TABLE_REGION_BYTES)
+    return fail(c, MM_EINVAL, "lookup tables too large");
+  c->hdr.n_cutoffs = (int32_t)c->cutoffs.size();
+  c->hdr.n_min_hits = (int32_t)c->min_hits.size();
+  CU(c, cudaMemcpy(c->blob + c->hdr.off_cutoffs, c->cutoffs.data(), c->cutoffs.size() * 4, cudaMemcpyHostToDevice));
+  CU(c, cudaMemcpy(c->blob + c->hdr.off_min_hits, c->min_hits.data(), c->min_hits.size() * 4, cudaMemcpyHostToDevice));
+  CU(c, cudaMemcpy(c->blob, &c->hdr, sizeof(c->hdr), cudaMemcpyHostToDevice));
+  resolve_index(c);
+  return MM_OK;
+}
+
+int check_ready(mm_ctx *c)
+{
+  if (!c) return MM_EINVAL;
+  if (!c->blob_ready) return fail(c, MM_ESTATE, "reference index not uploaded");
+  if (c->hdr.n_cutoffs <= 0 || c->hdr.n_min_hits <= 0) return fail(c, MM_ESTATE, "threshold tables not uploaded");
+  return MM_OK;
+}
+
+int validate_segments(mm_ctx *c, const mm_segment *segs, uint64_t n_segs, uint64_t n_bases)
+{
+  if (n_segs >= (1ULL << 31)) return fail(c, MM_EINVAL, "too many segments in one batch");
+  for (uint64_t i = 0; i < n_segs; i++) {
+    const mm_segment &s = segs[i];
+    if (s.length < 1 || s.length > c->params.seg_length)
+      return fail(c, MM_EINVAL, "segment %llu: length %d outside [1, seg_length=%d] (unsplit reads longer than "
+                  "seg_length are not supported)", (unsigned long long)i, s.length, c->params.seg_length);
+    if (s.offset + (uint64_t)s.length > n_bases) return fail(c, MM_EINVAL, "segment %llu exceeds the base buffer", (unsigned long long)i);
+  }
+  return MM_OK;
+}
+
+int upload_batch(mm_ctx *c, const char *bases, uint64_t n_bases, const mm_segment *segs, uint64_t n_segs)
+{
+  int rc = validate_segments(c, segs, n_segs, n_bases);
+  if (rc) return rc;
+  CU(c, cudaSetDevice(c->device));
+  if ((rc = grow(c, c->d_bases, c->bases_cap, n_bases, 256))) return rc;
+  if ((rc = grow(c, c->d_segs, c->segs_cap, n_segs, 1))) return rc;
+  const uint64_t S = (uint64_t)c->params.sketch_size;
+  if (n_segs * S + 1 > c->sk_cap || !c->d_sk_hash) {
+    if (c->d_sk_hash) cudaFree(c->d_sk_hash);
+    if (c->d_sk_pos) cudaFree(c->d_sk_pos);
+    if (c->d_sk_strand) cudaFree(c->d_sk_strand);
+    if (c->d_seg_res) cudaFree(c->d_seg_res);
+    c->d_sk_hash = nullptr; c->d_sk_pos = nullptr; c->d_sk_strand = nullptr; c->d_seg_res = nullptr; c->sk_cap = 0;
+    const uint64_t n = n_segs * S + 1;
+    CU(c, cudaMalloc((void **)&c->d_sk_hash, n * 8));
+    CU(c, cudaMalloc((void **)&c->d_sk_pos, n * 8));
+    CU(c, cudaMalloc((void **)&c->d_sk_strand, n));
+    CU(c, cudaMalloc((void **)&c->d_seg_res, (n_segs + 1) * sizeof(mm_segment_result)));
+    c->sk_cap = n;
+  }
+  if (!c->d_counters) CU(c, cudaMalloc((void **)&c->d_counters, 64));
+  CU(c, cudaEventRecord(c->ev[6], c->stream));
+  CU(c, cudaMemcpyAsync(c->d_bases, bases, n_bases, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemsetAsync(c->d_bases + n_bases, 'N', 256, c->stream));
+  CU(c, cudaMemcpyAsync(c->d_segs, segs, n_segs * sizeof(mm_segment), cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaEventRecord(c->ev[7], c->stream));
+  c->n_bases = n_bases;
+  c->n_segs = n_segs;
+  c->batch_mapped = false;
+  return MM_OK;
+}
+
+mm_dev_batch make_batch(mm_ctx *c)
+{
+  mm_dev_batch b{};
+  b.bases = c->d_bases; b.segs = c->d_segs; b.n_segs = (uint32_t)c->n_segs;
+  b.sk_hash = c->d_sk_hash; b.sk_pos = c->d_sk_pos; b.sk_strand = c->d_sk_strand;
+  b.seg_res = c->d_seg_res;
+  b.cands = c->d_cands; b.cand_cap = (uint32_t)std::min<uint64_t>(c->cand_cap, 0xffffffffu);
+  b.loci = c->d_loci; b.loci_cap = (uint32_t)std::min<uint64_t>(c->loci_cap, 0xffffffffu);
+  b.counters = c->d_counters;
+  b.scratch = c->d_scratch; b.scratch_slice = c->scratch_slice; b.scratch_pool_off = c->scratch_pool;
+  b.scratch_cap = c->scratch_cap;
+  return b;
+}
+
+int ensure_scratch(mm_ctx *c, uint64_t pool_elems)
+{
+  if (c->l1_grid == 0) {
+    c->l1_grid = mm_l1_grid_size(c->params, c->sm_count);
+    if (c->l1_grid == 0) return fail(c, MM_ECUDA, "cannot size the L1 grid");
+  }
+  const uint64_t slice = 3ULL << 16; /* 65536 points per CTA slice */
+  const uint64_t need = slice * c->l1_grid + pool_elems;
+  if (c->d_scratch && c->scratch_cap >= need) return MM_OK;
+  if (c->d_scratch) { cudaFree(c->d_scratch); c->d_scratch = nullptr; }
+  CU(c, cudaMalloc((void **)&c->d_scratch, need * 8));
+  c->scratch_cap = need;
+  c->scratch_slice = slice;
+  c->scratch_pool = slice * c->l1_grid;
+  return MM_OK;
+}
+
+/* K1 -> K2 -> K3 on the resident batch, growing output buffers and retrying on overflow */
+int run_pipeline(mm_ctx *c)
+{
+  int rc = check_ready(c);
+  if (rc) return rc;
+  CU(c, cudaSetDevice(c->device));
+  const uint64_t n_segs = c->n_segs;
+  if (c->cand_cap < 2 * n_segs + 1024) {
+    if (c->d_cands) { cudaFree(c->d_cands); c->d_cands = nullptr; }
+    c->cand_cap = 2 * n_segs + 1024;
+    CU(c, cudaMalloc((void **)&c->d_cands, c->cand_cap * sizeof(mm_l1_candidate)));
+  }
+  if (c->loci_cap < 2 * c->cand_cap) {
+    if (c->d_loci) { cudaFree(c->d_loci); c->d_loci = nullptr; }
+    c->loci_cap = 2 * c->cand_cap;
+    CU(c, cudaMalloc((void **)&c->d_loci, c->loci_cap * sizeof(mm_l2_locus)));
+  }
+  if ((rc = ensure_scratch(c, c->scratch_cap ? c->scratch_cap - c->scratch_pool : (32ULL << 20)))) return rc;
+
+  uint32_t h_cnt[16];
+  for (int attempt = 0; attempt < 6; attempt++) {
+    mm_dev_batch b = make_batch(c);
+    CU(c, cudaMemsetAsync(c->d_counters, 0, 64, c->stream));
+    CU(c, cudaEventRecord(c->ev[0], c->stream));
+    CU(c, mm_launch_sketch(c->params, b, c->stream, c->sm_count));
+    CU(c, cudaEventRecord(c->ev[1], c->stream));
+    CU(c, mm_launch_l1(c->params, c->ix, b, c->stream, c->sm_count));
+    CU(c, cudaEventRecord(c->ev[2], c->stream));
+    c->launches += 2;
+    CU(c, cudaMemcpyAsync(h_cnt, c->d_counters, 64, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    const uint64_t need_cands = h_cnt[0];
+    bool retry = false;
+    if (h_cnt[3] || need_cands > c->cand_cap) {
+      cudaFree(c->d_cands); c->d_cands = nullptr;
+      c->cand_cap = need_cands + need_cands / 4 + 1024;
+      CU(c, cudaMalloc((void **)&c->d_cands, c->cand_cap * sizeof(mm_l1_candidate)));
+      retry = true;
+    }
+    if (h_cnt[2]) { /* scratch pool exhausted: quadruple it */
+      const uint64_t pool = c->scratch_cap - c->scratch_pool;
+      cudaFree(c->d_scratch); c->d_scratch = nullptr; c->scratch_cap = 0;
+      if ((rc = ensure_scratch(c, pool * 4))) return rc;
+      retry = true;
+    }
+    if (retry) continue;
+    c->n_cands = need_cands;
+    /* K3, retried alone if the locus buffer is too small (it is idempotent) */
+    for (int a2 = 0; a2 < 4; a2++) {
+      b = make_batch(c);
+      CU(c, cudaMemsetAsync(c->d_counters + 1, 0, 4, c->stream));
+      CU(c, cudaMemsetAsync(c->d_counters + 6, 0, 4, c->stream));
+      CU(c, cudaEventRecord(c->ev[3], c->stream));
+      CU(c, mm_launch_l2(c->params, c->ix, b, (uint32_t)c->n_cands, c->stream, c->sm_count));
+      CU(c, cudaEventRecord(c->ev[4], c->stream));
+      if (c->n_cands) c->launches += 1;
+      CU(c, cudaMemcpyAsync(h_cnt, c->d_counters, 64, cudaMemcpyDeviceToHost, c->stream));
+      CU(c, cudaStreamSynchronize(c->stream));
+      if (h_cnt[1] == 2) return fail(c, MM_ECUDA, "L2 live-set overflow: the reference index has more than "
+                                     "sketch_size+64 overlapping minmer windows at one position");
+      if (h_cnt[1] == 1 || h_cnt[6] > c->loci_cap) {
+        cudaFree(c->d_loci); c->d_loci = nullptr;
+        c->loci_cap = (uint64_t)h_cnt[6] + h_cnt[6] / 4 + 1024;
+        CU(c, cudaMalloc((void **)&c->d_loci, c->loci_cap * sizeof(mm_l2_locus)));
+        continue;
+      }
+      c->n_loci = h_cnt[6];
+      cudaEventElapsedTime(&c->stage_ms[0], c->ev[0], c->ev[1]);
+      cudaEventElapsedTime(&c->stage_ms[1], c->ev[1], c->ev[2]);
+      cudaEventElapsedTime(&c->stage_ms[2], c->ev[3], c->ev[4]);
+      c->batch_mapped = true;
+      return MM_OK;
+    }
+    return fail(c, MM_ECUDA, "locus buffer kept overflowing");
+  }
+  return fail(c, MM_ECUDA, "candidate/scratch buffers kept overflowing");
+}
+
+} // namespace
+
+extern "C" {
+
+int mm_ctx_create(int device, const mm_params *params, mm_ctx **out)
+{
+  if (!params || !out) return fail(nullptr, MM_EINVAL, "null argument");
+  *out = nullptr;
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0)
+    return fail(nullptr, MM_ENODEVICE, "no CUDA device: %s (this library has no CPU path)", cudaGetErrorString(e));
+  if (device < 0 || device >= n_dev) return fail(nullptr, MM_ENODEVICE, "device %d out of range (%d devices)", device, n_dev);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(nullptr, MM_ENODEVICE, "cannot query device");
+  if (prop.major != 10) return fail(nullptr, MM_ENODEVICE, "device %d is sm_%d%d; this build is sm_100a only", device, prop.major, prop.minor);
+  if (!mm_sketch_kmer_supported(params->kmer_size))
+    return fail(nullptr, MM_EINVAL, "k-mer size %d is not compiled in", params->kmer_size);
+  if (params->sketch_size < 1 || params->seg_length < params->kmer_size)
+    return fail(nullptr, MM_EINVAL, "bad sketch_size / seg_length");
+  if (mm_sketch_smem_bytes(params->seg_length, params->sketch_size, nullptr) == 0)
+    return fail(nullptr, MM_EINVAL, "seg_length %d / sketch_size %d exceed the shared-memory budget of the sketch kernel",
+                params->seg_length, params->sketch_size);
+  mm_ctx *c = new mm_ctx();
+  c->device = device;
+  c->params = *params;
+  c->sm_count = prop.multiProcessorCount;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete c;
+    return fail(nullptr, MM_ECUDA, "cannot create stream");
+  }
+  for (auto &ev : c->ev) cudaEventCreate(&ev);
+  *out = c;
+  return MM_OK;
+}
+
+int mm_ctx_destroy(mm_ctx *c)
+{
+  if (!c) return MM_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (c->blob && c->blob_owned) cudaFree(c->blob);
+  cudaFree(c->d_bases); cudaFree(c->d_segs); cudaFree(c->d_sk_hash); cudaFree(c->d_sk_pos); cudaFree(c->d_sk_strand);
+  cudaFree(c->d_seg_res); cudaFree(c->d_cands); cudaFree(c->d_loci); cudaFree(c->d_counters); cudaFree(c->d_scratch);
+  for (auto &ev : c->ev) cudaEventDestroy(ev);
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return MM_OK;
+}
+
+const char *mm_last_error(const mm_ctx *c) { return c ? c->error.c_str() : g_create_error.c_str(); }
+uint64_t mm_kernel_launches(const mm_ctx *c) { return c ? c->launches : 0; }
+
+int mm_index_upload(mm_ctx *c, const mm_minmer *mi, uint64_t n_mi, const uint64_t *keys, const uint64_t *offsets,
+                    uint64_t n_keys, const mm_ipoint *points, uint64_t n_points, const uint8_t *key_is_freq,
+                    const int32_t *contig_len, const int32_t *contig_name_id, const int32_t *contig_group,
+                    int32_t n_contigs)
+{
+  if (!c) return MM_EINVAL;
+  if (n_contigs < 1 || !contig_len) return fail(c, MM_EINVAL, "no contigs");
+  if (n_keys && (!keys || !offsets || !key_is_freq)) return fail(c, MM_EINVAL, "null lookup arrays");
+  if (n_keys && offsets[n_keys] != n_points) return fail(c, MM_EINVAL, "offsets[n_keys] != n_points");
+  CU(c, cudaSetDevice(c->device));
+  if (c->blob && c->blob_owned) { cudaFree(c->blob); }
+  c->blob = nullptr; c->blob_ready = false;
+
+  /* contig_start: first index entry of each contig; the index must be ordered by (seqId, wpos) */
+  std::vector<uint64_t> cstart((size_t)n_contigs + 1, 0);
+  {
+    int32_t prev_seq = 0, prev_pos = -0x7fffffff;
+    for (uint64_t i = 0; i < n_mi; i++) {
+      const int32_t s = mi[i].seqId;
+      if (s < 0 || s >= n_contigs) return fail(c, MM_EINVAL, "minmer %llu: seqId %d out of range", (unsigned long long)i, s);
+      if (s < prev_seq || (s == prev_seq && mi[i].wpos < prev_pos))
+        return fail(c, MM_EINVAL, "minmer index not sorted by (seqId, wpos) at entry %llu", (unsigned long long)i);
+      if (s != prev_seq) prev_pos = -0x7fffffff;
+      prev_seq = s; prev_pos = mi[i].wpos;
+      cstart[(size_t)s + 1]++;
+    }
+    for (int32_t s = 0; s < n_contigs; s++) cstart[(size_t)s + 1] += cstart[(size_t)s];
+  }
+  int tab_log2 = 4;
+  while ((1ULL << tab_log2) < 2 * n_keys + 2) tab_log2++;
+  const uint64_t tab_slots = 1ULL << tab_log2;
+
+  mm_blob_header h{};
+  h.magic = MM_BLOB_MAGIC;
+  h.n_minmers = n_mi; h.n_keys = n_keys; h.n_points = n_points;
+  h.n_contigs = n_contigs; h.tab_log2 = tab_log2;
+  uint64_t o = align_up(sizeof(mm_blob_header), 256);
+  auto place = [&](uint64_t bytes) { uint64_t at = o; o = align_up(o + bytes, 256); return at; };
+  h.off_idx_hash = place((n_mi + 1) * 8);
+  h.off_idx_wpos = place((n_mi + 1) * 4);
+  h.off_idx_wend = place((n_mi + 1) * 4);
+  h.off_idx_strand = place(n_mi + 1);
+  h.off_contig_start = place(((uint64_t)n_contigs + 1) * 8);
+  h.off_tab = place(tab_slots * sizeof(mm_tab_slot));
+  h.off_pts = place((n_points + 1) * 8);
+  h.off_contig_len = place((uint64_t)n_contigs * 4);
+  h.off_contig_name_id = place((uint64_t)n_contigs * 4);
+  h.off_contig_group = place((uint64_t)n_contigs * 4);
+  h.off_cutoffs = place(TABLE_REGION_BYTES);
+  h.off_min_hits = place(TABLE_REGION_BYTES);
+  h.total_bytes = o;
+  CU(c, cudaMalloc((void **)&c->blob, o));
+  c->blob_bytes = o; c->blob_owned = true; c->hdr = h;
+
+  /* minmer index -> SoA, converted and copied in chunks to bound host memory */
+  {
+    const uint64_t CH = 1ULL << 22;
+    std::vector<uint64_t> bh(std::min(CH, n_mi + 1));
+    std::vector<int32_t> bw(bh.size()), be(bh.size());
+    std::vector<int8_t> bs(bh.size());
+    for (uint64_t at = 0; at < n_mi; at += CH) {
+      const uint64_t n = std::min(CH, n_mi - at);
+      for (uint64_t i = 0; i < n; i++) {
+        bh[i] = mi[at + i].hash; bw[i] = mi[at + i].wpos; be[i] = mi[at + i].wpos_end; bs[i] = (int8_t)mi[at + i].strand;
+      }
+      CU(c, cudaMemcpy(c->blob + h.off_idx_hash + at * 8, bh.data(), n * 8, cudaMemcpyHostToDevice));
+      CU(c, cudaMemcpy(c->blob + h.off_idx_wpos + at * 4, bw.data(), n * 4, cudaMemcpyHostToDevice));
+      CU(c, cudaMemcpy(c->blob + h.off_idx_wend + at * 4, be.data(), n * 4, cudaMemcpyHostToDevice));
+      CU(c, cudaMemcpy(c->blob + h.off_idx_strand + at, bs.data(), n, cudaMemcpyHostToDevice));
+    }
+  }
+  CU(c, cudaMemcpy(c->blob + h.off_contig_start, cstart.data(), cstart.size() * 8, cudaMemcpyHostToDevice));
+  /* interval points -> packed u64, in chunks */
+  {
+    const uint64_t CH = 1ULL << 22;
+    std::vector<uint64_t> bp(std::min(CH, n_points + 1));
+    for (uint64_t at = 0; at < n_points; at += CH) {
+      const uint64_t n = std::min(CH, n_points - at);
+      for (uint64_t i = 0; i < n; i++) {
+        const mm_ipoint &p = points[at + i];
+        if (p.seqId < 0 || p.seqId >= n_contigs || p.pos < 0) return fail(c, MM_EINVAL, "bad interval point %llu", (unsigned long long)(at + i));
+        bp[i] = mm_pack_point(p.seqId, p.pos, p.side > 0);
+      }
+      CU(c, cudaMemcpy(c->blob + h.off_pts + at * 8, bp.data(), n * 8, cudaMemcpyHostToDevice));
+    }
+  }
+  /* open-addressing table, built on the host */
+  {
+    std::vector<mm_tab_slot> tab(tab_slots);
+    memset(tab.data(), 0, tab_slots * sizeof(mm_tab_slot));
+    const uint32_t mask = (uint32_t)(tab_slots - 1);
+    for (uint64_t i = 0; i < n_keys; i++) {
+      const uint64_t cnt = offsets[i + 1] - offsets[i];
+      if (cnt == 0 || cnt > MM_VAL_CNT_MASK) return fail(c, MM_EINVAL, "key %llu has %llu interval points (unsupported)", (unsigned long long)i, (unsigned long long)cnt);
+      if (offsets[i] >= (1ULL << (64 - MM_VAL_OFF_SHIFT))) return fail(c, MM_EINVAL, "too many interval points");
+      uint32_t slot = mm_tab_slot_of(keys[i], tab_log2);
+      while (tab[slot].val != 0) {
+        if (tab[slot].key == keys[i]) return fail(c, MM_EINVAL, "duplicate key in lookup index");
+        slot = (slot + 1) & mask;
+      }
+      tab[slot].key = keys[i];
+      tab[slot].val = (offsets[i] << MM_VAL_OFF_SHIFT) | (cnt << 1) | (key_is_freq[i] ? 1ULL : 0ULL);
+    }
+    CU(c, cudaMemcpy(c->blob + h.off_tab, tab.data(), tab_slots * sizeof(mm_tab_slot), cudaMemcpyHostToDevice));
+  }
+  CU(c, cudaMemcpy(c->blob + h.off_contig_len, contig_len, (size_t)n_contigs * 4, cudaMemcpyHostToDevice));
+  std::vector<int32_t> tmp((size_t)n_contigs, -1);
+  CU(c, cudaMemcpy(c->blob + h.off_contig_name_id, contig_name_id ? contig_name_id : tmp.data(), (size_t)n_contigs * 4, cudaMemcpyHostToDevice));
+  std::fill(tmp.begin(), tmp.end(), 0);
+  CU(c, cudaMemcpy(c->blob + h.off_contig_group, contig_group ? contig_group : tmp.data(), (size_t)n_contigs * 4, cudaMemcpyHostToDevice));
+  CU(c, cudaMemcpy(c->blob, &c->hdr, sizeof(c->hdr), cudaMemcpyHostToDevice));
+  resolve_index(c);
+  c->blob_ready = true;
+  return write_tables(c);
+}
+
+int mm_tables_upload(mm_ctx *c, const int32_t *cut, int32_t n_cut, const int32_t *mh, int32_t n_mh)
+{
+  if (!c || !cut || !mh || n_cut < 1 || n_mh < 1) return fail(c, MM_EINVAL, "bad tables");
+  c->cutoffs.assign(cut, cut + n_cut);
+  c->min_hits.assign(mh, mh + n_mh);
+  CU(c, cudaSetDevice(c->device));
+  return write_tables(c);
+}
+
+int mm_index_blob(mm_ctx *c, void **blob, uint64_t *n_bytes)
+{
+  if (!c || !blob || !n_bytes) return MM_EINVAL;
+  if (!c->blob_ready) return fail(c, MM_ESTATE, "no index");
+  *blob = c->blob; *n_bytes = c->blob_bytes;
+  return MM_OK;
+}
+
+int mm_index_blob_alloc(mm_ctx *c, uint64_t n_bytes, void **blob)
+{
+  if (!c || !blob || n_bytes < sizeof(mm_blob_header)) return MM_EINVAL;
+  CU(c, cudaSetDevice(c->device));
+  if (c->blob && c->blob_owned) cudaFree(c->blob);
+  c->blob = nullptr; c->blob_ready = false;
+  CU(c, cudaMalloc((void **)&c->blob, n_bytes));
+  c->blob_bytes = n_bytes; c->blob_owned = true;
+  *blob = c->blob;
+  return MM_OK;
+}
+
+int mm_index_adopt_blob(mm_ctx *c)
+{
+  if (!c || !c->blob) return fail(c, MM_ESTATE, "no blob allocated");
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaMemcpy(&c->hdr, c->blob, sizeof(c->hdr), cudaMemcpyDeviceToHost));
+  if (c->hdr.magic != MM_BLOB_MAGIC || c->hdr.total_bytes != c->blob_bytes) return fail(c, MM_EINVAL, "blob header mismatch");
+  resolve_index(c);
+  c->blob_ready = true;
+  return MM_OK;
+}
+
+int mm_batch_upload(mm_ctx *c, const char *bases, uint64_t n_bases, const mm_segment *segs, uint64_t n_segs)
+{
+  if (!c || (!bases && n_bases) || (!segs && n_segs)) return fail(c, MM_EINVAL, "null argument");
+  int rc = upload_batch(c, bases, n_bases, segs, n_segs);
+  if (rc) return rc;
+  CU(c, cudaStreamSynchronize(c->stream));
+  cudaEventElapsedTime(&c->stage_ms[3], c->ev[6], c->ev[7]);
+  return MM_OK;
+}
+
+int mm_map_resident(mm_ctx *c, uint64_t *n_candidates, uint64_t *n_loci)
+{
+  if (!c) return MM_EINVAL;
+  int rc = run_pipeline(c);
+  if (rc) return rc;
+  if (n_candidates) *n_candidates = c->n_cands;
+  if (n_loci) *n_loci = c->n_loci;
+  return MM_OK;
+}
+
+int mm_batch_fetch(mm_ctx *c, mm_segment_result *seg_results, mm_l1_candidate *cands, uint64_t cand_cap,
+                   mm_l2_locus *loci, uint64_t loci_cap)
+{
+  if (!c || !c->batch_mapped) return fail(c, MM_ESTATE, "no mapped batch");
+  if (cand_cap < c->n_cands || loci_cap < c->n_loci) return fail(c, MM_ECAPACITY, "output capacity too small");
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaEventRecord(c->ev[5], c->stream));
+  if (seg_results) CU(c, cudaMemcpyAsync(seg_results, c->d_seg_res, c->n_segs * sizeof(mm_segment_result), cudaMemcpyDeviceToHost, c->stream));
+  if (cands && c->n_cands) CU(c, cudaMemcpyAsync(cands, c->d_cands, c->n_cands * sizeof(mm_l1_candidate), cudaMemcpyDeviceToHost, c->stream));
+  if (loci && c->n_loci) CU(c, cudaMemcpyAsync(loci, c->d_loci, c->n_loci * sizeof(mm_l2_locus), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaEventRecord(c->ev[6], c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  cudaEventElapsedTime(&c->stage_ms[4], c->ev[5], c->ev[6]);
+  return MM_OK;
+}
+
+int mm_batch_fetch_sketch(mm_ctx *c, mm_minmer *out, int32_t *out_count)
+{
+  if (!c || !c->batch_mapped || !out || !out_count) return fail(c, MM_ESTATE, "no mapped batch");
+  CU(c, cudaSetDevice(c->device));
+  const uint64_t S = (uint64_t)c->params.sketch_size, n = c->n_segs * S;
+  std::vector<uint64_t> hh(n);
+  std::vector<int2> pp(n);
+  std::vector<int8_t> ss(n);
+  std::vector<mm_segment_result> sr(c->n_segs);
+  std::vector<mm_segment> sg(c->n_segs);
+  CU(c, cudaMemcpy(hh.data(), c->d_sk_hash, n * 8, cudaMemcpyDeviceToHost));
+  CU(c, cudaMemcpy(pp.data(), c->d_sk_pos, n * 8, cudaMemcpyDeviceToHost));
+  CU(c, cudaMemcpy(ss.data(), c->d_sk_strand, n, cudaMemcpyDeviceToHost));
+  CU(c, cudaMemcpy(sr.data(), c->d_seg_res, c->n_segs * sizeof(mm_segment_result), cudaMemcpyDeviceToHost));
+  CU(c, cudaMemcpy(sg.data(), c->d_segs, c->n_segs * sizeof(mm_segment), cudaMemcpyDeviceToHost));
+  for (uint64_t s = 0; s < c->n_segs; s++) {
+    out_count[s] = sr[s].sketch_size;
+    for (int j = 0; j < sr[s].sketch_size; j++) {
+      mm_minmer &m = out[s * S + j];
+      m.hash = hh[s * S + j]; m.wpos = pp[s * S + j].x; m.wpos_end = pp[s * S + j].y;
+      m.seqId = sg[s].seq_counter; m.strand = ss[s * S + j]; m._pad = 0;
+    }
+  }
+  return MM_OK;
+}
+
+int mm_sketch_segments(mm_ctx *c, const char *bases, uint64_t n_bases, const mm_segment *segs, uint64_t n_segs,
+                       mm_minmer *out, int32_t *out_count)
+{
+  if (!c || !out || !out_count) return fail(c, MM_EINVAL, "null argument");
+  int rc = upload_batch(c, bases, n_bases, segs, n_segs);
+  if (rc) return rc;
+  mm_dev_batch b = make_batch(c);
+  CU(c, cudaEventRecord(c->ev[0], c->stream));
+  CU(c, mm_launch_sketch(c->params, b, c->stream, c->sm_count));
+  CU(c, cudaEventRecord(c->ev[1], c->stream));
+  c->launches += 1;
+  CU(c, cudaStreamSynchronize(c->stream));
+  cudaEventElapsedTime(&c->stage_ms[0], c->ev[0], c->ev[1]);
+  c->batch_mapped = true; /* sketches only; fetch_sketch reads sketch_size == raw count */
+  rc = mm_batch_fetch_sketch(c, out, out_count);
+  c->batch_mapped = false;
+  return rc;
+}
+
+int mm_map_segments(mm_ctx *c, const char *bases, uint64_t n_bases, const mm_segment *segs, uint64_t n_segs,
+                    mm_segment_result *seg_results, mm_l1_candidate *cands, uint64_t cand_cap, uint64_t *n_candidates,
+                    mm_l2_locus *loci, uint64_t loci_cap, uint64_t *n_loci)
+{
+  if (!c || !seg_results || !n_candidates || !n_loci) return fail(c, MM_EINVAL, "null argument");
+  int rc = upload_batch(c, bases, n_bases, segs, n_segs);
+  if (rc) return rc;
+  if ((rc = run_pipeline(c))) return rc;
+  cudaEventElapsedTime(&c->stage_ms[3], c->ev[6], c->ev[7]);
+  *n_candidates = c->n_cands;
+  *n_loci = c->n_loci;
+  if (cand_cap < c->n_cands || loci_cap < c->n_loci) return fail(c, MM_ECAPACITY, "need %llu candidates, %llu loci", (unsigned long long)c->n_cands, (unsigned long long)c->n_loci);
+  return mm_batch_fetch(c, seg_results, cands, cand_cap, loci, loci_cap);
+}
+
+int mm_last_stage_ms(const mm_ctx *c, float ms[8])
+{
+  if (!c || !ms) return MM_EINVAL;
+  for (int i = 0; i < 8; i++) ms[i] = c->stage_ms[i];
+  return MM_OK;
+}
+
+/* pinned host memory for the caller's batch buffers (H2D/D2H at full PCIe rate) */
+int mm_host_alloc(void **ptr, uint64_t bytes)
+{
+  if (!ptr) return MM_EINVAL;
+  return cudaHostAlloc(ptr, bytes, cudaHostAllocDefault) == cudaSuccess ? MM_OK : MM_ENOMEM;
+}
+int mm_host_free(void *ptr) { return cudaFreeHost(ptr) == cudaSuccess ? MM_OK : MM_ECUDA; }
+
+} // extern "C"

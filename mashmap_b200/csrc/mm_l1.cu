@@ -1,0 +1,476 @@
+/*
+ * mm_l1.cu -- K2: L1 candidate regions of every query segment.
+ *
+ * Replaces, per segment (rows a4-a10 of SURVEY 8(a)):
+ *   the frequent-seed removal of Map::getSeedHits                  computeMap.hpp:834-839
+ *   Map::getSeedIntervalPoints (hash-map probes + k-way heap merge) computeMap.hpp:856-912
+ *   Stat::estimateMinimumHitsRelaxed (host table, indexed by Q.sketchSize)   :1144
+ *   Map::computeL1CandidateRegions (two sweeps + cluster join)       computeMap.hpp:915-1116
+ *   the per-reference-group loop of Map::doL1Mapping                 computeMap.hpp:1146-1165
+ *
+ * The reference merges the per-hash point lists with a heap; only the final order
+ * (IntervalPoint::operator<, base_types.hpp:75-78) matters, so the points are gathered in any order
+ * and sorted (bitonic; shared memory, or global-memory scratch for segments with more points than fit).
+ * The two sweeps are restated in the stateless form of SURVEY A.5:
+ *   groups   = maximal runs of consecutive points with equal pos (seqId is NOT compared, :1047,:1051)
+ *   O_g      = #OPEN in points up to the end of group g
+ *              - #CLOSE among points whose (seqId,pos) <= (seqId,pos) of the group's FIRST point
+ *              (the trailing iterator of :1033-1046 with windowLen == 0)
+ *   best     = max_g O_g (sweep #1, :948-983); return early if best < minimumHits (:987-990);
+ *              HG filter raises minimumHits to sketchCutoffs[int(min(best,Q.s)/max(1,s/1000))] (:992-997)
+ *   sweep #2 tests, at each group, the overlap after the PREVIOUS group (:1026-1027,:1062), so every
+ *   group but the last is a candidate position iff O_g >= minimumHits; maximal stretches of flagged
+ *   consecutive groups on one contig become {seqId, first pos, last pos, max O} (:1065-1098,
+ *   stage2_full_scan is always true), and stretches closer than segLength are joined (:1102-1115).
+ *
+ * One CTA per segment (persistent grid). windowLen (computeMap.hpp:933) is 0 for every fragment of a
+ * split read and for reads no longer than segLength, which is all the C ABI accepts.
+ */
+#include "mm_internal.h"
+
+namespace {
+
+constexpr int L1_THREADS = 128;
+constexpr int L1_SMEM_POINTS = 2048; /* points handled in shared memory; more -> global scratch */
+constexpr int L1_LOCAL_CANDS = 64;
+
+struct l1_hit {
+  uint64_t off;
+  uint32_t cnt;
+  uint32_t dst; /* exclusive prefix of cnt */
+};
+
+/* exclusive prefix over the block; total = block sum. Contains two __syncthreads. */
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *warp_sums, uint32_t &total)
+{
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) warp_sums[wid] = incl;
+  __syncthreads();
+  uint32_t base = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < L1_THREADS / 32; w++) {
+    const uint32_t s = warp_sums[w];
+    if (w < wid) base += s;
+    tot += s;
+  }
+  __syncthreads();
+  total = tot;
+  return base + incl - v;
+}
+
+/* in-place bitonic sort of n (power of two) u64 keys by the whole block (shared or global memory) */
+__device__ void block_bitonic_sort(uint64_t *a, uint32_t n)
+{
+  for (uint32_t k = 2; k <= n; k <<= 1) {
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      for (uint32_t t = threadIdx.x; t < (n >> 1); t += L1_THREADS) {
+        const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1)); /* lower index of the pair */
+        const uint32_t p = i | j;
+        const bool up = (i & k) == 0;
+        const uint64_t x = a[i], y = a[p];
+        if ((x > y) == up) { a[i] = y; a[p] = x; }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+struct l1_out_list {
+  mm_l1_candidate *dst; /* where candidates go (shared-memory buffer or global array) */
+  uint32_t cap;         /* writes beyond cap are counted but not stored */
+  uint32_t n;           /* candidates produced so far */
+  uint32_t segment;
+};
+
+/* sweep #2 run state (computeMap.hpp:1009-1098) and the join (:1102-1115); uniform across warp 0 */
+struct l1_walk_state {
+  bool in_run;
+  int run_seq, run_start, run_end, run_isz;
+  int prev_group;
+  bool have_out;
+  int out_seq, out_start, out_end, out_isz;
+};
+
+__device__ __forceinline__ void l1_emit(l1_out_list &o, int seq, int start, int end, int isz)
+{
+  if (o.n < o.cap && (threadIdx.x & 31) == 0) {
+    mm_l1_candidate c;
+    c.seqId = seq; c.rangeStartPos = start; c.rangeEndPos = end; c.intersectionSize = isz;
+    c.segment = o.segment; c.first_locus = 0; c.n_loci = 0; c._pad = 0;
+    o.dst[o.n] = c;
+  }
+  o.n++;
+}
+
+__device__ __forceinline__ void l1_close_run(l1_walk_state &w, int seg_length, l1_out_list &o)
+{
+  if (!w.in_run) return;
+  w.in_run = false;
+  if (w.have_out && w.run_seq == w.out_seq && w.run_start <= w.out_end + seg_length) {
+    w.out_end = w.run_end; /* join (computeMap.hpp:1110-1114) */
+    w.out_isz = max(w.out_isz, w.run_isz);
+  } else {
+    if (w.have_out) l1_emit(o, w.out_seq, w.out_start, w.out_end, w.out_isz);
+    w.have_out = true;
+    w.out_seq = w.run_seq; w.out_start = w.run_start; w.out_end = w.run_end; w.out_isz = w.run_isz;
+  }
+}
+
+/* Executed by warp 0 only. keys[0..n): sorted points of one reference group; ginfo[i] = O_g stored at
+ * the last index of each group; head[i] = index of the group's first point. */
+__device__ void l1_walk(const uint64_t *keys, const uint32_t *ginfo, const uint32_t *head, uint32_t n, int mh,
+                        int seg_length, l1_out_list &o)
+{
+  const int lane = threadIdx.x & 31;
+  l1_walk_state w;
+  w.in_run = false; w.have_out = false; w.prev_group = -2;
+  w.run_seq = w.run_start = w.run_end = w.run_isz = 0;
+  w.out_seq = w.out_start = w.out_end = w.out_isz = 0;
+  int group_base = 0;
+  for (uint32_t base = 0; base < n; base += 32) {
+    const uint32_t i = base + lane;
+    bool last_of_group = false, flagged = false;
+    uint32_t ov = 0;
+    if (i < n) {
+      last_of_group = (i + 1 == n) || (mm_point_pos(keys[i + 1]) != mm_point_pos(keys[i]));
+      if (last_of_group) {
+        ov = ginfo[i];
+        /* the last group is never tested (the test lags one group behind, :1026-1027,:1062) */
+        flagged = (i + 1 != n) && ((int)ov >= mh);
+      }
+    }
+    const uint32_t glast = __ballot_sync(0xffffffffu, last_of_group);
+    uint32_t fl = __ballot_sync(0xffffffffu, flagged);
+    while (fl) {
+      const int l = __ffs(fl) - 1;
+      fl &= fl - 1;
+      const int g = group_base + __popc(glast & ((1u << l) - 1u));
+      const uint32_t idx = base + l;
+      const int O = (int)__shfl_sync(0xffffffffu, ov, l);
+      const uint64_t hk = keys[head[idx]];
+      const int seq = mm_point_seq(hk), pos = mm_point_pos(hk);
+      if (w.in_run && (g != w.prev_group + 1 || seq != w.run_seq)) l1_close_run(w, seg_length, o);
+      if (!w.in_run) {
+        w.in_run = true;
+        w.run_seq = seq; w.run_start = pos; w.run_end = pos; w.run_isz = O;
+      } else {
+        w.run_isz = max(w.run_isz, O); /* stage2_full_scan (:1077-1080) */
+        w.run_end = pos;
+      }
+      w.prev_group = g;
+    }
+    group_base += __popc(glast);
+  }
+  l1_close_run(w, seg_length, o);
+  if (w.have_out) l1_emit(o, w.out_seq, w.out_start, w.out_end, w.out_isz);
+}
+
+struct l1_shared {
+  uint32_t warp_sums[L1_THREADS / 32];
+  uint32_t hmax[L1_THREADS];
+  int best;
+  int fail;
+  uint32_t range_end;
+  uint32_t cand_base;
+  unsigned long long scratch_base;
+  uint32_t out_n;
+  mm_l1_candidate local[L1_LOCAL_CANDS];
+};
+
+/* computeL1CandidateRegions over the sorted points keys[0..n) of ONE reference group.
+ * Returns (uniformly) bestIntersectionSize; appends candidates through warp 0. */
+__device__ int l1_process_range(const mm_params &prm, const mm_dev_index &ix, const uint64_t *keys, uint32_t *copn,
+                                uint32_t *head, uint32_t *ginfo, uint32_t n, int qs, l1_shared &sh, l1_out_list &o,
+                                int &mh_out)
+{
+  const int tid = threadIdx.x;
+  const uint32_t chunk = (n + L1_THREADS - 1) / L1_THREADS;
+  const uint32_t a = min(n, tid * chunk), e = min(n, a + chunk);
+  if (tid == 0) sh.best = 0;
+  /* inclusive count of OPEN points and head index of each position-group */
+  uint32_t opens = 0, hmax = 0;
+  for (uint32_t i = a; i < e; i++) {
+    const uint64_t p = keys[i];
+    opens += (uint32_t)mm_point_open(p);
+    if (i == 0 || mm_point_pos(keys[i - 1]) != mm_point_pos(p)) hmax = i;
+  }
+  uint32_t dummy;
+  const uint32_t po = block_exclusive_scan(opens, sh.warp_sums, dummy);
+  sh.hmax[tid] = hmax;
+  __syncthreads();
+  uint32_t hd = 0;
+  for (int t = 0; t < tid; t++) hd = max(hd, sh.hmax[t]);
+  uint32_t co = po;
+  for (uint32_t i = a; i < e; i++) {
+    const uint64_t p = keys[i];
+    co += (uint32_t)mm_point_open(p);
+    if (i == 0 || mm_point_pos(keys[i - 1]) != mm_point_pos(p)) hd = i;
+    copn[i] = co;
+    head[i] = hd;
+  }
+  __syncthreads();
+  /* O_g at the last index of every group */
+  int best_local = 0;
+  for (uint32_t i = a; i < e; i++) {
+    const uint64_t p = keys[i];
+    const bool last_of_group = (i + 1 == n) || (mm_point_pos(keys[i + 1]) != mm_point_pos(p));
+    if (!last_of_group) continue;
+    const uint32_t h0 = head[i];
+    const uint64_t hk = keys[h0] >> 1; /* (seqId,pos) of the group's first point */
+    uint32_t sub_end = i + 1;
+    if ((p >> 1) != hk) { /* the group spans two contigs (equal pos): CLOSEs count up to the first sub-run only */
+      sub_end = h0 + 1;
+      while ((keys[sub_end] >> 1) == hk) sub_end++;
+    }
+    const uint32_t closes = sub_end - copn[sub_end - 1];
+    const int O = (int)copn[i] - (int)closes;
+    ginfo[i] = (uint32_t)O;
+    best_local = max(best_local, O);
+  }
+  atomicMax(&sh.best, best_local);
+  __syncthreads();
+  const int best = sh.best;
+  /* minimumHits (computeMap.hpp:1144, host table by Q.sketchSize) and the HG raise (:987-998) */
+  int mh = ix.min_hits[min(qs, ix.n_min_hits - 1)];
+  bool go = true;
+  if (prm.stage1_topani_filter) {
+    if (best < mh) go = false;
+    else {
+      const double denom = fmax(1.0, (double)prm.sketch_size / 1000.0);
+      int ci = (int)((double)min(best, qs) / denom);
+      ci = min(ci, ix.n_cutoffs - 1);
+      mh = max(ix.cutoffs[ci], mh);
+    }
+  }
+  mh_out = go ? mh : 0;
+  if (go && tid < 32) l1_walk(keys, ginfo, head, n, mh, prm.seg_length, o);
+  __syncthreads();
+  return best;
+}
+
+__global__ void __launch_bounds__(L1_THREADS)
+k_l1(const mm_params prm, const mm_dev_index ix, const mm_dev_batch b)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int S = prm.sketch_size;
+  /* dynamic: hits[S] | keys[P] u64 | copn[P] | head[P] | ginfo[P] */
+  l1_hit *hits = (l1_hit *)smem_raw;
+  uint64_t *skeys = (uint64_t *)(smem_raw + (((size_t)S * sizeof(l1_hit) + 15) & ~(size_t)15));
+  uint32_t *scopn = (uint32_t *)(skeys + L1_SMEM_POINTS);
+  uint32_t *shead = scopn + L1_SMEM_POINTS;
+  uint32_t *sginfo = shead + L1_SMEM_POINTS;
+  __shared__ l1_shared sh;
+
+  const int tid = threadIdx.x;
+
+  for (uint32_t seg = blockIdx.x; seg < b.n_segs; seg += gridDim.x) {
+    const mm_segment sg = b.segs[seg];
+    const size_t sbase = (size_t)seg * (size_t)S;
+    const int raw = b.seg_res[seg].sketch_raw_count;
+    if (tid == 0) { sh.fail = 0; }
+
+    /* ---- 1. probe the index for every sketch hash; drop frequent seeds; compact the sketch in place ---- */
+    uint32_t kept_total = 0; /* Q.sketchSize (computeMap.hpp:839) */
+    uint32_t hit_total = 0;  /* kept hashes present in the lookup index (:878-883) */
+    uint32_t m = 0;          /* interval points of those hashes */
+    const uint64_t max_hash = raw > 0 ? b.sk_hash[sbase + raw - 1] : 0;
+    for (int c0 = 0; c0 < raw; c0 += L1_THREADS) {
+      const int j = c0 + tid;
+      uint64_t h = 0, val = 0;
+      int2 ps = make_int2(0, 0);
+      int8_t st = 0;
+      bool keep = false;
+      if (j < raw) {
+        h = b.sk_hash[sbase + j];
+        ps = b.sk_pos[sbase + j];
+        st = b.sk_strand[sbase + j];
+        uint32_t slot = mm_tab_slot_of(h, ix.tab_log2);
+        const uint32_t tmask = (1u << ix.tab_log2) - 1u;
+        while (true) {
+          const mm_tab_slot t = ix.tab[slot];
+          if (t.val == MM_TAB_EMPTY_VAL) break;
+          if (t.key == h) { val = t.val; break; }
+          slot = (slot + 1) & tmask;
+        }
+        keep = !(val & 1ULL); /* !isFreqSeed (winSketch.hpp:506-509) */
+      }
+      const bool hit = keep && val != 0;
+      const uint32_t cnt = hit ? (uint32_t)((val >> 1) & MM_VAL_CNT_MASK) : 0u;
+      uint32_t tot_k, tot_h, tot_m;
+      const uint32_t pk = block_exclusive_scan(keep ? 1u : 0u, sh.warp_sums, tot_k);
+      const uint32_t ph = block_exclusive_scan(hit ? 1u : 0u, sh.warp_sums, tot_h);
+      const uint32_t pm = block_exclusive_scan(cnt, sh.warp_sums, tot_m);
+      if (keep) { /* destination index <= j: never overtakes the reads of a later chunk */
+        b.sk_hash[sbase + kept_total + pk] = h;
+        b.sk_pos[sbase + kept_total + pk] = ps;
+        b.sk_strand[sbase + kept_total + pk] = st;
+      }
+      if (hit) {
+        l1_hit hh;
+        hh.off = val >> MM_VAL_OFF_SHIFT; hh.cnt = cnt; hh.dst = m + pm;
+        hits[hit_total + ph] = hh;
+      }
+      kept_total += tot_k; hit_total += tot_h; m += tot_m;
+    }
+    __syncthreads();
+
+    /* ---- 2. gather the interval points (computeMap.hpp:887-907, order restored by the sort) ---- */
+    uint32_t n_pow2 = 1;
+    while (n_pow2 < m) n_pow2 <<= 1;
+    uint64_t *keys = skeys;
+    uint32_t *copn = scopn, *head = shead, *ginfo = sginfo;
+    if (m > (uint32_t)L1_SMEM_POINTS) {
+      const unsigned long long need = 3ULL * n_pow2; /* u64 units: keys + 3 u32 arrays */
+      if (need <= b.scratch_slice) {
+        keys = b.scratch + (size_t)blockIdx.x * b.scratch_slice; /* this CTA's slice, reused per segment */
+      } else {
+        if (tid == 0) {
+          const unsigned long long at = b.scratch_pool_off + atomicAdd((unsigned long long *)(b.counters + 4), need);
+          if (at + need > b.scratch_cap) { sh.fail = 1; atomicExch(b.counters + 2, 1u); }
+          sh.scratch_base = at;
+        }
+        __syncthreads();
+        if (!sh.fail) keys = b.scratch + sh.scratch_base;
+      }
+      if (keys != skeys) {
+        copn = (uint32_t *)(keys + n_pow2);
+        head = copn + n_pow2;
+        ginfo = head + n_pow2;
+      }
+    }
+    __syncthreads();
+    const bool fail = sh.fail != 0;
+    uint32_t mp = 0; /* points that pass the skip predicates */
+    if (!fail && m > 0) {
+      for (uint32_t i = m + tid; i < n_pow2; i += L1_THREADS) keys[i] = ~0ULL;
+      uint32_t dropped_local = 0;
+      for (uint32_t hi = tid; hi < hit_total; hi += L1_THREADS) {
+        const l1_hit hh = hits[hi];
+        for (uint32_t q = 0; q < hh.cnt; q++) {
+          uint64_t p = ix.pts[hh.off + q];
+          if (prm.skip_self | prm.skip_prefix | prm.lower_triangular) {
+            const int rs = mm_point_seq(p);
+            /* computeMap.hpp:891-893 */
+            const bool ok = (!prm.skip_self || sg.name_id < 0 || sg.name_id != ix.contig_name_id[rs]) &&
+                            (!prm.skip_prefix || ix.contig_group[rs] != sg.ref_group) &&
+                            (!prm.lower_triangular || sg.seq_counter > rs);
+            if (!ok) { p = ~0ULL; dropped_local++; }
+          }
+          keys[hh.dst + q] = p;
+        }
+      }
+      uint32_t dropped;
+      (void)block_exclusive_scan(dropped_local, sh.warp_sums, dropped);
+      mp = m - dropped;
+      /* ---- 3. sort by (seqId,pos,side); dropped points (all ones) go last ---- */
+      block_bitonic_sort(keys, n_pow2);
+    }
+
+    /* ---- 4./5./6. per reference group: scans, best, threshold, walk ---- */
+    int best_all = 0, mh_first = 0;
+    l1_out_list out;
+    out.dst = sh.local; out.cap = L1_LOCAL_CANDS; out.n = 0; out.segment = seg;
+    for (int pass = 0; pass < 2; pass++) {
+      uint32_t start = 0;
+      bool first_range = true;
+      while (start < mp) {
+        uint32_t end = mp;
+        if (prm.skip_prefix) { /* doL1Mapping groups points by reference prefix group (:1146-1165) */
+          if (tid == 0) sh.range_end = mp;
+          __syncthreads();
+          const int g0 = ix.contig_group[mm_point_seq(keys[start])];
+          uint32_t found = mp;
+          for (uint32_t i = start + 1 + tid; i < mp; i += L1_THREADS)
+            if (ix.contig_group[mm_point_seq(keys[i])] != g0) { found = i; break; }
+          if (found < mp) atomicMin(&sh.range_end, found);
+          __syncthreads();
+          end = sh.range_end;
+          __syncthreads();
+        }
+        int mh = 0;
+        const int best = l1_process_range(prm, ix, keys + start, copn, head, ginfo, end - start, (int)kept_total, sh,
+                                          out, mh);
+        if (pass == 0) {
+          best_all = max(best_all, best);
+          if (first_range) mh_first = mh;
+        }
+        first_range = false;
+        start = end;
+      }
+      /* candidates were produced by warp 0: publish the count */
+      if (tid == 0) sh.out_n = out.n;
+      __syncthreads();
+      const uint32_t n_out = sh.out_n;
+      if (pass == 0) {
+        if (tid == 0) {
+          uint32_t basec = 0;
+          if (n_out > 0) {
+            basec = atomicAdd(b.counters + 0, n_out);
+            if ((unsigned long long)basec + n_out > b.cand_cap) atomicExch(b.counters + 3, 1u);
+          }
+          sh.cand_base = basec;
+        }
+        __syncthreads();
+        const uint32_t basec = sh.cand_base;
+        const bool fits = (unsigned long long)basec + n_out <= b.cand_cap;
+        if (n_out <= (uint32_t)L1_LOCAL_CANDS) {
+          if (fits)
+            for (uint32_t i = tid; i < n_out; i += L1_THREADS) b.cands[basec + i] = sh.local[i];
+          break;
+        }
+        if (!fits) break;
+        /* rare: more candidates than the local buffer holds -> redo the walk writing to global memory */
+        out.dst = b.cands + basec; out.cap = n_out; out.n = 0;
+      }
+    }
+    if (tid == 0) {
+      mm_segment_result r;
+      r.sketch_max_hash = max_hash;
+      r.sketch_raw_count = raw;
+      r.sketch_size = (int32_t)kept_total;
+      r.n_points = fail ? -1 : (int32_t)mp;
+      r.minimum_hits = mh_first;
+      r.best_intersection = best_all;
+      r.first_candidate = sh.cand_base;
+      r.n_candidates = sh.out_n;
+      r._pad = 0;
+      b.seg_res[seg] = r;
+    }
+    __syncthreads();
+  }
+}
+
+} // namespace
+
+static size_t l1_smem_bytes(const mm_params &p)
+{
+  return (((size_t)p.sketch_size * sizeof(l1_hit) + 15) & ~(size_t)15) + (size_t)L1_SMEM_POINTS * (8 + 4 + 4 + 4);
+}
+
+/* CTAs of the persistent L1 grid (the scratch area holds one slice per CTA) */
+uint32_t mm_l1_grid_size(const mm_params &p, int sm_count)
+{
+  const size_t smem = l1_smem_bytes(p);
+  if (cudaFuncSetAttribute(k_l1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_l1, L1_THREADS, smem) != cudaSuccess) return 0;
+  if (occ < 1) occ = 1;
+  return (uint32_t)sm_count * (uint32_t)occ;
+}
+
+cudaError_t mm_launch_l1(const mm_params &p, const mm_dev_index &ix, const mm_dev_batch &b, cudaStream_t st,
+                         int sm_count)
+{
+  if (b.n_segs == 0) return cudaSuccess;
+  uint32_t grid = mm_l1_grid_size(p, sm_count);
+  if (grid == 0) return cudaErrorInvalidValue;
+  if (grid > b.n_segs) grid = b.n_segs;
+  k_l1<<<grid, L1_THREADS, l1_smem_bytes(p), st>>>(p, ix, b);
+  return cudaGetLastError();
+}

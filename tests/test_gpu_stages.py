@@ -1,0 +1,190 @@
+"""GPU parity, stage by stage, through the C ABI, against the UNMODIFIED reference (oracle/_ref harness):
+K1 sketch == CommonFunc::sketchSequence, K2 candidates == doL1Mapping, K3 loci == computeL2MappedRegions.
+Bit-exact (integer work)."""
+import numpy as np
+import pytest
+
+import datasets
+import refh
+from conftest import have_gpu
+from mashmap_b200 import synth
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not have_gpu(), reason="no GPU"),
+              pytest.mark.skipif(not refh.available(), reason="oracle/_ref not built")]
+
+
+def build_segments(d, seg_length, k, name_ids=None):
+    from mashmap_b200 import capi
+
+    lens = [len(r) for r in d["reads"]]
+    ridx, start, length = synth.split_segments(lens, seg_length, k)
+    offs = np.zeros(len(lens) + 1, dtype=np.int64)
+    offs[1:] = np.cumsum(lens)
+    bases = np.concatenate(d["reads"]).astype(np.uint8)
+    segs = np.zeros(len(ridx), dtype=capi.segment_dtype)
+    segs["offset"] = offs[ridx] + start
+    segs["length"] = length
+    segs["seq_counter"] = ridx
+    segs["name_id"] = -1 if name_ids is None else np.asarray(name_ids)[ridx]
+    segs["ref_group"] = -1
+    return bases, segs, ridx, start, length
+
+
+def upload_reference_index(ctx, R):
+    idx = R.index()
+    keys, offs, pts, fr = R.lookup()
+    ctx.index_upload(idx, keys, offs, pts, fr, R.contig_len)
+    ctx.tables_upload(R.cutoffs(), R.min_hits_table())
+
+
+def compare_stages(ctx, R, d, ridx, start, length, seg_res, cands, loci, dev_sketch, dev_count, max_report=10):
+    bad = []
+    n_cmp = 0
+    for i in range(len(ridx)):
+        r = d["reads"][ridx[i]]
+        seg = r[start[i] : start[i] + length[i]]
+        o = R.map_fragment(d["rnames"][ridx[i]], seg, full_len=len(r), seq_counter=int(ridx[i]))
+        sr = seg_res[i]
+        # sketch after frequent-seed removal
+        rs = o["sketch"]
+        ds = dev_sketch[i][: dev_count[i]]
+        if len(rs) != len(ds) or not (np.array_equal(rs["hash"], ds["hash"]) and np.array_equal(rs["wpos"], ds["wpos"])
+                                      and np.array_equal(rs["wpos_end"], ds["wpos_end"])
+                                      and np.array_equal(rs["strand"], ds["strand"])):
+            bad.append((i, "sketch", len(rs), len(ds)))
+            continue
+        if sr["sketch_size"] != len(rs):
+            bad.append((i, "sketch_size", len(rs), int(sr["sketch_size"])))
+        if sr["n_points"] != o["n_points"]:
+            bad.append((i, "n_points", o["n_points"], int(sr["n_points"])))
+        c = cands[sr["first_candidate"] : sr["first_candidate"] + sr["n_candidates"]]
+        rl1 = o["l1"]
+        same = len(c) == len(rl1) and all(
+            np.array_equal(c[f], rl1[f]) for f in ("seqId", "rangeStartPos", "rangeEndPos", "intersectionSize"))
+        if not same:
+            bad.append((i, "l1", rl1.tolist(), c[["seqId", "rangeStartPos", "rangeEndPos", "intersectionSize"]].tolist()))
+            continue
+        for ci in range(len(c)):
+            dl = loci[c[ci]["first_locus"] : c[ci]["first_locus"] + c[ci]["n_loci"]]
+            rl = o["l2"][o["l2_cand"] == ci]
+            n_cmp += 1
+            if len(dl) != len(rl) or not all(np.array_equal(dl[f], rl[f]) for f in rl.dtype.names):
+                bad.append((i, f"l2 cand {ci}", rl.tolist(), dl.tolist()))
+    for b in bad[:max_report]:
+        print("MISMATCH", b)
+    print(f"segments={len(ridx)} candidates_compared={n_cmp} mismatches={len(bad)}")
+    return bad
+
+
+@pytest.fixture(scope="module")
+def random_set(workdir):
+    return datasets.make_random_set(workdir)
+
+
+@pytest.fixture(scope="module")
+def panel_set(workdir):
+    return datasets.make_panel_set(workdir)
+
+
+@pytest.mark.parametrize("k,s", [(19, 130), (16, 40), (21, 250), (32, 17)])
+def test_sketch_matches_reference(random_set, k, s):
+    from mashmap_b200 import capi
+
+    d = random_set
+    ctx = capi.Context(kmer_size=k, seg_length=5000, sketch_size=s)
+    bases, segs, ridx, start, length = build_segments(d, 5000, k)
+    out, cnt = ctx.sketch_segments(bases, segs)
+    bad = 0
+    for i in range(len(segs)):
+        seg = d["reads"][ridx[i]][start[i] : start[i] + length[i]]
+        ref = refh.sketch_sequence(seg, k, s, seq_id=int(ridx[i]))
+        dev = out[i][: cnt[i]]
+        ok = len(ref) == len(dev) and all(np.array_equal(ref[f], dev[f]) for f in ("hash", "wpos", "wpos_end", "seqId", "strand"))
+        if not ok:
+            bad += 1
+            if bad <= 5:
+                print("sketch mismatch seg", i, "len", length[i], "ref n", len(ref), "dev n", len(dev))
+                if len(ref) and len(dev):
+                    print(ref[:3], dev[:3])
+    assert bad == 0
+    ctx.close()
+
+
+def test_sketch_degenerate_inputs():
+    """all-N, low-complexity (fewer than s distinct k-mers), tandem repeats, tiny and ragged segments"""
+    from mashmap_b200 import capi
+
+    rng = np.random.default_rng(5)
+    k, s, L = 19, 100, 5000
+    seqs = [np.full(5000, ord("N"), np.uint8), np.full(5000, ord("A"), np.uint8),
+            np.tile(np.frombuffer(b"ACGTTGCAAG", np.uint8), 500), np.tile(synth.random_sequence(300, rng), 17)[:5000],
+            synth.random_sequence(19, rng), synth.random_sequence(18, rng), synth.random_sequence(57, rng),
+            synth.random_sequence(4999, rng), np.frombuffer(b"acgtnACGTRYKM" * 300, np.uint8)]
+    mixed = synth.random_sequence(5000, rng)
+    mixed[100:140] = ord("N"); mixed[4990:] = ord("N"); mixed[0] = ord("N")
+    seqs.append(mixed)
+    pal = synth.random_sequence(2500, rng)
+    seqs.append(np.concatenate([pal, synth.revcomp(pal)]))  # every k-mer occurs on both strands -> vote sums of 0
+    ctx = capi.Context(kmer_size=k, seg_length=L, sketch_size=s)
+    segs = np.zeros(len(seqs), dtype=capi.segment_dtype)
+    off = 0
+    for i, q in enumerate(seqs):
+        segs[i]["offset"] = off; segs[i]["length"] = len(q); segs[i]["seq_counter"] = i; segs[i]["name_id"] = -1
+        off += len(q)
+    out, cnt = ctx.sketch_segments(np.concatenate(seqs), segs)
+    for i, q in enumerate(seqs):
+        ref = refh.sketch_sequence(q, k, s, seq_id=i)
+        dev = out[i][: cnt[i]]
+        assert len(ref) == len(dev), (i, len(ref), len(dev))
+        for f in ("hash", "wpos", "wpos_end", "strand"):
+            assert np.array_equal(ref[f], dev[f]), (i, f)
+    ctx.close()
+
+
+def run_stage_parity(d, args, seg_length, **ctx_kw):
+    from mashmap_b200 import capi
+
+    R = refh.RefSession(args)
+    try:
+        ctx = capi.Context(kmer_size=R.p.kmerSize, seg_length=R.p.segLength, sketch_size=R.p.sketchSize,
+                           stage1_topani_filter=bool(R.p.stage1_topANI_filter), **ctx_kw)
+        upload_reference_index(ctx, R)
+        bases, segs, ridx, start, length = build_segments(d, R.p.segLength, R.p.kmerSize)
+        seg_res, cands, loci = ctx.map_segments(bases, segs)
+        # resident path must give the same answer
+        ctx.batch_upload(bases, segs)
+        ctx.map_resident()
+        seg_res2, cands2, loci2 = ctx.batch_fetch()
+        dev_sketch, dev_count = ctx.batch_fetch_sketch()
+        assert np.array_equal(seg_res["n_candidates"], seg_res2["n_candidates"])
+        print("stage ms", ctx.stage_ms(), "launches", ctx.kernel_launches)
+        bad = compare_stages(ctx, R, d, ridx, start, length, seg_res2, cands2, loci2, dev_sketch, dev_count)
+        ctx.close()
+        return bad
+    finally:
+        R.close()
+
+
+def test_stages_random_genome_noisy_reads(random_set):
+    d = random_set
+    bad = run_stage_parity(d, ["-r", d["ref"], "-q", d["qry"], "-s", "5000", "--pi", "85", "-t", "4"], 5000)
+    assert not bad
+
+
+def test_stages_random_genome_dense(random_set):
+    d = random_set
+    bad = run_stage_parity(d, ["-r", d["ref"], "-q", d["qry"], "-s", "5000", "--pi", "95", "--dense", "-t", "4"], 5000)
+    assert not bad
+
+
+def test_stages_panel_selfmap(panel_set):
+    d = panel_set
+    bad = run_stage_parity(d, ["-r", d["ref"], "-q", d["qry"], "-s", "5000", "--pi", "85", "-t", "4"], 5000)
+    assert not bad
+
+
+def test_stages_panel_no_hg_filter_small_sketch(panel_set):
+    d = panel_set
+    bad = run_stage_parity(d, ["-r", d["ref"], "-q", d["qry"], "-s", "2000", "--pi", "90", "-J", "25", "--noHgFilter", "-t", "4"], 2000)
+    assert not bad
