@@ -1,0 +1,108 @@
+/*
+ * skch_cview.cpp -- a flat C view of the host-side classes for the ctypes tests (no GPU needed):
+ * the statistics tables, the host index builder, and the host tail fed with externally produced records.
+ * Not part of the drop-in boundary (that is include/mashmap_b200.h + the skch:: classes).
+ */
+#include <cstring>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "skch_index.hpp"
+#include "skch_stats.hpp"
+#include "skch_tail.hpp"
+
+using namespace skch;
+
+extern "C" {
+
+double skch_binomial_Q(unsigned k, double p, unsigned n) { return Stat::binomial_Q(k, p, n); }
+float skch_j2md(float j, int k) { return Stat::j2md(j, k); }
+float skch_md2j(float d, int k) { return Stat::md2j(d, k); }
+float skch_md_lower_bound(float d, int s, int k) { return Stat::md_lower_bound(d, s, k, fixed::confidence_interval); }
+int skch_min_hits(int s, int k, float pi) { return Stat::estimateMinimumHitsRelaxed(s, k, pi, fixed::confidence_interval); }
+int64_t skch_recommended_sketch_size(int k, float pi, int64_t segLength, uint64_t refSize)
+{
+  return Stat::recommendedSketchSize(fixed::pval_cutoff, fixed::confidence_interval, k, 4, pi, segLength, refSize);
+}
+int skch_sketch_cutoffs(int sketchSize, int k, float aniDiff, float aniDiffConf, int enabled, int *out, int cap)
+{
+  std::vector<int> c = Stat::sketchCutoffs(sketchSize, k, aniDiff, aniDiffConf, enabled != 0);
+  for (int i = 0; i < (int)c.size() && i < cap; i++) out[i] = c[i];
+  return (int)c.size();
+}
+
+int64_t skch_add_minmers(const char *seq, int64_t len, int k, int w, int s, int seqId, mm_minmer *out, int64_t cap)
+{
+  std::string buf(seq, (size_t)len);
+  std::vector<MinmerInfo> v;
+  CommonFunc::addMinmers(v, &buf[0], (offset_t)len, k, w, 4, s, seqId);
+  if ((int64_t)v.size() > cap) return -(int64_t)v.size();
+  if (!v.empty()) memcpy(out, v.data(), v.size() * sizeof(mm_minmer));
+  return (int64_t)v.size();
+}
+
+/* ---- host tail on caller-provided records ---- */
+struct skch_tail_params {
+  int32_t kmerSize, segLength, sketchSize, filterMode, numMappingsForSegment, numMappingsForShortSequence;
+  int32_t block_length, chain_gap, mergeMappings, stage1_topANI_filter, keep_low_pct_id, skip_self, skip_prefix;
+  int32_t prefix_delim, filterLengthMismatches, legacy_output, report_ANI_percentage;
+  float percentageIdentity, ANIDiff, ANIDiffConf, kmerComplexityThreshold;
+};
+
+struct TailHandle {
+  Parameters p;
+  std::vector<ContigInfo> meta;
+  std::vector<int> groups;
+  MapTail *tail = nullptr;
+  std::string text;
+  MappingResultsVector_t last;
+};
+
+void *skch_tail_create(const skch_tail_params *tp, int n_contigs, const char **names, const int32_t *lens, const int32_t *groups)
+{
+  TailHandle *h = new TailHandle();
+  Parameters &p = h->p;
+  p.kmerSize = tp->kmerSize; p.segLength = tp->segLength; p.sketchSize = tp->sketchSize; p.filterMode = tp->filterMode;
+  p.numMappingsForSegment = tp->numMappingsForSegment; p.numMappingsForShortSequence = tp->numMappingsForShortSequence;
+  p.block_length = tp->block_length; p.chain_gap = tp->chain_gap; p.mergeMappings = tp->mergeMappings;
+  p.stage1_topANI_filter = tp->stage1_topANI_filter; p.keep_low_pct_id = tp->keep_low_pct_id; p.skip_self = tp->skip_self;
+  p.skip_prefix = tp->skip_prefix; p.prefix_delim = (char)tp->prefix_delim; p.filterLengthMismatches = tp->filterLengthMismatches;
+  p.legacy_output = tp->legacy_output; p.report_ANI_percentage = tp->report_ANI_percentage;
+  p.percentageIdentity = tp->percentageIdentity; p.ANIDiff = tp->ANIDiff; p.ANIDiffConf = tp->ANIDiffConf;
+  p.kmerComplexityThreshold = tp->kmerComplexityThreshold;
+  for (int i = 0; i < n_contigs; i++) {
+    h->meta.push_back(ContigInfo{names[i], lens[i]});
+    h->groups.push_back(groups ? groups[i] : 0);
+  }
+  h->tail = new MapTail(h->p, h->meta, h->groups);
+  return h;
+}
+
+void skch_tail_destroy(void *hv)
+{
+  TailHandle *h = (TailHandle *)hv;
+  if (h) { delete h->tail; delete h; }
+}
+
+/* mapModule's host part for ONE read whose fragments are segs[0..n_seg). Returns the PAF text. */
+const char *skch_tail_map_read(void *hv, const char *name, int32_t len, int32_t seqCounter, int32_t refGroup,
+                               const mm_segment *segs, const mm_segment_result *segRes, uint32_t n_seg,
+                               const mm_l1_candidate *cands, const mm_l2_locus *loci, int32_t *n_out)
+{
+  TailHandle *h = (TailHandle *)hv;
+  h->tail->segs = segs; h->tail->segRes = segRes; h->tail->cands = cands; h->tail->loci = loci;
+  ReadRec rd;
+  rd.name = name; rd.len = len; rd.seqCounter = seqCounter; rd.first_seg = 0; rd.n_seg = n_seg; rd.refGroup = refGroup;
+  IdentityCache idc;
+  idc.k = h->p.kmerSize;
+  h->last.clear();
+  h->tail->mapRead(rd, idc, h->last);
+  std::ostringstream os;
+  h->tail->formatMappings(h->last, rd.name, os);
+  h->text = os.str();
+  if (n_out) *n_out = (int32_t)h->last.size();
+  return h->text.c_str();
+}
+
+}  // extern "C"

@@ -1,0 +1,483 @@
+#include "skch_index.hpp"
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <deque>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <numeric>
+#include <thread>
+#include <tuple>
+#include <unordered_set>
+
+#include "../mm_hash.h"
+#include "skch_seqio.hpp"
+
+namespace skch {
+
+namespace {
+
+/* getHash of the forward k-mer and of its reverse complement (commonFunc.hpp:138-147, :357-363) for a
+ * run-time k: the bytes are packed into 64-bit words exactly as the templated device code does. */
+struct HostKmerHasher {
+  int k;
+  explicit HostKmerHasher(int k_) : k(k_) {}
+  static uint64_t murmur(const unsigned char *d, int len)
+  { /* MurmurHash3_x64_128 low word, seed 42 (murmur3.h:236-303) */
+    const int nblocks = len / 16;
+    uint64_t h1 = MM_SEED, h2 = MM_SEED;
+    const uint64_t c1 = 0x87c37b91114253d5ULL, c2 = 0x4cf5ad432745937fULL;
+    for (int i = 0; i < nblocks; i++) {
+      uint64_t k1, k2;
+      memcpy(&k1, d + 16 * i, 8);
+      memcpy(&k2, d + 16 * i + 8, 8);
+      k1 *= c1; k1 = mm_rotl64(k1, 31); k1 *= c2; h1 ^= k1;
+      h1 = mm_rotl64(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729;
+      k2 *= c2; k2 = mm_rotl64(k2, 33); k2 *= c1; h2 ^= k2;
+      h2 = mm_rotl64(h2, 31); h2 += h1; h2 = h2 * 5 + 0x38495ab5;
+    }
+    const unsigned char *tail = d + nblocks * 16;
+    uint64_t k1 = 0, k2 = 0;
+    const int tl = len & 15;
+    for (int j = tl - 1; j >= 8; j--) k2 |= (uint64_t)tail[j] << (8 * (j - 8));
+    if (tl > 8) { k2 *= c2; k2 = mm_rotl64(k2, 33); k2 *= c1; h2 ^= k2; }
+    for (int j = std::min(tl, 8) - 1; j >= 0; j--) k1 |= (uint64_t)tail[j] << (8 * j);
+    if (tl > 0) { k1 *= c1; k1 = mm_rotl64(k1, 31); k1 *= c2; h1 ^= k1; }
+    h1 ^= (uint64_t)len; h2 ^= (uint64_t)len;
+    h1 += h2; h2 += h1;
+    h1 = mm_fmix64(h1); h2 = mm_fmix64(h2);
+    h1 += h2;
+    return h1;
+  }
+};
+
+inline void normalise(char *seq, offset_t len)
+{ /* makeUpperCaseAndValidDNA (commonFunc.hpp:97-107) */
+  for (offset_t i = 0; i < len; i++) {
+    unsigned char c = (unsigned char)seq[i];
+    if (c > 96 && c < 123) c -= 32;
+    if (!(c == 'A' || c == 'C' || c == 'G' || c == 'T')) c = 'N';
+    seq[i] = (char)c;
+  }
+}
+
+struct KmerOcc {  // base_types.hpp:139-145 (KmerInfo)
+  hash_t hash;
+  seqno_t seqId;
+  offset_t pos;
+  strand_t strand;
+};
+
+inline MinmerInfo make_mi(hash_t h, offset_t a, offset_t b, seqno_t s, strand_t st)
+{
+  MinmerInfo m;
+  m.hash = h; m.wpos = a; m.wpos_end = b; m.seqId = s; m.strand = st; m._pad = 0;
+  return m;
+}
+
+}  // namespace
+
+namespace CommonFunc {
+
+/*
+ * Sliding-window minmer intervals of one contig -- commonFunc.hpp:301-570, followed step by step:
+ * the same containers (ordered map of the sketch, binary heap of waiting k-mers, deque of the window),
+ * the same order of the per-base steps, the same post-processing (malformed-record removal :523-528,
+ * strand collapse :534, chunking to <= windowSize :535-555, std::sort on (wpos,wpos_end) :558, adjacent
+ * (wpos,hash) de-duplication :563-568). Record boundaries are L2 evaluation points, so none of the
+ * reference's quirks is "fixed" here.
+ */
+void addMinmers(std::vector<MinmerInfo> &out, char *seq, offset_t len, int kmerSize, int windowSize, int alphabetSize,
+                int sketchSize, seqno_t seqCounter)
+{
+  typedef std::pair<MinmerInfo, std::deque<KmerOcc>> Tracked;  // a sketch member and its occurrences in the window
+  std::deque<std::tuple<hash_t, strand_t, offset_t>> window;   // every valid k-mer of the current window
+  std::map<hash_t, Tracked> sketch;                            // the <= s smallest distinct hashes
+  std::vector<KmerOcc> waiting;                                // min-heap on (hash,pos) of the other k-mers
+  auto heap_after = [](const KmerOcc &a, const KmerOcc &b) { return std::tie(a.hash, a.pos) > std::tie(b.hash, b.pos); };
+
+  normalise(seq, len);
+  std::unique_ptr<char[]> rc(new char[kmerSize]);
+  int ambig = 0;
+
+  for (offset_t i = 0; i < len - kmerSize + 1; i++) {
+    const offset_t wid = i + kmerSize - windowSize;  // window that ends with this k-mer
+
+    if (waiting.size() > (size_t)(2 * windowSize)) {  // :344-354 occasional purge of expired entries
+      waiting.erase(std::remove_if(waiting.begin(), waiting.end(), [wid](KmerOcc &ki) { return ki.pos < wid; }),
+                    waiting.end());
+      std::make_heap(waiting.begin(), waiting.end(), heap_after);
+    }
+
+    const hash_t hashFwd = HostKmerHasher::murmur((const unsigned char *)seq + i, kmerSize);
+    hash_t hashBwd;
+    if (alphabetSize == 4) {
+      for (int j = 0; j < kmerSize; j++) {  // reverseComplement (commonFunc.hpp:50-73)
+        char b = seq[i + j];
+        b = b == 'A' ? 'T' : b == 'C' ? 'G' : b == 'G' ? 'C' : b == 'T' ? 'A' : b;
+        rc[kmerSize - j - 1] = b;
+      }
+      hashBwd = HostKmerHasher::murmur((const unsigned char *)rc.get(), kmerSize);
+    } else {
+      hashBwd = std::numeric_limits<hash_t>::max();
+    }
+    const hash_t cur = std::min(hashFwd, hashBwd);
+    const strand_t curStrand = hashFwd < hashBwd ? strnd::FWD : strnd::REV;
+
+    // :376-410 the k-mer that just left the window
+    if (!window.empty() && std::get<2>(window.front()) < wid) {
+      const hash_t lh = std::get<0>(window.front());
+      const strand_t ls = std::get<1>(window.front());
+      if (sketch.size() > 0 && lh <= std::prev(sketch.end())->first) {
+        Tracked &tr = sketch.find(lh)->second;
+        if (tr.second.size() == 1) {
+          tr.first.wpos_end = wid;
+          out.push_back(tr.first);
+          sketch.erase(lh);
+        } else {
+          if (tr.first.strand - ls == 0 || tr.first.strand == 0) {
+            tr.first.wpos_end = wid;
+            out.push_back(tr.first);
+            tr.first.wpos = wid;
+            tr.first.wpos_end = -1;
+          }
+          tr.first.strand -= ls;
+          tr.second.pop_front();
+        }
+      }
+      window.pop_front();
+    }
+
+    if (seq[i + kmerSize - 1] == 'N') ambig = kmerSize;
+    if (hashBwd != hashFwd && ambig == 0) {  // :417-445 the arriving k-mer
+      window.push_back(std::make_tuple(cur, curStrand, i));
+      auto it = sketch.find(cur);
+      if (it != sketch.end()) {
+        Tracked &tr = it->second;
+        tr.second.emplace_back(KmerOcc{cur, seqCounter, i, curStrand});
+        if (tr.first.strand + curStrand == 0 || tr.first.strand == 0) {
+          tr.first.wpos_end = wid;
+          out.push_back(tr.first);
+          tr.first.wpos = wid;
+          tr.first.wpos_end = -1;
+        }
+        tr.first.strand += curStrand;
+      } else {
+        waiting.emplace_back(KmerOcc{cur, seqCounter, i, curStrand});
+        std::push_heap(waiting.begin(), waiting.end(), heap_after);
+      }
+    }
+    if (ambig > 0) ambig--;
+
+    if (wid >= 0) {  // :455-505 refill the sketch from the waiting heap
+      while (!waiting.empty() && waiting.front().pos < wid) {
+        std::pop_heap(waiting.begin(), waiting.end(), heap_after);
+        waiting.pop_back();
+      }
+      if (sketch.size() > 0 && waiting.size() > 0 && sketch.size() == (size_t)sketchSize &&
+          (waiting.front().hash < std::prev(sketch.end())->first)) {
+        Tracked &largest = std::prev(sketch.end())->second;
+        largest.first.wpos_end = wid;
+        out.push_back(largest.first);
+        for (KmerOcc &km : largest.second) {
+          if (km.pos > wid) {
+            waiting.push_back(km);
+            std::push_heap(waiting.begin(), waiting.end(), heap_after);
+          }
+        }
+        sketch.erase(largest.first.hash);
+      }
+      while (!waiting.empty() && sketch.size() < (size_t)sketchSize) {
+        if (waiting.front().pos < wid) {
+          std::pop_heap(waiting.begin(), waiting.end(), heap_after);
+          waiting.pop_back();
+        }
+        // the reference reads front() even if that pop emptied the heap (:495); the vector's storage still
+        // holds the popped element there, which is what data()[0] returns
+        const KmerOcc nk = waiting.data()[0];
+        sketch[nk.hash].first = make_mi(nk.hash, wid, -1, seqCounter, 0);
+        while (!waiting.empty() && waiting.front().hash == nk.hash) {
+          sketch[nk.hash].second.push_back(waiting.front());
+          sketch[nk.hash].first.strand += waiting.front().strand;
+          std::pop_heap(waiting.begin(), waiting.end(), heap_after);
+          waiting.pop_back();
+        }
+      }
+    }
+  }
+
+  // :508-520 close the windows still open at the end of the contig
+  uint64_t rank = 1;
+  auto iter = sketch.begin();
+  while (iter != sketch.end() && rank <= (uint64_t)sketchSize) {
+    if (iter->second.first.wpos != -1) {
+      iter->second.first.wpos_end = len - kmerSize + 1;
+      out.push_back(iter->second.first);
+    }
+    std::advance(iter, 1);
+    rank += 1;
+  }
+
+  out.erase(std::remove_if(out.begin(), out.end(),
+                           [](MinmerInfo &mi) { return mi.wpos < 0 || mi.wpos_end < 0 || mi.wpos == mi.wpos_end; }),
+            out.end());
+
+  std::vector<MinmerInfo> chunked;
+  std::for_each(out.begin(), out.end(), [&chunked, windowSize](MinmerInfo &mi) {
+    mi.strand = mi.strand < 0 ? (mi.strand == 0 ? strnd::AMBIG : strnd::REV) : strnd::FWD;  // :534
+    if (mi.wpos_end > mi.wpos + windowSize) {
+      for (int chunk = 0; chunk < std::ceil(float(mi.wpos_end - mi.wpos) / float(windowSize)); chunk++) {
+        chunked.push_back(make_mi(mi.hash, mi.wpos + chunk * windowSize,
+                                  std::min(mi.wpos + chunk * windowSize + windowSize, mi.wpos_end), mi.seqId, mi.strand));
+      }
+    }
+  });
+  out.erase(std::remove_if(out.begin(), out.end(), [windowSize](MinmerInfo &mi) { return mi.wpos_end - mi.wpos > windowSize; }),
+            out.end());
+  out.insert(out.end(), chunked.begin(), chunked.end());
+
+  std::sort(out.begin(), out.end(),
+            [](MinmerInfo &l, MinmerInfo &r) { return std::tie(l.wpos, l.wpos_end) < std::tie(r.wpos, r.wpos_end); });
+
+  out.erase(std::unique(out.begin(), out.end(),
+                        [](MinmerInfo &l, MinmerInfo &r) { return (l.wpos == r.wpos) && (l.hash == r.hash); }),
+            out.end());
+}
+
+uint64_t getReferenceSize(const std::vector<std::string> &refSequences)
+{
+  uint64_t count = 0;
+  for (auto &f : refSequences) {
+    std::ifstream in(f, std::ifstream::ate | std::ifstream::binary);
+    count += (uint64_t)(in.tellg());
+  }
+  return count;
+}
+
+}  // namespace CommonFunc
+
+Sketch::Sketch(const Parameters &p) : param(p)
+{
+  build();
+  index();
+  if (!param.saveIndexFilename.empty()) {  // winSketch.hpp:127-134: saved BEFORE frequent seeds are dropped
+    if (param.saveIndexFilename.extension() == ".tsv") saveIndexTSV(param.saveIndexFilename.string());
+    else saveIndexBinary(param.saveIndexFilename.string());
+    savePosListBinary(param.saveIndexFilename.string());
+  }
+  computeFreqHist();
+  dropFreqSeedSet();
+}
+
+void Sketch::build()
+{  // winSketch.hpp:147-230
+  std::unordered_set<std::string> allowed;
+  if (!param.target_list.empty()) {
+    std::ifstream fl(param.target_list);
+    std::string name;
+    while (getline(fl, name)) allowed.insert(name);
+  }
+  if (!param.loadIndexFilename.empty()) {
+    bool ok = param.loadIndexFilename.extension() == ".tsv" ? loadIndexTSV(param.loadIndexFilename.string())
+                                                            : loadIndexBinary(param.loadIndexFilename.string());
+    if (!ok) {
+      std::cerr << "[mashmap-b200::skch::Sketch::build] ERROR: cannot load index " << param.loadIndexFilename << std::endl;
+      exit(1);
+    }
+  }
+  // contigs are read by this thread and sketched by a pool; outputs are appended in input order
+  struct Task { std::string seq; seqno_t id; };
+  std::vector<std::unique_ptr<Task>> tasks;
+  seqno_t seqCounter = 0;
+  for (const auto &fileName : param.refSequences) {
+    bool ok = seqio::for_each_seq_in_file(fileName, allowed, param.target_prefix,
+                                          [&](const std::string &name, const std::string &seq) {
+                                            offset_t len = seq.length();
+                                            metadata.push_back(ContigInfo{name, len});
+                                            if (len >= param.kmerSize && param.loadIndexFilename.empty()) {
+                                              tasks.emplace_back(new Task{seq, seqCounter});
+                                            }
+                                            seqCounter++;
+                                          });
+    if (!ok) exit(1);
+    sequencesByFileInfo.push_back(seqCounter);
+  }
+  if (seqCounter == 0) {
+    std::cerr << "[mashmap-b200::skch::Sketch::build] ERROR: No sequences indexed!" << std::endl;
+    exit(1);
+  }
+  if (param.loadIndexFilename.empty()) {
+    std::vector<MI_Type> outputs(tasks.size());
+    std::atomic<size_t> next{0};
+    const int nthreads = std::max(1, param.threads);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthreads; t++) {
+      pool.emplace_back([&]() {
+        while (true) {
+          const size_t i = next.fetch_add(1);
+          if (i >= tasks.size()) break;
+          Task &tk = *tasks[i];
+          CommonFunc::addMinmers(outputs[i], &tk.seq[0], (offset_t)tk.seq.size(), param.kmerSize, param.segLength,
+                                 param.alphabetSize, param.sketchSize, tk.id);
+          std::string().swap(tk.seq);
+        }
+      });
+    }
+    for (auto &th : pool) th.join();
+    size_t total = 0;
+    for (auto &o : outputs) total += o.size();
+    minmerIndex.reserve(total);
+    for (auto &o : outputs) {
+      minmerIndex.insert(minmerIndex.end(), o.begin(), o.end());
+      MI_Type().swap(o);
+    }
+  }
+  std::cerr << "[mashmap-b200::skch::Sketch::build] minmer windows picked from reference = " << minmerIndex.size() << std::endl;
+}
+
+void Sketch::index()
+{  // winSketch.hpp:379-404, producing the flattened form: per hash, OPEN/CLOSE points in index order, with
+   // an interval that starts where the previous one of the same hash closed fused into it (:388-396)
+  const size_t n = minmerIndex.size();
+  std::vector<uint32_t> order32;
+  std::vector<uint64_t> order;
+  order.resize(n);
+  std::iota(order.begin(), order.end(), (uint64_t)0);
+  std::stable_sort(order.begin(), order.end(),
+                   [this](uint64_t a, uint64_t b) { return minmerIndex[a].hash < minmerIndex[b].hash; });
+  lookupKeys.clear(); lookupOffsets.clear(); lookupPoints.clear();
+  lookupPoints.reserve(2 * n);
+  size_t i = 0;
+  while (i < n) {
+    const hash_t h = minmerIndex[order[i]].hash;
+    lookupKeys.push_back(h);
+    lookupOffsets.push_back(lookupPoints.size());
+    const size_t first_pt = lookupPoints.size();
+    for (; i < n && minmerIndex[order[i]].hash == h; i++) {
+      const MinmerInfo &mi = minmerIndex[order[i]];
+      if (lookupPoints.size() == first_pt || lookupPoints.back().pos != mi.wpos) {
+        IntervalPoint a{}; a.pos = mi.wpos; a.hash = mi.hash; a.seqId = mi.seqId; a.side = side::OPEN;
+        IntervalPoint b{}; b.pos = mi.wpos_end; b.hash = mi.hash; b.seqId = mi.seqId; b.side = side::CLOSE;
+        lookupPoints.push_back(a);
+        lookupPoints.push_back(b);
+      } else {
+        lookupPoints.back().pos = mi.wpos_end;
+      }
+    }
+  }
+  lookupOffsets.push_back(lookupPoints.size());
+  std::cerr << "[mashmap-b200::skch::Sketch::index] unique minmers = " << lookupKeys.size() << std::endl;
+}
+
+void Sketch::computeFreqHist()
+{  // winSketch.hpp:410-453 and computeFreqSeedSet :488-495
+  lookupKeyIsFreq.assign(lookupKeys.size(), 0);
+  if (lookupKeys.empty()) {
+    std::cerr << "[mashmap-b200::skch::Sketch::computeFreqHist] No minmers." << std::endl;
+    return;
+  }
+  std::map<int, int> hist;
+  for (size_t i = 0; i < lookupKeys.size(); i++) hist[(int)(lookupOffsets[i + 1] - lookupOffsets[i])] += 1;
+  std::cerr << "[mashmap-b200::skch::Sketch::computeFreqHist] Frequency histogram of minmer interval points = ("
+            << hist.begin()->first << ", " << hist.begin()->second << ") ... (" << hist.rbegin()->first << ", "
+            << hist.rbegin()->second << ")" << std::endl;
+  int64_t totalUniqueMinmers = lookupKeys.size();
+  int64_t minmerToIgnore = totalUniqueMinmers * param.kmer_pct_threshold / 100;
+  int64_t sum = 0;
+  for (auto it = hist.rbegin(); it != hist.rend(); it++) {
+    sum += it->second;
+    if (sum < minmerToIgnore) {
+      freqThreshold = it->first;
+    } else if (sum == minmerToIgnore) {
+      freqThreshold = it->first;
+      break;
+    } else {
+      break;
+    }
+  }
+  if (freqThreshold != std::numeric_limits<int>::max())
+    std::cerr << "[mashmap-b200::skch::Sketch::computeFreqHist] With threshold " << param.kmer_pct_threshold
+              << "%, ignore minmers occurring >= " << freqThreshold << " times during lookup." << std::endl;
+  else
+    std::cerr << "[mashmap-b200::skch::Sketch::computeFreqHist] With threshold " << param.kmer_pct_threshold
+              << "%, consider all minmers during lookup." << std::endl;
+  for (size_t i = 0; i < lookupKeys.size(); i++)
+    if ((int64_t)(lookupOffsets[i + 1] - lookupOffsets[i]) >= (int64_t)freqThreshold) lookupKeyIsFreq[i] = 1;
+}
+
+bool Sketch::isFreqSeed(hash_t h) const
+{
+  auto it = std::lower_bound(lookupKeys.begin(), lookupKeys.end(), h);
+  if (it == lookupKeys.end() || *it != h) return false;
+  return lookupKeyIsFreq[(size_t)(it - lookupKeys.begin())] != 0;
+}
+
+void Sketch::dropFreqSeedSet()
+{  // winSketch.hpp:497-504: frequent hashes leave minmerIndex only (the lookup keeps them, flagged)
+  bool any = false;
+  for (uint8_t f : lookupKeyIsFreq) any |= f != 0;
+  if (!any) return;
+  minmerIndex.erase(std::remove_if(minmerIndex.begin(), minmerIndex.end(), [this](MinmerInfo &mi) { return isFreqSeed(mi.hash); }),
+                    minmerIndex.end());
+}
+
+void Sketch::saveIndexTSV(const std::string &path) const
+{  // winSketch.hpp:270-279
+  std::ofstream o(path);
+  o << "seqId" << "\t" << "strand" << "\t" << "start" << "\t" << "end" << "\t" << "hash\n";
+  for (auto &mi : minmerIndex)
+    o << mi.seqId << "\t" << std::to_string(mi.strand) << "\t" << mi.wpos << "\t" << mi.wpos_end << "\t" << mi.hash << "\n";
+}
+
+void Sketch::saveIndexBinary(const std::string &prefix) const
+{  // winSketch.hpp:284-293
+  std::ofstream o(prefix + ".index", std::ios::binary);
+  size_t size = minmerIndex.size();
+  o.write((const char *)&size, sizeof(size));
+  o.write((const char *)minmerIndex.data(), size * sizeof(MinmerInfo));
+}
+
+void Sketch::savePosListBinary(const std::string &prefix) const
+{  // winSketch.hpp:298-315 (key order is unspecified in the reference's hash map; ascending here)
+  std::ofstream o(prefix + ".map", std::ios::binary);
+  size_t size = lookupKeys.size();
+  o.write((const char *)&size, sizeof(size));
+  for (size_t i = 0; i < lookupKeys.size(); i++) {
+    hash_t key = lookupKeys[i];
+    o.write((const char *)&key, sizeof(key));
+    size_t n = lookupOffsets[i + 1] - lookupOffsets[i];
+    o.write((const char *)&n, sizeof(n));
+    o.write((const char *)&lookupPoints[lookupOffsets[i]], n * sizeof(IntervalPoint));
+  }
+}
+
+bool Sketch::loadIndexTSV(const std::string &path)
+{  // winSketch.hpp:321-333
+  std::ifstream in(path);
+  if (!in) return false;
+  std::string header;
+  std::getline(in, header);
+  long long seqId, strand, start, end;
+  unsigned long long hash;
+  while (in >> seqId >> strand >> start >> end >> hash)
+    minmerIndex.push_back(make_mi(hash, (offset_t)start, (offset_t)end, (seqno_t)seqId, (strand_t)strand));
+  return true;
+}
+
+bool Sketch::loadIndexBinary(const std::string &prefix)
+{  // winSketch.hpp:338-348 (the interval points are rebuilt from the minmers, which gives the same lists)
+  std::ifstream in(prefix + ".index", std::ios::binary);
+  if (!in) return false;
+  size_t size = 0;
+  in.read((char *)&size, sizeof(size));
+  minmerIndex.resize(size);
+  in.read((char *)minmerIndex.data(), size * sizeof(MinmerInfo));
+  return (bool)in;
+}
+
+}  // namespace skch

@@ -1,0 +1,74 @@
+/*
+ * skch_index.hpp -- skch::Sketch: the reference minmer index (reference src/map/include/winSketch.hpp).
+ *
+ * Same constructor contract and public members as the reference class (winSketch.hpp:57-511): the
+ * constructor builds and indexes (blocking); `metadata`, `minmerIndex`, the frequent-seed predicate and
+ * threshold are public. The hash -> interval-point map (`minmerPosLookupIndex`, winSketch.hpp:100-101)
+ * is kept flattened (keys ascending / offsets / points), which is the form the device consumes.
+ *
+ * Round-1 builder: minmer windows are computed on the host by a step-for-step restatement of
+ * CommonFunc::addMinmers (commonFunc.hpp:301-570), one task per contig, because every record's wpos is an
+ * L2 evaluation point and the reference's record boundaries (vote-sum zero crossings, chunking, the
+ * unstable sort's tie order) are only reproducible by following the same steps with the same libstdc++
+ * (SURVEY 7.2, A.6). A device builder is the first "next" row of SURVEY 8(f).
+ */
+#ifndef SKCH_INDEX_HPP
+#define SKCH_INDEX_HPP
+
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "skch_types.hpp"
+
+namespace skch {
+
+namespace CommonFunc {
+/* commonFunc.hpp:301-570 */
+void addMinmers(std::vector<MinmerInfo> &minmerIndex, char *seq, offset_t len, int kmerSize, int windowSize,
+                int alphabetSize, int sketchSize, seqno_t seqCounter);
+/* commonFunc.hpp:591-603 */
+uint64_t getReferenceSize(const std::vector<std::string> &refSequences);
+}  // namespace CommonFunc
+
+class Sketch {
+ public:
+  typedef std::vector<MinmerInfo> MI_Type;
+
+  explicit Sketch(const Parameters &p);  // winSketch.hpp:122-138: build + index + frequency filter
+
+  std::vector<ContigInfo> metadata;          // winSketch.hpp:79
+  std::vector<int> sequencesByFileInfo;      // winSketch.hpp:88
+  MI_Type minmerIndex;                       // winSketch.hpp:102 (after dropFreqSeedSet)
+
+  // minmerPosLookupIndex (winSketch.hpp:101), flattened: keys ascending; points of keys[i] are
+  // lookupPoints[lookupOffsets[i] .. lookupOffsets[i+1]) in reference per-key order
+  std::vector<hash_t> lookupKeys;
+  std::vector<uint64_t> lookupOffsets;
+  std::vector<IntervalPoint> lookupPoints;
+  std::vector<uint8_t> lookupKeyIsFreq;      // frequentSeeds membership per key (winSketch.hpp:488-495)
+
+  int getFreqThreshold() const { return freqThreshold; }   // winSketch.hpp:483-486
+  bool isFreqSeed(hash_t h) const;                         // winSketch.hpp:506-509
+  bool isMinmerIndexEnd(MI_Type::const_iterator it) const { return it == minmerIndex.end(); }
+  MI_Type::const_iterator getMinmerIndexEnd() const { return minmerIndex.end(); }
+
+  // --saveIndex / --loadIndex (winSketch.hpp:270-374): TSV and PREFIX.index/.map binary formats
+  void saveIndexTSV(const std::string &path) const;
+  void saveIndexBinary(const std::string &prefix) const;
+  void savePosListBinary(const std::string &prefix) const;
+
+ private:
+  const Parameters &param;
+  int freqThreshold = std::numeric_limits<int>::max();
+
+  void build();
+  void index();
+  void computeFreqHist();
+  void dropFreqSeedSet();
+  bool loadIndexTSV(const std::string &path);
+  bool loadIndexBinary(const std::string &prefix);
+};
+
+}  // namespace skch
+#endif

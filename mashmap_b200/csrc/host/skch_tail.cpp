@@ -1,0 +1,328 @@
+#include "skch_tail.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <limits>
+#include <numeric>
+#include <tuple>
+
+#include "skch_filter.hpp"
+#include "skch_stats.hpp"
+
+namespace skch {
+
+size_t MappingResult::hash() const
+{  // base_types.hpp:146-151, :188-204
+  size_t res = 0;
+  auto combine = [&res](auto v) {
+    std::hash<decltype(v)> h;
+    res ^= h(v) + 0x9e3779b9 + (res << 6) + (res >> 2);
+  };
+  combine(queryLen); combine(refStartPos); combine(refEndPos); combine(queryStartPos); combine(queryEndPos);
+  combine(refSeqId); combine(querySeqId); combine(blockLength); combine(nucIdentity); combine(nucIdentityUpperBound);
+  combine(sketchSize); combine(conservedSketches); combine(strand); combine(approxMatches);
+  return res;
+}
+
+std::pair<float, float> IdentityCache::get(int shared, int qs)
+{
+  const uint64_t key = ((uint64_t)(uint32_t)shared << 32) | (uint32_t)qs;
+  auto it = memo.find(key);
+  if (it != memo.end()) return it->second;
+  float mash_dist = Stat::j2md(1.0 * shared / qs, k);
+  float nucIdentity = (1 - mash_dist);
+  float nucIdentityUpperBound = 1 - Stat::md_lower_bound(mash_dist, qs, k, fixed::confidence_interval);
+  auto v = std::make_pair(nucIdentity, nucIdentityUpperBound);
+  memo.emplace(key, v);
+  return v;
+}
+
+namespace {
+
+/* union-find with the merge rule of dsets::DisjointSets (reference src/common/dset64.hpp:62-124):
+ * the root of lower rank goes under the other; on equal rank the larger id goes under the smaller. */
+struct UnionFind {
+  std::vector<uint32_t> parent, rnk;
+  explicit UnionFind(size_t n) : parent(n), rnk(n, 0) { std::iota(parent.begin(), parent.end(), 0u); }
+  uint32_t find(uint32_t x)
+  {
+    while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; }
+    return x;
+  }
+  void unite(uint32_t a, uint32_t b)
+  {
+    a = find(a); b = find(b);
+    if (a == b) return;
+    uint32_t ra = rnk[a], rb = rnk[b];
+    if (ra > rb || (ra == rb && a < b)) { std::swap(ra, rb); std::swap(a, b); }
+    parent[a] = b;
+    if (ra == rb) rnk[b] = rb + 1;
+  }
+};
+
+
+}  // namespace
+
+/* ---- doL2Mapping on the device's records (computeMap.hpp:1181-1267) ---- */
+void MapTail::fragmentMappings(const mm_segment &sg, const mm_segment_result &sr, const ReadRec &rd, IdentityCache &idc,
+                      std::vector<mm_l1_candidate> &work, MappingResultsVector_t &l2Mappings) const
+{
+  l2Mappings.clear();
+  if (sr.sketch_raw_count == 0 || sr.sketch_size == 0) return;  // :822-825, :1136
+  // Q.kmerComplexity (computeMap.hpp:830-831): long double ratio -> double -> float
+  const double max_hash_01 = (long double)(sr.sketch_max_hash) / std::numeric_limits<hash_t>::max();
+  const float kmerComplexity = (double(sr.sketch_raw_count) / max_hash_01) / ((sg.length - param.kmerSize + 1) * 2);
+  if (kmerComplexity < param.kmerComplexityThreshold) return;  // :1136
+  if (sr.n_candidates == 0) return;
+  const int qs = sr.sketch_size;
+  work.assign(cands + sr.first_candidate, cands + sr.first_candidate + sr.n_candidates);
+  auto cmp = [](const mm_l1_candidate &a, const mm_l1_candidate &b) { return a.intersectionSize < b.intersectionSize; };
+  size_t gb = 0;
+  while (gb < work.size()) {  // mapSingleQueryFrag's per-reference-group loop (:772-797)
+    size_t ge = work.size();
+    if (param.skip_prefix) {
+      const int g = refIdGroup[work[gb].seqId];
+      ge = gb;
+      while (ge < work.size() && refIdGroup[work[ge].seqId] == g) ge++;
+    }
+    if (param.stage1_topANI_filter) std::make_heap(work.begin() + gb, work.begin() + ge, cmp);
+    double bestJaccardNumerator = 0;
+    size_t it = gb, end = ge;
+    while (it != end) {
+      const mm_l1_candidate &cd = work[it];
+      if (param.stage1_topANI_filter) {
+        double cutoff_ani = std::max(0.0, double((1 - Stat::j2md(bestJaccardNumerator / qs, param.kmerSize)) - param.ANIDiff));
+        double cutoff_j = Stat::md2j(1 - cutoff_ani, param.kmerSize);
+        if (double(cd.intersectionSize) / qs < cutoff_j) break;
+      }
+      for (uint32_t li = 0; li < cd.n_loci; li++) {
+        const mm_l2_locus &l2 = loci[cd.first_locus + li];
+        const auto id = idc.get(l2.sharedSketchSize, qs);
+        const float nucIdentity = id.first, nucIdentityUpperBound = id.second;
+        if ((param.keep_low_pct_id && nucIdentityUpperBound >= param.percentageIdentity) ||
+            nucIdentity >= param.percentageIdentity) {
+          bestJaccardNumerator = std::max<double>(bestJaccardNumerator, l2.sharedSketchSize);
+          MappingResult res{};
+          res.n_merged = 1;  // see skch_tail.hpp: the reference leaves this uninitialised
+          res.queryLen = sg.length;
+          res.refStartPos = l2.meanOptimalPos;
+          res.refEndPos = l2.meanOptimalPos + sg.length;
+          res.queryStartPos = 0;
+          res.queryEndPos = sg.length;
+          res.refSeqId = l2.seqId;
+          res.querySeqId = rd.seqCounter;
+          res.nucIdentity = nucIdentity;
+          res.nucIdentityUpperBound = nucIdentityUpperBound;
+          res.sketchSize = qs;
+          res.conservedSketches = l2.sharedSketchSize;
+          res.blockLength = std::max(res.refEndPos - res.refStartPos, res.queryEndPos - res.queryStartPos);
+          res.approxMatches = std::round(res.nucIdentity * res.blockLength / 100.0);
+          res.strand = (strand_t)l2.strand;
+          res.kmerComplexity = kmerComplexity;
+          res.selfMapFilter = ((param.skip_self || param.skip_prefix) && rd.len > metadata[l2.seqId].len);
+          l2Mappings.push_back(res);
+        }
+      }
+      if (param.stage1_topANI_filter) {
+        std::pop_heap(work.begin() + gb, work.begin() + end, cmp);
+        end--;
+      } else {
+        it++;
+      }
+    }
+    gb = ge;
+  }
+  std::sort(l2Mappings.begin(), l2Mappings.end(), [](const MappingResult &a, const MappingResult &b) {
+    return std::tie(a.refSeqId, a.refStartPos) < std::tie(b.refSeqId, b.refStartPos);
+  });  // :800-801
+}
+
+/* ---- mergeMappingsInRange (computeMap.hpp:1579-1704) ---- */
+void MapTail::mergeMappingsInRange(MappingResultsVector_t &readMappings, int max_dist) const
+{
+  if (readMappings.size() < 2) return;
+  std::sort(readMappings.begin(), readMappings.end(), [](const MappingResult &a, const MappingResult &b) {
+    return std::tie(a.refSeqId, a.refStartPos, a.queryStartPos) < std::tie(b.refSeqId, b.refStartPos, b.queryStartPos);
+  });
+  for (size_t i = 0; i < readMappings.size(); i++) { readMappings[i].splitMappingId = (offset_t)i; readMappings[i].discard = 0; }
+  UnionFind uf(readMappings.size());
+  std::vector<std::pair<double, uint64_t>> distances;
+  for (auto it = readMappings.begin(); it != readMappings.end(); it++) {
+    distances.clear();
+    for (auto it2 = std::next(it); it2 != readMappings.end(); it2++) {
+      if (it2->refSeqId != it->refSeqId || it2->refStartPos > it->refEndPos + max_dist) break;
+      if (it2->strand == it->strand) {
+        int ref_dist = it2->refStartPos - it->refEndPos;
+        int query_dist = 0;
+        auto dist = std::numeric_limits<double>::max();
+        auto score = std::numeric_limits<double>::max();
+        if (it->strand == strnd::FWD && it->queryStartPos <= it2->queryStartPos) {
+          query_dist = it2->queryStartPos - it->queryEndPos;
+          dist = std::sqrt(std::pow(query_dist, 2) + std::pow(ref_dist, 2));
+          score = std::pow(query_dist - ref_dist, 2);
+        } else if (it->strand != strnd::FWD && it->queryEndPos >= it2->queryEndPos) {
+          query_dist = it->queryStartPos - it2->queryEndPos;
+          dist = std::sqrt(std::pow(query_dist, 2) + std::pow(ref_dist, 2));
+          score = std::pow(query_dist - ref_dist, 2);
+        }
+        if (dist < max_dist) distances.push_back(std::make_pair(dist + score, (uint64_t)it2->splitMappingId));
+      }
+    }
+    if (distances.size()) {
+      std::sort(distances.begin(), distances.end());
+      uf.unite((uint32_t)it->splitMappingId, (uint32_t)distances.front().second);
+    }
+  }
+  for (auto &m : readMappings) m.splitMappingId = (offset_t)uf.find((uint32_t)m.splitMappingId);
+  std::sort(readMappings.begin(), readMappings.end(),
+            [](const MappingResult &a, const MappingResult &b) { return a.splitMappingId < b.splitMappingId; });
+  for (auto it = readMappings.begin(); it != readMappings.end();) {
+    auto it_end = std::find_if(it, readMappings.end(), [&](const MappingResult &e) { return e.splitMappingId != it->splitMappingId; });
+    std::for_each(it, it_end, [&](MappingResult &e) {
+      it->queryStartPos = std::min(it->queryStartPos, e.queryStartPos);
+      it->refStartPos = std::min(it->refStartPos, e.refStartPos);
+      it->queryEndPos = std::max(it->queryEndPos, e.queryEndPos);
+      it->refEndPos = std::max(it->refEndPos, e.refEndPos);
+      it->blockLength = std::max(it->refEndPos - it->refStartPos, it->queryEndPos - it->queryStartPos);
+      it->approxMatches = std::round(it->nucIdentity * it->blockLength / 100.0);
+    });
+    it->n_merged = std::distance(it, it_end);
+    it->nucIdentity = (std::accumulate(it, it_end, 0.0, [](double x, MappingResult &e) { return x + e.nucIdentity; })) / it->n_merged;
+    it->kmerComplexity = (std::accumulate(it, it_end, 0.0, [](double x, MappingResult &e) { return x + e.kmerComplexity; })) / it->n_merged;
+    std::for_each(std::next(it), it_end, [&](MappingResult &e) { e.discard = 1; });
+    it = it_end;
+  }
+  readMappings.erase(std::remove_if(readMappings.begin(), readMappings.end(), [](MappingResult &e) { return e.discard == 1; }),
+                     readMappings.end());
+}
+
+/* ---- filterByGroup (computeMap.hpp:504-561) ---- */
+void MapTail::filterByGroup(MappingResultsVector_t &unfiltered, MappingResultsVector_t &filtered, int n_mappings, bool filter_ref) const
+{
+  filtered.reserve(unfiltered.size());
+  std::sort(unfiltered.begin(), unfiltered.end(), [](const MappingResult &a, const MappingResult &b) {
+    return std::tie(a.refSeqId, a.refStartPos) < std::tie(b.refSeqId, b.refStartPos);
+  });
+  auto sb = unfiltered.begin(), se = unfiltered.begin();
+  if (param.filterMode == filter::MAP || param.filterMode == filter::ONETOONE) {
+    MappingResultsVector_t tmp;
+    while (se != unfiltered.end()) {
+      if (param.skip_prefix) {
+        const int g = refIdGroup[sb->refSeqId];
+        se = std::find_if_not(sb, unfiltered.end(), [&](const MappingResult &c) { return g == refIdGroup[c.refSeqId]; });
+      } else {
+        se = unfiltered.end();
+      }
+      tmp.insert(tmp.end(), std::make_move_iterator(sb), std::make_move_iterator(se));
+      std::sort(tmp.begin(), tmp.end(), [](const MappingResult &a, const MappingResult &b) {
+        return std::tie(a.queryStartPos, a.refSeqId, a.refStartPos) < std::tie(b.queryStartPos, b.refSeqId, b.refStartPos);
+      });
+      if (filter_ref) Filter::ref::filterMappings(tmp, metadata, (uint16_t)n_mappings);
+      else Filter::query::filterMappings(tmp, (uint16_t)n_mappings);
+      filtered.insert(filtered.end(), std::make_move_iterator(tmp.begin()), std::make_move_iterator(tmp.end()));
+      tmp.clear();
+      sb = se;
+    }
+  }
+  std::sort(filtered.begin(), filtered.end(), [](const MappingResult &a, const MappingResult &b) {
+    return std::tie(a.queryStartPos, a.refSeqId, a.refStartPos) < std::tie(b.queryStartPos, b.refSeqId, b.refStartPos);
+  });
+}
+
+/* ---- mapModule for one read, given the device results of its fragments (computeMap.hpp:570-714) ---- */
+void MapTail::mapRead(const ReadRec &rd, IdentityCache &idc, MappingResultsVector_t &out) const
+{
+  MappingResultsVector_t unfiltered, l2Mappings;
+  std::vector<mm_l1_candidate> work;
+  bool split_mapping = true;
+  if (rd.len <= param.segLength) {  // :587-607 (param.split is always true here)
+    fragmentMappings(segs[rd.first_seg], segRes[rd.first_seg], rd, idc, work, l2Mappings);
+    unfiltered.insert(unfiltered.end(), l2Mappings.begin(), l2Mappings.end());
+    split_mapping = false;
+  } else {
+    const int noOverlapFragmentCount = rd.len / param.segLength;
+    for (int i = 0; i < noOverlapFragmentCount; i++) {  // :613-641
+      fragmentMappings(segs[rd.first_seg + i], segRes[rd.first_seg + i], rd, idc, work, l2Mappings);
+      for (auto &e : l2Mappings) {
+        e.queryLen = rd.len;
+        e.queryStartPos = i * param.segLength;
+        e.queryEndPos = i * param.segLength + param.segLength;
+      }
+      unfiltered.insert(unfiltered.end(), l2Mappings.begin(), l2Mappings.end());
+    }
+    if (noOverlapFragmentCount >= 1 && rd.len % param.segLength != 0) {  // :644-671
+      const uint64_t s = rd.first_seg + noOverlapFragmentCount;
+      fragmentMappings(segs[s], segRes[s], rd, idc, work, l2Mappings);
+      for (auto &e : l2Mappings) {
+        e.queryLen = rd.len;
+        e.queryStartPos = rd.len - param.segLength;
+        e.queryEndPos = rd.len;
+      }
+      unfiltered.insert(unfiltered.end(), l2Mappings.begin(), l2Mappings.end());
+    }
+  }
+  const int n_mappings = (rd.len < param.segLength ? param.numMappingsForShortSequence : param.numMappingsForSegment) - 1;
+  if (split_mapping && param.mergeMappings) {
+    mergeMappingsInRange(unfiltered, param.chain_gap);
+    const int64_t min_count = std::floor(param.block_length / param.segLength);  // filterWeakMappings :423-433
+    unfiltered.erase(std::remove_if(unfiltered.begin(), unfiltered.end(),
+                                    [&](MappingResult &e) { return e.queryLen > e.blockLength && e.n_merged < min_count; }),
+                     unfiltered.end());
+  }
+  if (param.filterMode == filter::MAP || param.filterMode == filter::ONETOONE) {
+    MappingResultsVector_t tmp;
+    filterByGroup(unfiltered, tmp, n_mappings, false);
+    unfiltered = std::move(tmp);
+  }
+  out.swap(unfiltered);
+  if (param.filterLengthMismatches) {  // filterFalseHighIdentity :441-454
+    out.erase(std::remove_if(out.begin(), out.end(),
+                             [&](MappingResult &e) {
+                               int64_t q_l = (int64_t)e.queryEndPos - (int64_t)e.queryStartPos;
+                               int64_t r_l = (int64_t)e.refEndPos + 1 - (int64_t)e.refStartPos;
+                               uint64_t delta = std::abs(r_l - q_l);
+                               float len_id_bound = (1.0 - (float)delta / (float)q_l);
+                               return len_id_bound < std::min(0.7, std::pow(param.percentageIdentity, 3));
+                             }),
+              out.end());
+  }
+  for (auto &e : out) {  // mappingBoundarySanityCheck :1713-1750
+    const offset_t rlen = metadata[e.refSeqId].len;
+    if (e.refStartPos < 0) e.refStartPos = 0;
+    if (e.refStartPos >= rlen) e.refStartPos = rlen - 1;
+    if (e.refEndPos < e.refStartPos) e.refEndPos = e.refStartPos;
+    if (e.refEndPos >= rlen) e.refEndPos = rlen - 1;
+    if (e.queryStartPos < 0) e.queryStartPos = 0;
+    if (e.queryStartPos >= rd.len) e.queryStartPos = rd.len;
+    if (e.queryEndPos < e.queryStartPos) e.queryEndPos = e.queryStartPos;
+    if (e.queryEndPos >= rd.len) e.queryEndPos = rd.len;
+  }
+  if (param.sparsity_hash_threshold < std::numeric_limits<uint64_t>::max()) {  // sparsifyMappings :482-493
+    out.erase(std::remove_if(out.begin(), out.end(), [&](MappingResult &e) { return e.hash() > param.sparsity_hash_threshold; }),
+              out.end());
+  }
+}
+
+/* ---- reportReadMappings (computeMap.hpp:1758-1805): same stream formatting ---- */
+void MapTail::formatMappings(const MappingResultsVector_t &readMappings, const std::string &queryName, std::ostream &os) const
+{
+  for (auto &e : readMappings) {
+    float fakeMapQ = e.nucIdentity == 1 ? 255 : std::round(-10.0 * std::log10(1 - (e.nucIdentity)));
+    std::string sep = param.legacy_output ? " " : "\t";
+    os << (param.filterMode == filter::ONETOONE ? (*qmetadata)[e.querySeqId].name : queryName) << sep << e.queryLen << sep
+       << e.queryStartPos << sep << e.queryEndPos - (param.legacy_output ? 1 : 0) << sep
+       << (e.strand == strnd::FWD ? "+" : "-") << sep << metadata[e.refSeqId].name << sep
+       << metadata[e.refSeqId].len << sep << e.refStartPos << sep << e.refEndPos - (param.legacy_output ? 1 : 0);
+    if (!param.legacy_output) {
+      os << sep << e.conservedSketches << sep << e.blockLength << sep << fakeMapQ << sep << "id:f:"
+         << (param.report_ANI_percentage ? 100.0 : 1.0) * e.nucIdentity << sep << "kc:f:" << e.kmerComplexity;
+      if (!param.mergeMappings) os << sep << "jc:f:" << float(e.conservedSketches) / e.sketchSize;
+    } else {
+      os << sep << e.nucIdentity * 100.0;
+    }
+    os << "\n";
+  }
+}
+
+
+}  // namespace skch

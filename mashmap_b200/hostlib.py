@@ -1,0 +1,104 @@
+"""ctypes view of the host-side C++ (libmashmap_host.so: skch::Stat, the host index builder, the host
+tail) for tests and bench.py. The mapping itself is only reachable through capi (the CUDA library)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import capi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmashmap_host.so")
+CLI_PATH = os.path.join(_HERE, "mashmap-b200")
+
+
+class TailParams(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "kmerSize", "segLength", "sketchSize", "filterMode", "numMappingsForSegment", "numMappingsForShortSequence",
+        "block_length", "chain_gap", "mergeMappings", "stage1_topANI_filter", "keep_low_pct_id", "skip_self",
+        "skip_prefix", "prefix_delim", "filterLengthMismatches", "legacy_output", "report_ANI_percentage")] + [
+        (n, C.c_float) for n in ("percentageIdentity", "ANIDiff", "ANIDiffConf", "kmerComplexityThreshold")]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} not built: run __graft_entry__.build()")
+        capi.lib()  # dependency (same directory, rpath $ORIGIN)
+        L = C.CDLL(LIB_PATH)
+        L.skch_binomial_Q.argtypes = [C.c_uint, C.c_double, C.c_uint]
+        L.skch_binomial_Q.restype = C.c_double
+        L.skch_j2md.argtypes = [C.c_float, C.c_int]
+        L.skch_j2md.restype = C.c_float
+        L.skch_md2j.argtypes = [C.c_float, C.c_int]
+        L.skch_md2j.restype = C.c_float
+        L.skch_md_lower_bound.argtypes = [C.c_float, C.c_int, C.c_int]
+        L.skch_md_lower_bound.restype = C.c_float
+        L.skch_min_hits.argtypes = [C.c_int, C.c_int, C.c_float]
+        L.skch_recommended_sketch_size.argtypes = [C.c_int, C.c_float, C.c_int64, C.c_uint64]
+        L.skch_recommended_sketch_size.restype = C.c_int64
+        L.skch_sketch_cutoffs.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_int]
+        L.skch_add_minmers.argtypes = [C.c_char_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64]
+        L.skch_add_minmers.restype = C.c_int64
+        L.skch_tail_create.argtypes = [C.POINTER(TailParams), C.c_int, C.POINTER(C.c_char_p), C.c_void_p, C.c_void_p]
+        L.skch_tail_create.restype = C.c_void_p
+        L.skch_tail_destroy.argtypes = [C.c_void_p]
+        L.skch_tail_map_read.argtypes = [C.c_void_p, C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                         C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
+        L.skch_tail_map_read.restype = C.c_char_p
+        _lib = L
+    return _lib
+
+
+def min_hits_table(sketch_size, k, pi):
+    L = lib()
+    return np.array([0] + [L.skch_min_hits(s, k, pi) for s in range(1, sketch_size + 1)], dtype=np.int32)
+
+
+def sketch_cutoffs(sketch_size, k, ani_diff=0.0, ani_diff_conf=0.999, enabled=True):
+    out = np.zeros(1002, dtype=np.int32)
+    n = lib().skch_sketch_cutoffs(sketch_size, k, ani_diff, ani_diff_conf, int(enabled), out.ctypes.data, len(out))
+    return out[:n].copy()
+
+
+def add_minmers(seq, k, w, s, seq_id=0):
+    b = seq.tobytes() if isinstance(seq, np.ndarray) else bytes(seq)
+    cap = max(1024, 4 * (len(b) // max(1, w) + 2) * (s + 2) + 4 * len(b) // 10)
+    while True:
+        out = np.zeros(cap, dtype=capi.minmer_dtype)
+        n = lib().skch_add_minmers(b, len(b), k, w, s, seq_id, out.ctypes.data, cap)
+        if n >= 0:
+            return out[:n].copy()
+        cap = -n + 16
+
+
+class HostTail:
+    def __init__(self, tp: TailParams, names, lens, groups=None):
+        L = lib()
+        arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
+        self._lens = np.ascontiguousarray(lens, dtype=np.int32)
+        self._groups = None if groups is None else np.ascontiguousarray(groups, dtype=np.int32)
+        self.h = L.skch_tail_create(C.byref(tp), len(names), arr, self._lens.ctypes.data,
+                                    None if self._groups is None else self._groups.ctypes.data)
+
+    def map_read(self, name, length, seq_counter, segs, seg_res, cands, loci, ref_group=-1):
+        segs = np.ascontiguousarray(segs, dtype=capi.segment_dtype)
+        seg_res = np.ascontiguousarray(seg_res, dtype=capi.segres_dtype)
+        cands = np.ascontiguousarray(cands, dtype=capi.l1_dtype)
+        loci = np.ascontiguousarray(loci, dtype=capi.l2_dtype)
+        n = C.c_int32()
+        txt = lib().skch_tail_map_read(self.h, name.encode(), length, seq_counter, ref_group, segs.ctypes.data,
+                                       seg_res.ctypes.data, len(segs), cands.ctypes.data if len(cands) else None,
+                                       loci.ctypes.data if len(loci) else None, C.byref(n))
+        return txt.decode(), n.value
+
+    def close(self):
+        if self.h:
+            lib().skch_tail_destroy(self.h)
+            self.h = None

@@ -94,6 +94,7 @@ void copy_points(const std::vector<skch::IntervalPoint> &v, orc_ipoint *out, siz
 
 } // namespace
 
+#pragma GCC visibility push(default)
 extern "C" {
 
 /* argv as for the mashmap CLI, without the program name. The query list is stashed so the
@@ -318,3 +319,4 @@ int refh_map_read(void *hv, const char *name, const char *seq, int len, int seqC
 }
 
 } // extern "C"
+#pragma GCC visibility pop
