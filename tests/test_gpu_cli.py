@@ -1,0 +1,120 @@
+"""End-to-end parity on the GPU: `mashmap-b200` (skch::Sketch + skch::Map over the C ABI) against the UNMODIFIED
+reference CLI (oracle/_ref/mashmap_ref) on the same FASTA files. Coordinates / strand / counts bit-exact,
+identity within 1e-4 (BASELINE.json north_star).
+
+One documented divergence class is tolerated and counted ("reference UB"): a split read whose
+fragments yield exactly ONE mapping. The reference reads an uninitialised MappingResult::n_merged there
+(computeMap.hpp:1227, :1584, :429-430); its CLI build drops such a mapping unless it came from fragment 0,
+its harness build keeps it; this repo keeps it (n_merged = 1).
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import datasets
+import refh
+from conftest import have_gpu
+from mashmap_b200 import hostlib, synth
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not have_gpu(), reason="no GPU"),
+              pytest.mark.skipif(not os.path.exists(refh.REF_BIN), reason="oracle/_ref not built")]
+
+
+def run(cmd):
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert p.returncode == 0, (cmd, p.stderr[-2000:])
+    return p.stderr
+
+
+def parse(path):
+    rows = []
+    for line in open(path):
+        f = line.rstrip("\n").split("\t")
+        rows.append(f)
+    return rows
+
+
+def compare_paf(ref_rows, got_rows, seg_length):
+    """returns (n_equal, tolerated_extra, problems)"""
+    def key(f):
+        return tuple(f[:12])
+
+    ref_by_key = {}
+    for f in ref_rows:
+        ref_by_key.setdefault(key(f), []).append(f)
+    problems, tolerated, n_equal = [], 0, 0
+    got_per_query = {}
+    for f in got_rows:
+        got_per_query.setdefault(f[0], []).append(f)
+    matched = set()
+    for f in got_rows:
+        k = key(f)
+        if k in ref_by_key and ref_by_key[k]:
+            r = ref_by_key[k].pop()
+            idg = float(f[12].split(":")[2]); idr = float(r[12].split(":")[2])
+            kcg = float(f[13].split(":")[2]); kcr = float(r[13].split(":")[2])
+            if abs(idg - idr) > 1e-4 or abs(kcg - kcr) > 1e-4 * max(1.0, abs(kcr)):
+                problems.append(("value", f, r))
+            else:
+                n_equal += 1
+            matched.add(id(f))
+        else:
+            qlen, qs, qe = int(f[1]), int(f[2]), int(f[3])
+            single = len(got_per_query[f[0]]) == 1 and qlen > seg_length and (qe - qs) == seg_length and qs > 0
+            if single:
+                tolerated += 1
+            else:
+                problems.append(("extra", f))
+    for k, v in ref_by_key.items():
+        for r in v:
+            problems.append(("missing", r))
+    return n_equal, tolerated, problems
+
+
+CONFIGS = [
+    ("random", ["-s", "5000", "--pi", "85"]),
+    ("random", ["-s", "5000", "--pi", "95", "--dense"]),
+    ("random", ["-s", "5000", "--pi", "85", "-f", "none", "--noMerge"]),
+    ("panel", ["-s", "5000", "--pi", "85"]),
+    ("panel", ["-s", "5000", "--pi", "95", "-n", "1", "-Y", "#"]),
+    ("panel", ["-s", "3000", "--pi", "90", "-f", "one-to-one", "-X"]),
+    ("panel", ["-s", "5000", "--pi", "90", "--lowerTriangular", "-n", "2"]),
+    ("panel", ["-s", "2000", "--pi", "90", "-J", "25", "--noHgFilter", "-k", "16"]),
+]
+
+
+@pytest.mark.parametrize("which,args", CONFIGS)
+def test_paf_matches_reference_cli(workdir, which, args):
+    d = datasets.make_random_set(workdir, tag="cli") if which == "random" else datasets.make_panel_set(workdir, tag="clip")
+    tag = "_".join(a.strip("-#") for a in args)
+    ref_out = os.path.join(workdir, f"ref_{which}_{tag}.paf")
+    got_out = os.path.join(workdir, f"got_{which}_{tag}.paf")
+    run([refh.REF_BIN, "-r", d["ref"], "-q", d["qry"], "-t", "8", "-o", ref_out] + args)
+    log = run([hostlib.CLI_PATH, "-r", d["ref"], "-q", d["qry"], "-t", "8", "-o", got_out] + args)
+    seg = int(args[args.index("-s") + 1])
+    ref_rows, got_rows = parse(ref_out), parse(got_out)
+    n_equal, tolerated, problems = compare_paf(ref_rows, got_rows, seg)
+    print(f"{which} {args}: reference {len(ref_rows)} lines, ours {len(got_rows)}, equal {n_equal}, "
+          f"tolerated single-fragment {tolerated}, problems {len(problems)}")
+    for p in problems[:8]:
+        print("  ", p)
+    assert not problems
+    assert n_equal > 0
+    # line order must be the reference's too (ordered output, ThreadPool.hpp:187-211)
+    if tolerated == 0:
+        assert [r[:12] for r in ref_rows] == [g[:12] for g in got_rows]
+
+
+def test_small_batches_and_threads_do_not_change_output(workdir):
+    """device batching (--batchBases) and host thread count are invisible in the output"""
+    d = datasets.make_panel_set(workdir, tag="clip")
+    outs = []
+    for bb, t in (("1000000000", "1"), ("200000", "8"), ("60000", "3")):
+        o = os.path.join(workdir, f"bb_{bb}_{t}.paf")
+        run([hostlib.CLI_PATH, "-r", d["ref"], "-q", d["qry"], "-s", "5000", "--pi", "85", "-t", t, "--batchBases", bb, "-o", o])
+        outs.append(open(o).read())
+    assert outs[0] == outs[1] == outs[2]
+    assert len(outs[0]) > 0
