@@ -42,6 +42,72 @@ int64_t skch_add_minmers(const char *seq, int64_t len, int k, int w, int s, int 
   return (int64_t)v.size();
 }
 
+/* ---- the reference index as flat arrays (keys ascending / offsets / points / frequent flags) ---- */
+struct IndexHandle {
+  Parameters p;
+  Sketch *sk = nullptr;
+};
+
+/* index + frequency filter over an existing minmer list */
+void *skch_index_from_minmers(const mm_minmer *mi, uint64_t n, int n_contigs, float kmer_pct_threshold)
+{
+  IndexHandle *h = new IndexHandle();
+  h->p.kmer_pct_threshold = kmer_pct_threshold;
+  std::vector<ContigInfo> meta;
+  for (int i = 0; i < n_contigs; i++) meta.push_back(ContigInfo{std::to_string(i), 0});
+  Sketch::MI_Type v(mi, mi + n);
+  h->sk = new Sketch(h->p, meta, std::move(v));
+  return h;
+}
+
+/* full host build from sequences in memory: seqs = concatenated contigs, offs[n_contigs+1] */
+void *skch_index_build(const char *seqs, const uint64_t *offs, int n_contigs, int k, int segLength, int sketchSize, int threads,
+                       float kmer_pct_threshold)
+{
+  IndexHandle *h = new IndexHandle();
+  h->p.kmerSize = k; h->p.segLength = segLength; h->p.sketchSize = sketchSize; h->p.threads = threads;
+  h->p.kmer_pct_threshold = kmer_pct_threshold;
+  std::vector<ContigInfo> meta;
+  std::vector<const char *> ptrs;
+  for (int i = 0; i < n_contigs; i++) {
+    meta.push_back(ContigInfo{"ctg" + std::to_string(i), (offset_t)(offs[i + 1] - offs[i])});
+    ptrs.push_back(seqs + offs[i]);
+  }
+  h->sk = new Sketch(h->p, meta, ptrs);
+  return h;
+}
+
+void skch_index_destroy(void *hv)
+{
+  IndexHandle *h = (IndexHandle *)hv;
+  if (h) { delete h->sk; delete h; }
+}
+void skch_index_sizes(void *hv, uint64_t *n_minmers, uint64_t *n_keys, uint64_t *n_points, int32_t *freq_threshold)
+{
+  Sketch *s = ((IndexHandle *)hv)->sk;
+  *n_minmers = s->minmerIndex.size(); *n_keys = s->lookupKeys.size(); *n_points = s->lookupPoints.size();
+  *freq_threshold = s->getFreqThreshold();
+}
+void skch_index_copy(void *hv, mm_minmer *mi, uint64_t *keys, uint64_t *offs, mm_ipoint *pts, uint8_t *is_freq)
+{
+  Sketch *s = ((IndexHandle *)hv)->sk;
+  if (mi && !s->minmerIndex.empty()) memcpy(mi, s->minmerIndex.data(), s->minmerIndex.size() * sizeof(mm_minmer));
+  if (keys && !s->lookupKeys.empty()) memcpy(keys, s->lookupKeys.data(), s->lookupKeys.size() * 8);
+  if (offs) memcpy(offs, s->lookupOffsets.data(), s->lookupOffsets.size() * 8);
+  if (pts && !s->lookupPoints.empty()) memcpy(pts, s->lookupPoints.data(), s->lookupPoints.size() * sizeof(mm_ipoint));
+  if (is_freq && !s->lookupKeyIsFreq.empty()) memcpy(is_freq, s->lookupKeyIsFreq.data(), s->lookupKeyIsFreq.size());
+}
+/* upload straight into a device context (no copies through Python) */
+int skch_index_upload(void *hv, mm_ctx *ctx)
+{
+  Sketch *s = ((IndexHandle *)hv)->sk;
+  std::vector<int32_t> clen(s->metadata.size());
+  for (size_t i = 0; i < clen.size(); i++) clen[i] = s->metadata[i].len;
+  return mm_index_upload(ctx, s->minmerIndex.data(), s->minmerIndex.size(), s->lookupKeys.data(), s->lookupOffsets.data(),
+                         s->lookupKeys.size(), s->lookupPoints.data(), s->lookupPoints.size(), s->lookupKeyIsFreq.data(),
+                         clen.data(), nullptr, nullptr, (int32_t)clen.size());
+}
+
 /* ---- host tail on caller-provided records ---- */
 struct skch_tail_params {
   int32_t kmerSize, segLength, sketchSize, filterMode, numMappingsForSegment, numMappingsForShortSequence;

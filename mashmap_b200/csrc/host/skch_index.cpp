@@ -264,6 +264,56 @@ uint64_t getReferenceSize(const std::vector<std::string> &refSequences)
 Sketch::Sketch(const Parameters &p) : param(p)
 {
   build();
+  finish();
+}
+
+Sketch::Sketch(const Parameters &p, const std::vector<ContigInfo> &contigs, const std::vector<const char *> &seqs)
+    : metadata(contigs), param(p)
+{
+  sequencesByFileInfo.push_back((int)contigs.size());
+  buildFromMemory(seqs);
+  finish();
+}
+
+Sketch::Sketch(const Parameters &p, const std::vector<ContigInfo> &contigs, MI_Type &&minmers)
+    : metadata(contigs), minmerIndex(std::move(minmers)), param(p)
+{
+  sequencesByFileInfo.push_back((int)contigs.size());
+  finish();
+}
+
+void Sketch::buildFromMemory(const std::vector<const char *> &seqs)
+{
+  std::vector<MI_Type> outputs(seqs.size());
+  std::atomic<size_t> next{0};
+  const int nthreads = std::max(1, param.threads);
+  std::vector<std::thread> pool;
+  for (int t = 0; t < nthreads; t++) {
+    pool.emplace_back([&]() {
+      while (true) {
+        const size_t i = next.fetch_add(1);
+        if (i >= seqs.size()) break;
+        const offset_t len = metadata[i].len;
+        if (len < param.kmerSize) continue;
+        std::string buf(seqs[i], (size_t)len);  // addMinmers normalises in place
+        CommonFunc::addMinmers(outputs[i], &buf[0], len, param.kmerSize, param.segLength, param.alphabetSize,
+                               param.sketchSize, (seqno_t)i);
+      }
+    });
+  }
+  for (auto &th : pool) th.join();
+  size_t total = 0;
+  for (auto &o : outputs) total += o.size();
+  minmerIndex.reserve(total);
+  for (auto &o : outputs) {
+    minmerIndex.insert(minmerIndex.end(), o.begin(), o.end());
+    MI_Type().swap(o);
+  }
+  std::cerr << "[mashmap-b200::skch::Sketch::build] minmer windows picked from reference = " << minmerIndex.size() << std::endl;
+}
+
+void Sketch::finish()
+{
   index();
   if (!param.saveIndexFilename.empty()) {  // winSketch.hpp:127-134: saved BEFORE frequent seeds are dropped
     if (param.saveIndexFilename.extension() == ".tsv") saveIndexTSV(param.saveIndexFilename.string());

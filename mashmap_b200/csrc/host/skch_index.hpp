@@ -36,6 +36,10 @@ class Sketch {
   typedef std::vector<MinmerInfo> MI_Type;
 
   explicit Sketch(const Parameters &p);  // winSketch.hpp:122-138: build + index + frequency filter
+  // same pipeline on sequences already in memory (seqs[i] has metadata[i].len bases); used by bench.py
+  Sketch(const Parameters &p, const std::vector<ContigInfo> &contigs, const std::vector<const char *> &seqs);
+  // index + frequency filter over an existing minmer list (winSketch.hpp:379-504 without build())
+  Sketch(const Parameters &p, const std::vector<ContigInfo> &contigs, MI_Type &&minmers);
 
   std::vector<ContigInfo> metadata;          // winSketch.hpp:79
   std::vector<int> sequencesByFileInfo;      // winSketch.hpp:88
@@ -63,6 +67,8 @@ class Sketch {
   int freqThreshold = std::numeric_limits<int>::max();
 
   void build();
+  void buildFromMemory(const std::vector<const char *> &seqs);
+  void finish();
   void index();
   void computeFreqHist();
   void dropFreqSeedSet();

@@ -52,8 +52,66 @@ def lib():
         L.skch_tail_map_read.argtypes = [C.c_void_p, C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                          C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
         L.skch_tail_map_read.restype = C.c_char_p
+        L.skch_index_from_minmers.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_float]
+        L.skch_index_from_minmers.restype = C.c_void_p
+        L.skch_index_build.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float]
+        L.skch_index_build.restype = C.c_void_p
+        L.skch_index_destroy.argtypes = [C.c_void_p]
+        L.skch_index_sizes.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                       C.POINTER(C.c_int32)]
+        L.skch_index_copy.argtypes = [C.c_void_p] * 6
+        L.skch_index_upload.argtypes = [C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
+
+
+class HostIndex:
+    """skch::Sketch built by the host library (from sequences in memory, or from an existing minmer list)."""
+
+    def __init__(self, handle):
+        self.h = handle
+        a, b, c, t = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_int32()
+        lib().skch_index_sizes(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(t))
+        self.n_minmers, self.n_keys, self.n_points, self.freq_threshold = a.value, b.value, c.value, t.value
+
+    @classmethod
+    def build(cls, seqs, offs, k, seg_length, sketch_size, threads=8, kmer_pct_threshold=0.001):
+        seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        h = lib().skch_index_build(seqs.ctypes.data, offs.ctypes.data, len(offs) - 1, k, seg_length, sketch_size, threads,
+                                   kmer_pct_threshold)
+        return cls(h)
+
+    @classmethod
+    def from_minmers(cls, minmers, n_contigs, kmer_pct_threshold=0.001):
+        m = np.ascontiguousarray(minmers, dtype=capi.minmer_dtype)
+        return cls(lib().skch_index_from_minmers(m.ctypes.data, len(m), n_contigs, kmer_pct_threshold))
+
+    def arrays(self):
+        mi = np.zeros(self.n_minmers, dtype=capi.minmer_dtype)
+        keys = np.zeros(self.n_keys, dtype=np.uint64)
+        offs = np.zeros(self.n_keys + 1, dtype=np.uint64)
+        pts = np.zeros(self.n_points, dtype=capi.ipoint_dtype)
+        fr = np.zeros(self.n_keys, dtype=np.uint8)
+        lib().skch_index_copy(self.h, mi.ctypes.data, keys.ctypes.data, offs.ctypes.data, pts.ctypes.data, fr.ctypes.data)
+        return mi, keys, offs, pts, fr
+
+    def upload(self, ctx):
+        rc = lib().skch_index_upload(self.h, ctx._h)
+        ctx._check(rc)
+
+    def close(self):
+        if self.h:
+            lib().skch_index_destroy(self.h)
+            self.h = None
+
+
+def lookup_from_minmers(minmers, n_contigs, kmer_pct_threshold=0.001):
+    """Sketch::index + frequency filter: (minmers after dropFreqSeedSet, keys, offsets, points, is_freq)"""
+    hi = HostIndex.from_minmers(minmers, n_contigs, kmer_pct_threshold)
+    out = hi.arrays()
+    hi.close()
+    return out
 
 
 def min_hits_table(sketch_size, k, pi):

@@ -45,6 +45,18 @@ class OrcParams(C.Structure):
     ]
 
 
+def is_uninitialised_n_merged_case(mappings, seg_length, read_len):
+    """A split read whose fragments produced exactly ONE mapping: the reference then reads
+    MappingResult::n_merged uninitialised (computeMap.hpp:1227 declares it, mergeMappingsInRange returns early
+    at :1584, filterWeakMappings reads it at :429-430). Whether the mapping survives depends on stack garbage
+    (observed: the CLI build drops it unless it came from fragment 0; the harness build varies). This repo and
+    the oracle define n_merged = 1 (kept)."""
+    if read_len <= seg_length or len(mappings) != 1:
+        return False
+    m = mappings[0]
+    return int(m["queryEndPos"]) - int(m["queryStartPos"]) == seg_length and int(m["n_merged"]) == 1
+
+
 def available():
     return os.path.exists(REF_LIB)
 
