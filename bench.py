@@ -1,0 +1,425 @@
+#!/usr/bin/env python
+"""bench.py -- mapped query Gbp/s of the B200 mapping hot path (BASELINE.json metric).
+
+Workload (BASELINE.json configs[1]): 1 M synthetic ONT-like reads x 10 kb (per-read error ~ U[2 %,14 %],
+sub:ins:del 4:3:3) against a 3 Gbp uniform-random reference, MashMap defaults `-s 5000 --pi 85`
+(k = 19, sketch size = Stat::recommendedSketchSize for a 3.05 GB FASTA = 220).
+
+A "step" = one pass of the hot path over the whole read batch (2 M segments):
+  value  -- inputs resident in HBM: K1 sketch -> K2 L1 -> K3 L2 (mm_map_resident of the C ABI), timed with CUDA
+            events on the launching stream (first launch -> last kernel end, including the counter read-backs).
+  e2e    -- the same batch through the reference-facing host API (skch::BatchMapper = mm_map_segments with HOST
+            buffers + the host tail to PAF text): H2D and D2H copies and the host tail inside the timed region.
+N > 1 (torchrun): weak scaling -- every rank maps its own 1 M reads against the same index; rank 0 builds the
+index and broadcasts the device image (one NCCL broadcast over NVLink); mapping records of all ranks are
+gathered on rank 0 at the end of every e2e step (one all_gather of counts + one of padded records).
+
+--impl reference: the reference's CPU implementation of the same path on the host cores (bounded sample per
+step), see cpu_arm().
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K, SEG, PI = 19, 5000, 0.85
+READ_LEN = 10_000
+REF_FASTA_BYTES_PER_BASE = 81.0 / 80.0  # 80-column FASTA: what recommendedSketchSize is fed (file size in bytes)
+
+
+def log(*a):
+    print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    # workload overrides (tests / quick runs only; the defaults are the BASELINE configuration)
+    ap.add_argument("--reads", type=int, default=1_000_000)
+    ap.add_argument("--ref-bp", type=int, default=3_000_000_000)
+    ap.add_argument("--contigs", type=int, default=256)
+    ap.add_argument("--cpu-sample-reads", type=int, default=0, help="reads per CPU-baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons during the timed region"""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for t, line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9 or not (t0 - 0.05 <= t <= t1 + 0.15):
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples in the timed region"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def roofline_traffic():
+    """dram bytes per launch of the sketch kernel from the committed ncu capture, if any"""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            return {}
+    return {}
+
+
+def setup_workload(args, rank, world, device):
+    """reference on the GPU -> host index (rank 0) -> device; reads generated on the GPU"""
+    import torch
+
+    from mashmap_b200 import hostlib, synth_gpu
+
+    contig_len = args.ref_bp // args.contigs
+    t0 = time.time()
+    ref = synth_gpu.random_reference(args.contigs, contig_len, seed=1, device=device)
+    torch.cuda.synchronize()
+    log(f"rank {rank}: reference {args.contigs} x {contig_len} bp generated in {time.time() - t0:.1f} s")
+    sketch = int(hostlib.lib().skch_recommended_sketch_size(K, PI, SEG, int(args.ref_bp * REF_FASTA_BYTES_PER_BASE) + 16 * args.contigs))
+    t0 = time.time()
+    reads_dev, truth = synth_gpu.simulate_reads(ref, args.reads, READ_LEN, 0.02, 0.14, seed=2 + rank, chunk=8192)
+    torch.cuda.synchronize()
+    log(f"rank {rank}: {args.reads} reads simulated in {time.time() - t0:.1f} s; sketch size {sketch}")
+    ref_host = None
+    if rank == 0:
+        ref_host = ref.cpu().numpy().reshape(-1)
+    contig_of, start_of, strand_of = truth["contig"].cpu().numpy(), truth["start"].cpu().numpy(), truth["strand"].cpu().numpy()
+    del ref
+    torch.cuda.empty_cache()
+    return dict(ref_host=ref_host, contig_len=contig_len, sketch=sketch, reads_dev=reads_dev,
+                truth=(contig_of, start_of, strand_of))
+
+
+def build_index(args, wl, threads):
+    from mashmap_b200 import hostlib
+
+    t0 = time.time()
+    offs = np.arange(args.contigs + 1, dtype=np.uint64) * np.uint64(wl["contig_len"])
+    hi = hostlib.HostIndex.build(wl["ref_host"], offs, K, SEG, wl["sketch"], threads=threads)
+    log(f"host index: {hi.n_minmers} minmers, {hi.n_keys} keys, {hi.n_points} points, freq threshold {hi.freq_threshold} "
+        f"in {time.time() - t0:.1f} s ({threads} threads)")
+    return hi
+
+
+def gpu_arm(args):
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device(f"cuda:{local_rank}")
+    from mashmap_b200 import capi, hostlib
+
+    host_threads = max(1, (os.cpu_count() or 8) // max(1, world))
+    wl = setup_workload(args, rank, world, device)
+    S = wl["sketch"]
+
+    # ---- index: built on the host by rank 0, uploaded; other ranks receive the device image over NCCL ----
+    t_index = time.time()
+    if rank == 0:
+        hi = build_index(args, wl, os.cpu_count() or 8)
+    else:
+        hi = hostlib.HostIndex.metadata_only(args.contigs, wl["contig_len"], K, SEG, S)  # the index arrives by broadcast
+    bm = hostlib.BatchMapper(hi, pi=PI, device=local_rank, threads=host_threads)
+    ctx = capi.Context.from_handle(bm.ctx_handle, S, device=local_rank)
+    if world > 1:
+        nbytes = torch.zeros(1, dtype=torch.int64, device=device)
+        if rank == 0:
+            ptr, n = ctx.index_blob()
+            nbytes[0] = n
+        dist.broadcast(nbytes, 0)
+        n = int(nbytes.item())
+        if rank != 0:
+            ptr = ctx.index_blob_alloc(n)
+        blob = _wrap_device(ptr, n, device)
+        t0 = time.time()
+        dist.broadcast(blob, 0)
+        torch.cuda.synchronize()
+        if rank != 0:
+            ctx.index_adopt_blob()
+        log(f"rank {rank}: index image {n / 1e9:.2f} GB broadcast in {time.time() - t0:.2f} s")
+    index_seconds = time.time() - t_index
+    wl["ref_host"] = None
+
+    # ---- the batch: pinned host copy (e2e) and device-resident copy (value) ----
+    batch = bm.make_batch(args.reads, READ_LEN, first_seq_counter=rank * args.reads)
+    torch.from_numpy(batch.bases).copy_(wl["reads_dev"].reshape(-1))
+    del wl["reads_dev"]
+    torch.cuda.empty_cache()
+    n_bases = args.reads * READ_LEN
+    n_segs = len(batch.segments)
+    ctx.batch_upload(batch.bases, batch.segments)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: resident inputs ----
+    for _ in range(args.warmup):
+        ctx.map_resident()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    barrier()
+    t0 = time.time()
+    launches0 = ctx.kernel_launches
+    ev_ms, k_ms = 0.0, np.zeros(3)
+    for _ in range(args.steps):
+        nc, nl = ctx.map_resident()
+        ms = ctx.stage_ms()
+        ev_ms += ms[5]
+        k_ms += np.array(ms[:3])
+    barrier()
+    t1 = time.time()
+    launches = ctx.kernel_launches - launches0
+    clocks = sampler.stop(t0, t1)
+    wall_ms = (t1 - t0) * 1e3
+    seg_res, cands, loci = ctx.batch_fetch()
+
+    # ---- e2e: host buffers -> C ABI -> records -> host tail -> PAF text ----
+    for _ in range(min(args.warmup, 1)):
+        bm.map(batch)
+    barrier()
+    t0 = time.time()
+    e2e_info = None
+    gathered = 0
+    for _ in range(args.steps):
+        e2e_info = bm.map(batch)
+        if dist is not None:  # all ranks' mapping records on rank 0
+            gathered = _gather_records(dist, bm, device, rank, world)
+    barrier()
+    e2e_ms = (time.time() - t0) * 1e3
+    h2d = n_bases + n_segs * capi.segment_dtype.itemsize
+    d2h = n_segs * capi.segres_dtype.itemsize + len(cands) * capi.l1_dtype.itemsize + len(loci) * capi.l2_dtype.itemsize
+
+    # ---- correctness of what was timed: reads land on their true locus ----
+    res = bm.results()
+    acc = _accuracy(res, wl["truth"], wl["contig_len"], rank * args.reads)
+
+    # max over ranks
+    times = torch.tensor([ev_ms, wall_ms, e2e_ms], dtype=torch.float64, device=device)
+    if dist is not None:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ev_ms, wall_ms, e2e_ms = [float(x) for x in times.tolist()]
+    total_bases = n_bases * world * args.steps
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        b1 = SEG + 24 * S  # K1 algorithmic bytes per segment = L + 24 s
+        k1_ms = k_ms[0] / args.steps
+        achieved = b1 * n_segs / (k1_ms * 1e-3) / 1e9
+        traffic = roofline_traffic()
+        out = {
+            "metric": "mapped query Gbp/s", "value": total_bases / (ev_ms * 1e-3) / 1e9, "unit": "Gbp/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ev_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": f"{args.reads} synthetic ONT reads x {READ_LEN} bp (err U[2%,14%]) vs {args.ref_bp / 1e9:.2f} Gbp "
+                                   f"uniform-random reference ({args.contigs} contigs), -s {SEG} --pi {int(PI * 100)}, k={K}, sketch={S} "
+                                   "(BASELINE.json configs[1])",
+                       "segments_per_step": n_segs * world, "l2_policy": "inputs (10 GB reads + index) larger than L2, no flush",
+                       "timing": "CUDA events on the launching stream, first kernel launch -> last kernel end, max over ranks",
+                       "wall_ms_per_step": wall_ms / args.steps, "index_build_seconds": index_seconds,
+                       "index": {"minmers": hi.n_minmers, "keys": hi.n_keys, "points": hi.n_points},
+                       "candidates": int(nc), "loci": int(nl), "host_threads": host_threads,
+                       "mapped_read_fraction": acc["mapped"], "true_locus_fraction": acc["correct"]},
+            "clocks": clocks,
+            "e2e": {"value": total_bases / (e2e_ms * 1e-3) / 1e9, "unit": "Gbp/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps,
+                    "stage_seconds_last_step": {"device_call": e2e_info["sec_device"], "host_tail": e2e_info["sec_tail"]},
+                    "paf_bytes_per_step": int(e2e_info["paf_bytes"]), "records_gathered_on_rank0": int(gathered)},
+            "gpu_launches": int(launches),
+            "kernel_ms_per_step": {"sketch": k_ms[0] / args.steps, "l1": k_ms[1] / args.steps, "l2": k_ms[2] / args.steps},
+            "roofline": {"kernel": "k_sketch (K1)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic.get("k_sketch_dram_bytes_per_launch"),
+                         "peak_source": peak_src, "algorithmic_bytes_per_segment": b1,
+                         "note": "bit-exact Murmur3 makes K1 INT-ALU bound (SURVEY 8(d)); see DESIGN.md for the instruction roofline"},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            out["cpu_baseline"] = cpu_baseline(args, hi, batch, S)
+        print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def _wrap_device(ptr, nbytes, device):
+    """a torch uint8 tensor over raw device memory (for the NCCL broadcast of the index image)"""
+    import torch
+
+    class _Arr:
+        pass
+
+    a = _Arr()
+    a.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+    return torch.as_tensor(a, device=device)
+
+
+def _gather_records(dist, bm, device, rank, world):
+    import torch
+
+    res = torch.from_numpy(bm.results()).to(device)
+    n = torch.tensor([res.shape[0]], dtype=torch.int64, device=device)
+    counts = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(counts, n)
+    m = int(max(c.item() for c in counts))
+    pad = torch.zeros((m, 10), dtype=torch.int32, device=device)
+    pad[: res.shape[0]] = res
+    out = [torch.zeros((m, 10), dtype=torch.int32, device=device) for _ in range(world)]
+    dist.all_gather(out, pad)
+    return int(sum(c.item() for c in counts))
+
+
+def _accuracy(res, truth, contig_len, first_counter):
+    contig_of, start_of, strand_of = truth
+    if len(res) == 0:
+        return {"mapped": 0.0, "correct": 0.0}
+    q = res[:, 0] - first_counter
+    ok = (res[:, 3] == contig_of[q]) & (np.abs(res[:, 4].astype(np.int64) - start_of[q]) < 20_000) & (res[:, 6] == strand_of[q])
+    mapped = len(np.unique(q)) / len(contig_of)
+    return {"mapped": float(mapped), "correct": float(ok.mean())}
+
+
+def cpu_baseline(args, hi, batch, S, threads=None, n_reads=None):
+    """The oracle port of the reference path (oracle/libmm_oracle.so, mapModule per read, one task per read on
+    all host threads) on a bounded sample of the same batch, with the same index content."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_py
+
+    threads = threads or (os.cpu_count() or 8)
+    n_reads = n_reads or args.cpu_sample_reads or min(args.reads, 40 * threads)
+    mi, keys, offs, pts, fr = hi.arrays()
+    O = oracle_py.Oracle(K, SEG, S, PI)
+    O.set_index(mi, keys, offs, pts, fr, np.full(args.contigs, args.ref_bp // args.contigs, dtype=np.int32))
+    L = oracle_py.lib()
+    import ctypes as C
+
+    L.orc_map_reads_mt.restype = C.c_int64
+    L.orc_map_reads_mt.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64)]
+    mapped = C.c_int64()
+    t0 = time.time()
+    n_map = L.orc_map_reads_mt(O.h, batch.bases.ctypes.data, n_reads, READ_LEN, 0, threads, C.byref(mapped))
+    dt = time.time() - t0
+    O.close()
+    return {"value": n_reads * READ_LEN / dt / 1e9, "unit": "Gbp/s", "cores": threads, "kind": "port",
+            "sample": f"first {n_reads} reads of the batch ({n_reads * READ_LEN / 1e6:.0f} Mbp), oracle/libmm_oracle.so mapModule per read "
+                      f"on {threads} threads, {dt:.1f} s; {mapped.value} reads mapped, {n_map} mappings"}
+
+
+def cpu_arm(args):
+    """--impl reference: the reference's CPU path on the host cores. oracle/_ref (the unmodified reference) builds its own
+    index from FASTA single-threaded per contig, which for a 3 Gbp reference takes minutes per run, so the arm times the
+    oracle port of the same path (kind = "port") on the index content the product's host builder produced -- tested
+    bit-identical to the reference's own index (tests/test_host_cpu.py)."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    import torch
+
+    from mashmap_b200 import hostlib
+
+    device = torch.device("cuda:0") if torch.cuda.is_available() else torch.device("cpu")
+    threads = os.cpu_count() or 8
+    sample = args.cpu_sample_reads or 40 * threads
+    a2 = argparse.Namespace(**vars(args))
+    a2.reads = sample
+    wl = setup_workload(a2, 0, 1, device)
+    hi = build_index(a2, wl, threads)
+    S = wl["sketch"]
+    bases = wl["reads_dev"].reshape(-1).cpu().numpy()
+
+    class B:
+        pass
+
+    b = B()
+    b.bases = bases
+    times, last = [], None
+    for i in range(args.warmup + args.steps):
+        last = cpu_baseline(a2, hi, b, S, threads=threads, n_reads=sample)
+        if i >= args.warmup:
+            times.append(sample * READ_LEN / last["value"] / 1e9)
+    dt = sum(times)
+    val = sample * READ_LEN * args.steps / dt / 1e9
+    last["value"] = val
+    print(json.dumps({
+        "impl": "reference", "metric": "mapped query Gbp/s", "value": val, "unit": "Gbp/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": f"bounded sample: {sample} synthetic ONT reads x {READ_LEN} bp vs {args.ref_bp / 1e9:.2f} Gbp uniform-random "
+                               f"reference, -s {SEG} --pi {int(PI * 100)}, k={K}, sketch={S} (BASELINE.json configs[1])"},
+        "cpu_baseline": last,
+        "e2e": {"value": val, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        cpu_arm(a)
+    else:
+        gpu_arm(a)

@@ -181,7 +181,9 @@ int mm_batch_fetch(mm_ctx *ctx, mm_segment_result *seg_results,
 int mm_batch_fetch_sketch(mm_ctx *ctx, mm_minmer *out_sketch, int32_t *out_count);
 
 /* CUDA-event time in milliseconds of each stage of the last mm_map_resident / mm_map_segments:
- * [0] sketch kernel  [1] L1 kernels  [2] L2 kernel  [3] H2D  [4] D2H  [5..7] reserved. */
+ * [0] sketch kernel  [1] L1 kernel  [2] L2 kernel  [3] H2D  [4] D2H
+ * [5] first kernel launch -> last kernel end (events on the launching stream; includes the two counter
+ *     read-backs between kernels)  [6..7] reserved. */
 int mm_last_stage_ms(const mm_ctx *ctx, float ms[8]);
 
 /* Pinned host memory for the caller's batch buffers (so the copies inside mm_map_segments run at full

@@ -148,10 +148,21 @@ class Context:
         self.sketch_size = sketch_size
         self.device = device
 
+    @classmethod
+    def from_handle(cls, handle, sketch_size, device=0):
+        """wrap an mm_ctx owned by someone else (the host library's BatchMapper); close() will not destroy it"""
+        self = cls.__new__(cls)
+        self._L = lib()
+        self._h = C.c_void_p(handle)
+        self._borrowed = True
+        self.sketch_size = sketch_size
+        self.device = device
+        return self
+
     def close(self):
-        if self._h:
+        if self._h and not getattr(self, "_borrowed", False):
             self._L.mm_ctx_destroy(self._h)
-            self._h = C.c_void_p()
+        self._h = C.c_void_p()
 
     def __del__(self):
         try:

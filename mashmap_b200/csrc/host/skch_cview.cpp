@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "skch_index.hpp"
+#include "skch_map.hpp"
 #include "skch_stats.hpp"
 #include "skch_tail.hpp"
 
@@ -77,6 +78,17 @@ void *skch_index_build(const char *seqs, const uint64_t *offs, int n_contigs, in
   return h;
 }
 
+/* contig metadata only (ranks that receive the device index image by broadcast) */
+void *skch_index_metadata_only(int n_contigs, int contig_len, int k, int segLength, int sketchSize)
+{
+  IndexHandle *h = new IndexHandle();
+  h->p.kmerSize = k; h->p.segLength = segLength; h->p.sketchSize = sketchSize;
+  std::vector<ContigInfo> meta;
+  for (int i = 0; i < n_contigs; i++) meta.push_back(ContigInfo{"ctg" + std::to_string(i), (offset_t)contig_len});
+  h->sk = new Sketch(h->p, meta, Sketch::MI_Type());
+  return h;
+}
+
 void skch_index_destroy(void *hv)
 {
   IndexHandle *h = (IndexHandle *)hv;
@@ -106,6 +118,112 @@ int skch_index_upload(void *hv, mm_ctx *ctx)
   return mm_index_upload(ctx, s->minmerIndex.data(), s->minmerIndex.size(), s->lookupKeys.data(), s->lookupOffsets.data(),
                          s->lookupKeys.size(), s->lookupPoints.data(), s->lookupPoints.size(), s->lookupKeyIsFreq.data(),
                          clen.data(), nullptr, nullptr, (int32_t)clen.size());
+}
+
+/* ---- BatchMapper on reads already in (pinned) memory: the end-to-end call bench.py times ---- */
+struct BmHandle {
+  IndexHandle *ih;
+  BatchMapper *bm;
+  std::vector<MappingResultsVector_t> results;
+  std::vector<std::string> text;
+  std::string paf;
+};
+struct BmBatch {
+  BmHandle *owner;
+  ReadBatch batch;
+};
+
+void *skch_bm_create(void *index_handle, float percentageIdentity, int device, int threads)
+{
+  IndexHandle *ih = (IndexHandle *)index_handle;
+  ih->p.percentageIdentity = percentageIdentity;
+  ih->p.device = device;
+  ih->p.threads = threads;
+  ih->p.block_length = ih->p.segLength;
+  ih->p.chain_gap = ih->p.segLength;
+  BmHandle *h = new BmHandle();
+  h->ih = ih;
+  h->bm = new BatchMapper(ih->p, *ih->sk);
+  return h;
+}
+void skch_bm_destroy(void *hv)
+{
+  BmHandle *h = (BmHandle *)hv;
+  if (h) { delete h->bm; delete h; }
+}
+mm_ctx *skch_bm_ctx(void *hv) { return ((BmHandle *)hv)->bm->context(); }
+
+/* n_reads reads of read_len bases each, laid out back to back in a pinned buffer the caller fills */
+void *skch_bm_batch_create(void *hv, uint64_t n_reads, int32_t read_len, int32_t first_seq_counter)
+{
+  BmHandle *h = (BmHandle *)hv;
+  BmBatch *b = new BmBatch();
+  b->owner = h;
+  b->batch.capacity = n_reads * (uint64_t)read_len + 64;
+  b->batch.bases = h->bm->allocBases(b->batch.capacity);
+  for (uint64_t i = 0; i < n_reads; i++)
+    h->bm->addRead(b->batch, "read" + std::to_string(first_seq_counter + (int64_t)i), nullptr, read_len, (seqno_t)(first_seq_counter + i));
+  return b;
+}
+char *skch_bm_batch_bases(void *bv) { return ((BmBatch *)bv)->batch.bases; }
+uint64_t skch_bm_batch_segments(void *bv, const mm_segment **segs)
+{
+  BmBatch *b = (BmBatch *)bv;
+  if (segs) *segs = b->batch.segs.data();
+  return b->batch.segs.size();
+}
+void skch_bm_batch_destroy(void *bv)
+{
+  BmBatch *b = (BmBatch *)bv;
+  if (b) { b->owner->bm->freeBases(b->batch.bases); delete b; }
+}
+
+/* host buffers -> H2D -> K1/K2/K3 -> D2H -> host tail -> PAF text (kept in the handle). */
+int skch_bm_map(void *hv, void *bv, uint64_t *paf_bytes, uint64_t *n_mapped_reads, uint64_t *n_mappings, float stage_ms[8],
+                double *sec_device, double *sec_tail)
+{
+  BmHandle *h = (BmHandle *)hv;
+  BmBatch *b = (BmBatch *)bv;
+  const double d0 = h->bm->secondsDevice, t0 = h->bm->secondsHostTail;
+  h->bm->mapBatch(b->batch, h->results, &h->text, nullptr);
+  uint64_t bytes = 0, mapped = 0, maps = 0;
+  for (size_t r = 0; r < h->results.size(); r++) {
+    bytes += h->text[r].size();
+    mapped += h->results[r].empty() ? 0 : 1;
+    maps += h->results[r].size();
+  }
+  if (paf_bytes) *paf_bytes = bytes;
+  if (n_mapped_reads) *n_mapped_reads = mapped;
+  if (n_mappings) *n_mappings = maps;
+  if (stage_ms) memcpy(stage_ms, h->bm->lastStageMs, 8 * sizeof(float));
+  if (sec_device) *sec_device = h->bm->secondsDevice - d0;
+  if (sec_tail) *sec_tail = h->bm->secondsHostTail - t0;
+  return 0;
+}
+/* the PAF text of the last skch_bm_map, concatenated in read order */
+const char *skch_bm_paf(void *hv, uint64_t *n)
+{
+  BmHandle *h = (BmHandle *)hv;
+  h->paf.clear();
+  for (auto &t : h->text) h->paf += t;
+  if (n) *n = h->paf.size();
+  return h->paf.c_str();
+}
+/* flat copy of the last results (one row per mapping) for parity checks */
+uint64_t skch_bm_results(void *hv, int32_t *out, uint64_t cap_rows)
+{ /* row: querySeqId, queryStartPos, queryEndPos, refSeqId, refStartPos, refEndPos, strand, conservedSketches, blockLength, id*1e6 */
+  BmHandle *h = (BmHandle *)hv;
+  uint64_t n = 0;
+  for (auto &v : h->results)
+    for (auto &m : v) {
+      if (n < cap_rows) {
+        int32_t *r = out + n * 10;
+        r[0] = m.querySeqId; r[1] = m.queryStartPos; r[2] = m.queryEndPos; r[3] = m.refSeqId; r[4] = m.refStartPos;
+        r[5] = m.refEndPos; r[6] = m.strand; r[7] = m.conservedSketches; r[8] = m.blockLength; r[9] = (int32_t)(m.nucIdentity * 1e6f);
+      }
+      n++;
+    }
+  return n;
 }
 
 /* ---- host tail on caller-provided records ---- */

@@ -3,20 +3,15 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
-#include <cmath>
 #include <cstring>
 #include <fstream>
 #include <iostream>
-#include <limits>
-#include <numeric>
 #include <sstream>
 #include <thread>
 #include <tuple>
-#include <unordered_map>
 
 #include "skch_seqio.hpp"
 #include "skch_stats.hpp"
-#include "skch_tail.hpp"
 
 namespace skch {
 
@@ -31,158 +26,198 @@ double since(Clock::time_point t0) { return std::chrono::duration<double>(Clock:
   exit(1);
 }
 
+std::string prefix(const std::string &s, const char c) { return s.substr(0, s.find_last_of(c)); }  // computeMap.hpp:1170-1173
+
 }  // namespace
+
+/* ------------------------------------------------------------------------------------------------------ */
+
+void BatchMapper::setRefGroups()
+{  // computeMap.hpp:144-161
+  refIdGroup.assign(refSketch.metadata.size(), 0);
+  if (!param.skip_prefix) return;
+  int group = 0;
+  size_t start_idx = 0, idx = 0;
+  while (start_idx < refSketch.metadata.size()) {
+    const auto currPrefix = prefix(refSketch.metadata[start_idx].name, param.prefix_delim);
+    idx = start_idx;
+    while (idx < refSketch.metadata.size() && currPrefix == prefix(refSketch.metadata[idx].name, param.prefix_delim))
+      refIdGroup[idx++] = group;
+    group++;
+    start_idx = idx;
+  }
+}
+
+int BatchMapper::getRefGroup(const std::string &seqName) const
+{  // computeMap.hpp:164-177
+  const auto queryPrefix = prefix(seqName, param.prefix_delim);
+  for (size_t i = 0; i < refSketch.metadata.size(); i++)
+    if (queryPrefix == prefix(refSketch.metadata[i].name, param.prefix_delim)) return refIdGroup[i];
+  return -1;
+}
+
+BatchMapper::BatchMapper(const Parameters &p, const Sketch &refsketch) : param(p), refSketch(refsketch)
+{
+  if (!param.split) die("--noSplit is not supported by the B200 path (fragments longer than the segment length)");
+  // Map::Map (computeMap.hpp:123-139): setProbs, setRefGroups; plus the per-sketch-size minimum-hit table
+  sketchCutoffs = Stat::sketchCutoffs(param.sketchSize, param.kmerSize, param.ANIDiff, param.ANIDiffConf, param.stage1_topANI_filter);
+  setRefGroups();
+  minHits.assign((size_t)param.sketchSize + 1, 0);
+  for (int s = 1; s <= param.sketchSize; s++)
+    minHits[s] = Stat::estimateMinimumHitsRelaxed(s, param.kmerSize, param.percentageIdentity, fixed::confidence_interval);
+  contigNameId.resize(refSketch.metadata.size());
+  for (size_t i = 0; i < refSketch.metadata.size(); i++) {
+    auto it = refNameId.find(refSketch.metadata[i].name);
+    if (it == refNameId.end()) it = refNameId.emplace(refSketch.metadata[i].name, (int)refNameId.size()).first;
+    contigNameId[i] = it->second;
+  }
+  mm_params mp{};
+  mp.kmer_size = param.kmerSize; mp.seg_length = param.segLength; mp.sketch_size = param.sketchSize;
+  mp.stage1_topani_filter = param.stage1_topANI_filter; mp.skip_self = param.skip_self;
+  mp.skip_prefix = param.skip_prefix; mp.lower_triangular = param.lower_triangular;
+  int rc = mm_ctx_create(param.device, &mp, &ctx);
+  if (rc != MM_OK) die(std::string("mm_ctx_create: ") + mm_last_error(nullptr));
+  std::vector<int32_t> clen(refSketch.metadata.size());
+  for (size_t i = 0; i < clen.size(); i++) clen[i] = refSketch.metadata[i].len;
+  rc = mm_index_upload(ctx, refSketch.minmerIndex.data(), refSketch.minmerIndex.size(), refSketch.lookupKeys.data(),
+                       refSketch.lookupOffsets.data(), refSketch.lookupKeys.size(), refSketch.lookupPoints.data(),
+                       refSketch.lookupPoints.size(), refSketch.lookupKeyIsFreq.data(), clen.data(), contigNameId.data(),
+                       refIdGroup.data(), (int32_t)clen.size());
+  if (rc != MM_OK) die(std::string("mm_index_upload: ") + mm_last_error(ctx));
+  rc = mm_tables_upload(ctx, sketchCutoffs.data(), (int32_t)sketchCutoffs.size(), minHits.data(), (int32_t)minHits.size());
+  if (rc != MM_OK) die(std::string("mm_tables_upload: ") + mm_last_error(ctx));
+  tail_ = new MapTail(param, refSketch.metadata, refIdGroup);
+}
+
+BatchMapper::~BatchMapper()
+{
+  delete tail_;
+  if (ctx) mm_ctx_destroy(ctx);
+}
+
+char *BatchMapper::allocBases(uint64_t bytes)
+{
+  char *p = nullptr;
+  if (mm_host_alloc((void **)&p, bytes) != MM_OK) die("cannot allocate the pinned batch buffer");
+  return p;
+}
+void BatchMapper::freeBases(char *p) { if (p) mm_host_free(p); }
+
+void BatchMapper::addRead(ReadBatch &b, const std::string &name, const char *seq, offset_t len, seqno_t seqCounter) const
+{
+  ReadRec rd;
+  rd.name = name; rd.len = len; rd.seqCounter = seqCounter; rd.first_seg = b.segs.size();
+  rd.refGroup = param.skip_prefix ? getRefGroup(name) : -1;
+  int name_id = -1;
+  if (param.skip_self) {
+    auto it = refNameId.find(name);
+    if (it != refNameId.end()) name_id = it->second;
+  }
+  if (seq) memcpy(b.bases + b.used, seq, (size_t)len);
+  auto push = [&](offset_t start, offset_t flen) {
+    mm_segment s;
+    s.offset = b.used + (uint64_t)start; s.length = flen; s.seq_counter = seqCounter; s.name_id = name_id; s.ref_group = rd.refGroup;
+    b.segs.push_back(s);
+  };
+  if (len <= param.segLength) push(0, len);  // computeMap.hpp:587-607
+  else {
+    const int n = len / param.segLength;  // :610-641
+    for (int i = 0; i < n; i++) push(i * param.segLength, param.segLength);
+    if (len % param.segLength != 0) push(len - param.segLength, param.segLength);  // :644-671
+  }
+  rd.n_seg = (uint32_t)(b.segs.size() - rd.first_seg);
+  b.used += (uint64_t)len;
+  b.reads.push_back(std::move(rd));
+}
+
+void BatchMapper::mapBatch(const ReadBatch &b, std::vector<MappingResultsVector_t> &results, std::vector<std::string> *text,
+                           const std::vector<ContigInfo> *qmetadata)
+{
+  const size_t nreads = b.reads.size();
+  results.assign(nreads, MappingResultsVector_t());
+  if (text) text->assign(nreads, std::string());
+  if (nreads == 0) return;
+  auto t0 = Clock::now();
+  segRes.resize(b.segs.size());
+  uint64_t nc = 0, nl = 0;
+  if (cands.size() < 2 * b.segs.size() + 1024) cands.resize(2 * b.segs.size() + 1024);
+  if (loci.size() < 2 * cands.size()) loci.resize(2 * cands.size());
+  while (true) {
+    int rc = mm_map_segments(ctx, b.bases, b.used, b.segs.data(), b.segs.size(), segRes.data(), cands.data(), cands.size(), &nc,
+                             loci.data(), loci.size(), &nl);
+    if (rc == MM_ECAPACITY) {
+      cands.resize(std::max<uint64_t>(cands.size(), nc));
+      loci.resize(std::max<uint64_t>(loci.size(), nl));
+      continue;
+    }
+    if (rc != MM_OK) die(std::string("mm_map_segments: ") + mm_last_error(ctx));
+    break;
+  }
+  mm_last_stage_ms(ctx, lastStageMs);
+  secondsDevice += since(t0);
+  t0 = Clock::now();
+
+  tail_->segs = b.segs.data(); tail_->segRes = segRes.data(); tail_->cands = cands.data(); tail_->loci = loci.data();
+  tail_->qmetadata = qmetadata;
+  const int nthreads = std::max(1, std::min<int>(param.threads, (int)((nreads + 255) / 256)));
+  std::atomic<size_t> next{0};
+  auto worker = [&]() {
+    IdentityCache idc;
+    idc.k = param.kmerSize;
+    std::ostringstream os;
+    while (true) {
+      const size_t lo = next.fetch_add(256);
+      if (lo >= nreads) break;
+      const size_t hi = std::min(nreads, lo + 256);
+      for (size_t r = lo; r < hi; r++) {
+        tail_->mapRead(b.reads[r], idc, results[r]);
+        if (text && !results[r].empty()) {
+          os.str(std::string());
+          tail_->formatMappings(results[r], b.reads[r].name, os);
+          (*text)[r] = os.str();
+        }
+      }
+    }
+  };
+  if (nthreads == 1) worker();
+  else {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthreads; t++) pool.emplace_back(worker);
+    for (auto &th : pool) th.join();
+  }
+  secondsHostTail += since(t0);
+}
+
+/* ------------------------------------------------------------------------------------------------------ */
 
 struct Map::Impl {
   const Parameters &param;
   const Sketch &refSketch;
   PostProcessResultsFn_t processMappingResults;
   Map &self;
+  BatchMapper bm;
   std::vector<ContigInfo> qmetadata;  // computeMap.hpp:105 (one-to-one only)
-  std::vector<int> sketchCutoffs;     // :109
-  std::vector<int> refIdGroup;        // :113
-  std::vector<int> minHits;           // estimateMinimumHitsRelaxed by Q.sketchSize
-  std::unordered_map<std::string, int> refNameId;
-  std::vector<int> contigNameId;
-  mm_ctx *ctx = nullptr;
-  MapTail *tail = nullptr;
-
-  // batch state
-  char *h_bases = nullptr;  // pinned
-  uint64_t bases_cap = 0, bases_used = 0;
-  std::vector<mm_segment> segs;
-  std::vector<ReadRec> reads;
-  std::vector<mm_segment_result> segRes;
-  std::vector<mm_l1_candidate> cands;
-  std::vector<mm_l2_locus> loci;
+  ReadBatch batch;
   std::ofstream outstrm;
   MappingResultsVector_t allReadMappings;
   seqno_t totalReadsMapped = 0, totalReadsPicked = 0, seqCounter = 0;
 
   Impl(const Parameters &p, const Sketch &s, PostProcessResultsFn_t f, Map &m)
-      : param(p), refSketch(s), processMappingResults(f), self(m) {}
-
-  static std::string prefix(const std::string &s, const char c) { return s.substr(0, s.find_last_of(c)); }  // :1170-1173
-
-  void setRefGroups()
-  {  // computeMap.hpp:144-161
-    refIdGroup.assign(refSketch.metadata.size(), 0);
-    if (!param.skip_prefix) return;
-    int group = 0;
-    size_t start_idx = 0, idx = 0;
-    while (start_idx < refSketch.metadata.size()) {
-      const auto currPrefix = prefix(refSketch.metadata[start_idx].name, param.prefix_delim);
-      idx = start_idx;
-      while (idx < refSketch.metadata.size() && currPrefix == prefix(refSketch.metadata[idx].name, param.prefix_delim))
-        refIdGroup[idx++] = group;
-      group++;
-      start_idx = idx;
-    }
-  }
-  int getRefGroup(const std::string &seqName) const
-  {  // computeMap.hpp:164-177
-    const auto queryPrefix = prefix(seqName, param.prefix_delim);
-    for (size_t i = 0; i < refSketch.metadata.size(); i++)
-      if (queryPrefix == prefix(refSketch.metadata[i].name, param.prefix_delim)) return refIdGroup[i];
-    return -1;
-  }
-
-  void check(int rc, const char *what)
+      : param(p), refSketch(s), processMappingResults(f), self(m), bm(p, s)
   {
-    if (rc != MM_OK) die(std::string(what) + ": " + mm_last_error(ctx));
+    batch.capacity = param.batch_bases + (uint64_t)param.segLength + 64;
+    batch.bases = bm.allocBases(batch.capacity);
   }
+  ~Impl() { bm.freeBases(batch.bases); }
 
-  void setup()
-  {
-    if (!param.split) die("--noSplit is not supported by the B200 path (fragments longer than the segment length)");
-    sketchCutoffs = Stat::sketchCutoffs(param.sketchSize, param.kmerSize, param.ANIDiff, param.ANIDiffConf,
-                                        param.stage1_topANI_filter);
-    setRefGroups();
-    minHits.assign((size_t)param.sketchSize + 1, 0);
-    for (int s = 1; s <= param.sketchSize; s++)
-      minHits[s] = Stat::estimateMinimumHitsRelaxed(s, param.kmerSize, param.percentageIdentity, fixed::confidence_interval);
-    contigNameId.resize(refSketch.metadata.size());
-    for (size_t i = 0; i < refSketch.metadata.size(); i++) {
-      auto it = refNameId.find(refSketch.metadata[i].name);
-      if (it == refNameId.end()) it = refNameId.emplace(refSketch.metadata[i].name, (int)refNameId.size()).first;
-      contigNameId[i] = it->second;
-    }
-    mm_params mp{};
-    mp.kmer_size = param.kmerSize; mp.seg_length = param.segLength; mp.sketch_size = param.sketchSize;
-    mp.stage1_topani_filter = param.stage1_topANI_filter; mp.skip_self = param.skip_self;
-    mp.skip_prefix = param.skip_prefix; mp.lower_triangular = param.lower_triangular;
-    int rc = mm_ctx_create(param.device, &mp, &ctx);
-    if (rc != MM_OK) die(std::string("mm_ctx_create: ") + mm_last_error(nullptr));
-    std::vector<int32_t> clen(refSketch.metadata.size());
-    for (size_t i = 0; i < clen.size(); i++) clen[i] = refSketch.metadata[i].len;
-    check(mm_index_upload(ctx, refSketch.minmerIndex.data(), refSketch.minmerIndex.size(), refSketch.lookupKeys.data(),
-                          refSketch.lookupOffsets.data(), refSketch.lookupKeys.size(), refSketch.lookupPoints.data(),
-                          refSketch.lookupPoints.size(), refSketch.lookupKeyIsFreq.data(), clen.data(), contigNameId.data(),
-                          refIdGroup.data(), (int32_t)clen.size()),
-          "mm_index_upload");
-    check(mm_tables_upload(ctx, sketchCutoffs.data(), (int32_t)sketchCutoffs.size(), minHits.data(), (int32_t)minHits.size()),
-          "mm_tables_upload");
-    tail = new MapTail(param, refSketch.metadata, refIdGroup);
-    tail->qmetadata = &qmetadata;
-    bases_cap = param.batch_bases + (uint64_t)param.segLength + 64;
-    if (mm_host_alloc((void **)&h_bases, bases_cap) != MM_OK) die("cannot allocate the pinned batch buffer");
-  }
-
-  /* ---- one device batch: map all fragments, then the per-read tail on the worker threads ---- */
   void flushBatch()
   {
-    if (reads.empty()) return;
-    auto t0 = Clock::now();
-    segRes.resize(segs.size());
-    uint64_t nc = 0, nl = 0;
-    if (cands.size() < 2 * segs.size() + 1024) cands.resize(2 * segs.size() + 1024);
-    if (loci.size() < 2 * cands.size()) loci.resize(2 * cands.size());
-    while (true) {
-      int rc = mm_map_segments(ctx, h_bases, bases_used, segs.data(), segs.size(), segRes.data(), cands.data(), cands.size(), &nc,
-                               loci.data(), loci.size(), &nl);
-      if (rc == MM_ECAPACITY) {
-        cands.resize(std::max<uint64_t>(cands.size(), nc));
-        loci.resize(std::max<uint64_t>(loci.size(), nl));
-        continue;
-      }
-      check(rc, "mm_map_segments");
-      break;
-    }
-    self.secondsDevice += since(t0);
-    t0 = Clock::now();
-
-    tail->segs = segs.data(); tail->segRes = segRes.data(); tail->cands = cands.data(); tail->loci = loci.data();
-    const size_t nreads = reads.size();
-    std::vector<MappingResultsVector_t> results(nreads);
-    std::vector<std::string> text(nreads);
+    if (batch.reads.empty()) return;
+    std::vector<MappingResultsVector_t> results;
+    std::vector<std::string> text;
     const bool report_now = param.filterMode != filter::ONETOONE;
-    const int nthreads = std::max(1, std::min<int>(param.threads, (int)nreads));
-    std::atomic<size_t> next{0};
-    auto worker = [&]() {
-      IdentityCache idc;
-      idc.k = param.kmerSize;
-      std::ostringstream os;
-      while (true) {
-        const size_t lo = next.fetch_add(256);
-        if (lo >= nreads) break;
-        const size_t hi = std::min(nreads, lo + 256);
-        for (size_t r = lo; r < hi; r++) {
-          tail->mapRead(reads[r], idc, results[r]);
-          if (report_now && !results[r].empty()) {
-            os.str(std::string());
-            tail->formatMappings(results[r], reads[r].name, os);
-            text[r] = os.str();
-          }
-        }
-      }
-    };
-    if (nthreads == 1) worker();
-    else {
-      std::vector<std::thread> pool;
-      for (int t = 0; t < nthreads; t++) pool.emplace_back(worker);
-      for (auto &th : pool) th.join();
-    }
-    for (size_t r = 0; r < nreads; r++) {  // mapModuleHandleOutput :724-747, in input order
+    bm.mapBatch(batch, results, report_now ? &text : nullptr, &qmetadata);
+    for (size_t r = 0; r < results.size(); r++) {  // mapModuleHandleOutput (computeMap.hpp:724-747), in input order
       if (!results[r].empty()) totalReadsMapped++;
       if (!report_now) allReadMappings.insert(allReadMappings.end(), results[r].begin(), results[r].end());
       else {
@@ -191,14 +226,11 @@ struct Map::Impl {
           for (auto &e : results[r]) processMappingResults(e);
       }
     }
-    self.secondsHostTail += since(t0);
-    reads.clear();
-    segs.clear();
-    bases_used = 0;
+    batch.clear();
   }
 
-  void addRead(const std::string &name, const std::string &seq)
-  {  // the body of mapQuery's per-sequence callback (:317-349) + mapModule's fragmenting (:587-671)
+  void onSequence(const std::string &name, const std::string &seq)
+  {  // the body of mapQuery's per-sequence callback (computeMap.hpp:317-349)
     const offset_t len = seq.length();
     if (param.filterMode == filter::ONETOONE) qmetadata.push_back(ContigInfo{name, len});
     if (len < param.kmerSize) {
@@ -206,39 +238,16 @@ struct Map::Impl {
                 << " is not long enough for mapping at segment length " << param.segLength << std::endl;
     } else {
       totalReadsPicked++;
-      // a read must fit in one batch; flush first if it does not fit in what is left
-      if (bases_used + (uint64_t)len > param.batch_bases && !reads.empty()) flushBatch();
-      if ((uint64_t)len + 64 > bases_cap) {  // a single sequence larger than the batch buffer: grow it
+      // a read lives in one batch: flush first if it does not fit in what is left
+      if (batch.used + (uint64_t)len > param.batch_bases && !batch.reads.empty()) flushBatch();
+      if ((uint64_t)len + 64 > batch.capacity) {  // a single sequence larger than the batch buffer: grow it
         flushBatch();
-        mm_host_free(h_bases);
-        bases_cap = (uint64_t)len + 64;
-        if (mm_host_alloc((void **)&h_bases, bases_cap) != MM_OK) die("cannot allocate the pinned batch buffer");
+        bm.freeBases(batch.bases);
+        batch.capacity = (uint64_t)len + 64;
+        batch.bases = bm.allocBases(batch.capacity);
       }
-      ReadRec rd;
-      rd.name = name; rd.len = len; rd.seqCounter = seqCounter; rd.first_seg = segs.size();
-      rd.refGroup = param.skip_prefix ? getRefGroup(name) : -1;
-      int name_id = -1;
-      if (param.skip_self) {
-        auto it = refNameId.find(name);
-        if (it != refNameId.end()) name_id = it->second;
-      }
-      memcpy(h_bases + bases_used, seq.data(), (size_t)len);
-      auto push = [&](offset_t start, offset_t flen) {
-        mm_segment s;
-        s.offset = bases_used + (uint64_t)start; s.length = flen; s.seq_counter = seqCounter; s.name_id = name_id;
-        s.ref_group = rd.refGroup;
-        segs.push_back(s);
-      };
-      if (len <= param.segLength) push(0, len);
-      else {
-        const int n = len / param.segLength;
-        for (int i = 0; i < n; i++) push(i * param.segLength, param.segLength);
-        if (len % param.segLength != 0) push(len - param.segLength, param.segLength);
-      }
-      rd.n_seg = (uint32_t)(segs.size() - rd.first_seg);
-      bases_used += (uint64_t)len;
+      bm.addRead(batch, name, seq.data(), len, seqCounter);
       self.totalQueryBases += (uint64_t)len;
-      reads.push_back(std::move(rd));
     }
     seqCounter++;
   }
@@ -248,14 +257,12 @@ struct Map::Impl {
     outstrm.open(param.outFileName);
     auto t0 = Clock::now();
     for (const auto &fileName : param.querySequences) {
-      bool ok = seqio::for_each_seq_in_file(fileName, {}, "", [&](const std::string &name, const std::string &seq) {
-        auto t1 = Clock::now();
-        addRead(name, seq);
-        (void)t1;
-      });
+      bool ok = seqio::for_each_seq_in_file(fileName, {}, "", [&](const std::string &name, const std::string &seq) { onSequence(name, seq); });
       if (!ok) exit(1);
     }
     flushBatch();
+    self.secondsDevice = bm.secondsDevice;
+    self.secondsHostTail = bm.secondsHostTail;
     self.secondsInput = since(t0) - self.secondsDevice - self.secondsHostTail;
 
     if (param.filterMode == filter::ONETOONE) {  // :358-405
@@ -264,14 +271,14 @@ struct Map::Impl {
       MappingResultsVector_t tmp, filtered;
       while (se != allReadMappings.end()) {
         if (param.skip_prefix) {
-          const int g = getRefGroup(qmetadata[sb->querySeqId].name);
+          const int g = bm.getRefGroup(qmetadata[sb->querySeqId].name);
           se = std::find_if_not(sb, allReadMappings.end(),
-                                [&](const MappingResult &c) { return g == getRefGroup(qmetadata[c.querySeqId].name); });
+                                [&](const MappingResult &c) { return g == bm.getRefGroup(qmetadata[c.querySeqId].name); });
         } else {
           se = allReadMappings.end();
         }
         tmp.insert(tmp.end(), std::make_move_iterator(sb), std::make_move_iterator(se));
-        tail->filterByGroup(tmp, filtered, n_mappings, true);
+        bm.tail().filterByGroup(tmp, filtered, n_mappings, true);
         tmp.clear();
         sb = se;
       }
@@ -281,7 +288,8 @@ struct Map::Impl {
                std::tie(b.querySeqId, b.queryStartPos, b.refSeqId, b.refStartPos);
       });
       std::ostringstream os;
-      tail->formatMappings(allReadMappings, "", os);
+      const_cast<MapTail &>(bm.tail()).qmetadata = &qmetadata;
+      bm.tail().formatMappings(allReadMappings, "", os);
       outstrm << os.str();
       if (processMappingResults != nullptr)
         for (auto &e : allReadMappings) processMappingResults(e);
@@ -295,18 +303,9 @@ struct Map::Impl {
 
 Map::Map(const Parameters &p, const Sketch &refsketch, PostProcessResultsFn_t f) : impl(new Impl(p, refsketch, f, *this))
 {
-  impl->setup();
   impl->mapQuery();
 }
 
-Map::~Map()
-{
-  if (impl) {
-    if (impl->h_bases) mm_host_free(impl->h_bases);
-    if (impl->ctx) mm_ctx_destroy(impl->ctx);
-    delete impl->tail;
-    delete impl;
-  }
-}
+Map::~Map() { delete impl; }
 
 }  // namespace skch

@@ -6,28 +6,80 @@
  * once per reported mapping, in output order, from the constructing thread (:100, :1802-1803).
  *
  * What moved to the GPU: everything mapSingleQueryFrag does per fragment up to the L2 loci
- * (computeMap.hpp:755-815 -> mm_map_segments of the C ABI). What stays on the host, restated:
+ * (computeMap.hpp:755-815 -> mm_map_segments of the C ABI). What stays on the host, restated (skch_tail.hpp):
  *   the identity / confidence-bound test and HG early break of doL2Mapping       (:1181-1267)
  *   read segmentation and query-coordinate rewriting of mapModule                (:587-672)
  *   mergeMappingsInRange, filterWeakMappings, filterByGroup + plane sweeps,
  *   filterFalseHighIdentity, mappingBoundarySanityCheck, sparsifyMappings        (:423-561, :1579-1750)
  *   reportReadMappings (PAF text)                                                (:1758-1805)
- * Reads are batched (param.batch_bases query bases per device call); the per-read host tail of a batch
- * runs on param.threads worker threads; output order == input order, as in the reference.
+ *
+ * skch::BatchMapper is the same machinery for reads that are already in memory: a batch of reads is laid out
+ * in one (pinned) base buffer, fragmented with the reference's rule, mapped with ONE device call, and its
+ * per-read host tail runs on param.threads worker threads. skch::Map = FASTA reader + BatchMapper; output
+ * order == input order, as in the reference (ThreadPool.hpp:187-211).
  */
 #ifndef SKCH_MAP_HPP
 #define SKCH_MAP_HPP
 
 #include <functional>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "skch_index.hpp"
+#include "skch_tail.hpp"
 #include "skch_types.hpp"
 
 struct mm_ctx;
 
 namespace skch {
+
+/* one device batch of reads */
+struct ReadBatch {
+  char *bases = nullptr;  // pinned host memory (BatchMapper::allocBases)
+  uint64_t capacity = 0, used = 0;
+  std::vector<mm_segment> segs;
+  std::vector<ReadRec> reads;
+  void clear() { used = 0; segs.clear(); reads.clear(); }
+};
+
+class BatchMapper {
+ public:
+  BatchMapper(const Parameters &p, const Sketch &refsketch);  // creates the device context, uploads index + tables
+  ~BatchMapper();
+  BatchMapper(const BatchMapper &) = delete;
+
+  char *allocBases(uint64_t bytes);
+  void freeBases(char *p);
+  /* mapModule's fragmenting (computeMap.hpp:587-671): appends the read's fragments to the batch.
+   * `seq` may be nullptr when the bases are already in place at batch.bases + batch.used. */
+  void addRead(ReadBatch &b, const std::string &name, const char *seq, offset_t len, seqno_t seqCounter) const;
+  /* one device call + the host tail; results[r] = final mappings of batch.reads[r]; text[r] = their PAF lines */
+  void mapBatch(const ReadBatch &b, std::vector<MappingResultsVector_t> &results, std::vector<std::string> *text,
+                const std::vector<ContigInfo> *qmetadata);
+
+  int getRefGroup(const std::string &seqName) const;  // computeMap.hpp:164-177
+  const std::vector<int> &refGroups() const { return refIdGroup; }
+  const MapTail &tail() const { return *tail_; }
+  mm_ctx *context() const { return ctx; }
+  double secondsDevice = 0, secondsHostTail = 0;
+  float lastStageMs[8] = {0};
+
+ private:
+  const Parameters &param;
+  const Sketch &refSketch;
+  std::vector<int> sketchCutoffs;  // computeMap.hpp:109
+  std::vector<int> refIdGroup;     // computeMap.hpp:113
+  std::vector<int> minHits;        // estimateMinimumHitsRelaxed by Q.sketchSize (computeMap.hpp:1144)
+  std::unordered_map<std::string, int> refNameId;
+  std::vector<int> contigNameId;
+  mm_ctx *ctx = nullptr;
+  MapTail *tail_ = nullptr;
+  std::vector<mm_segment_result> segRes;
+  std::vector<mm_l1_candidate> cands;
+  std::vector<mm_l2_locus> loci;
+  void setRefGroups();
+};
 
 class Map {
  public:
@@ -52,7 +104,7 @@ class Map {
 
   static void insertL2ResultsToVec(MappingResultsVector_t &v, const MappingResult &r) { v.push_back(r); }  // :1813
 
-  // timing of the last run (seconds), for the driver program
+  // timing of the run (seconds), for the driver program
   double secondsDevice = 0, secondsHostTail = 0, secondsInput = 0;
   uint64_t totalQueryBases = 0;
 

@@ -281,6 +281,7 @@ int run_pipeline(mm_ctx *c)
       cudaEventElapsedTime(&c->stage_ms[0], c->ev[0], c->ev[1]);
       cudaEventElapsedTime(&c->stage_ms[1], c->ev[1], c->ev[2]);
       cudaEventElapsedTime(&c->stage_ms[2], c->ev[3], c->ev[4]);
+      cudaEventElapsedTime(&c->stage_ms[5], c->ev[0], c->ev[4]); /* first launch -> last kernel end, incl. host gaps */
       c->batch_mapped = true;
       return MM_OK;
     }

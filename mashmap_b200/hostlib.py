@@ -56,13 +56,87 @@ def lib():
         L.skch_index_from_minmers.restype = C.c_void_p
         L.skch_index_build.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float]
         L.skch_index_build.restype = C.c_void_p
+        L.skch_index_metadata_only.argtypes = [C.c_int] * 5
+        L.skch_index_metadata_only.restype = C.c_void_p
         L.skch_index_destroy.argtypes = [C.c_void_p]
         L.skch_index_sizes.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                        C.POINTER(C.c_int32)]
         L.skch_index_copy.argtypes = [C.c_void_p] * 6
         L.skch_index_upload.argtypes = [C.c_void_p, C.c_void_p]
+        vp = C.c_void_p
+        L.skch_bm_create.argtypes = [vp, C.c_float, C.c_int, C.c_int]
+        L.skch_bm_create.restype = vp
+        L.skch_bm_destroy.argtypes = [vp]
+        L.skch_bm_ctx.argtypes = [vp]
+        L.skch_bm_ctx.restype = vp
+        L.skch_bm_batch_create.argtypes = [vp, C.c_uint64, C.c_int32, C.c_int32]
+        L.skch_bm_batch_create.restype = vp
+        L.skch_bm_batch_bases.argtypes = [vp]
+        L.skch_bm_batch_bases.restype = vp
+        L.skch_bm_batch_segments.argtypes = [vp, C.POINTER(vp)]
+        L.skch_bm_batch_segments.restype = C.c_uint64
+        L.skch_bm_batch_destroy.argtypes = [vp]
+        L.skch_bm_map.argtypes = [vp, vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                  C.POINTER(C.c_float * 8), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.skch_bm_paf.argtypes = [vp, C.POINTER(C.c_uint64)]
+        L.skch_bm_paf.restype = vp
+        L.skch_bm_results.argtypes = [vp, vp, C.c_uint64]
+        L.skch_bm_results.restype = C.c_uint64
         _lib = L
     return _lib
+
+
+class BatchMapper:
+    """skch::BatchMapper: reads in pinned host memory -> one device call -> host tail -> PAF text."""
+
+    def __init__(self, host_index, pi=0.85, device=0, threads=8):
+        self.index = host_index
+        self.h = lib().skch_bm_create(host_index.h, pi, device, threads)
+        self.ctx_handle = lib().skch_bm_ctx(self.h)
+
+    def make_batch(self, n_reads, read_len, first_seq_counter=0):
+        return ReadBatch(self, n_reads, read_len, first_seq_counter)
+
+    def map(self, batch):
+        pb, nr, nm = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        ms = (C.c_float * 8)()
+        sd, st = C.c_double(), C.c_double()
+        lib().skch_bm_map(self.h, batch.h, C.byref(pb), C.byref(nr), C.byref(nm), C.byref(ms), C.byref(sd), C.byref(st))
+        return dict(paf_bytes=pb.value, mapped_reads=nr.value, mappings=nm.value, stage_ms=list(ms), sec_device=sd.value,
+                    sec_tail=st.value)
+
+    def paf(self):
+        n = C.c_uint64()
+        p = lib().skch_bm_paf(self.h, C.byref(n))
+        return C.string_at(p, n.value).decode()
+
+    def results(self):
+        n = lib().skch_bm_results(self.h, None, 0)
+        out = np.zeros((max(n, 1), 10), dtype=np.int32)
+        lib().skch_bm_results(self.h, out.ctypes.data, n)
+        return out[:n]
+
+    def close(self):
+        if self.h:
+            lib().skch_bm_destroy(self.h)
+            self.h = None
+
+
+class ReadBatch:
+    def __init__(self, bm, n_reads, read_len, first_seq_counter):
+        self.h = lib().skch_bm_batch_create(bm.h, n_reads, read_len, first_seq_counter)
+        self.n_reads, self.read_len = n_reads, read_len
+        ptr = lib().skch_bm_batch_bases(self.h)
+        self.bases = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(n_reads * read_len,))
+        sp = C.c_void_p()
+        ns = lib().skch_bm_batch_segments(self.h, C.byref(sp))
+        buf = (C.c_char * (ns * capi.segment_dtype.itemsize)).from_address(sp.value)
+        self.segments = np.frombuffer(buf, dtype=capi.segment_dtype, count=ns)
+
+    def close(self):
+        if self.h:
+            lib().skch_bm_batch_destroy(self.h)
+            self.h = None
 
 
 class HostIndex:
@@ -81,6 +155,10 @@ class HostIndex:
         h = lib().skch_index_build(seqs.ctypes.data, offs.ctypes.data, len(offs) - 1, k, seg_length, sketch_size, threads,
                                    kmer_pct_threshold)
         return cls(h)
+
+    @classmethod
+    def metadata_only(cls, n_contigs, contig_len, k, seg_length, sketch_size):
+        return cls(lib().skch_index_metadata_only(n_contigs, contig_len, k, seg_length, sketch_size))
 
     @classmethod
     def from_minmers(cls, minmers, n_contigs, kmer_pct_threshold=0.001):

@@ -21,6 +21,8 @@
 #include <set>
 #include <string>
 #include <tuple>
+#include <thread>
+#include <atomic>
 #include <unordered_map>
 #include <vector>
 
@@ -1015,6 +1017,33 @@ ORC_API int orc_map_fragment(void *cv, const char *seq, int len, int fullLen, in
     if ((int)res.size() > map_cap) rc |= 8;
   }
   return rc;
+}
+
+/* cpu_baseline / --impl reference driver: maps n_reads reads of read_len bases (back to back in `bases`) with
+ * `threads` worker threads, one read per task like the reference's pool (ThreadPool.hpp:176-215; mapModule is the
+ * task, computeMap.hpp:275,340). Returns the number of mappings; *mapped_reads = reads with >= 1 mapping. */
+ORC_API int64_t orc_map_reads_mt(void *cv, const char *bases, int64_t n_reads, int read_len, int first_seq_counter, int threads,
+                                 int64_t *mapped_reads)
+{
+  Ctx &c0 = *(Ctx *)cv;
+  for (int s = 1; s <= c0.p.sketchSize; s++) minimumHitsFor(c0, s); /* fill the memo before the threads read it */
+  std::atomic<int64_t> next{0}, total{0}, mapped{0};
+  auto work = [&]() {
+    std::vector<orc_mapping> res;
+    while (true) {
+      const int64_t i = next.fetch_add(1);
+      if (i >= n_reads) break;
+      res.clear();
+      mapModule(c0, bases + i * (int64_t)read_len, read_len, first_seq_counter + (int)i, -1, -1, res);
+      total += (int64_t)res.size();
+      if (!res.empty()) mapped++;
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 0; t < std::max(1, threads); t++) pool.emplace_back(work);
+  for (auto &th : pool) th.join();
+  if (mapped_reads) *mapped_reads = mapped.load();
+  return total.load();
 }
 
 ORC_API int orc_map_read(void *cv, const char *seq, int len, int seqCounter, int nameId, int refGroup, orc_mapping *out, int cap)
