@@ -46,6 +46,10 @@ struct mm_ctx {
   uint64_t *d_scratch = nullptr; uint64_t scratch_cap = 0; uint64_t scratch_slice = 0; uint64_t scratch_pool = 0;
   uint32_t l1_grid = 0;
   uint64_t n_cands = 0, n_loci = 0;
+  mm_l2_range *d_l2_ranges = nullptr; uint64_t *d_l2_rec_off = nullptr; uint64_t l2_cand_cap = 0;
+  uint2 *d_l2_recs = nullptr; uint64_t l2_recs_cap = 0;
+  void *d_scan_tmp = nullptr; size_t scan_tmp_bytes = 0;
+  int l2_mode = 1; /* 1 = stream kernels (mm_l2_stream.cu), 0 = general kernel only (MM_L2_GENERAL=1) */
   bool batch_mapped = false;
 
   cudaEvent_t ev[8]{};
@@ -96,6 +100,8 @@ void resolve_index(mm_ctx *c)
   ix.idx_wend = (const int32_t *)(b + h.off_idx_wend);
   ix.idx_strand = (const int8_t *)(b + h.off_idx_strand);
   ix.contig_start = (const uint64_t *)(b + h.off_contig_start);
+  ix.idx2_hash = (const uint64_t *)(b + h.off_idx2_hash);
+  ix.idx2_wend = (const int32_t *)(b + h.off_idx2_wend);
   ix.tab = (const mm_tab_slot *)(b + h.off_tab);
   ix.pts = (const uint64_t *)(b + h.off_pts);
   ix.contig_len = (const int32_t *)(b + h.off_contig_len);
@@ -191,6 +197,8 @@ mm_dev_batch make_batch(mm_ctx *c)
   b.counters = c->d_counters;
   b.scratch = c->d_scratch; b.scratch_slice = c->scratch_slice; b.scratch_pool_off = c->scratch_pool;
   b.scratch_cap = c->scratch_cap;
+  b.l2_ranges = c->d_l2_ranges; b.l2_rec_off = c->d_l2_rec_off; b.l2_recs = c->d_l2_recs; b.l2_recs_cap = c->l2_recs_cap;
+  b.l2_loci_per_cand = 2;
   return b;
 }
 
@@ -209,6 +217,86 @@ int ensure_scratch(mm_ctx *c, uint64_t pool_elems)
   c->scratch_slice = slice;
   c->scratch_pool = slice * c->l1_grid;
   return MM_OK;
+}
+
+/* K3 fast path (mm_l2_stream.cu): ranges+scan -> records -> lane-per-candidate scan -> general kernel for the
+ * candidates that need more locus slots. Returns MM_ENOMEM if the record buffer cannot be allocated. */
+int run_l2_stream(mm_ctx *c, uint32_t *h_cnt)
+{
+  const uint64_t nc = c->n_cands;
+  const uint32_t LPC = 2;
+  CU(c, cudaEventRecord(c->ev[3], c->stream));
+  if (nc == 0) {
+    CU(c, cudaEventRecord(c->ev[4], c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    c->n_loci = 0;
+    return MM_OK;
+  }
+  if (nc + 1 > c->l2_cand_cap) {
+    if (c->d_l2_ranges) cudaFree(c->d_l2_ranges);
+    if (c->d_l2_rec_off) cudaFree(c->d_l2_rec_off);
+    if (c->d_scan_tmp) cudaFree(c->d_scan_tmp);
+    c->d_l2_ranges = nullptr; c->d_l2_rec_off = nullptr; c->d_scan_tmp = nullptr;
+    c->l2_cand_cap = nc + nc / 8 + 1024;
+    CU(c, cudaMalloc((void **)&c->d_l2_ranges, c->l2_cand_cap * sizeof(mm_l2_range)));
+    CU(c, cudaMalloc((void **)&c->d_l2_rec_off, (c->l2_cand_cap + 1) * 8));
+    c->scan_tmp_bytes = mm_l2_scan_tmp_bytes((uint32_t)c->l2_cand_cap);
+    CU(c, cudaMalloc(&c->d_scan_tmp, c->scan_tmp_bytes + 256));
+  }
+  if (c->loci_cap < nc * LPC + 1024) {
+    if (c->d_loci) cudaFree(c->d_loci);
+    c->d_loci = nullptr;
+    c->loci_cap = nc * LPC + nc / 8 + 4096;
+    CU(c, cudaMalloc((void **)&c->d_loci, c->loci_cap * sizeof(mm_l2_locus)));
+  }
+  mm_dev_batch b = make_batch(c);
+  CU(c, cudaMemsetAsync(c->d_l2_rec_off + nc, 0, 8, c->stream));
+  CU(c, mm_launch_l2_ranges(c->params, c->ix, b, (uint32_t)nc, c->d_scan_tmp, c->scan_tmp_bytes + 256, c->stream));
+  uint64_t total = 0;
+  CU(c, cudaMemcpyAsync(&total, c->d_l2_rec_off + nc, 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  if (total + 16 > c->l2_recs_cap) {
+    if (c->d_l2_recs) cudaFree(c->d_l2_recs);
+    c->d_l2_recs = nullptr; c->l2_recs_cap = 0;
+    const uint64_t want = total + total / 16 + 1024;
+    if (cudaMalloc((void **)&c->d_l2_recs, want * sizeof(uint2)) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(c, MM_ENOMEM, "cannot allocate %llu L2 operation records", (unsigned long long)want);
+    }
+    c->l2_recs_cap = want;
+  }
+  for (int attempt = 0; attempt < 4; attempt++) {
+    b = make_batch(c);
+    CU(c, cudaMemsetAsync(c->d_counters + 1, 0, 4, c->stream));
+    CU(c, cudaMemsetAsync(c->d_counters + 6, 0, 8, c->stream));
+    CU(c, mm_launch_l2_prep(c->params, c->ix, b, (uint32_t)nc, c->stream, c->sm_count));
+    CU(c, mm_launch_l2_scan(c->params, c->ix, b, (uint32_t)nc, c->stream, c->sm_count));
+    c->launches += 4; /* ranges, scan (library), prep, scan */
+    CU(c, cudaMemcpyAsync(h_cnt, c->d_counters, 64, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    uint64_t extent = nc * LPC;
+    if (h_cnt[7] > 0) { /* candidates with more than LPC loci: general kernel, loci appended after the fixed slots */
+      const uint32_t base = (uint32_t)extent;
+      CU(c, cudaMemcpyAsync(c->d_counters + 6, &base, 4, cudaMemcpyHostToDevice, c->stream));
+      CU(c, mm_launch_l2_overflow(c->params, c->ix, b, (uint32_t)nc, c->stream, c->sm_count));
+      c->launches += 1;
+      CU(c, cudaMemcpyAsync(h_cnt, c->d_counters, 64, cudaMemcpyDeviceToHost, c->stream));
+      CU(c, cudaStreamSynchronize(c->stream));
+      if (h_cnt[1] == 2) return fail(c, MM_ECUDA, "L2 live-set overflow in the general kernel");
+      if (h_cnt[1] == 1 || h_cnt[6] > c->loci_cap) { /* grow and redo prep+scan+overflow */
+        cudaFree(c->d_loci); c->d_loci = nullptr;
+        c->loci_cap = (uint64_t)h_cnt[6] + h_cnt[6] / 4 + 1024;
+        CU(c, cudaMalloc((void **)&c->d_loci, c->loci_cap * sizeof(mm_l2_locus)));
+        continue;
+      }
+      extent = h_cnt[6];
+    }
+    CU(c, cudaEventRecord(c->ev[4], c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    c->n_loci = extent;
+    return MM_OK;
+  }
+  return fail(c, MM_ECUDA, "locus buffer kept overflowing");
 }
 
 /* K1 -> K2 -> K3 on the resident batch, growing output buffers and retrying on overflow */
@@ -258,11 +346,25 @@ int run_pipeline(mm_ctx *c)
     }
     if (retry) continue;
     c->n_cands = need_cands;
-    /* K3, retried alone if the locus buffer is too small (it is idempotent) */
+    /* K3 */
+    if (c->l2_mode == 1) {
+      int rc2 = run_l2_stream(c, h_cnt);
+      if (rc2 == MM_OK) {
+        cudaEventElapsedTime(&c->stage_ms[0], c->ev[0], c->ev[1]);
+        cudaEventElapsedTime(&c->stage_ms[1], c->ev[1], c->ev[2]);
+        cudaEventElapsedTime(&c->stage_ms[2], c->ev[3], c->ev[4]);
+        cudaEventElapsedTime(&c->stage_ms[5], c->ev[0], c->ev[4]);
+        c->batch_mapped = true;
+        return MM_OK;
+      }
+      if (rc2 != MM_ENOMEM) return rc2;
+      /* not enough memory for the operation records: fall through to the general kernel */
+    }
+    /* general kernel, retried alone if the locus buffer is too small (it is idempotent) */
     for (int a2 = 0; a2 < 4; a2++) {
       b = make_batch(c);
       CU(c, cudaMemsetAsync(c->d_counters + 1, 0, 4, c->stream));
-      CU(c, cudaMemsetAsync(c->d_counters + 6, 0, 4, c->stream));
+      CU(c, cudaMemsetAsync(c->d_counters + 6, 0, 8, c->stream));
       CU(c, cudaEventRecord(c->ev[3], c->stream));
       CU(c, mm_launch_l2(c->params, c->ix, b, (uint32_t)c->n_cands, c->stream, c->sm_count));
       CU(c, cudaEventRecord(c->ev[4], c->stream));
@@ -322,6 +424,7 @@ int mm_ctx_create(int device, const mm_params *params, mm_ctx **out)
     return fail(nullptr, MM_ECUDA, "cannot create stream");
   }
   for (auto &ev : c->ev) cudaEventCreate(&ev);
+  if (const char *g = getenv("MM_L2_GENERAL")) c->l2_mode = (g[0] == '1') ? 0 : 1; /* test hook: general kernel only */
   *out = c;
   return MM_OK;
 }
@@ -334,6 +437,7 @@ int mm_ctx_destroy(mm_ctx *c)
   if (c->blob && c->blob_owned) cudaFree(c->blob);
   cudaFree(c->d_bases); cudaFree(c->d_segs); cudaFree(c->d_sk_hash); cudaFree(c->d_sk_pos); cudaFree(c->d_sk_strand);
   cudaFree(c->d_seg_res); cudaFree(c->d_cands); cudaFree(c->d_loci); cudaFree(c->d_counters); cudaFree(c->d_scratch);
+  cudaFree(c->d_l2_ranges); cudaFree(c->d_l2_rec_off); cudaFree(c->d_l2_recs); cudaFree(c->d_scan_tmp);
   for (auto &ev : c->ev) cudaEventDestroy(ev);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -386,6 +490,8 @@ int mm_index_upload(mm_ctx *c, const mm_minmer *mi, uint64_t n_mi, const uint64_
   h.off_idx_wend = place((n_mi + 1) * 4);
   h.off_idx_strand = place(n_mi + 1);
   h.off_contig_start = place(((uint64_t)n_contigs + 1) * 8);
+  h.off_idx2_hash = place((n_mi + 1) * 8);
+  h.off_idx2_wend = place((n_mi + 1) * 4);
   h.off_tab = place(tab_slots * sizeof(mm_tab_slot));
   h.off_pts = place((n_points + 1) * 8);
   h.off_contig_len = place((uint64_t)n_contigs * 4);
@@ -415,6 +521,10 @@ int mm_index_upload(mm_ctx *c, const mm_minmer *mi, uint64_t n_mi, const uint64_
     }
   }
   CU(c, cudaMemcpy(c->blob + h.off_contig_start, cstart.data(), cstart.size() * 8, cudaMemcpyHostToDevice));
+  /* the same entries per contig in wpos_end order (device sort), for the L2 stream merge */
+  CU(c, mm_build_death_order((const uint64_t *)(c->blob + h.off_idx_hash), (const int32_t *)(c->blob + h.off_idx_wend),
+                             (const uint64_t *)(c->blob + h.off_contig_start), n_contigs, n_mi,
+                             (uint64_t *)(c->blob + h.off_idx2_hash), (int32_t *)(c->blob + h.off_idx2_wend), c->stream));
   /* interval points -> packed u64, in chunks */
   {
     const uint64_t CH = 1ULL << 22;

@@ -7,6 +7,9 @@
  *   minmer index, structure-of-arrays in reference order (seqId, wpos) (winSketch.hpp:102):
  *     idx_hash[n]  u64   idx_wpos[n] i32   idx_wend[n] i32   idx_strand[n] i8
  *     contig_start[n_contigs+1] u64   first index entry of each contig (seqId is implied)
+ *   the same entries in "death order" -- per contig sorted by wpos_end (stable) -- for the L2 scan, which
+ *   merges the insert stream (by wpos) with the delete stream (by wpos_end) instead of keeping a heap:
+ *     idx2_hash[n] u64   idx2_wend[n] i32
  *   hash -> interval points (winSketch.hpp:100-101, ankerl map replaced by open addressing):
  *     tab[2^tab_log2] {u64 key, u64 val}; val = offset<<25 | count<<1 | is_freq; val==0 = empty
  *     pts[n_points] u64 = seqId<<33 | pos<<1 | (side==OPEN)        (8 B instead of 24 B)
@@ -36,6 +39,7 @@ struct mm_blob_header {
   uint64_t n_minmers, n_keys, n_points;
   int32_t n_contigs, tab_log2, n_cutoffs, n_min_hits;
   uint64_t off_idx_hash, off_idx_wpos, off_idx_wend, off_idx_strand, off_contig_start;
+  uint64_t off_idx2_hash, off_idx2_wend;
   uint64_t off_tab, off_pts;
   uint64_t off_contig_len, off_contig_name_id, off_contig_group;
   uint64_t off_cutoffs, off_min_hits;
@@ -49,6 +53,8 @@ struct mm_dev_index {
   const int32_t *idx_wend;
   const int8_t *idx_strand;
   const uint64_t *contig_start;
+  const uint64_t *idx2_hash;
+  const int32_t *idx2_wend;
   const mm_tab_slot *tab;
   const uint64_t *pts;
   const int32_t *contig_len;
@@ -85,7 +91,26 @@ struct mm_dev_batch {
   uint64_t scratch_slice;     /* u64 elements per CTA slice                                            */
   uint64_t scratch_pool_off;  /* first u64 element of the pool                                         */
   uint64_t scratch_cap;       /* total u64 elements                                                    */
+  /* L2 work area */
+  struct mm_l2_range *l2_ranges; /* per candidate: where its insert / delete streams are                */
+  uint64_t *l2_rec_off;          /* per candidate (+1): first op record (exclusive prefix of the counts)   */
+  uint2 *l2_recs;                /* op records {pos, info}                                                 */
+  uint64_t l2_recs_cap;
+  uint32_t l2_loci_per_cand;     /* fixed locus slots per candidate in `loci`; overflow -> general kernel  */
 };
+
+/* insert stream = index entries [it0, it0+nI) (by wpos); delete stream = death-order entries [d0, d0+nD) */
+struct mm_l2_range {
+  uint64_t it0, d0;
+  uint32_t nI, nD;
+  int32_t next_wpos; /* wpos of entry it0+nI if it is on the same contig, else wpos of the last insert entry */
+  uint32_t _pad;
+};
+
+/* op record info word */
+#define MM_L2_SLOT_MASK 0xFFFFu   /* slot (1-based) of the hash in the query sketch; n+1 = above every query hash */
+#define MM_L2_MATCH (1u << 16)    /* hash == query hash of that slot */
+/* bits 17..18 of an insert record: q_strand * ref strand as 2-bit two's complement (-1, 0, +1) */
 
 MM_HD uint32_t mm_tab_slot_of(uint64_t key, int log2)
 {
@@ -99,6 +124,19 @@ cudaError_t mm_launch_l1(const mm_params &p, const mm_dev_index &ix, const mm_de
                          cudaStream_t st, int sm_count);
 cudaError_t mm_launch_l2(const mm_params &p, const mm_dev_index &ix, const mm_dev_batch &b,
                          uint32_t n_cands, cudaStream_t st, int sm_count);
+/* new L2: ranges -> (host reads the total) -> prep -> lane-per-candidate scan -> general kernel for overflow */
+cudaError_t mm_launch_l2_ranges(const mm_params &p, const mm_dev_index &ix, const mm_dev_batch &b, uint32_t n_cands,
+                                void *scan_tmp, size_t scan_tmp_bytes, cudaStream_t st);
+size_t mm_l2_scan_tmp_bytes(uint32_t n_cands);
+cudaError_t mm_launch_l2_prep(const mm_params &p, const mm_dev_index &ix, const mm_dev_batch &b, uint32_t n_cands,
+                              cudaStream_t st, int sm_count);
+cudaError_t mm_launch_l2_scan(const mm_params &p, const mm_dev_index &ix, const mm_dev_batch &b, uint32_t n_cands,
+                              cudaStream_t st, int sm_count);
+cudaError_t mm_launch_l2_overflow(const mm_params &p, const mm_dev_index &ix, const mm_dev_batch &b, uint32_t n_cands,
+                                  cudaStream_t st, int sm_count);
+/* death-order arrays of the index (device-side sort) */
+cudaError_t mm_build_death_order(const uint64_t *idx_hash, const int32_t *idx_wend, const uint64_t *contig_start,
+                                 int32_t n_contigs, uint64_t n, uint64_t *idx2_hash, int32_t *idx2_wend, cudaStream_t st);
 uint32_t mm_l1_grid_size(const mm_params &p, int sm_count);
 int mm_sketch_kmer_supported(int k);
 /* dynamic shared memory the sketch kernel needs for (seg_length, sketch_size); 0 if unsupported */

@@ -310,7 +310,7 @@ __device__ int l2_scan(const mm_params &prm, const mm_dev_index &ix, const mm_l1
 }
 
 __global__ void __launch_bounds__(L2_THREADS)
-k_l2(const mm_params prm, const mm_dev_index ix, const mm_dev_batch b, uint32_t n_cands, int live_cap)
+k_l2(const mm_params prm, const mm_dev_index ix, const mm_dev_batch b, uint32_t n_cands, int live_cap, int only_flagged)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int S = prm.sketch_size;
@@ -330,6 +330,7 @@ k_l2(const mm_params prm, const mm_dev_index ix, const mm_dev_batch b, uint32_t 
 
   for (uint32_t c = blockIdx.x * L2_WARPS + wid; c < n_cands; c += gridDim.x * L2_WARPS) {
     mm_l1_candidate cd = b.cands[c];
+    if (only_flagged && cd.n_loci != 0xFFFFFFFFu) continue; /* overflow pass after the stream kernels (mm_l2_stream.cu) */
     const uint32_t seg = cd.segment;
     const int n = b.seg_res[seg].sketch_size;
     const size_t sbase = (size_t)seg * (size_t)S;
@@ -369,8 +370,8 @@ k_l2(const mm_params prm, const mm_dev_index ix, const mm_dev_batch b, uint32_t 
 
 } // namespace
 
-cudaError_t mm_launch_l2(const mm_params &p, const mm_dev_index &ix, const mm_dev_batch &b, uint32_t n_cands,
-                         cudaStream_t st, int sm_count)
+static cudaError_t launch_general(const mm_params &p, const mm_dev_index &ix, const mm_dev_batch &b, uint32_t n_cands,
+                                  cudaStream_t st, int sm_count, int only_flagged)
 {
   if (n_cands == 0) return cudaSuccess;
   const int S = p.sketch_size;
@@ -389,6 +390,20 @@ cudaError_t mm_launch_l2(const mm_params &p, const mm_dev_index &ix, const mm_de
   uint32_t grid = (uint32_t)sm_count * (uint32_t)occ;
   const uint32_t need = (n_cands + L2_WARPS - 1) / L2_WARPS;
   if (grid > need) grid = need;
-  k_l2<<<grid, L2_THREADS, smem, st>>>(p, ix, b, n_cands, live_cap);
+  k_l2<<<grid, L2_THREADS, smem, st>>>(p, ix, b, n_cands, live_cap, only_flagged);
   return cudaGetLastError();
+}
+
+/* general warp-per-candidate kernel over every candidate */
+cudaError_t mm_launch_l2(const mm_params &p, const mm_dev_index &ix, const mm_dev_batch &b, uint32_t n_cands,
+                         cudaStream_t st, int sm_count)
+{
+  return launch_general(p, ix, b, n_cands, st, sm_count, 0);
+}
+
+/* only the candidates the stream kernels flagged (more loci than their fixed slots) */
+cudaError_t mm_launch_l2_overflow(const mm_params &p, const mm_dev_index &ix, const mm_dev_batch &b, uint32_t n_cands,
+                                  cudaStream_t st, int sm_count)
+{
+  return launch_general(p, ix, b, n_cands, st, sm_count, 1);
 }
