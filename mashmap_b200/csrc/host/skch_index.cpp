@@ -2,10 +2,12 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <deque>
 #include <fstream>
+#include <functional>
 #include <iostream>
 #include <map>
 #include <memory>
@@ -284,6 +286,7 @@ Sketch::Sketch(const Parameters &p, const std::vector<ContigInfo> &contigs, MI_T
 
 void Sketch::buildFromMemory(const std::vector<const char *> &seqs)
 {
+  auto tb0 = std::chrono::steady_clock::now();
   std::vector<MI_Type> outputs(seqs.size());
   std::atomic<size_t> next{0};
   const int nthreads = std::max(1, param.threads);
@@ -302,6 +305,8 @@ void Sketch::buildFromMemory(const std::vector<const char *> &seqs)
     });
   }
   for (auto &th : pool) th.join();
+  std::cerr << "[mashmap-b200::skch::Sketch] minmer windows computed in "
+            << std::chrono::duration<double>(std::chrono::steady_clock::now() - tb0).count() << " s" << std::endl;
   size_t total = 0;
   for (auto &o : outputs) total += o.size();
   minmerIndex.reserve(total);
@@ -314,14 +319,18 @@ void Sketch::buildFromMemory(const std::vector<const char *> &seqs)
 
 void Sketch::finish()
 {
-  index();
+  auto t0 = std::chrono::steady_clock::now();
   if (!param.saveIndexFilename.empty()) {  // winSketch.hpp:127-134: saved BEFORE frequent seeds are dropped
+    saving_ = true;
+    index();
+    saving_ = false;
     if (param.saveIndexFilename.extension() == ".tsv") saveIndexTSV(param.saveIndexFilename.string());
     else saveIndexBinary(param.saveIndexFilename.string());
     savePosListBinary(param.saveIndexFilename.string());
   }
-  computeFreqHist();
-  dropFreqSeedSet();
+  index();
+  std::cerr << "[mashmap-b200::skch::Sketch] lookup index + frequency filter in "
+            << std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() << " s" << std::endl;
 }
 
 void Sketch::build()
@@ -390,49 +399,138 @@ void Sketch::build()
   std::cerr << "[mashmap-b200::skch::Sketch::build] minmer windows picked from reference = " << minmerIndex.size() << std::endl;
 }
 
+/*
+ * index() + computeFreqHist() + computeFreqSeedSet() + dropFreqSeedSet() of the reference
+ * (winSketch.hpp:379-453, :488-504), producing the flattened lookup (keys ascending) and dropping the frequent
+ * hashes from minmerIndex -- done in one parallel pass structure instead of a hash map of vectors:
+ *   1. partition the entries by hash range (sampled splitters) keeping index order inside each part,
+ *   2. per part (one thread each): stable sort by hash, then per hash emit OPEN/CLOSE points in index order,
+ *      fusing an interval that starts where the previous one of the same hash closed (:388-396),
+ *   3. histogram of points per hash -> freqThreshold (:415-441),
+ *   4. per part: flag the entries of frequent hashes; compact minmerIndex (:497-504).
+ */
 void Sketch::index()
-{  // winSketch.hpp:379-404, producing the flattened form: per hash, OPEN/CLOSE points in index order, with
-   // an interval that starts where the previous one of the same hash closed fused into it (:388-396)
+{
   const size_t n = minmerIndex.size();
-  std::vector<uint32_t> order32;
-  std::vector<uint64_t> order;
-  order.resize(n);
-  std::iota(order.begin(), order.end(), (uint64_t)0);
-  std::stable_sort(order.begin(), order.end(),
-                   [this](uint64_t a, uint64_t b) { return minmerIndex[a].hash < minmerIndex[b].hash; });
-  lookupKeys.clear(); lookupOffsets.clear(); lookupPoints.clear();
-  lookupPoints.reserve(2 * n);
-  size_t i = 0;
-  while (i < n) {
-    const hash_t h = minmerIndex[order[i]].hash;
-    lookupKeys.push_back(h);
-    lookupOffsets.push_back(lookupPoints.size());
-    const size_t first_pt = lookupPoints.size();
-    for (; i < n && minmerIndex[order[i]].hash == h; i++) {
-      const MinmerInfo &mi = minmerIndex[order[i]];
-      if (lookupPoints.size() == first_pt || lookupPoints.back().pos != mi.wpos) {
-        IntervalPoint a{}; a.pos = mi.wpos; a.hash = mi.hash; a.seqId = mi.seqId; a.side = side::OPEN;
-        IntervalPoint b{}; b.pos = mi.wpos_end; b.hash = mi.hash; b.seqId = mi.seqId; b.side = side::CLOSE;
-        lookupPoints.push_back(a);
-        lookupPoints.push_back(b);
-      } else {
-        lookupPoints.back().pos = mi.wpos_end;
-      }
-    }
+  lookupKeys.clear(); lookupOffsets.clear(); lookupPoints.clear(); lookupKeyIsFreq.clear();
+  const int T = std::max(1, std::min(param.threads, 256));
+  const size_t P = (size_t)T * 4; /* parts */
+  std::vector<hash_t> splitters;
+  if (n > 0 && P > 1) {
+    const size_t ns = std::min<size_t>(n, 1 << 16);
+    std::vector<hash_t> sample(ns);
+    for (size_t i = 0; i < ns; i++) sample[i] = minmerIndex[(size_t)((double)i * n / ns)].hash;
+    std::sort(sample.begin(), sample.end());
+    for (size_t p = 1; p < P; p++) splitters.push_back(sample[p * ns / P]);
   }
-  lookupOffsets.push_back(lookupPoints.size());
+  auto part_of = [&](hash_t h) { return (size_t)(std::upper_bound(splitters.begin(), splitters.end(), h) - splitters.begin()); };
+  const size_t NP = splitters.size() + 1;
+  auto run_threads = [&](size_t n_tasks, const std::function<void(size_t)> &fn) {
+    std::atomic<size_t> next{0};
+    std::vector<std::thread> pool;
+    const int nt = (int)std::min<size_t>((size_t)T, std::max<size_t>(n_tasks, 1));
+    for (int t = 0; t < nt; t++)
+      pool.emplace_back([&]() {
+        while (true) {
+          const size_t i = next.fetch_add(1);
+          if (i >= n_tasks) break;
+          fn(i);
+        }
+      });
+    for (auto &th : pool) th.join();
+  };
+  /* 1. counting partition: chunk c of the entries x part p */
+  const size_t C = (size_t)T;
+  const size_t chunk = (n + C - 1) / std::max<size_t>(C, 1);
+  std::vector<std::vector<uint64_t>> cnt(C, std::vector<uint64_t>(NP, 0));
+  std::vector<uint32_t> part_id(n);
+  run_threads(C, [&](size_t c) {
+    const size_t lo = std::min(n, c * chunk), hi = std::min(n, lo + chunk);
+    for (size_t i = lo; i < hi; i++) {
+      const uint32_t p = (uint32_t)part_of(minmerIndex[i].hash);
+      part_id[i] = p;
+      cnt[c][p]++;
+    }
+  });
+  std::vector<uint64_t> part_start(NP + 1, 0);
+  std::vector<std::vector<uint64_t>> at(C, std::vector<uint64_t>(NP, 0));
+  {
+    uint64_t run = 0;
+    for (size_t p = 0; p < NP; p++) {
+      part_start[p] = run;
+      for (size_t c = 0; c < C; c++) { at[c][p] = run; run += cnt[c][p]; }
+    }
+    part_start[NP] = run;
+  }
+  std::vector<uint64_t> order(n);
+  run_threads(C, [&](size_t c) {
+    const size_t lo = std::min(n, c * chunk), hi = std::min(n, lo + chunk);
+    std::vector<uint64_t> &pos = at[c];
+    for (size_t i = lo; i < hi; i++) order[pos[part_id[i]]++] = i;
+  });
+  std::vector<uint32_t>().swap(part_id);
+  /* 2. per part: sort by hash (index order kept), emit keys / point counts / points */
+  struct PartOut {
+    std::vector<hash_t> keys;
+    std::vector<uint32_t> n_points;   /* per key */
+    std::vector<uint32_t> n_entries;  /* per key: minmer entries with that hash */
+    std::vector<IntervalPoint> points;
+  };
+  std::vector<PartOut> parts(NP);
+  run_threads(NP, [&](size_t p) {
+    uint64_t *b = order.data() + part_start[p], *e = order.data() + part_start[p + 1];
+    std::stable_sort(b, e, [this](uint64_t x, uint64_t y) { return minmerIndex[x].hash < minmerIndex[y].hash; });
+    PartOut &o = parts[p];
+    o.points.reserve((size_t)(e - b) * 2);
+    for (uint64_t *it = b; it != e;) {
+      const hash_t h = minmerIndex[*it].hash;
+      const size_t first_pt = o.points.size();
+      uint32_t ne = 0;
+      for (; it != e && minmerIndex[*it].hash == h; ++it, ++ne) {
+        const MinmerInfo &mi = minmerIndex[*it];
+        if (o.points.size() == first_pt || o.points.back().pos != mi.wpos) {
+          IntervalPoint a{}; a.pos = mi.wpos; a.hash = mi.hash; a.seqId = mi.seqId; a.side = side::OPEN;
+          IntervalPoint c2{}; c2.pos = mi.wpos_end; c2.hash = mi.hash; c2.seqId = mi.seqId; c2.side = side::CLOSE;
+          o.points.push_back(a);
+          o.points.push_back(c2);
+        } else {
+          o.points.back().pos = mi.wpos_end;
+        }
+      }
+      o.keys.push_back(h);
+      o.n_points.push_back((uint32_t)(o.points.size() - first_pt));
+      o.n_entries.push_back(ne);
+    }
+  });
+  /* concatenate (parts are ascending hash ranges) */
+  std::vector<uint64_t> key_base(NP + 1, 0), pt_base(NP + 1, 0);
+  for (size_t p = 0; p < NP; p++) {
+    key_base[p + 1] = key_base[p] + parts[p].keys.size();
+    pt_base[p + 1] = pt_base[p] + parts[p].points.size();
+  }
+  lookupKeys.resize(key_base[NP]);
+  lookupOffsets.resize(key_base[NP] + 1);
+  lookupPoints.resize(pt_base[NP]);
+  lookupKeyIsFreq.assign(key_base[NP], 0);
+  run_threads(NP, [&](size_t p) {
+    const PartOut &o = parts[p];
+    if (!o.keys.empty()) memcpy(&lookupKeys[key_base[p]], o.keys.data(), o.keys.size() * sizeof(hash_t));
+    if (!o.points.empty()) memcpy(&lookupPoints[pt_base[p]], o.points.data(), o.points.size() * sizeof(IntervalPoint));
+    uint64_t run = pt_base[p];
+    for (size_t k = 0; k < o.keys.size(); k++) { lookupOffsets[key_base[p] + k] = run; run += o.n_points[k]; }
+  });
+  lookupOffsets[key_base[NP]] = pt_base[NP];
   std::cerr << "[mashmap-b200::skch::Sketch::index] unique minmers = " << lookupKeys.size() << std::endl;
-}
+  if (saving_) return; /* the caller saves the un-filtered index first (winSketch.hpp:127-134) and calls again */
 
-void Sketch::computeFreqHist()
-{  // winSketch.hpp:410-453 and computeFreqSeedSet :488-495
-  lookupKeyIsFreq.assign(lookupKeys.size(), 0);
+  /* 3. frequency threshold (winSketch.hpp:410-453) */
   if (lookupKeys.empty()) {
     std::cerr << "[mashmap-b200::skch::Sketch::computeFreqHist] No minmers." << std::endl;
     return;
   }
   std::map<int, int> hist;
-  for (size_t i = 0; i < lookupKeys.size(); i++) hist[(int)(lookupOffsets[i + 1] - lookupOffsets[i])] += 1;
+  for (size_t p = 0; p < NP; p++)
+    for (uint32_t c : parts[p].n_points) hist[(int)c] += 1;
   std::cerr << "[mashmap-b200::skch::Sketch::computeFreqHist] Frequency histogram of minmer interval points = ("
             << hist.begin()->first << ", " << hist.begin()->second << ") ... (" << hist.rbegin()->first << ", "
             << hist.rbegin()->second << ")" << std::endl;
@@ -456,24 +554,41 @@ void Sketch::computeFreqHist()
   else
     std::cerr << "[mashmap-b200::skch::Sketch::computeFreqHist] With threshold " << param.kmer_pct_threshold
               << "%, consider all minmers during lookup." << std::endl;
-  for (size_t i = 0; i < lookupKeys.size(); i++)
-    if ((int64_t)(lookupOffsets[i + 1] - lookupOffsets[i]) >= (int64_t)freqThreshold) lookupKeyIsFreq[i] = 1;
+  /* 4. frequent seeds (:488-504): flag the keys, drop their entries from minmerIndex only */
+  if (freqThreshold == std::numeric_limits<int>::max()) return;
+  std::vector<uint8_t> drop(n, 0);
+  std::atomic<uint64_t> n_drop{0};
+  run_threads(NP, [&](size_t p) {
+    const PartOut &o = parts[p];
+    const uint64_t *it = order.data() + part_start[p];
+    uint64_t local = 0;
+    for (size_t k = 0; k < o.keys.size(); k++) {
+      const bool fr = (int64_t)o.n_points[k] >= (int64_t)freqThreshold;
+      if (fr) {
+        lookupKeyIsFreq[key_base[p] + k] = 1;
+        for (uint32_t j = 0; j < o.n_entries[k]; j++) drop[it[j]] = 1;
+        local += o.n_entries[k];
+      }
+      it += o.n_entries[k];
+    }
+    n_drop += local;
+  });
+  if (n_drop.load() > 0) {
+    size_t w = 0;
+    for (size_t i = 0; i < n; i++)
+      if (!drop[i]) { if (w != i) minmerIndex[w] = minmerIndex[i]; w++; }
+    minmerIndex.resize(w);
+  }
 }
+
+void Sketch::computeFreqHist() {}  /* folded into index() */
+void Sketch::dropFreqSeedSet() {}  /* folded into index() */
 
 bool Sketch::isFreqSeed(hash_t h) const
 {
   auto it = std::lower_bound(lookupKeys.begin(), lookupKeys.end(), h);
   if (it == lookupKeys.end() || *it != h) return false;
   return lookupKeyIsFreq[(size_t)(it - lookupKeys.begin())] != 0;
-}
-
-void Sketch::dropFreqSeedSet()
-{  // winSketch.hpp:497-504: frequent hashes leave minmerIndex only (the lookup keeps them, flagged)
-  bool any = false;
-  for (uint8_t f : lookupKeyIsFreq) any |= f != 0;
-  if (!any) return;
-  minmerIndex.erase(std::remove_if(minmerIndex.begin(), minmerIndex.end(), [this](MinmerInfo &mi) { return isFreqSeed(mi.hash); }),
-                    minmerIndex.end());
 }
 
 void Sketch::saveIndexTSV(const std::string &path) const

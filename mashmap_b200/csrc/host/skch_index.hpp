@@ -65,6 +65,7 @@ class Sketch {
  private:
   const Parameters &param;
   int freqThreshold = std::numeric_limits<int>::max();
+  bool saving_ = false;
 
   void build();
   void buildFromMemory(const std::vector<const char *> &seqs);

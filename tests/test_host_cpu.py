@@ -204,3 +204,31 @@ def test_host_tail_matches_reference_mapModule(workdir, which, args):
         tail.close()
     finally:
         R.close()
+
+
+@needs_ref
+@pytest.mark.parametrize("which,args,threads", [("random", ["-s", "5000", "--pi", "85"], 1), ("panel", ["-s", "5000", "--pi", "85"], 5),
+                                                ("panel", ["-s", "1000", "--pi", "90", "-J", "40", "--kmerThreshold", "1"], 3)])
+def test_host_index_equals_reference_sketch(workdir, which, args, threads):
+    """skch::Sketch of the product (build + index + frequency filter) == the reference's Sketch members"""
+    d = datasets.make_random_set(workdir, tag="hx") if which == "random" else datasets.make_panel_set(workdir, tag="hxp")
+    R = refh.RefSession(["-r", d["ref"], "-q", d["ref"], "-t", "2"] + args)
+    try:
+        seqs = np.concatenate(d["genome"])
+        offs = np.zeros(len(d["genome"]) + 1, dtype=np.uint64)
+        offs[1:] = np.cumsum([len(g) for g in d["genome"]])
+        pct = float(args[args.index("--kmerThreshold") + 1]) if "--kmerThreshold" in args else 0.001
+        hi = hostlib.HostIndex.build(seqs, offs, R.p.kmerSize, R.p.segLength, R.p.sketchSize, threads=threads, kmer_pct_threshold=pct)
+        mi, keys, offs2, pts, fr = hi.arrays()
+        ref_mi = R.index()
+        rkeys, roffs, rpts, rfr = R.lookup()
+        assert hi.freq_threshold == R.freq_threshold()
+        assert len(mi) == len(ref_mi)
+        for f in ("hash", "wpos", "wpos_end", "seqId", "strand"):
+            assert np.array_equal(mi[f], ref_mi[f]), f
+        assert np.array_equal(keys, rkeys) and np.array_equal(offs2, roffs) and np.array_equal(fr, rfr)
+        for f in ("pos", "hash", "seqId", "side"):
+            assert np.array_equal(pts[f], rpts[f]), f
+        hi.close()
+    finally:
+        R.close()
