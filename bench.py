@@ -351,7 +351,6 @@ def cpu_baseline(args, hi, batch, S, threads=None, n_reads=None):
     import oracle_py
 
     threads = threads or (os.cpu_count() or 8)
-    n_reads = n_reads or args.cpu_sample_reads or min(args.reads, 40 * threads)
     mi, keys, offs, pts, fr = hi.arrays()
     O = oracle_py.Oracle(K, SEG, S, PI)
     O.set_index(mi, keys, offs, pts, fr, np.full(args.contigs, args.ref_bp // args.contigs, dtype=np.int32))
@@ -361,6 +360,15 @@ def cpu_baseline(args, hi, batch, S, threads=None, n_reads=None):
     L.orc_map_reads_mt.restype = C.c_int64
     L.orc_map_reads_mt.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64)]
     mapped = C.c_int64()
+    total_reads = len(batch.bases) // READ_LEN
+    if not n_reads:
+        n_reads = args.cpu_sample_reads
+    if not n_reads:  # pilot run, then a sample sized for about 15 s of wall time on all cores
+        pilot = min(total_reads, 4 * threads)
+        t0 = time.time()
+        L.orc_map_reads_mt(O.h, batch.bases.ctypes.data, pilot, READ_LEN, 0, threads, C.byref(mapped))
+        rate = pilot / max(time.time() - t0, 1e-3)
+        n_reads = int(min(total_reads, max(pilot, rate * 15.0)))
     t0 = time.time()
     n_map = L.orc_map_reads_mt(O.h, batch.bases.ctypes.data, n_reads, READ_LEN, 0, threads, C.byref(mapped))
     dt = time.time() - t0
@@ -385,7 +393,7 @@ def cpu_arm(args):
 
     device = torch.device("cuda:0") if torch.cuda.is_available() else torch.device("cpu")
     threads = os.cpu_count() or 8
-    sample = args.cpu_sample_reads or 40 * threads
+    sample = args.cpu_sample_reads or 1500 * threads  # ~15 s per step at ~0.1 Gbp/s on 128 cores
     a2 = argparse.Namespace(**vars(args))
     a2.reads = sample
     wl = setup_workload(a2, 0, 1, device)

@@ -503,60 +503,55 @@ int mm_index_upload(mm_ctx *c, const mm_minmer *mi, uint64_t n_mi, const uint64_
   CU(c, cudaMalloc((void **)&c->blob, o));
   c->blob_bytes = o; c->blob_owned = true; c->hdr = h;
 
-  /* minmer index -> SoA, converted and copied in chunks to bound host memory */
+  /* AoS records go up in chunks and are re-laid out on the device (SoA index, packed points, hash table) */
   {
-    const uint64_t CH = 1ULL << 22;
-    std::vector<uint64_t> bh(std::min(CH, n_mi + 1));
-    std::vector<int32_t> bw(bh.size()), be(bh.size());
-    std::vector<int8_t> bs(bh.size());
+    const uint64_t CH = 1ULL << 24;
+    void *stage = nullptr;
+    CU(c, cudaMalloc(&stage, CH * 24));
     for (uint64_t at = 0; at < n_mi; at += CH) {
       const uint64_t n = std::min(CH, n_mi - at);
-      for (uint64_t i = 0; i < n; i++) {
-        bh[i] = mi[at + i].hash; bw[i] = mi[at + i].wpos; be[i] = mi[at + i].wpos_end; bs[i] = (int8_t)mi[at + i].strand;
-      }
-      CU(c, cudaMemcpy(c->blob + h.off_idx_hash + at * 8, bh.data(), n * 8, cudaMemcpyHostToDevice));
-      CU(c, cudaMemcpy(c->blob + h.off_idx_wpos + at * 4, bw.data(), n * 4, cudaMemcpyHostToDevice));
-      CU(c, cudaMemcpy(c->blob + h.off_idx_wend + at * 4, be.data(), n * 4, cudaMemcpyHostToDevice));
-      CU(c, cudaMemcpy(c->blob + h.off_idx_strand + at, bs.data(), n, cudaMemcpyHostToDevice));
+      CU(c, cudaMemcpy(stage, mi + at, n * sizeof(mm_minmer), cudaMemcpyHostToDevice));
+      CU(c, mm_upload_split_minmers((const mm_minmer *)stage, n, (uint64_t *)(c->blob + h.off_idx_hash) + at,
+                                    (int32_t *)(c->blob + h.off_idx_wpos) + at, (int32_t *)(c->blob + h.off_idx_wend) + at,
+                                    (int8_t *)(c->blob + h.off_idx_strand) + at, c->stream));
+      CU(c, cudaStreamSynchronize(c->stream));
     }
-  }
-  CU(c, cudaMemcpy(c->blob + h.off_contig_start, cstart.data(), cstart.size() * 8, cudaMemcpyHostToDevice));
-  /* the same entries per contig in wpos_end order (device sort), for the L2 stream merge */
-  CU(c, mm_build_death_order((const uint64_t *)(c->blob + h.off_idx_hash), (const int32_t *)(c->blob + h.off_idx_wend),
-                             (const uint64_t *)(c->blob + h.off_contig_start), n_contigs, n_mi,
-                             (uint64_t *)(c->blob + h.off_idx2_hash), (int32_t *)(c->blob + h.off_idx2_wend), c->stream));
-  /* interval points -> packed u64, in chunks */
-  {
-    const uint64_t CH = 1ULL << 22;
-    std::vector<uint64_t> bp(std::min(CH, n_points + 1));
+    CU(c, cudaMemcpy(c->blob + h.off_contig_start, cstart.data(), cstart.size() * 8, cudaMemcpyHostToDevice));
+    /* the same entries per contig in wpos_end order (device sort), for the L2 stream merge */
+    CU(c, mm_build_death_order((const uint64_t *)(c->blob + h.off_idx_hash), (const int32_t *)(c->blob + h.off_idx_wend),
+                               (const uint64_t *)(c->blob + h.off_contig_start), n_contigs, n_mi,
+                               (uint64_t *)(c->blob + h.off_idx2_hash), (int32_t *)(c->blob + h.off_idx2_wend), c->stream));
+    uint32_t *d_err = nullptr;
+    CU(c, cudaMalloc((void **)&d_err, 4));
+    CU(c, cudaMemset(d_err, 0, 4));
     for (uint64_t at = 0; at < n_points; at += CH) {
       const uint64_t n = std::min(CH, n_points - at);
-      for (uint64_t i = 0; i < n; i++) {
-        const mm_ipoint &p = points[at + i];
-        if (p.seqId < 0 || p.seqId >= n_contigs || p.pos < 0) return fail(c, MM_EINVAL, "bad interval point %llu", (unsigned long long)(at + i));
-        bp[i] = mm_pack_point(p.seqId, p.pos, p.side > 0);
-      }
-      CU(c, cudaMemcpy(c->blob + h.off_pts + at * 8, bp.data(), n * 8, cudaMemcpyHostToDevice));
+      CU(c, cudaMemcpy(stage, points + at, n * sizeof(mm_ipoint), cudaMemcpyHostToDevice));
+      CU(c, mm_upload_pack_points((const mm_ipoint *)stage, n, n_contigs, (uint64_t *)(c->blob + h.off_pts) + at, d_err, c->stream));
+      CU(c, cudaStreamSynchronize(c->stream));
     }
-  }
-  /* open-addressing table, built on the host */
-  {
-    std::vector<mm_tab_slot> tab(tab_slots);
-    memset(tab.data(), 0, tab_slots * sizeof(mm_tab_slot));
-    const uint32_t mask = (uint32_t)(tab_slots - 1);
-    for (uint64_t i = 0; i < n_keys; i++) {
-      const uint64_t cnt = offsets[i + 1] - offsets[i];
-      if (cnt == 0 || cnt > MM_VAL_CNT_MASK) return fail(c, MM_EINVAL, "key %llu has %llu interval points (unsupported)", (unsigned long long)i, (unsigned long long)cnt);
-      if (offsets[i] >= (1ULL << (64 - MM_VAL_OFF_SHIFT))) return fail(c, MM_EINVAL, "too many interval points");
-      uint32_t slot = mm_tab_slot_of(keys[i], tab_log2);
-      while (tab[slot].val != 0) {
-        if (tab[slot].key == keys[i]) return fail(c, MM_EINVAL, "duplicate key in lookup index");
-        slot = (slot + 1) & mask;
-      }
-      tab[slot].key = keys[i];
-      tab[slot].val = (offsets[i] << MM_VAL_OFF_SHIFT) | (cnt << 1) | (key_is_freq[i] ? 1ULL : 0ULL);
+    cudaFree(stage);
+    /* open-addressing table, filled on the device */
+    CU(c, cudaMemset(c->blob + h.off_tab, 0, tab_slots * sizeof(mm_tab_slot)));
+    if (n_keys) {
+      uint64_t *d_keys = nullptr, *d_offs = nullptr;
+      uint8_t *d_freq = nullptr;
+      CU(c, cudaMalloc((void **)&d_keys, n_keys * 8));
+      CU(c, cudaMalloc((void **)&d_offs, (n_keys + 1) * 8));
+      CU(c, cudaMalloc((void **)&d_freq, n_keys));
+      CU(c, cudaMemcpy(d_keys, keys, n_keys * 8, cudaMemcpyHostToDevice));
+      CU(c, cudaMemcpy(d_offs, offsets, (n_keys + 1) * 8, cudaMemcpyHostToDevice));
+      CU(c, cudaMemcpy(d_freq, key_is_freq, n_keys, cudaMemcpyHostToDevice));
+      CU(c, mm_upload_build_table(d_keys, d_offs, d_freq, n_keys, (mm_tab_slot *)(c->blob + h.off_tab), tab_log2, d_err, c->stream));
+      CU(c, cudaStreamSynchronize(c->stream));
+      cudaFree(d_keys); cudaFree(d_offs); cudaFree(d_freq);
     }
-    CU(c, cudaMemcpy(c->blob + h.off_tab, tab.data(), tab_slots * sizeof(mm_tab_slot), cudaMemcpyHostToDevice));
+    uint32_t err = 0;
+    CU(c, cudaMemcpy(&err, d_err, 4, cudaMemcpyDeviceToHost));
+    cudaFree(d_err);
+    if (err & 1) return fail(c, MM_EINVAL, "an interval point has a bad seqId or a negative position");
+    if (err & 2) return fail(c, MM_EINVAL, "a key has no or too many (>= 2^24) interval points, or offsets overflow");
+    if (err & 4) return fail(c, MM_EINVAL, "duplicate key in the lookup index");
   }
   CU(c, cudaMemcpy(c->blob + h.off_contig_len, contig_len, (size_t)n_contigs * 4, cudaMemcpyHostToDevice));
   std::vector<int32_t> tmp((size_t)n_contigs, -1);

@@ -134,6 +134,13 @@ cudaError_t mm_launch_l2_scan(const mm_params &p, const mm_dev_index &ix, const 
                               cudaStream_t st, int sm_count);
 cudaError_t mm_launch_l2_overflow(const mm_params &p, const mm_dev_index &ix, const mm_dev_batch &b, uint32_t n_cands,
                                   cudaStream_t st, int sm_count);
+/* index upload helpers (mm_l2_stream.cu): AoS -> device layouts */
+cudaError_t mm_upload_split_minmers(const mm_minmer *aos, uint64_t n, uint64_t *hash, int32_t *wpos, int32_t *wend,
+                                    int8_t *strand, cudaStream_t st);
+cudaError_t mm_upload_pack_points(const mm_ipoint *aos, uint64_t n, int32_t n_contigs, uint64_t *packed, uint32_t *err,
+                                  cudaStream_t st);
+cudaError_t mm_upload_build_table(const uint64_t *keys, const uint64_t *offs, const uint8_t *is_freq, uint64_t n_keys,
+                                  mm_tab_slot *tab, int tab_log2, uint32_t *err, cudaStream_t st);
 /* death-order arrays of the index (device-side sort) */
 cudaError_t mm_build_death_order(const uint64_t *idx_hash, const int32_t *idx_wend, const uint64_t *contig_start,
                                  int32_t n_contigs, uint64_t n, uint64_t *idx2_hash, int32_t *idx2_wend, cudaStream_t st);
