@@ -425,6 +425,7 @@ int mm_ctx_create(int device, const mm_params *params, mm_ctx **out)
   }
   for (auto &ev : c->ev) cudaEventCreate(&ev);
   if (const char *g = getenv("MM_L2_GENERAL")) c->l2_mode = (g[0] == '1') ? 0 : 1; /* test hook: general kernel only */
+  if (params->sketch_size > 1000) c->l2_mode = 0; /* the stream kernel packs its counters in 11 bits */
   *out = c;
   return MM_OK;
 }

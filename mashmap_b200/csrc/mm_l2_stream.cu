@@ -37,12 +37,14 @@ namespace {
 
 constexpr int L2S_WARPS = 4;
 constexpr int L2S_THREADS = L2S_WARPS * 32;
-constexpr uint32_t W_NBI_MASK = 0xFFFFu; /* num_before_inc */
-constexpr uint32_t W_ACT = 1u << 16;     /* active */
-/* strand_vote: bits 24..31, signed */
+constexpr int L2C_WARPS = 2;              /* k_l2_scan: warps per CTA (each warp = 32 candidates) */
+constexpr int L2C_THREADS = L2C_WARPS * 32;
+/* per-slot state word (16 bits): num_before_inc bits 0..10, active bit 11, strand_vote bits 12..15 (signed) */
+constexpr uint32_t W_NBI_MASK = 0x7FFu;
+constexpr uint32_t W_ACT = 1u << 11;
 
-__device__ __forceinline__ int w_sv(uint32_t w) { return (int)w >> 24; }
-__device__ __forceinline__ uint32_t w_set_sv(uint32_t w, int sv) { return (w & 0x00FFFFFFu) | ((uint32_t)sv << 24); }
+__device__ __forceinline__ int w_sv(uint32_t w) { return ((int)(w << 16)) >> 28; }
+__device__ __forceinline__ uint32_t w_set_sv(uint32_t w, int sv) { return (w & 0x0FFFu) | (((uint32_t)sv & 0xFu) << 12); }
 
 /* first index in [lo,hi) with a[i] >= v */
 __device__ __forceinline__ uint64_t lower_bound_i32(const int32_t *a, uint64_t lo, uint64_t hi, int32_t v)
@@ -169,18 +171,18 @@ struct lane_locus {
   int start, end, mean, shared, strand;
 };
 
-__global__ void __launch_bounds__(L2S_THREADS)
+__global__ void __launch_bounds__(L2C_THREADS)
 k_l2_scan(const mm_params prm, const mm_dev_index ix, const mm_dev_batch b, uint32_t n_cands)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int S = prm.sketch_size;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint32_t *words = (uint32_t *)smem_raw + (size_t)wid * (size_t)(S + 2) * 32; /* [slot][lane] */
+  uint16_t *words = (uint16_t *)smem_raw + (size_t)wid * (size_t)(S + 2) * 32; /* [slot][lane] */
   const uint32_t FULL = 0xffffffffu;
   const int LPC = (int)b.l2_loci_per_cand;
   const int segL = prm.seg_length;
 
-  for (uint32_t cbase = (blockIdx.x * L2S_WARPS + wid) * 32; cbase < n_cands; cbase += gridDim.x * L2S_WARPS * 32) {
+  for (uint32_t cbase = (blockIdx.x * L2C_WARPS + wid) * 32; cbase < n_cands; cbase += gridDim.x * L2C_WARPS * 32) {
     const uint32_t c = cbase + lane;
     const bool valid = c < n_cands;
     mm_l1_candidate cd;
@@ -204,8 +206,8 @@ k_l2_scan(const mm_params prm, const mm_dev_index ix, const mm_dev_batch b, uint
     for (int j = 0; j <= nmax + 1; j++) {
       uint32_t w = 1u;
       if (j == 0) w = 0u;
-      if (j > n) w = 0x7FFFu; /* beyond the sketch: rank can never fit */
-      words[j * 32 + lane] = w;
+      if (j > n) w = W_NBI_MASK; /* beyond the sketch: rank can never fit */
+      words[j * 32 + lane] = (uint16_t)w;
     }
     __syncwarp();
     int pivot = n, pivRank = n, shared = 0, votes = 0;
@@ -279,7 +281,7 @@ k_l2_scan(const mm_params prm, const mm_dev_index ix, const mm_dev_batch b, uint
               }
             }
           }
-          words[slot * 32 + lane] = w;
+          words[slot * 32 + lane] = (uint16_t)w;
         }
         if (do_del) {
           d++;
@@ -476,7 +478,7 @@ cudaError_t mm_launch_l2_ranges(const mm_params &p, const mm_dev_index &ix, cons
 }
 
 static size_t l2_prep_smem(const mm_params &p) { return (size_t)L2S_WARPS * (size_t)(p.sketch_size + 2) * 9 + 16; }
-static size_t l2_scan_smem(const mm_params &p) { return (size_t)L2S_WARPS * (size_t)(p.sketch_size + 2) * 32 * 4; }
+static size_t l2_scan_smem(const mm_params &p) { return (size_t)L2C_WARPS * (size_t)(p.sketch_size + 2) * 32 * 2; }
 
 cudaError_t mm_launch_l2_prep(const mm_params &p, const mm_dev_index &ix, const mm_dev_batch &b, uint32_t n_cands, cudaStream_t st,
                               int sm_count)
@@ -499,14 +501,14 @@ cudaError_t mm_launch_l2_scan(const mm_params &p, const mm_dev_index &ix, const 
 {
   if (n_cands == 0) return cudaSuccess;
   const size_t smem = l2_scan_smem(p);
-  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  if (smem > 227 * 1024 || p.sketch_size > 1000) return cudaErrorInvalidValue; /* 11-bit counters: caller falls back */
   cudaError_t e = cudaFuncSetAttribute(k_l2_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int occ = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_l2_scan, L2S_THREADS, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_l2_scan, L2C_THREADS, smem);
   if (e != cudaSuccess) return e;
   uint32_t grid = (uint32_t)sm_count * (uint32_t)max(occ, 1);
-  grid = min(grid, (n_cands + L2S_THREADS - 1) / L2S_THREADS);
-  k_l2_scan<<<grid, L2S_THREADS, smem, st>>>(p, ix, b, n_cands);
+  grid = min(grid, (n_cands + L2C_THREADS - 1) / L2C_THREADS);
+  k_l2_scan<<<grid, L2C_THREADS, smem, st>>>(p, ix, b, n_cands);
   return cudaGetLastError();
 }

@@ -83,10 +83,13 @@ struct sk_ctrl {
   int _pad;
 };
 
+constexpr int SK_WARPS = SK_THREADS / 32;
+constexpr int SK_LIST_PER_WARP = 128; /* survivors buffered per warp before they are inserted into the table */
+
 struct sk_smem_layout {
   uint32_t stage_bytes;  /* per staging buffer */
   uint32_t off_bar, off_keys, off_first, off_last, off_votes, off_order, off_bcnt, off_bstart, off_bfill,
-      off_ctrl, total;
+      off_ctrl, off_list_h, off_list_m, total;
 };
 
 __host__ __device__ inline sk_smem_layout sk_layout(int seg_length, int C)
@@ -104,6 +107,9 @@ __host__ __device__ inline sk_smem_layout sk_layout(int seg_length, int C)
   L.off_bstart = o; o += 4u * SK_BUCKETS;
   L.off_bfill = o; o += 4u * SK_BUCKETS;
   L.off_ctrl = o; o += (uint32_t)sizeof(sk_ctrl);
+  o = (o + 15) & ~15u;
+  L.off_list_h = o; o += 8u * SK_WARPS * SK_LIST_PER_WARP;
+  L.off_list_m = o; o += 4u * SK_WARPS * SK_LIST_PER_WARP;
   L.total = (o + 15) & ~15u;
   return L;
 }
@@ -160,6 +166,9 @@ k_sketch(const uint8_t *__restrict__ bases, const mm_segment *__restrict__ segs,
   uint32_t *bstart = (uint32_t *)(smem + L.off_bstart);
   uint32_t *bfill = (uint32_t *)(smem + L.off_bfill);
   sk_ctrl *ctrl = (sk_ctrl *)(smem + L.off_ctrl);
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint64_t *list_h = (uint64_t *)(smem + L.off_list_h) + (size_t)wid * SK_LIST_PER_WARP;
+  uint32_t *list_m = (uint32_t *)(smem + L.off_list_m) + (size_t)wid * SK_LIST_PER_WARP;
 
   const int tid = threadIdx.x;
   const uint32_t mask = (uint32_t)C - 1;
@@ -201,12 +210,13 @@ k_sketch(const uint8_t *__restrict__ bases, const mm_segment *__restrict__ segs,
     const int p0 = tid * P;
     const int p1 = min(n, p0 + P);
 
-    /* initial threshold: expect c*S distinct survivors, c = 1.1 + 6/sqrt(S) */
+    /* initial threshold: expect c*S distinct survivors, c = 1.1 + 6/sqrt(S). The canonical hash is the MIN of two
+     * uniform hashes, so P(canonical <= t) = 1 - (1-t)^2: solve that for the wanted fraction f = c*S/n. */
     uint64_t T = SK_EMPTY;
     if (n > 0) {
       const double c = 1.1 + 6.0 / sqrt((double)S);
-      const double frac = c * (double)S / (double)n;
-      if (frac < 1.0) T = (uint64_t)(frac * 18446744073709551616.0);
+      const double f = c * (double)S / (double)n;
+      if (f < 1.0) T = (uint64_t)((1.0 - sqrt(1.0 - f)) * 18446744073709551616.0);
     }
     uint64_t lo = 0, hi = 0;
     bool have_lo = false, have_hi = false;
@@ -225,35 +235,63 @@ k_sketch(const uint8_t *__restrict__ bases, const mm_segment *__restrict__ segs,
       }
       __syncthreads();
 
-      if (p0 < p1) {
+      /* Hashing pass. Survivors (canonical hash <= T) are appended to this warp's list -- ballot + popc, no atomics --
+       * and inserted into the table afterwards by all threads, so that the rare insert path (7 % of the positions, but
+       * some lane of almost every warp iteration) does not serialise the hashing loop. */
+      uint32_t wcount = 0; /* warp-uniform */
+      {
         mm_kmer_window<K> w;
         w.reset();
         int run = 0; /* consecutive non-N bases ending at the current byte */
         bool above = false;
+        const bool has_work = p0 < p1;
+        if (has_work) {
 #pragma unroll 1
-        for (int j = 0; j < K - 1; j++) {
-          bool isn;
-          const uint32_t code = mm_base_code(s[p0 + j], isn);
-          run = isn ? 0 : run + 1;
-          w.push(code);
+          for (int j = 0; j < K - 1; j++) {
+            bool isn;
+            const uint32_t code = mm_base_code(s[p0 + j], isn);
+            run = isn ? 0 : run + 1;
+            w.push(code);
+          }
         }
 #pragma unroll 1
-        for (int i = p0; i < p1; i++) {
-          bool isn;
-          const uint32_t code = mm_base_code(s[i + K - 1], isn);
-          run = isn ? 0 : run + 1;
-          w.push(code);
-          const uint64_t hf = w.hash_fwd();
-          const uint64_t hb = w.hash_rev();
-          if (run >= K && hf != hb) { /* commonFunc.hpp:234 */
-            const uint64_t h = hf < hb ? hf : hb;
-            if (h <= T)
-              sk_insert(keys, first, last, votes, mask, limit, ctrl, h, i, hf < hb ? 1 : -1);
-            else
-              above = true;
+        for (int jj = 0; jj < P; jj++) {
+          const int i = p0 + jj;
+          bool surv = false;
+          uint64_t h = 0;
+          uint32_t meta = 0;
+          if (i < p1) {
+            bool isn;
+            const uint32_t code = mm_base_code(s[i + K - 1], isn);
+            run = isn ? 0 : run + 1;
+            w.push(code);
+            const uint64_t hf = w.hash_fwd();
+            const uint64_t hb = w.hash_rev();
+            if (run >= K && hf != hb) { /* commonFunc.hpp:234 */
+              h = hf < hb ? hf : hb;
+              meta = ((uint32_t)i << 1) | (hf < hb ? 1u : 0u);
+              if (h <= T) surv = true; else above = true;
+            }
+          }
+          const uint32_t sm = __ballot_sync(0xffffffffu, surv);
+          if (sm) {
+            const uint32_t idx = wcount + __popc(sm & ((1u << lane) - 1u));
+            if (surv) {
+              if (idx < (uint32_t)SK_LIST_PER_WARP) { list_h[idx] = h; list_m[idx] = meta; }
+              else sk_insert(keys, first, last, votes, mask, limit, ctrl, h, (int)(meta >> 1), (meta & 1u) ? 1 : -1);
+            }
+            wcount += __popc(sm);
           }
         }
         if (above) ctrl->above = 1;
+      }
+      __syncwarp();
+      {
+        const uint32_t nl = min(wcount, (uint32_t)SK_LIST_PER_WARP);
+        for (uint32_t q = lane; q < nl; q += 32) {
+          const uint32_t meta = list_m[q];
+          sk_insert(keys, first, last, votes, mask, limit, ctrl, list_h[q], (int)(meta >> 1), (meta & 1u) ? 1 : -1);
+        }
       }
       __syncthreads();
       const int d = ctrl->distinct + ctrl->has_max;
