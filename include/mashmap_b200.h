@@ -147,6 +147,9 @@ int mm_tables_upload(mm_ctx *ctx, const int32_t *sketch_cutoffs, int32_t n_cutof
 int mm_index_blob(mm_ctx *ctx, void **blob, uint64_t *n_bytes);
 int mm_index_blob_alloc(mm_ctx *ctx, uint64_t n_bytes, void **blob);
 int mm_index_adopt_blob(mm_ctx *ctx);
+/* A second context on the SAME device that reads the index image of `src` (not copied, not owned): lets a host
+ * pipeline keep two batches in flight (copies of one overlapping the kernels of the other). `src` must outlive it. */
+int mm_ctx_share_index(mm_ctx *ctx, const mm_ctx *src);
 
 /* ---- the hot path ------------------------------------------------------------------------------ */
 

@@ -82,6 +82,7 @@ def lib():
         L.mm_index_blob.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
         L.mm_index_blob_alloc.argtypes = [vp, u64, C.POINTER(vp)]
         L.mm_index_adopt_blob.argtypes = [vp]
+        L.mm_ctx_share_index.argtypes = [vp, vp]
         L.mm_sketch_segments.argtypes = [vp, vp, u64, vp, u64, vp, vp]
         L.mm_map_segments.argtypes = [vp, vp, u64, vp, u64, vp, vp, u64, C.POINTER(u64), vp, u64, C.POINTER(u64)]
         L.mm_batch_upload.argtypes = [vp, vp, u64, vp, u64]
@@ -97,7 +98,7 @@ def lib():
 
 EXPORTED_SYMBOLS = [
     "mm_ctx_create", "mm_ctx_destroy", "mm_last_error", "mm_kernel_launches", "mm_index_upload",
-    "mm_tables_upload", "mm_index_blob", "mm_index_blob_alloc", "mm_index_adopt_blob", "mm_sketch_segments",
+    "mm_tables_upload", "mm_index_blob", "mm_index_blob_alloc", "mm_index_adopt_blob", "mm_ctx_share_index", "mm_sketch_segments",
     "mm_map_segments", "mm_batch_upload", "mm_map_resident", "mm_batch_fetch", "mm_batch_fetch_sketch",
     "mm_last_stage_ms", "mm_host_alloc", "mm_host_free",
 ]

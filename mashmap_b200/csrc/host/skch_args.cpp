@@ -32,7 +32,7 @@ const OptDef kOptions[] = {
     {"sparsifyMappings", "x", true}, {"filter_mode", "f", true}, {"noMerge", "M", false}, {"legacy", nullptr, false},
     {"reportPercentage", nullptr, false},
     // B200-specific
-    {"device", nullptr, true}, {"batchBases", nullptr, true},
+    {"device", nullptr, true}, {"batchBases", nullptr, true}, {"subBatchBases", nullptr, true},
 };
 
 [[noreturn]] void usage_error(const std::string &msg)
@@ -235,6 +235,7 @@ void parseandSave(int argc, char **argv, Parameters &parameters)
   parameters.report_ANI_percentage = found("reportPercentage");
   if (found("device")) parameters.device = to<int>(opt["device"]);
   if (found("batchBases")) parameters.batch_bases = to<uint64_t>(opt["batchBases"]);
+  if (found("subBatchBases")) parameters.sub_batch_bases = to<uint64_t>(opt["subBatchBases"]);
 
   printCmdOptions(parameters);
 

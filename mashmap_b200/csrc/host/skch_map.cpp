@@ -87,11 +87,17 @@ BatchMapper::BatchMapper(const Parameters &p, const Sketch &refsketch) : param(p
   rc = mm_tables_upload(ctx, sketchCutoffs.data(), (int32_t)sketchCutoffs.size(), minHits.data(), (int32_t)minHits.size());
   if (rc != MM_OK) die(std::string("mm_tables_upload: ") + mm_last_error(ctx));
   tail_ = new MapTail(param, refSketch.metadata, refIdGroup);
+  if (mm_ctx_create(param.device, &mp, &ctx2) == MM_OK) {
+    if (mm_ctx_share_index(ctx2, ctx) != MM_OK) { mm_ctx_destroy(ctx2); ctx2 = nullptr; }
+  } else {
+    ctx2 = nullptr;
+  }
 }
 
 BatchMapper::~BatchMapper()
 {
   delete tail_;
+  if (ctx2) mm_ctx_destroy(ctx2);
   if (ctx) mm_ctx_destroy(ctx);
 }
 
@@ -130,50 +136,63 @@ void BatchMapper::addRead(ReadBatch &b, const std::string &name, const char *seq
   b.reads.push_back(std::move(rd));
 }
 
-void BatchMapper::mapBatch(const ReadBatch &b, std::vector<MappingResultsVector_t> &results, std::vector<std::string> *text,
-                           const std::vector<ContigInfo> *qmetadata)
+/* reads [r0, r1) of the batch: one device call on this lane's context, then their host tail on tail_threads threads */
+void BatchMapper::mapRange(Lane &ln, const ReadBatch &b, size_t r0, size_t r1, std::vector<MappingResultsVector_t> &results,
+                           std::vector<std::string> *text, const std::vector<ContigInfo> *qmetadata, int tail_threads)
 {
-  const size_t nreads = b.reads.size();
-  results.assign(nreads, MappingResultsVector_t());
-  if (text) text->assign(nreads, std::string());
-  if (nreads == 0) return;
   auto t0 = Clock::now();
-  segRes.resize(b.segs.size());
+  const size_t s0 = b.reads[r0].first_seg, s1 = b.reads[r1 - 1].first_seg + b.reads[r1 - 1].n_seg;
+  const uint64_t b0 = b.segs[s0].offset;  // a read's first fragment starts at the read's first base
+  uint64_t b1 = b0;
+  for (size_t r = r0; r < r1; r++) b1 += (uint64_t)b.reads[r].len;
+  const mm_segment *segp = b.segs.data() + s0;
+  if (b0 != 0) {  // fragment offsets are relative to the buffer handed to the device call
+    ln.segs.assign(b.segs.begin() + s0, b.segs.begin() + s1);
+    for (auto &sg : ln.segs) sg.offset -= b0;
+    segp = ln.segs.data();
+  }
+  const size_t nseg = s1 - s0;
+  ln.segRes.resize(nseg);
   uint64_t nc = 0, nl = 0;
-  if (cands.size() < 2 * b.segs.size() + 1024) cands.resize(2 * b.segs.size() + 1024);
-  if (loci.size() < 2 * cands.size()) loci.resize(2 * cands.size());
+  if (ln.cands.size() < 2 * nseg + 1024) ln.cands.resize(2 * nseg + 1024);
+  if (ln.loci.size() < 2 * ln.cands.size()) ln.loci.resize(2 * ln.cands.size());
   while (true) {
-    int rc = mm_map_segments(ctx, b.bases, b.used, b.segs.data(), b.segs.size(), segRes.data(), cands.data(), cands.size(), &nc,
-                             loci.data(), loci.size(), &nl);
+    int rc = mm_map_segments(ln.ctx, b.bases + b0, b1 - b0, segp, nseg, ln.segRes.data(), ln.cands.data(), ln.cands.size(), &nc,
+                             ln.loci.data(), ln.loci.size(), &nl);
     if (rc == MM_ECAPACITY) {
-      cands.resize(std::max<uint64_t>(cands.size(), nc));
-      loci.resize(std::max<uint64_t>(loci.size(), nl));
+      ln.cands.resize(std::max<uint64_t>(ln.cands.size(), nc));
+      ln.loci.resize(std::max<uint64_t>(ln.loci.size(), nl));
       continue;
     }
-    if (rc != MM_OK) die(std::string("mm_map_segments: ") + mm_last_error(ctx));
+    if (rc != MM_OK) die(std::string("mm_map_segments: ") + mm_last_error(ln.ctx));
     break;
   }
-  mm_last_stage_ms(ctx, lastStageMs);
-  secondsDevice += since(t0);
+  mm_last_stage_ms(ln.ctx, ln.stageMs);
+  ln.secDevice += since(t0);
   t0 = Clock::now();
 
-  tail_->segs = b.segs.data(); tail_->segRes = segRes.data(); tail_->cands = cands.data(); tail_->loci = loci.data();
-  tail_->qmetadata = qmetadata;
-  const int nthreads = std::max(1, std::min<int>(param.threads, (int)((nreads + 255) / 256)));
-  std::atomic<size_t> next{0};
+  MapTail tail(param, refSketch.metadata, refIdGroup);
+  tail.segs = b.segs.data();              // absolute fragment indices (only the lengths are read)
+  tail.segRes = ln.segRes.data() - s0;    // so that indexing by the absolute fragment index works
+  tail.cands = ln.cands.data();
+  tail.loci = ln.loci.data();
+  tail.qmetadata = qmetadata;
+  const size_t nreads = r1 - r0;
+  const int nthreads = std::max(1, std::min<int>(tail_threads, (int)((nreads + 255) / 256)));
+  std::atomic<size_t> next{r0};
   auto worker = [&]() {
     IdentityCache idc;
     idc.k = param.kmerSize;
     std::ostringstream os;
     while (true) {
       const size_t lo = next.fetch_add(256);
-      if (lo >= nreads) break;
-      const size_t hi = std::min(nreads, lo + 256);
+      if (lo >= r1) break;
+      const size_t hi = std::min(r1, lo + 256);
       for (size_t r = lo; r < hi; r++) {
-        tail_->mapRead(b.reads[r], idc, results[r]);
+        tail.mapRead(b.reads[r], idc, results[r]);
         if (text && !results[r].empty()) {
           os.str(std::string());
-          tail_->formatMappings(results[r], b.reads[r].name, os);
+          tail.formatMappings(results[r], b.reads[r].name, os);
           (*text)[r] = os.str();
         }
       }
@@ -185,7 +204,48 @@ void BatchMapper::mapBatch(const ReadBatch &b, std::vector<MappingResultsVector_
     for (int t = 0; t < nthreads; t++) pool.emplace_back(worker);
     for (auto &th : pool) th.join();
   }
-  secondsHostTail += since(t0);
+  ln.secTail += since(t0);
+}
+
+void BatchMapper::mapBatch(const ReadBatch &b, std::vector<MappingResultsVector_t> &results, std::vector<std::string> *text,
+                           const std::vector<ContigInfo> *qmetadata)
+{
+  const size_t nreads = b.reads.size();
+  results.assign(nreads, MappingResultsVector_t());
+  if (text) text->assign(nreads, std::string());
+  if (nreads == 0) return;
+  lanes[0].ctx = ctx; lanes[1].ctx = ctx2;
+  const double d0 = lanes[0].secDevice + lanes[1].secDevice, t0 = lanes[0].secTail + lanes[1].secTail;
+  // sub-batches of ~SUB bases; with two or more of them, two lanes keep the copies / kernels of one sub-batch
+  // overlapped with the kernels / host tail of the other
+  const uint64_t SUB = std::max<uint64_t>(param.sub_batch_bases, 1);
+  std::vector<std::pair<size_t, size_t>> parts;
+  {
+    size_t r0 = 0;
+    uint64_t acc = 0;
+    for (size_t r = 0; r < nreads; r++) {
+      acc += (uint64_t)b.reads[r].len;
+      if (acc >= SUB || r + 1 == nreads) { parts.emplace_back(r0, r + 1); r0 = r + 1; acc = 0; }
+    }
+  }
+  if (parts.size() < 2 || !ctx2) {
+    for (auto &p : parts) mapRange(lanes[0], b, p.first, p.second, results, text, qmetadata, param.threads);
+  } else {
+    std::atomic<size_t> next{0};
+    auto lane_fn = [&](int w) {
+      while (true) {
+        const size_t i = next.fetch_add(1);
+        if (i >= parts.size()) break;
+        mapRange(lanes[w], b, parts[i].first, parts[i].second, results, text, qmetadata, std::max(1, param.threads / 2));
+      }
+    };
+    std::thread t1(lane_fn, 1);
+    lane_fn(0);
+    t1.join();
+  }
+  memcpy(lastStageMs, lanes[0].stageMs, sizeof(lastStageMs));
+  secondsDevice += lanes[0].secDevice + lanes[1].secDevice - d0;
+  secondsHostTail += lanes[0].secTail + lanes[1].secTail - t0;
 }
 
 /* ------------------------------------------------------------------------------------------------------ */

@@ -74,11 +74,21 @@ class BatchMapper {
   std::unordered_map<std::string, int> refNameId;
   std::vector<int> contigNameId;
   mm_ctx *ctx = nullptr;
+  mm_ctx *ctx2 = nullptr;  // second context sharing the index image: two sub-batches in flight
   MapTail *tail_ = nullptr;
-  std::vector<mm_segment_result> segRes;
-  std::vector<mm_l1_candidate> cands;
-  std::vector<mm_l2_locus> loci;
+  struct Lane {  // per pipeline lane: device context + its host-side record buffers
+    mm_ctx *ctx = nullptr;
+    std::vector<mm_segment> segs;
+    std::vector<mm_segment_result> segRes;
+    std::vector<mm_l1_candidate> cands;
+    std::vector<mm_l2_locus> loci;
+    double secDevice = 0, secTail = 0;
+    float stageMs[8] = {0};
+  };
+  Lane lanes[2];
   void setRefGroups();
+  void mapRange(Lane &ln, const ReadBatch &b, size_t r0, size_t r1, std::vector<MappingResultsVector_t> &results,
+                std::vector<std::string> *text, const std::vector<ContigInfo> *qmetadata, int tail_threads);
 };
 
 class Map {

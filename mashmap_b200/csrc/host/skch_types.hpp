@@ -108,6 +108,7 @@ struct Parameters {
   // B200 additions (not in the reference)
   int device = 0;                 // CUDA device ordinal
   uint64_t batch_bases = 1ULL << 30;  // query bases per device batch
+  uint64_t sub_batch_bases = 640ULL << 20;  // a batch is mapped as sub-batches of this size on two pipelined lanes
 };
 
 namespace fixed {  // map_parameters.hpp:86-102

@@ -605,6 +605,20 @@ int mm_index_adopt_blob(mm_ctx *c)
   return MM_OK;
 }
 
+int mm_ctx_share_index(mm_ctx *c, const mm_ctx *src)
+{
+  if (!c || !src) return MM_EINVAL;
+  if (!src->blob_ready) return fail(c, MM_ESTATE, "source context has no index");
+  if (c->device != src->device) return fail(c, MM_EINVAL, "contexts are on different devices");
+  if (c->blob && c->blob_owned) { cudaSetDevice(c->device); cudaFree(c->blob); }
+  c->blob = src->blob; c->blob_bytes = src->blob_bytes; c->blob_owned = false;
+  c->hdr = src->hdr;
+  c->cutoffs = src->cutoffs; c->min_hits = src->min_hits;
+  resolve_index(c);
+  c->blob_ready = true;
+  return MM_OK;
+}
+
 int mm_batch_upload(mm_ctx *c, const char *bases, uint64_t n_bases, const mm_segment *segs, uint64_t n_segs)
 {
   if (!c || (!bases && n_bases) || (!segs && n_segs)) return fail(c, MM_EINVAL, "null argument");

@@ -112,9 +112,11 @@ def test_small_batches_and_threads_do_not_change_output(workdir):
     """device batching (--batchBases) and host thread count are invisible in the output"""
     d = datasets.make_panel_set(workdir, tag="clip")
     outs = []
-    for bb, t in (("1000000000", "1"), ("200000", "8"), ("60000", "3")):
-        o = os.path.join(workdir, f"bb_{bb}_{t}.paf")
-        run([hostlib.CLI_PATH, "-r", d["ref"], "-q", d["qry"], "-s", "5000", "--pi", "85", "-t", t, "--batchBases", bb, "-o", o])
+    for bb, sb, t in (("1000000000", "1000000000", "1"), ("200000", "640000000", "8"), ("60000", "20000", "3"),
+                      ("1000000000", "100000", "6")):  # the last two run the two-lane pipeline
+        o = os.path.join(workdir, f"bb_{bb}_{sb}_{t}.paf")
+        run([hostlib.CLI_PATH, "-r", d["ref"], "-q", d["qry"], "-s", "5000", "--pi", "85", "-t", t, "--batchBases", bb,
+             "--subBatchBases", sb, "-o", o])
         outs.append(open(o).read())
-    assert outs[0] == outs[1] == outs[2]
+    assert outs[0] == outs[1] == outs[2] == outs[3]
     assert len(outs[0]) > 0
