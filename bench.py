@@ -368,7 +368,7 @@ def cpu_baseline(args, hi, batch, S, threads=None, n_reads=None):
         t0 = time.time()
         L.orc_map_reads_mt(O.h, batch.bases.ctypes.data, pilot, READ_LEN, 0, threads, C.byref(mapped))
         rate = pilot / max(time.time() - t0, 1e-3)
-        n_reads = int(min(total_reads, max(pilot, rate * 15.0)))
+        n_reads = int(min(total_reads, max(pilot, rate * 4.0)))  # the pilot over-estimates the sustained rate ~4x
     t0 = time.time()
     n_map = L.orc_map_reads_mt(O.h, batch.bases.ctypes.data, n_reads, READ_LEN, 0, threads, C.byref(mapped))
     dt = time.time() - t0

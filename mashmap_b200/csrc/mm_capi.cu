@@ -49,6 +49,8 @@ struct mm_ctx {
   mm_l2_range *d_l2_ranges = nullptr; uint64_t *d_l2_rec_off = nullptr; uint64_t l2_cand_cap = 0;
   uint2 *d_l2_recs = nullptr; uint64_t l2_recs_cap = 0;
   void *d_scan_tmp = nullptr; size_t scan_tmp_bytes = 0;
+  uint32_t *d_l1_slow = nullptr; uint64_t l1_slow_cap = 0;
+  int l1_warp = 1; /* 1 = warp-per-segment fast path + CTA path for big segments; 0 = CTA path only (MM_L1_CTA=1) */
   int l2_mode = 1; /* 1 = stream kernels (mm_l2_stream.cu), 0 = general kernel only (MM_L2_GENERAL=1) */
   bool batch_mapped = false;
 
@@ -317,6 +319,12 @@ int run_pipeline(mm_ctx *c)
     CU(c, cudaMalloc((void **)&c->d_loci, c->loci_cap * sizeof(mm_l2_locus)));
   }
   if ((rc = ensure_scratch(c, c->scratch_cap ? c->scratch_cap - c->scratch_pool : (32ULL << 20)))) return rc;
+  if (c->l1_slow_cap < n_segs + 1) {
+    if (c->d_l1_slow) cudaFree(c->d_l1_slow);
+    c->d_l1_slow = nullptr;
+    c->l1_slow_cap = n_segs + n_segs / 8 + 1024;
+    CU(c, cudaMalloc((void **)&c->d_l1_slow, c->l1_slow_cap * 4));
+  }
 
   uint32_t h_cnt[16];
   for (int attempt = 0; attempt < 6; attempt++) {
@@ -325,9 +333,10 @@ int run_pipeline(mm_ctx *c)
     CU(c, cudaEventRecord(c->ev[0], c->stream));
     CU(c, mm_launch_sketch(c->params, b, c->stream, c->sm_count));
     CU(c, cudaEventRecord(c->ev[1], c->stream));
-    CU(c, mm_launch_l1(c->params, c->ix, b, c->stream, c->sm_count));
+    int l1_launches = 0;
+    CU(c, mm_launch_l1(c->params, c->ix, b, c->stream, c->sm_count, c->d_l1_slow, c->l1_warp, &l1_launches));
     CU(c, cudaEventRecord(c->ev[2], c->stream));
-    c->launches += 2;
+    c->launches += 1 + (uint64_t)l1_launches;
     CU(c, cudaMemcpyAsync(h_cnt, c->d_counters, 64, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     const uint64_t need_cands = h_cnt[0];
@@ -425,6 +434,7 @@ int mm_ctx_create(int device, const mm_params *params, mm_ctx **out)
   }
   for (auto &ev : c->ev) cudaEventCreate(&ev);
   if (const char *g = getenv("MM_L2_GENERAL")) c->l2_mode = (g[0] == '1') ? 0 : 1; /* test hook: general kernel only */
+  if (const char *g = getenv("MM_L1_CTA")) c->l1_warp = (g[0] == '1') ? 0 : 1; /* test hook: general L1 path only */
   if (params->sketch_size > 1000) c->l2_mode = 0; /* the stream kernel packs its counters in 11 bits */
   *out = c;
   return MM_OK;
@@ -438,7 +448,7 @@ int mm_ctx_destroy(mm_ctx *c)
   if (c->blob && c->blob_owned) cudaFree(c->blob);
   cudaFree(c->d_bases); cudaFree(c->d_segs); cudaFree(c->d_sk_hash); cudaFree(c->d_sk_pos); cudaFree(c->d_sk_strand);
   cudaFree(c->d_seg_res); cudaFree(c->d_cands); cudaFree(c->d_loci); cudaFree(c->d_counters); cudaFree(c->d_scratch);
-  cudaFree(c->d_l2_ranges); cudaFree(c->d_l2_rec_off); cudaFree(c->d_l2_recs); cudaFree(c->d_scan_tmp);
+  cudaFree(c->d_l1_slow); cudaFree(c->d_l2_ranges); cudaFree(c->d_l2_rec_off); cudaFree(c->d_l2_recs); cudaFree(c->d_scan_tmp);
   for (auto &ev : c->ev) cudaEventDestroy(ev);
   cudaStreamDestroy(c->stream);
   delete c;

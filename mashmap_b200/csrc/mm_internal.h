@@ -85,7 +85,8 @@ struct mm_dev_batch {
   uint32_t loci_cap;
   uint32_t *counters;         /* [0] candidates needed, [1] loci overflow (1) / live-set overflow (2), */
                               /* [2] scratch overflow, [3] candidate overflow,                         */
-                              /* [4..5] u64 bump pointer into the scratch pool, [6] loci needed        */
+                              /* [4..5] u64 bump pointer into the scratch pool, [6] loci needed,       */
+                              /* [7] L2 candidates to redo, [8] segments handed to the general L1 path */
   uint64_t *scratch;          /* global-memory work area for segments with many interval points:       */
                               /* one slice per CTA of the L1 grid, then a bump-allocated pool          */
   uint64_t scratch_slice;     /* u64 elements per CTA slice                                            */
@@ -121,7 +122,7 @@ MM_HD uint32_t mm_tab_slot_of(uint64_t key, int log2)
 /* launchers implemented in the .cu files; all return cudaError_t from the launch */
 cudaError_t mm_launch_sketch(const mm_params &p, const mm_dev_batch &b, cudaStream_t st, int sm_count);
 cudaError_t mm_launch_l1(const mm_params &p, const mm_dev_index &ix, const mm_dev_batch &b,
-                         cudaStream_t st, int sm_count);
+                         cudaStream_t st, int sm_count, uint32_t *slow_list, int use_warp_path, int *n_launched);
 cudaError_t mm_launch_l2(const mm_params &p, const mm_dev_index &ix, const mm_dev_batch &b,
                          uint32_t n_cands, cudaStream_t st, int sm_count);
 /* new L2: ranges -> (host reads the total) -> prep -> lane-per-candidate scan -> general kernel for overflow */

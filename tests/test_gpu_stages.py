@@ -142,6 +142,15 @@ def test_sketch_degenerate_inputs():
     ctx.close()
 
 
+@pytest.fixture(params=["fast-paths", "general-kernels"])
+def kernel_paths(request, monkeypatch):
+    """the warp-per-segment L1 + stream L2 kernels (default), or the general CTA / warp-per-candidate kernels alone"""
+    if request.param == "general-kernels":
+        monkeypatch.setenv("MM_L1_CTA", "1")
+        monkeypatch.setenv("MM_L2_GENERAL", "1")
+    return request.param
+
+
 def run_stage_parity(d, args, seg_length, **ctx_kw):
     from mashmap_b200 import capi
 
@@ -166,25 +175,25 @@ def run_stage_parity(d, args, seg_length, **ctx_kw):
         R.close()
 
 
-def test_stages_random_genome_noisy_reads(random_set):
+def test_stages_random_genome_noisy_reads(random_set, kernel_paths):
     d = random_set
     bad = run_stage_parity(d, ["-r", d["ref"], "-q", d["qry"], "-s", "5000", "--pi", "85", "-t", "4"], 5000)
     assert not bad
 
 
-def test_stages_random_genome_dense(random_set):
+def test_stages_random_genome_dense(random_set, kernel_paths):
     d = random_set
     bad = run_stage_parity(d, ["-r", d["ref"], "-q", d["qry"], "-s", "5000", "--pi", "95", "--dense", "-t", "4"], 5000)
     assert not bad
 
 
-def test_stages_panel_selfmap(panel_set):
+def test_stages_panel_selfmap(panel_set, kernel_paths):
     d = panel_set
     bad = run_stage_parity(d, ["-r", d["ref"], "-q", d["qry"], "-s", "5000", "--pi", "85", "-t", "4"], 5000)
     assert not bad
 
 
-def test_stages_panel_no_hg_filter_small_sketch(panel_set):
+def test_stages_panel_no_hg_filter_small_sketch(panel_set, kernel_paths):
     d = panel_set
     bad = run_stage_parity(d, ["-r", d["ref"], "-q", d["qry"], "-s", "2000", "--pi", "90", "-J", "25", "--noHgFilter", "-t", "4"], 2000)
     assert not bad
