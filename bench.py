@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--contigs", type=int, default=256)
     ap.add_argument("--cpu-sample-reads", type=int, default=0, help="reads per CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sketch", type=int, default=0, help="sketch size override (0 = the reference's automatic choice)")
     return ap.parse_args()
 
 
@@ -133,7 +134,7 @@ def setup_workload(args, rank, world, device):
     ref = synth_gpu.random_reference(args.contigs, contig_len, seed=1, device=device)
     torch.cuda.synchronize()
     log(f"rank {rank}: reference {args.contigs} x {contig_len} bp generated in {time.time() - t0:.1f} s")
-    sketch = int(hostlib.lib().skch_recommended_sketch_size(K, PI, SEG, int(args.ref_bp * REF_FASTA_BYTES_PER_BASE) + 16 * args.contigs))
+    sketch = args.sketch or int(hostlib.lib().skch_recommended_sketch_size(K, PI, SEG, int(args.ref_bp * REF_FASTA_BYTES_PER_BASE) + 16 * args.contigs))
     t0 = time.time()
     reads_dev, truth = synth_gpu.simulate_reads(ref, args.reads, READ_LEN, 0.02, 0.14, seed=2 + rank, chunk=8192)
     torch.cuda.synchronize()
@@ -173,6 +174,7 @@ def gpu_arm(args):
     torch.cuda.set_device(local_rank)
     device = torch.device(f"cuda:{local_rank}")
     from mashmap_b200 import capi, hostlib
+    from mashmap_b200 import dist as mdist
 
     host_threads = max(1, (os.cpu_count() or 8) // max(1, world))
     wl = setup_workload(args, rank, world, device)
@@ -187,20 +189,9 @@ def gpu_arm(args):
     bm = hostlib.BatchMapper(hi, pi=PI, device=local_rank, threads=host_threads)
     ctx = capi.Context.from_handle(bm.ctx_handle, S, device=local_rank)
     if world > 1:
-        nbytes = torch.zeros(1, dtype=torch.int64, device=device)
-        if rank == 0:
-            ptr, n = ctx.index_blob()
-            nbytes[0] = n
-        dist.broadcast(nbytes, 0)
-        n = int(nbytes.item())
-        if rank != 0:
-            ptr = ctx.index_blob_alloc(n)
-        blob = _wrap_device(ptr, n, device)
         t0 = time.time()
-        dist.broadcast(blob, 0)
+        n = mdist.broadcast_index(dist, ctx, rank, device)
         torch.cuda.synchronize()
-        if rank != 0:
-            ctx.index_adopt_blob()
         log(f"rank {rank}: index image {n / 1e9:.2f} GB broadcast in {time.time() - t0:.2f} s")
     index_seconds = time.time() - t_index
     wl["ref_host"] = None
@@ -251,7 +242,7 @@ def gpu_arm(args):
     for _ in range(args.steps):
         e2e_info = bm.map(batch)
         if dist is not None:  # all ranks' mapping records on rank 0
-            gathered = _gather_records(dist, bm, device, rank, world)
+            _, gathered = mdist.gather_records(dist, torch.from_numpy(bm.results()).to(device), world)
     barrier()
     e2e_ms = (time.time() - t0) * 1e3
     h2d = n_bases + n_segs * capi.segment_dtype.itemsize
@@ -295,7 +286,8 @@ def gpu_arm(args):
             "gpu_launches": int(launches),
             "kernel_ms_per_step": {"sketch": k_ms[0] / args.steps, "l1": k_ms[1] / args.steps, "l2": k_ms[2] / args.steps},
             "roofline": {"kernel": "k_sketch (K1)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic.get("k_sketch_dram_bytes_per_launch"),
+                         "frac": achieved / peak,
+                         "traffic": (traffic["k_sketch_dram_bytes_per_segment"] * n_segs if "k_sketch_dram_bytes_per_segment" in traffic else None),
                          "peak_source": peak_src, "algorithmic_bytes_per_segment": b1,
                          "note": "bit-exact Murmur3 makes K1 INT-ALU bound (SURVEY 8(d)); see DESIGN.md for the instruction roofline"},
         }
@@ -305,33 +297,6 @@ def gpu_arm(args):
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
-
-
-def _wrap_device(ptr, nbytes, device):
-    """a torch uint8 tensor over raw device memory (for the NCCL broadcast of the index image)"""
-    import torch
-
-    class _Arr:
-        pass
-
-    a = _Arr()
-    a.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
-    return torch.as_tensor(a, device=device)
-
-
-def _gather_records(dist, bm, device, rank, world):
-    import torch
-
-    res = torch.from_numpy(bm.results()).to(device)
-    n = torch.tensor([res.shape[0]], dtype=torch.int64, device=device)
-    counts = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
-    dist.all_gather(counts, n)
-    m = int(max(c.item() for c in counts))
-    pad = torch.zeros((m, 10), dtype=torch.int32, device=device)
-    pad[: res.shape[0]] = res
-    out = [torch.zeros((m, 10), dtype=torch.int32, device=device) for _ in range(world)]
-    dist.all_gather(out, pad)
-    return int(sum(c.item() for c in counts))
 
 
 def _accuracy(res, truth, contig_len, first_counter):
