@@ -127,9 +127,10 @@ int write_tables(mm_ctx *c)
     return fail(c, MM_EINVAL, "lookup tables too large");
   c->hdr.n_cutoffs = (int32_t)c->cutoffs.size();
   c->hdr.n_min_hits = (int32_t)c->min_hits.size();
-  CU(c, cudaMemcpy(c->blob + c->hdr.off_cutoffs, c->cutoffs.data(), c->cutoffs.size() * 4, cudaMemcpyHostToDevice));
-  CU(c, cudaMemcpy(c->blob + c->hdr.off_min_hits, c->min_hits.data(), c->min_hits.size() * 4, cudaMemcpyHostToDevice));
-  CU(c, cudaMemcpy(c->blob, &c->hdr, sizeof(c->hdr), cudaMemcpyHostToDevice));
+  CU(c, cudaMemcpyAsync(c->blob + c->hdr.off_cutoffs, c->cutoffs.data(), c->cutoffs.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemcpyAsync(c->blob + c->hdr.off_min_hits, c->min_hits.data(), c->min_hits.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemcpyAsync(c->blob, &c->hdr, sizeof(c->hdr), cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
   resolve_index(c);
   return MM_OK;
 }
@@ -521,55 +522,58 @@ int mm_index_upload(mm_ctx *c, const mm_minmer *mi, uint64_t n_mi, const uint64_
     CU(c, cudaMalloc(&stage, CH * 24));
     for (uint64_t at = 0; at < n_mi; at += CH) {
       const uint64_t n = std::min(CH, n_mi - at);
-      CU(c, cudaMemcpy(stage, mi + at, n * sizeof(mm_minmer), cudaMemcpyHostToDevice));
+      CU(c, cudaMemcpyAsync(stage, mi + at, n * sizeof(mm_minmer), cudaMemcpyHostToDevice, c->stream));
       CU(c, mm_upload_split_minmers((const mm_minmer *)stage, n, (uint64_t *)(c->blob + h.off_idx_hash) + at,
                                     (int32_t *)(c->blob + h.off_idx_wpos) + at, (int32_t *)(c->blob + h.off_idx_wend) + at,
                                     (int8_t *)(c->blob + h.off_idx_strand) + at, c->stream));
       CU(c, cudaStreamSynchronize(c->stream));
     }
-    CU(c, cudaMemcpy(c->blob + h.off_contig_start, cstart.data(), cstart.size() * 8, cudaMemcpyHostToDevice));
+    CU(c, cudaMemcpyAsync(c->blob + h.off_contig_start, cstart.data(), cstart.size() * 8, cudaMemcpyHostToDevice, c->stream));
     /* the same entries per contig in wpos_end order (device sort), for the L2 stream merge */
     CU(c, mm_build_death_order((const uint64_t *)(c->blob + h.off_idx_hash), (const int32_t *)(c->blob + h.off_idx_wend),
                                (const uint64_t *)(c->blob + h.off_contig_start), n_contigs, n_mi,
                                (uint64_t *)(c->blob + h.off_idx2_hash), (int32_t *)(c->blob + h.off_idx2_wend), c->stream));
     uint32_t *d_err = nullptr;
     CU(c, cudaMalloc((void **)&d_err, 4));
-    CU(c, cudaMemset(d_err, 0, 4));
+    CU(c, cudaMemsetAsync(d_err, 0, 4, c->stream));
     for (uint64_t at = 0; at < n_points; at += CH) {
       const uint64_t n = std::min(CH, n_points - at);
-      CU(c, cudaMemcpy(stage, points + at, n * sizeof(mm_ipoint), cudaMemcpyHostToDevice));
+      CU(c, cudaMemcpyAsync(stage, points + at, n * sizeof(mm_ipoint), cudaMemcpyHostToDevice, c->stream));
       CU(c, mm_upload_pack_points((const mm_ipoint *)stage, n, n_contigs, (uint64_t *)(c->blob + h.off_pts) + at, d_err, c->stream));
       CU(c, cudaStreamSynchronize(c->stream));
     }
     cudaFree(stage);
     /* open-addressing table, filled on the device */
-    CU(c, cudaMemset(c->blob + h.off_tab, 0, tab_slots * sizeof(mm_tab_slot)));
+    CU(c, cudaMemsetAsync(c->blob + h.off_tab, 0, tab_slots * sizeof(mm_tab_slot), c->stream));
     if (n_keys) {
       uint64_t *d_keys = nullptr, *d_offs = nullptr;
       uint8_t *d_freq = nullptr;
       CU(c, cudaMalloc((void **)&d_keys, n_keys * 8));
       CU(c, cudaMalloc((void **)&d_offs, (n_keys + 1) * 8));
       CU(c, cudaMalloc((void **)&d_freq, n_keys));
-      CU(c, cudaMemcpy(d_keys, keys, n_keys * 8, cudaMemcpyHostToDevice));
-      CU(c, cudaMemcpy(d_offs, offsets, (n_keys + 1) * 8, cudaMemcpyHostToDevice));
-      CU(c, cudaMemcpy(d_freq, key_is_freq, n_keys, cudaMemcpyHostToDevice));
+      CU(c, cudaMemcpyAsync(d_keys, keys, n_keys * 8, cudaMemcpyHostToDevice, c->stream));
+      CU(c, cudaMemcpyAsync(d_offs, offsets, (n_keys + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+      CU(c, cudaMemcpyAsync(d_freq, key_is_freq, n_keys, cudaMemcpyHostToDevice, c->stream));
       CU(c, mm_upload_build_table(d_keys, d_offs, d_freq, n_keys, (mm_tab_slot *)(c->blob + h.off_tab), tab_log2, d_err, c->stream));
       CU(c, cudaStreamSynchronize(c->stream));
       cudaFree(d_keys); cudaFree(d_offs); cudaFree(d_freq);
     }
     uint32_t err = 0;
-    CU(c, cudaMemcpy(&err, d_err, 4, cudaMemcpyDeviceToHost));
+    CU(c, cudaMemcpyAsync(&err, d_err, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
     cudaFree(d_err);
     if (err & 1) return fail(c, MM_EINVAL, "an interval point has a bad seqId or a negative position");
     if (err & 2) return fail(c, MM_EINVAL, "a key has no or too many (>= 2^24) interval points, or offsets overflow");
     if (err & 4) return fail(c, MM_EINVAL, "duplicate key in the lookup index");
   }
-  CU(c, cudaMemcpy(c->blob + h.off_contig_len, contig_len, (size_t)n_contigs * 4, cudaMemcpyHostToDevice));
+  CU(c, cudaMemcpyAsync(c->blob + h.off_contig_len, contig_len, (size_t)n_contigs * 4, cudaMemcpyHostToDevice, c->stream));
   std::vector<int32_t> tmp((size_t)n_contigs, -1);
-  CU(c, cudaMemcpy(c->blob + h.off_contig_name_id, contig_name_id ? contig_name_id : tmp.data(), (size_t)n_contigs * 4, cudaMemcpyHostToDevice));
+  CU(c, cudaMemcpyAsync(c->blob + h.off_contig_name_id, contig_name_id ? contig_name_id : tmp.data(), (size_t)n_contigs * 4, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream)); /* tmp is rewritten below */
   std::fill(tmp.begin(), tmp.end(), 0);
-  CU(c, cudaMemcpy(c->blob + h.off_contig_group, contig_group ? contig_group : tmp.data(), (size_t)n_contigs * 4, cudaMemcpyHostToDevice));
-  CU(c, cudaMemcpy(c->blob, &c->hdr, sizeof(c->hdr), cudaMemcpyHostToDevice));
+  CU(c, cudaMemcpyAsync(c->blob + h.off_contig_group, contig_group ? contig_group : tmp.data(), (size_t)n_contigs * 4, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemcpyAsync(c->blob, &c->hdr, sizeof(c->hdr), cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
   resolve_index(c);
   c->blob_ready = true;
   return write_tables(c);
@@ -608,7 +612,8 @@ int mm_index_adopt_blob(mm_ctx *c)
 {
   if (!c || !c->blob) return fail(c, MM_ESTATE, "no blob allocated");
   CU(c, cudaSetDevice(c->device));
-  CU(c, cudaMemcpy(&c->hdr, c->blob, sizeof(c->hdr), cudaMemcpyDeviceToHost));
+  CU(c, cudaMemcpyAsync(&c->hdr, c->blob, sizeof(c->hdr), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
   if (c->hdr.magic != MM_BLOB_MAGIC || c->hdr.total_bytes != c->blob_bytes) return fail(c, MM_EINVAL, "blob header mismatch");
   resolve_index(c);
   c->blob_ready = true;
@@ -675,11 +680,12 @@ int mm_batch_fetch_sketch(mm_ctx *c, mm_minmer *out, int32_t *out_count)
   std::vector<int8_t> ss(n);
   std::vector<mm_segment_result> sr(c->n_segs);
   std::vector<mm_segment> sg(c->n_segs);
-  CU(c, cudaMemcpy(hh.data(), c->d_sk_hash, n * 8, cudaMemcpyDeviceToHost));
-  CU(c, cudaMemcpy(pp.data(), c->d_sk_pos, n * 8, cudaMemcpyDeviceToHost));
-  CU(c, cudaMemcpy(ss.data(), c->d_sk_strand, n, cudaMemcpyDeviceToHost));
-  CU(c, cudaMemcpy(sr.data(), c->d_seg_res, c->n_segs * sizeof(mm_segment_result), cudaMemcpyDeviceToHost));
-  CU(c, cudaMemcpy(sg.data(), c->d_segs, c->n_segs * sizeof(mm_segment), cudaMemcpyDeviceToHost));
+  CU(c, cudaMemcpyAsync(hh.data(), c->d_sk_hash, n * 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemcpyAsync(pp.data(), c->d_sk_pos, n * 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemcpyAsync(ss.data(), c->d_sk_strand, n, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemcpyAsync(sr.data(), c->d_seg_res, c->n_segs * sizeof(mm_segment_result), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemcpyAsync(sg.data(), c->d_segs, c->n_segs * sizeof(mm_segment), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
   for (uint64_t s = 0; s < c->n_segs; s++) {
     out_count[s] = sr[s].sketch_size;
     for (int j = 0; j < sr[s].sketch_size; j++) {

@@ -38,7 +38,7 @@ def upload_reference_index(ctx, R):
     ctx.tables_upload(R.cutoffs(), R.min_hits_table())
 
 
-def compare_stages(ctx, R, d, ridx, start, length, seg_res, cands, loci, dev_sketch, dev_count, max_report=10):
+def compare_stages(ctx, R, d, ridx, start, length, seg_res, cands, loci, dev_sketch, dev_count, max_report=10, diag=None):
     bad = []
     n_cmp = 0
     for i in range(len(ridx)):
@@ -64,6 +64,12 @@ def compare_stages(ctx, R, d, ridx, start, length, seg_res, cands, loci, dev_ske
             np.array_equal(c[f], rl1[f]) for f in ("seqId", "rangeStartPos", "rangeEndPos", "intersectionSize"))
         if not same:
             bad.append((i, "l1", rl1.tolist(), c[["seqId", "rangeStartPos", "rangeEndPos", "intersectionSize"]].tolist()))
+            o2 = R.map_fragment(d["rnames"][ridx[i]], seg, full_len=len(r), seq_counter=int(ridx[i]))
+            print(f"DIAG seg {i}: reference minimumHits {o['minimumHits']} n_points {o['n_points']}; reference again l1 "
+                  f"{o2['l1'].tolist()} minimumHits {o2['minimumHits']}; device minimum_hits {sr['minimum_hits']} best "
+                  f"{sr['best_intersection']} n_points {sr['n_points']} sketch_size {sr['sketch_size']}")
+            if diag is not None:
+                diag(i, seg, len(r), int(ridx[i]), o)
             continue
         for ci in range(len(c)):
             dl = loci[c[ci]["first_locus"] : c[ci]["first_locus"] + c[ci]["n_loci"]]
@@ -168,7 +174,23 @@ def run_stage_parity(d, args, seg_length, **ctx_kw):
         dev_sketch, dev_count = ctx.batch_fetch_sketch()
         assert np.array_equal(seg_res["n_candidates"], seg_res2["n_candidates"])
         print("stage ms", ctx.stage_ms(), "launches", ctx.kernel_launches)
-        bad = compare_stages(ctx, R, d, ridx, start, length, seg_res2, cands2, loci2, dev_sketch, dev_count)
+        def diag(i, seg, full_len, counter, o):
+            import oracle_py
+
+            sr1 = seg_res[i]
+            c1 = cands[sr1["first_candidate"] : sr1["first_candidate"] + sr1["n_candidates"]]
+            print("   first (host-buffer) call gave", c1[["seqId", "rangeStartPos", "rangeEndPos", "intersectionSize"]].tolist())
+            if oracle_py.available():
+                O = oracle_py.Oracle(params=R.p)
+                idx = R.index()
+                keys, offs, pts, fr = R.lookup()
+                O.set_index(idx, keys, offs, pts, fr, R.contig_len, R.contig_names)
+                b = O.map_fragment(seg, seq_counter=counter, full_len=full_len)
+                print("   oracle on the same index:", b["l1"].tolist(), "minimumHits", b["minimumHits"], "n_points", b["n_points"],
+                      "points equal reference:", np.array_equal(o["points"], b["points"]))
+                O.close()
+
+        bad = compare_stages(ctx, R, d, ridx, start, length, seg_res2, cands2, loci2, dev_sketch, dev_count, diag=diag)
         ctx.close()
         return bad
     finally:
