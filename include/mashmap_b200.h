@@ -183,10 +183,21 @@ int mm_batch_fetch(mm_ctx *ctx, mm_segment_result *seg_results,
 /* Device sketches of the resident batch (after frequent-seed removal), for stage-level tests. */
 int mm_batch_fetch_sketch(mm_ctx *ctx, mm_minmer *out_sketch, int32_t *out_count);
 
+/* Scheduling hook for host pipelines that keep several contexts in flight on one device. The library calls
+ * hook(user, phase, 1) before and hook(user, phase, 0) after
+ *   MM_PHASE_UPLOAD_CHUNK  each <= 64 MiB piece of a batch upload (mm_batch_upload / mm_map_segments), and
+ *   MM_PHASE_L2            the L2 kernels of mm_map_resident / mm_map_segments (bandwidth-bound: measured 4x slower
+ *                          while another context's PCIe upload is writing HBM),
+ * from the calling thread. A pipeline uses it to keep the two from overlapping (skch::BatchMapper does). NULL clears. */
+#define MM_PHASE_UPLOAD_CHUNK 1
+#define MM_PHASE_L2 2
+typedef void (*mm_phase_hook)(void *user, int phase, int begin);
+int mm_ctx_set_phase_hook(mm_ctx *ctx, mm_phase_hook hook, void *user);
+
 /* CUDA-event time in milliseconds of each stage of the last mm_map_resident / mm_map_segments:
  * [0] sketch kernel  [1] L1 kernel  [2] L2 kernel  [3] H2D  [4] D2H
  * [5] first kernel launch -> last kernel end (events on the launching stream; includes the two counter
- *     read-backs between kernels)  [6..7] reserved. */
+ *     read-backs between kernels)  [6] L2 record-preparation kernel  [7] L2 scan kernel(s). */
 int mm_last_stage_ms(const mm_ctx *ctx, float ms[8]);
 
 /* Pinned host memory for the caller's batch buffers (so the copies inside mm_map_segments run at full

@@ -1,8 +1,12 @@
 #include "skch_map.hpp"
+#include <cstdio>
+#include <cstdlib>
 
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <mutex>
 #include <cstring>
 #include <fstream>
 #include <iostream>
@@ -56,6 +60,38 @@ int BatchMapper::getRefGroup(const std::string &seqName) const
   return -1;
 }
 
+/* Upload chunks and the L2 phase exclude each other; a waiting L2 phase has priority over the next chunk. */
+struct BatchMapper::Gate {
+  std::mutex mu;
+  std::condition_variable cv;
+  int uploading = 0, l2_active = 0, l2_waiting = 0;
+};
+
+void BatchMapper::phaseHook(void *user, int phase, int begin)
+{
+  Gate &g = *static_cast<Gate *>(user);
+  std::unique_lock<std::mutex> lk(g.mu);
+  if (phase == MM_PHASE_UPLOAD_CHUNK) {
+    if (begin) {
+      g.cv.wait(lk, [&] { return g.l2_active == 0 && g.l2_waiting == 0; });
+      g.uploading++;
+    } else {
+      g.uploading--;
+      g.cv.notify_all();
+    }
+  } else if (phase == MM_PHASE_L2) {
+    if (begin) {
+      g.l2_waiting++;
+      g.cv.wait(lk, [&] { return g.uploading == 0; });
+      g.l2_waiting--;
+      g.l2_active++;
+    } else {
+      g.l2_active--;
+      g.cv.notify_all();
+    }
+  }
+}
+
 BatchMapper::BatchMapper(const Parameters &p, const Sketch &refsketch) : param(p), refSketch(refsketch)
 {
   if (!param.split) die("--noSplit is not supported by the B200 path (fragments longer than the segment length)");
@@ -87,18 +123,28 @@ BatchMapper::BatchMapper(const Parameters &p, const Sketch &refsketch) : param(p
   rc = mm_tables_upload(ctx, sketchCutoffs.data(), (int32_t)sketchCutoffs.size(), minHits.data(), (int32_t)minHits.size());
   if (rc != MM_OK) die(std::string("mm_tables_upload: ") + mm_last_error(ctx));
   tail_ = new MapTail(param, refSketch.metadata, refIdGroup);
-  if (mm_ctx_create(param.device, &mp, &ctx2) == MM_OK) {
-    if (mm_ctx_share_index(ctx2, ctx) != MM_OK) { mm_ctx_destroy(ctx2); ctx2 = nullptr; }
-  } else {
-    ctx2 = nullptr;
+  // further contexts share the index image: one lane per pipeline stage in flight (upload / kernels / fetch + tail)
+  lanes[0].ctx = ctx;
+  nLanes = 1;
+  for (int l = 1; l < MAX_LANES; l++) {
+    mm_ctx *c2 = nullptr;
+    if (mm_ctx_create(param.device, &mp, &c2) != MM_OK) break;
+    if (mm_ctx_share_index(c2, ctx) != MM_OK) { mm_ctx_destroy(c2); break; }
+    lanes[l].ctx = c2;
+    nLanes = l + 1;
+  }
+  if (nLanes > 1 && !getenv("MM_NO_GATE")) {
+    gate = new Gate();
+    for (int l = 0; l < nLanes; l++) mm_ctx_set_phase_hook(lanes[l].ctx, &BatchMapper::phaseHook, gate);
   }
 }
 
 BatchMapper::~BatchMapper()
 {
   delete tail_;
-  if (ctx2) mm_ctx_destroy(ctx2);
+  for (int l = nLanes - 1; l >= 1; l--) mm_ctx_destroy(lanes[l].ctx);
   if (ctx) mm_ctx_destroy(ctx);
+  delete gate;
 }
 
 char *BatchMapper::allocBases(uint64_t bytes)
@@ -136,44 +182,58 @@ void BatchMapper::addRead(ReadBatch &b, const std::string &name, const char *seq
   b.reads.push_back(std::move(rd));
 }
 
-/* reads [r0, r1) of the batch: one device call on this lane's context, then their host tail on tail_threads threads */
-void BatchMapper::mapRange(Lane &ln, const ReadBatch &b, size_t r0, size_t r1, std::vector<MappingResultsVector_t> &results,
-                           std::vector<std::string> *text, const std::vector<ContigInfo> *qmetadata, int tail_threads)
+/* The three stages of one part (reads [r0, r1) of the batch) on one lane (= one device context with its own stream
+ * and buffers). mapBatch runs them as a pipeline: uploads on one thread, kernels on another, fetch + host tail on a
+ * third, so that the PCIe copy of part i+1 and the host tail of part i-1 are hidden behind the kernels of part i. */
+void BatchMapper::laneUpload(Lane &ln, const ReadBatch &b, size_t r0, size_t r1)
 {
   auto t0 = Clock::now();
-  const size_t s0 = b.reads[r0].first_seg, s1 = b.reads[r1 - 1].first_seg + b.reads[r1 - 1].n_seg;
-  const uint64_t b0 = b.segs[s0].offset;  // a read's first fragment starts at the read's first base
+  ln.r0 = r0; ln.r1 = r1;
+  ln.s0 = b.reads[r0].first_seg;
+  const size_t s1 = b.reads[r1 - 1].first_seg + b.reads[r1 - 1].n_seg;
+  const uint64_t b0 = b.segs[ln.s0].offset;  // a read's first fragment starts at the read's first base
   uint64_t b1 = b0;
   for (size_t r = r0; r < r1; r++) b1 += (uint64_t)b.reads[r].len;
-  const mm_segment *segp = b.segs.data() + s0;
+  const mm_segment *segp = b.segs.data() + ln.s0;
   if (b0 != 0) {  // fragment offsets are relative to the buffer handed to the device call
-    ln.segs.assign(b.segs.begin() + s0, b.segs.begin() + s1);
+    ln.segs.assign(b.segs.begin() + ln.s0, b.segs.begin() + s1);
     for (auto &sg : ln.segs) sg.offset -= b0;
     segp = ln.segs.data();
   }
-  const size_t nseg = s1 - s0;
-  ln.segRes.resize(nseg);
-  uint64_t nc = 0, nl = 0;
-  if (ln.cands.size() < 2 * nseg + 1024) ln.cands.resize(2 * nseg + 1024);
-  if (ln.loci.size() < 2 * ln.cands.size()) ln.loci.resize(2 * ln.cands.size());
-  while (true) {
-    int rc = mm_map_segments(ln.ctx, b.bases + b0, b1 - b0, segp, nseg, ln.segRes.data(), ln.cands.data(), ln.cands.size(), &nc,
-                             ln.loci.data(), ln.loci.size(), &nl);
-    if (rc == MM_ECAPACITY) {
-      ln.cands.resize(std::max<uint64_t>(ln.cands.size(), nc));
-      ln.loci.resize(std::max<uint64_t>(ln.loci.size(), nl));
-      continue;
-    }
-    if (rc != MM_OK) die(std::string("mm_map_segments: ") + mm_last_error(ln.ctx));
-    break;
-  }
+  ln.nseg = s1 - ln.s0;
+  int rc = mm_batch_upload(ln.ctx, b.bases + b0, b1 - b0, segp, ln.nseg);
+  if (rc != MM_OK) die(std::string("mm_batch_upload: ") + mm_last_error(ln.ctx));
+  ln.msUpload = since(t0) * 1e3;
+  ln.secDevice += since(t0);
+}
+
+void BatchMapper::laneCompute(Lane &ln)
+{
+  auto t0 = Clock::now();
+  int rc = mm_map_resident(ln.ctx, &ln.nc, &ln.nl);
+  if (rc != MM_OK) die(std::string("mm_map_resident: ") + mm_last_error(ln.ctx));
+  ln.msCompute = since(t0) * 1e3;
+  ln.secDevice += since(t0);
+}
+
+void BatchMapper::laneFinish(Lane &ln, const ReadBatch &b, std::vector<MappingResultsVector_t> &results,
+                             std::vector<std::string> *text, const std::vector<ContigInfo> *qmetadata, int tail_threads)
+{
+  auto t0 = Clock::now();
+  const size_t r0 = ln.r0, r1 = ln.r1;
+  if (ln.segRes.size() < ln.nseg) ln.segRes.resize(ln.nseg);
+  if (ln.cands.size() < ln.nc) ln.cands.resize(ln.nc + ln.nc / 8 + 1024);
+  if (ln.loci.size() < ln.nl) ln.loci.resize(ln.nl + ln.nl / 8 + 1024);
+  int rc = mm_batch_fetch(ln.ctx, ln.segRes.data(), ln.cands.data(), ln.cands.size(), ln.loci.data(), ln.loci.size());
+  if (rc != MM_OK) die(std::string("mm_batch_fetch: ") + mm_last_error(ln.ctx));
   mm_last_stage_ms(ln.ctx, ln.stageMs);
+  const double msFetch = since(t0) * 1e3;
   ln.secDevice += since(t0);
   t0 = Clock::now();
 
   MapTail tail(param, refSketch.metadata, refIdGroup);
   tail.segs = b.segs.data();              // absolute fragment indices (only the lengths are read)
-  tail.segRes = ln.segRes.data() - s0;    // so that indexing by the absolute fragment index works
+  tail.segRes = ln.segRes.data() - ln.s0; // so that indexing by the absolute fragment index works
   tail.cands = ln.cands.data();
   tail.loci = ln.loci.data();
   tail.qmetadata = qmetadata;
@@ -205,6 +265,11 @@ void BatchMapper::mapRange(Lane &ln, const ReadBatch &b, size_t r0, size_t r1, s
     for (auto &th : pool) th.join();
   }
   ln.secTail += since(t0);
+  static const bool trace = getenv("MM_TRACE") != nullptr;
+  if (trace)
+    fprintf(stderr, "[trace] lane %d reads %zu-%zu segs %zu: upload %.2f ms (h2d %.2f) compute %.2f ms (kernels %.2f [k1 %.2f k2 %.2f k3 %.2f: prep %.2f scan %.2f]) "
+            "fetch %.2f ms (d2h %.2f) tail %.2f ms (%d threads)\n", (int)(&ln - lanes), r0, r1, ln.nseg, ln.msUpload, ln.stageMs[3],
+            ln.msCompute, ln.stageMs[5], ln.stageMs[0], ln.stageMs[1], ln.stageMs[2], ln.stageMs[6], ln.stageMs[7], msFetch, ln.stageMs[4], since(t0) * 1e3, nthreads);
 }
 
 void BatchMapper::mapBatch(const ReadBatch &b, std::vector<MappingResultsVector_t> &results, std::vector<std::string> *text,
@@ -214,10 +279,9 @@ void BatchMapper::mapBatch(const ReadBatch &b, std::vector<MappingResultsVector_
   results.assign(nreads, MappingResultsVector_t());
   if (text) text->assign(nreads, std::string());
   if (nreads == 0) return;
-  lanes[0].ctx = ctx; lanes[1].ctx = ctx2;
-  const double d0 = lanes[0].secDevice + lanes[1].secDevice, t0 = lanes[0].secTail + lanes[1].secTail;
-  // sub-batches of ~SUB bases; with two or more of them, two lanes keep the copies / kernels of one sub-batch
-  // overlapped with the kernels / host tail of the other
+  double d0 = 0, t0 = 0;
+  for (auto &ln : lanes) { d0 += ln.secDevice; t0 += ln.secTail; }
+  // parts of ~SUB bases (a read is never split across parts)
   const uint64_t SUB = std::max<uint64_t>(param.sub_batch_bases, 1);
   std::vector<std::pair<size_t, size_t>> parts;
   {
@@ -228,24 +292,52 @@ void BatchMapper::mapBatch(const ReadBatch &b, std::vector<MappingResultsVector_
       if (acc >= SUB || r + 1 == nreads) { parts.emplace_back(r0, r + 1); r0 = r + 1; acc = 0; }
     }
   }
-  if (parts.size() < 2 || !ctx2) {
-    for (auto &p : parts) mapRange(lanes[0], b, p.first, p.second, results, text, qmetadata, param.threads);
+  const size_t np = parts.size();
+  if (np < 2 || nLanes < 2) {
+    for (auto &p : parts) {
+      laneUpload(lanes[0], b, p.first, p.second);
+      laneCompute(lanes[0]);
+      laneFinish(lanes[0], b, results, text, qmetadata, param.threads);
+    }
   } else {
-    std::atomic<size_t> next{0};
-    auto lane_fn = [&](int w) {
-      while (true) {
-        const size_t i = next.fetch_add(1);
-        if (i >= parts.size()) break;
-        mapRange(lanes[w], b, parts[i].first, parts[i].second, results, text, qmetadata, std::max(1, param.threads / 2));
-      }
+    // part i lives on lane i % nLanes; state: 0 waiting, 1 uploaded, 2 computed, 3 finished (its lane is free again)
+    const size_t NL = (size_t)nLanes;
+    std::vector<int> state(np, 0);
+    std::mutex mu;
+    std::condition_variable cv;
+    auto wait_for = [&](size_t i, int st) {
+      std::unique_lock<std::mutex> lk(mu);
+      cv.wait(lk, [&] { return state[i] >= st; });
     };
-    std::thread t1(lane_fn, 1);
-    lane_fn(0);
-    t1.join();
+    auto publish = [&](size_t i, int st) {
+      { std::lock_guard<std::mutex> lk(mu); state[i] = st; }
+      cv.notify_all();
+    };
+    std::thread uploader([&] {
+      for (size_t i = 0; i < np; i++) {
+        if (i >= NL) wait_for(i - NL, 3);
+        laneUpload(lanes[i % NL], b, parts[i].first, parts[i].second);
+        publish(i, 1);
+      }
+    });
+    std::thread finisher([&] {
+      for (size_t i = 0; i < np; i++) {
+        wait_for(i, 2);
+        laneFinish(lanes[i % NL], b, results, text, qmetadata, param.threads);
+        publish(i, 3);
+      }
+    });
+    for (size_t i = 0; i < np; i++) {  // kernels of successive parts run back to back from this thread
+      wait_for(i, 1);
+      laneCompute(lanes[i % NL]);
+      publish(i, 2);
+    }
+    uploader.join();
+    finisher.join();
   }
   memcpy(lastStageMs, lanes[0].stageMs, sizeof(lastStageMs));
-  secondsDevice += lanes[0].secDevice + lanes[1].secDevice - d0;
-  secondsHostTail += lanes[0].secTail + lanes[1].secTail - t0;
+  for (auto &ln : lanes) { secondsDevice += ln.secDevice; secondsHostTail += ln.secTail; }
+  secondsDevice -= d0; secondsHostTail -= t0;
 }
 
 /* ------------------------------------------------------------------------------------------------------ */

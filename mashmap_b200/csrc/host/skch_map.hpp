@@ -14,8 +14,9 @@
  *   reportReadMappings (PAF text)                                                (:1758-1805)
  *
  * skch::BatchMapper is the same machinery for reads that are already in memory: a batch of reads is laid out
- * in one (pinned) base buffer, fragmented with the reference's rule, mapped with ONE device call, and its
- * per-read host tail runs on param.threads worker threads. skch::Map = FASTA reader + BatchMapper; output
+ * in one (pinned) base buffer, fragmented with the reference's rule and mapped in parts of sub_batch_bases through a
+ * three-stage pipeline (PCIe upload | kernels | record fetch + per-read host tail on param.threads threads), each part
+ * on one of three device contexts that share the index image. skch::Map = FASTA reader + BatchMapper; output
  * order == input order, as in the reference (ThreadPool.hpp:187-211).
  */
 #ifndef SKCH_MAP_HPP
@@ -73,22 +74,31 @@ class BatchMapper {
   std::vector<int> minHits;        // estimateMinimumHitsRelaxed by Q.sketchSize (computeMap.hpp:1144)
   std::unordered_map<std::string, int> refNameId;
   std::vector<int> contigNameId;
-  mm_ctx *ctx = nullptr;
-  mm_ctx *ctx2 = nullptr;  // second context sharing the index image: two sub-batches in flight
+  mm_ctx *ctx = nullptr;   // owns the index image
   MapTail *tail_ = nullptr;
-  struct Lane {  // per pipeline lane: device context + its host-side record buffers
+  struct Lane {  // per pipeline lane: device context (own stream + buffers) and its host-side record buffers
     mm_ctx *ctx = nullptr;
     std::vector<mm_segment> segs;
     std::vector<mm_segment_result> segRes;
     std::vector<mm_l1_candidate> cands;
     std::vector<mm_l2_locus> loci;
-    double secDevice = 0, secTail = 0;
+    size_t r0 = 0, r1 = 0, s0 = 0, nseg = 0;  // the part in flight on this lane
+    uint64_t nc = 0, nl = 0;
+    double secDevice = 0, secTail = 0, msUpload = 0, msCompute = 0;
     float stageMs[8] = {0};
   };
-  Lane lanes[2];
+  // scheduler state of the phase hook: batch uploads wait while the L2 kernels of another lane run
+  struct Gate;
+  Gate *gate = nullptr;
+  static void phaseHook(void *user, int phase, int begin);
+  static constexpr int MAX_LANES = 3;
+  Lane lanes[MAX_LANES];
+  int nLanes = 1;
   void setRefGroups();
-  void mapRange(Lane &ln, const ReadBatch &b, size_t r0, size_t r1, std::vector<MappingResultsVector_t> &results,
-                std::vector<std::string> *text, const std::vector<ContigInfo> *qmetadata, int tail_threads);
+  void laneUpload(Lane &ln, const ReadBatch &b, size_t r0, size_t r1);
+  void laneCompute(Lane &ln);
+  void laneFinish(Lane &ln, const ReadBatch &b, std::vector<MappingResultsVector_t> &results, std::vector<std::string> *text,
+                  const std::vector<ContigInfo> *qmetadata, int tail_threads);
 };
 
 class Map {

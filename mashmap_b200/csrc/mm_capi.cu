@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "mm_internal.h"
+#include <chrono>
 
 static thread_local std::string g_create_error;
 
@@ -43,6 +44,9 @@ struct mm_ctx {
   mm_l1_candidate *d_cands = nullptr; uint64_t cand_cap = 0;
   mm_l2_locus *d_loci = nullptr; uint64_t loci_cap = 0;
   uint32_t *d_counters = nullptr;
+  mm_phase_hook hook = nullptr;
+  void *hook_user = nullptr;
+  uint32_t *h_pub = nullptr; /* pinned, device-mapped: kernels publish counters here (no copy engine involved) */
   uint64_t *d_scratch = nullptr; uint64_t scratch_cap = 0; uint64_t scratch_slice = 0; uint64_t scratch_pool = 0;
   uint32_t l1_grid = 0;
   uint64_t n_cands = 0, n_loci = 0;
@@ -54,7 +58,7 @@ struct mm_ctx {
   int l2_mode = 1; /* 1 = stream kernels (mm_l2_stream.cu), 0 = general kernel only (MM_L2_GENERAL=1) */
   bool batch_mapped = false;
 
-  cudaEvent_t ev[8]{};
+  cudaEvent_t ev[10]{};
   float stage_ms[8]{};
 };
 
@@ -179,7 +183,19 @@ int upload_batch(mm_ctx *c, const char *bases, uint64_t n_bases, const mm_segmen
   }
   if (!c->d_counters) CU(c, cudaMalloc((void **)&c->d_counters, 64));
   CU(c, cudaEventRecord(c->ev[6], c->stream));
-  CU(c, cudaMemcpyAsync(c->d_bases, bases, n_bases, cudaMemcpyHostToDevice, c->stream));
+  if (!c->hook) {
+    CU(c, cudaMemcpyAsync(c->d_bases, bases, n_bases, cudaMemcpyHostToDevice, c->stream));
+  } else { /* in pieces, so that the pipeline's scheduler can hold the upload back (MM_PHASE_UPLOAD_CHUNK) */
+    const uint64_t CH = 64ULL << 20;
+    for (uint64_t at = 0; at < n_bases; at += CH) {
+      const uint64_t n = std::min(CH, n_bases - at);
+      c->hook(c->hook_user, MM_PHASE_UPLOAD_CHUNK, 1);
+      cudaError_t e = cudaMemcpyAsync(c->d_bases + at, bases + at, n, cudaMemcpyHostToDevice, c->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+      c->hook(c->hook_user, MM_PHASE_UPLOAD_CHUNK, 0);
+      CU(c, e);
+    }
+  }
   CU(c, cudaMemsetAsync(c->d_bases + n_bases, 'N', 256, c->stream));
   CU(c, cudaMemcpyAsync(c->d_segs, segs, n_segs * sizeof(mm_segment), cudaMemcpyHostToDevice, c->stream));
   CU(c, cudaEventRecord(c->ev[7], c->stream));
@@ -222,6 +238,28 @@ int ensure_scratch(mm_ctx *c, uint64_t pool_elems)
   return MM_OK;
 }
 
+/* Small device->host readbacks do not go through a copy engine: a DMA queued while another context's batch upload
+ * (hundreds of MB) is in flight waits for it. A one-warp kernel stores the words into pinned, device-mapped host memory. */
+__global__ void k_publish(const uint32_t *__restrict__ src, volatile uint32_t *dst, int n)
+{
+  if ((int)threadIdx.x < n) dst[threadIdx.x] = src[threadIdx.x];
+  __threadfence_system();
+}
+__global__ void k_set_u32(uint32_t *dst, uint32_t v) { *dst = v; }
+/* cudaMemsetAsync of a few words may be executed by a copy engine too: zero them with a kernel */
+__global__ void k_zero_words(uint32_t *dst, int n) { if ((int)threadIdx.x < n) dst[threadIdx.x] = 0; }
+#define ZERO_WORDS(c, ptr, n) do { k_zero_words<<<1, 32, 0, (c)->stream>>>((uint32_t *)(ptr), (n)); CU((c), cudaGetLastError()); } while (0)
+
+int read_words(mm_ctx *c, const void *dev, uint32_t *out, int n_words)
+{
+  k_publish<<<1, 32, 0, c->stream>>>((const uint32_t *)dev, c->h_pub, n_words);
+  CU(c, cudaGetLastError());
+  CU(c, cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < n_words; i++) out[i] = c->h_pub[i];
+  return MM_OK;
+}
+#define RD(c, dev, out, n) do { int rc__ = read_words((c), (dev), (out), (n)); if (rc__) return rc__; } while (0)
+
 /* K3 fast path (mm_l2_stream.cu): ranges+scan -> records -> lane-per-candidate scan -> general kernel for the
  * candidates that need more locus slots. Returns MM_ENOMEM if the record buffer cannot be allocated. */
 int run_l2_stream(mm_ctx *c, uint32_t *h_cnt)
@@ -253,11 +291,13 @@ int run_l2_stream(mm_ctx *c, uint32_t *h_cnt)
     CU(c, cudaMalloc((void **)&c->d_loci, c->loci_cap * sizeof(mm_l2_locus)));
   }
   mm_dev_batch b = make_batch(c);
-  CU(c, cudaMemsetAsync(c->d_l2_rec_off + nc, 0, 8, c->stream));
+  const auto tk0 = std::chrono::steady_clock::now();
+  ZERO_WORDS(c, c->d_l2_rec_off + nc, 2);
   CU(c, mm_launch_l2_ranges(c->params, c->ix, b, (uint32_t)nc, c->d_scan_tmp, c->scan_tmp_bytes + 256, c->stream));
   uint64_t total = 0;
-  CU(c, cudaMemcpyAsync(&total, c->d_l2_rec_off + nc, 8, cudaMemcpyDeviceToHost, c->stream));
-  CU(c, cudaStreamSynchronize(c->stream));
+  RD(c, c->d_l2_rec_off + nc, (uint32_t *)&total, 2);
+  const auto tk1 = std::chrono::steady_clock::now();
+  c->stage_ms[6] = std::chrono::duration<float, std::milli>(tk1 - tk0).count(); /* host view: ranges + scan + readback */
   if (total + 16 > c->l2_recs_cap) {
     if (c->d_l2_recs) cudaFree(c->d_l2_recs);
     c->d_l2_recs = nullptr; c->l2_recs_cap = 0;
@@ -270,21 +310,21 @@ int run_l2_stream(mm_ctx *c, uint32_t *h_cnt)
   }
   for (int attempt = 0; attempt < 4; attempt++) {
     b = make_batch(c);
-    CU(c, cudaMemsetAsync(c->d_counters + 1, 0, 4, c->stream));
-    CU(c, cudaMemsetAsync(c->d_counters + 6, 0, 8, c->stream));
+    ZERO_WORDS(c, c->d_counters + 1, 1);
+    ZERO_WORDS(c, c->d_counters + 6, 2);
+    CU(c, cudaEventRecord(c->ev[8], c->stream));
     CU(c, mm_launch_l2_prep(c->params, c->ix, b, (uint32_t)nc, c->stream, c->sm_count));
+    CU(c, cudaEventRecord(c->ev[9], c->stream));
     CU(c, mm_launch_l2_scan(c->params, c->ix, b, (uint32_t)nc, c->stream, c->sm_count));
     c->launches += 4; /* ranges, scan (library), prep, scan */
-    CU(c, cudaMemcpyAsync(h_cnt, c->d_counters, 64, cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaStreamSynchronize(c->stream));
+    RD(c, c->d_counters, h_cnt, 16);
     uint64_t extent = nc * LPC;
     if (h_cnt[7] > 0) { /* candidates with more than LPC loci: general kernel, loci appended after the fixed slots */
       const uint32_t base = (uint32_t)extent;
-      CU(c, cudaMemcpyAsync(c->d_counters + 6, &base, 4, cudaMemcpyHostToDevice, c->stream));
+      k_set_u32<<<1, 1, 0, c->stream>>>(c->d_counters + 6, base);
       CU(c, mm_launch_l2_overflow(c->params, c->ix, b, (uint32_t)nc, c->stream, c->sm_count));
       c->launches += 1;
-      CU(c, cudaMemcpyAsync(h_cnt, c->d_counters, 64, cudaMemcpyDeviceToHost, c->stream));
-      CU(c, cudaStreamSynchronize(c->stream));
+      RD(c, c->d_counters, h_cnt, 16);
       if (h_cnt[1] == 2) return fail(c, MM_ECUDA, "L2 live-set overflow in the general kernel");
       if (h_cnt[1] == 1 || h_cnt[6] > c->loci_cap) { /* grow and redo prep+scan+overflow */
         cudaFree(c->d_loci); c->d_loci = nullptr;
@@ -296,6 +336,8 @@ int run_l2_stream(mm_ctx *c, uint32_t *h_cnt)
     }
     CU(c, cudaEventRecord(c->ev[4], c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
+    cudaEventElapsedTime(&c->stage_ms[6], c->ev[8], c->ev[9]); /* k_l2_prep */
+    cudaEventElapsedTime(&c->stage_ms[7], c->ev[9], c->ev[4]); /* k_l2_scan (+ overflow kernel) */
     c->n_loci = extent;
     return MM_OK;
   }
@@ -330,7 +372,7 @@ int run_pipeline(mm_ctx *c)
   uint32_t h_cnt[16];
   for (int attempt = 0; attempt < 6; attempt++) {
     mm_dev_batch b = make_batch(c);
-    CU(c, cudaMemsetAsync(c->d_counters, 0, 64, c->stream));
+    ZERO_WORDS(c, c->d_counters, 16);
     CU(c, cudaEventRecord(c->ev[0], c->stream));
     CU(c, mm_launch_sketch(c->params, b, c->stream, c->sm_count));
     CU(c, cudaEventRecord(c->ev[1], c->stream));
@@ -338,8 +380,7 @@ int run_pipeline(mm_ctx *c)
     CU(c, mm_launch_l1(c->params, c->ix, b, c->stream, c->sm_count, c->d_l1_slow, c->l1_warp, &l1_launches));
     CU(c, cudaEventRecord(c->ev[2], c->stream));
     c->launches += 1 + (uint64_t)l1_launches;
-    CU(c, cudaMemcpyAsync(h_cnt, c->d_counters, 64, cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaStreamSynchronize(c->stream));
+    RD(c, c->d_counters, h_cnt, 16);
     const uint64_t need_cands = h_cnt[0];
     bool retry = false;
     if (h_cnt[3] || need_cands > c->cand_cap) {
@@ -358,7 +399,9 @@ int run_pipeline(mm_ctx *c)
     c->n_cands = need_cands;
     /* K3 */
     if (c->l2_mode == 1) {
+      if (c->hook) c->hook(c->hook_user, MM_PHASE_L2, 1);
       int rc2 = run_l2_stream(c, h_cnt);
+      if (c->hook) c->hook(c->hook_user, MM_PHASE_L2, 0);
       if (rc2 == MM_OK) {
         cudaEventElapsedTime(&c->stage_ms[0], c->ev[0], c->ev[1]);
         cudaEventElapsedTime(&c->stage_ms[1], c->ev[1], c->ev[2]);
@@ -373,14 +416,13 @@ int run_pipeline(mm_ctx *c)
     /* general kernel, retried alone if the locus buffer is too small (it is idempotent) */
     for (int a2 = 0; a2 < 4; a2++) {
       b = make_batch(c);
-      CU(c, cudaMemsetAsync(c->d_counters + 1, 0, 4, c->stream));
-      CU(c, cudaMemsetAsync(c->d_counters + 6, 0, 8, c->stream));
+      ZERO_WORDS(c, c->d_counters + 1, 1);
+      ZERO_WORDS(c, c->d_counters + 6, 2);
       CU(c, cudaEventRecord(c->ev[3], c->stream));
       CU(c, mm_launch_l2(c->params, c->ix, b, (uint32_t)c->n_cands, c->stream, c->sm_count));
       CU(c, cudaEventRecord(c->ev[4], c->stream));
       if (c->n_cands) c->launches += 1;
-      CU(c, cudaMemcpyAsync(h_cnt, c->d_counters, 64, cudaMemcpyDeviceToHost, c->stream));
-      CU(c, cudaStreamSynchronize(c->stream));
+      RD(c, c->d_counters, h_cnt, 16);
       if (h_cnt[1] == 2) return fail(c, MM_ECUDA, "L2 live-set overflow: the reference index has more than "
                                      "sketch_size+64 overlapping minmer windows at one position");
       if (h_cnt[1] == 1 || h_cnt[6] > c->loci_cap) {
@@ -434,6 +476,11 @@ int mm_ctx_create(int device, const mm_params *params, mm_ctx **out)
     return fail(nullptr, MM_ECUDA, "cannot create stream");
   }
   for (auto &ev : c->ev) cudaEventCreate(&ev);
+  if (cudaHostAlloc((void **)&c->h_pub, 256, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return fail(nullptr, MM_ENOMEM, "cannot allocate the pinned counter page");
+  }
   if (const char *g = getenv("MM_L2_GENERAL")) c->l2_mode = (g[0] == '1') ? 0 : 1; /* test hook: general kernel only */
   if (const char *g = getenv("MM_L1_CTA")) c->l1_warp = (g[0] == '1') ? 0 : 1; /* test hook: general L1 path only */
   if (params->sketch_size > 1000) c->l2_mode = 0; /* the stream kernel packs its counters in 11 bits */
@@ -451,6 +498,7 @@ int mm_ctx_destroy(mm_ctx *c)
   cudaFree(c->d_seg_res); cudaFree(c->d_cands); cudaFree(c->d_loci); cudaFree(c->d_counters); cudaFree(c->d_scratch);
   cudaFree(c->d_l1_slow); cudaFree(c->d_l2_ranges); cudaFree(c->d_l2_rec_off); cudaFree(c->d_l2_recs); cudaFree(c->d_scan_tmp);
   for (auto &ev : c->ev) cudaEventDestroy(ev);
+  if (c->h_pub) cudaFreeHost(c->h_pub);
   cudaStreamDestroy(c->stream);
   delete c;
   return MM_OK;
@@ -729,6 +777,13 @@ int mm_map_segments(mm_ctx *c, const char *bases, uint64_t n_bases, const mm_seg
   *n_loci = c->n_loci;
   if (cand_cap < c->n_cands || loci_cap < c->n_loci) return fail(c, MM_ECAPACITY, "need %llu candidates, %llu loci", (unsigned long long)c->n_cands, (unsigned long long)c->n_loci);
   return mm_batch_fetch(c, seg_results, cands, cand_cap, loci, loci_cap);
+}
+
+int mm_ctx_set_phase_hook(mm_ctx *c, mm_phase_hook hook, void *user)
+{
+  if (!c) return MM_EINVAL;
+  c->hook = hook; c->hook_user = user;
+  return MM_OK;
 }
 
 int mm_last_stage_ms(const mm_ctx *c, float ms[8])
