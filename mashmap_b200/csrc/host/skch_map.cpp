@@ -249,6 +249,8 @@ void BatchMapper::laneFinish(Lane &ln, const ReadBatch &b, std::vector<MappingRe
       if (lo >= r1) break;
       const size_t hi = std::min(r1, lo + 256);
       for (size_t r = lo; r < hi; r++) {
+        results[r].clear();
+        if (text) (*text)[r].clear();
         tail.mapRead(b.reads[r], idc, results[r]);
         if (text && !results[r].empty()) {
           os.str(std::string());
@@ -276,8 +278,10 @@ void BatchMapper::mapBatch(const ReadBatch &b, std::vector<MappingResultsVector_
                            const std::vector<ContigInfo> *qmetadata)
 {
   const size_t nreads = b.reads.size();
-  results.assign(nreads, MappingResultsVector_t());
-  if (text) text->assign(nreads, std::string());
+  // no up-front clearing: the tail workers reset each read's slot themselves (a million small frees on one thread
+  // would cost tens of milliseconds per batch), capacity is reused from the previous batch
+  results.resize(nreads);
+  if (text) text->resize(nreads);
   if (nreads == 0) return;
   double d0 = 0, t0 = 0;
   for (auto &ln : lanes) { d0 += ln.secDevice; t0 += ln.secTail; }

@@ -39,7 +39,7 @@ struct mm_ctx {
   /* batch */
   uint8_t *d_bases = nullptr; uint64_t bases_cap = 0; uint64_t n_bases = 0;
   mm_segment *d_segs = nullptr; uint64_t segs_cap = 0; uint64_t n_segs = 0;
-  uint64_t *d_sk_hash = nullptr; int2 *d_sk_pos = nullptr; int8_t *d_sk_strand = nullptr; uint64_t sk_cap = 0;
+  uint64_t *d_sk_hash = nullptr; uint64_t *d_sk_val = nullptr; int2 *d_sk_pos = nullptr; int8_t *d_sk_strand = nullptr; uint64_t sk_cap = 0;
   mm_segment_result *d_seg_res = nullptr;
   mm_l1_candidate *d_cands = nullptr; uint64_t cand_cap = 0;
   mm_l2_locus *d_loci = nullptr; uint64_t loci_cap = 0;
@@ -170,12 +170,14 @@ int upload_batch(mm_ctx *c, const char *bases, uint64_t n_bases, const mm_segmen
   const uint64_t S = (uint64_t)c->params.sketch_size;
   if (n_segs * S + 1 > c->sk_cap || !c->d_sk_hash) {
     if (c->d_sk_hash) cudaFree(c->d_sk_hash);
+    if (c->d_sk_val) cudaFree(c->d_sk_val);
     if (c->d_sk_pos) cudaFree(c->d_sk_pos);
     if (c->d_sk_strand) cudaFree(c->d_sk_strand);
     if (c->d_seg_res) cudaFree(c->d_seg_res);
-    c->d_sk_hash = nullptr; c->d_sk_pos = nullptr; c->d_sk_strand = nullptr; c->d_seg_res = nullptr; c->sk_cap = 0;
+    c->d_sk_hash = nullptr; c->d_sk_val = nullptr; c->d_sk_pos = nullptr; c->d_sk_strand = nullptr; c->d_seg_res = nullptr; c->sk_cap = 0;
     const uint64_t n = n_segs * S + 1;
     CU(c, cudaMalloc((void **)&c->d_sk_hash, n * 8));
+    CU(c, cudaMalloc((void **)&c->d_sk_val, n * 8));
     CU(c, cudaMalloc((void **)&c->d_sk_pos, n * 8));
     CU(c, cudaMalloc((void **)&c->d_sk_strand, n));
     CU(c, cudaMalloc((void **)&c->d_seg_res, (n_segs + 1) * sizeof(mm_segment_result)));
@@ -209,7 +211,7 @@ mm_dev_batch make_batch(mm_ctx *c)
 {
   mm_dev_batch b{};
   b.bases = c->d_bases; b.segs = c->d_segs; b.n_segs = (uint32_t)c->n_segs;
-  b.sk_hash = c->d_sk_hash; b.sk_pos = c->d_sk_pos; b.sk_strand = c->d_sk_strand;
+  b.sk_hash = c->d_sk_hash; b.sk_val = c->d_sk_val; b.sk_pos = c->d_sk_pos; b.sk_strand = c->d_sk_strand;
   b.seg_res = c->d_seg_res;
   b.cands = c->d_cands; b.cand_cap = (uint32_t)std::min<uint64_t>(c->cand_cap, 0xffffffffu);
   b.loci = c->d_loci; b.loci_cap = (uint32_t)std::min<uint64_t>(c->loci_cap, 0xffffffffu);
@@ -494,7 +496,7 @@ int mm_ctx_destroy(mm_ctx *c)
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   if (c->blob && c->blob_owned) cudaFree(c->blob);
-  cudaFree(c->d_bases); cudaFree(c->d_segs); cudaFree(c->d_sk_hash); cudaFree(c->d_sk_pos); cudaFree(c->d_sk_strand);
+  cudaFree(c->d_bases); cudaFree(c->d_segs); cudaFree(c->d_sk_hash); cudaFree(c->d_sk_val); cudaFree(c->d_sk_pos); cudaFree(c->d_sk_strand);
   cudaFree(c->d_seg_res); cudaFree(c->d_cands); cudaFree(c->d_loci); cudaFree(c->d_counters); cudaFree(c->d_scratch);
   cudaFree(c->d_l1_slow); cudaFree(c->d_l2_ranges); cudaFree(c->d_l2_rec_off); cudaFree(c->d_l2_recs); cudaFree(c->d_scan_tmp);
   for (auto &ev : c->ev) cudaEventDestroy(ev);

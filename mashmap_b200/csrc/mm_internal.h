@@ -76,6 +76,7 @@ struct mm_dev_batch {
   uint32_t n_segs;
   /* query sketches, slot seg*S + j (ascending hash); compacted in place by the L1 kernel      */
   uint64_t *sk_hash;
+  uint64_t *sk_val;   /* lookup-table value of every sketch hash (written by k_l1_probe): 0 = absent */
   int2 *sk_pos;               /* (first position, last position)                                */
   int8_t *sk_strand;
   mm_segment_result *seg_res;

@@ -30,6 +30,8 @@
  * windowLen (computeMap.hpp:933) is 0 for every fragment of a split read and for reads no longer than
  * segLength, which is all the C ABI accepts.
  */
+#include <algorithm>
+
 #include "mm_internal.h"
 
 namespace {
@@ -310,11 +312,24 @@ __device__ __forceinline__ uint64_t l1_probe(const mm_dev_index &ix, uint64_t h)
   }
 }
 
-/* One segment, processed by a group of NT threads. `vals` (NT == 32 only) is a per-warp array of S probe results.
+/* K2a: one thread per sketch entry -- the random table probes of the whole batch with full memory-level parallelism
+ * (the per-segment kernels below are latency-bound when they probe themselves: 7 dependent DRAM round trips per lane). */
+__global__ void __launch_bounds__(256) k_l1_probe(const mm_dev_index ix, const mm_dev_batch b, int S)
+{
+  const uint64_t total = (uint64_t)b.n_segs * (uint64_t)S;
+  for (uint64_t e = (uint64_t)blockIdx.x * 256ULL + threadIdx.x; e < total; e += (uint64_t)gridDim.x * 256ULL) {
+    const uint32_t seg = (uint32_t)(e / (uint32_t)S);
+    const int j = (int)(e - (uint64_t)seg * (uint32_t)S);
+    if (j >= b.seg_res[seg].sketch_raw_count) continue;
+    b.sk_val[e] = l1_probe(ix, b.sk_hash[e]);
+  }
+}
+
+/* One segment, processed by a group of NT threads (the table values of its hashes are in b.sk_val).
  * Returns false (NT == 32 only) if the segment has more points than the warp path holds: nothing was modified. */
 template <int NT, int LOCAL, int SMEM_POINTS>
 __device__ bool l1_segment(const mm_params &prm, const mm_dev_index &ix, const mm_dev_batch &b, uint32_t seg, l1_hit *hits,
-                           uint64_t *vals, uint64_t *skeys, uint32_t *scopn, uint32_t *shead, uint32_t *sginfo,
+                           uint64_t *skeys, uint32_t *scopn, uint32_t *shead, uint32_t *sginfo,
                            l1_shared<NT, LOCAL> &sh, uint32_t scratch_slot)
 {
   const int S = prm.sketch_size;
@@ -324,15 +339,12 @@ __device__ bool l1_segment(const mm_params &prm, const mm_dev_index &ix, const m
   const int raw = b.seg_res[seg].sketch_raw_count;
   if (tid == 0) { sh.fail = 0; sh.cand_base = 0; sh.out_n = 0; }
 
-  if (NT == 32) { /* pass A: probe only, so that an oversized segment can be handed over untouched */
+  if (NT == 32) { /* pass A: count the points, so that an oversized segment can be handed over untouched */
     uint32_t m_probe = 0;
     for (int c0 = 0; c0 < raw; c0 += 32) {
       const int j = c0 + tid;
       uint64_t val = 0;
-      if (j < raw) {
-        val = l1_probe(ix, b.sk_hash[sbase + j]);
-        vals[j] = val;
-      }
+      if (j < raw) val = b.sk_val[sbase + j];
       m_probe += (val != 0 && !(val & 1ULL)) ? (uint32_t)((val >> 1) & MM_VAL_CNT_MASK) : 0u;
     }
 #pragma unroll
@@ -356,7 +368,7 @@ __device__ bool l1_segment(const mm_params &prm, const mm_dev_index &ix, const m
       h = b.sk_hash[sbase + j];
       ps = b.sk_pos[sbase + j];
       st = b.sk_strand[sbase + j];
-      val = (NT == 32) ? vals[j] : l1_probe(ix, h);
+      val = b.sk_val[sbase + j];
       keep = !(val & 1ULL); /* !isFreqSeed (winSketch.hpp:506-509) */
     }
     const bool hit = keep && val != 0;
@@ -409,19 +421,46 @@ __device__ bool l1_segment(const mm_params &prm, const mm_dev_index &ix, const m
   if (!fail && m > 0) {
     for (uint32_t i = m + tid; i < n_pow2; i += NT) keys[i] = ~0ULL;
     uint32_t dropped_local = 0;
-    for (uint32_t hi = tid; hi < hit_total; hi += NT) {
-      const l1_hit hh = hits[hi];
-      for (uint32_t q = 0; q < hh.cnt; q++) {
-        uint64_t p = ix.pts[hh.off + q];
-        if (prm.skip_self | prm.skip_prefix | prm.lower_triangular) {
-          const int rs = mm_point_seq(p);
-          /* computeMap.hpp:891-893 */
-          const bool ok = (!prm.skip_self || sg.name_id < 0 || sg.name_id != ix.contig_name_id[rs]) &&
-                          (!prm.skip_prefix || ix.contig_group[rs] != sg.ref_group) &&
-                          (!prm.lower_triangular || sg.seq_counter > rs);
-          if (!ok) { p = ~0ULL; dropped_local++; }
+    const bool preds = prm.skip_self | prm.skip_prefix | prm.lower_triangular;
+    auto admit = [&](uint64_t p) -> uint64_t { /* computeMap.hpp:891-893 */
+      if (!preds) return p;
+      const int rs = mm_point_seq(p);
+      const bool ok = (!prm.skip_self || sg.name_id < 0 || sg.name_id != ix.contig_name_id[rs]) &&
+                      (!prm.skip_prefix || ix.contig_group[rs] != sg.ref_group) &&
+                      (!prm.lower_triangular || sg.seq_counter > rs);
+      if (!ok) { dropped_local++; return ~0ULL; }
+      return p;
+    };
+    if (keys == skeys) {
+      /* point-parallel gather: owner[p] = hit that point p belongs to (head[] is free until the scans), then every
+       * thread fetches 4 independent points per round -- the loads of a round are all in flight together */
+      uint32_t *owner = head;
+      for (uint32_t hi = tid; hi < hit_total; hi += NT) {
+        const l1_hit hh = hits[hi];
+        for (uint32_t q = 0; q < hh.cnt; q++) owner[hh.dst + q] = hi;
+      }
+      grp<NT>::sync();
+      for (uint32_t p0 = tid; p0 < m; p0 += 4 * NT) {
+        uint64_t v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const uint32_t p = p0 + u * NT;
+          v[u] = ~0ULL;
+          if (p < m) {
+            const l1_hit hh = hits[owner[p]];
+            v[u] = ix.pts[hh.off + (p - hh.dst)];
+          }
         }
-        keys[hh.dst + q] = p;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const uint32_t p = p0 + u * NT;
+          if (p < m) keys[p] = admit(v[u]);
+        }
+      }
+    } else {
+      for (uint32_t hi = tid; hi < hit_total; hi += NT) {
+        const l1_hit hh = hits[hi];
+        for (uint32_t q = 0; q < hh.cnt; q++) keys[hh.dst + q] = admit(ix.pts[hh.off + q]);
       }
     }
     uint32_t dropped;
@@ -509,7 +548,6 @@ __device__ bool l1_segment(const mm_params &prm, const mm_dev_index &ix, const m
 __host__ __device__ inline size_t l1_warp_smem(int S)
 {
   size_t o = (((size_t)S * sizeof(l1_hit) + 15) & ~(size_t)15);
-  o += (size_t)S * 8;                            /* probe results */
   o += (size_t)L1_WARP_POINTS * (8 + 4 + 4 + 4); /* keys, copn, head, ginfo */
   o += (sizeof(l1_shared<32, L1_LOCAL_CANDS_WARP>) + 15) & ~(size_t)15;
   return (o + 15) & ~(size_t)15;
@@ -524,7 +562,6 @@ k_l1_warp(const mm_params prm, const mm_dev_index ix, const mm_dev_batch b, uint
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned char *base = smem_raw + l1_warp_smem(S) * wid;
   l1_hit *hits = (l1_hit *)base; base += (((size_t)S * sizeof(l1_hit) + 15) & ~(size_t)15);
-  uint64_t *vals = (uint64_t *)base; base += (size_t)S * 8;
   uint64_t *keys = (uint64_t *)base; base += (size_t)L1_WARP_POINTS * 8;
   uint32_t *copn = (uint32_t *)base; base += (size_t)L1_WARP_POINTS * 4;
   uint32_t *head = (uint32_t *)base; base += (size_t)L1_WARP_POINTS * 4;
@@ -533,7 +570,7 @@ k_l1_warp(const mm_params prm, const mm_dev_index ix, const mm_dev_batch b, uint
 
   for (uint32_t seg = blockIdx.x * L1_WARPS_PER_CTA + wid; seg < b.n_segs; seg += gridDim.x * L1_WARPS_PER_CTA) {
     __syncwarp();
-    const bool done = l1_segment<32, L1_LOCAL_CANDS_WARP, L1_WARP_POINTS>(prm, ix, b, seg, hits, vals, keys, copn, head, ginfo, sh, 0);
+    const bool done = l1_segment<32, L1_LOCAL_CANDS_WARP, L1_WARP_POINTS>(prm, ix, b, seg, hits, keys, copn, head, ginfo, sh, 0);
     if (!done && lane == 0) slow_list[atomicAdd(b.counters + 8, 1u)] = seg;
   }
 }
@@ -553,7 +590,7 @@ k_l1_cta(const mm_params prm, const mm_dev_index ix, const mm_dev_batch b, const
   const uint32_t n_work = slow_list ? b.counters[8] : b.n_segs;
   for (uint32_t w = blockIdx.x; w < n_work; w += gridDim.x) {
     const uint32_t seg = slow_list ? slow_list[w] : w;
-    l1_segment<128, L1_LOCAL_CANDS_CTA, L1_CTA_POINTS>(prm, ix, b, seg, hits, nullptr, skeys, scopn, shead, sginfo, sh, blockIdx.x);
+    l1_segment<128, L1_LOCAL_CANDS_CTA, L1_CTA_POINTS>(prm, ix, b, seg, hits, skeys, scopn, shead, sginfo, sh, blockIdx.x);
   }
 }
 
@@ -583,10 +620,17 @@ cudaError_t mm_launch_l1(const mm_params &p, const mm_dev_index &ix, const mm_de
   if (b.n_segs == 0) return cudaSuccess;
   uint32_t grid = mm_l1_grid_size(p, sm_count);
   if (grid == 0) return cudaErrorInvalidValue;
+  {
+    const uint64_t total = (uint64_t)b.n_segs * (uint64_t)p.sketch_size;
+    const uint64_t blocks = (total + 255) / 256;
+    k_l1_probe<<<(uint32_t)std::min<uint64_t>(blocks, 1u << 30), 256, 0, st>>>(ix, b, p.sketch_size);
+    cudaError_t e0 = cudaGetLastError();
+    if (e0 != cudaSuccess) return e0;
+  }
   const size_t wsmem = l1_warp_smem(p.sketch_size) * L1_WARPS_PER_CTA;
   if (!use_warp_path || !slow_list || wsmem > 227 * 1024) {
     k_l1_cta<<<min(grid, b.n_segs), 128, l1_cta_smem(p), st>>>(p, ix, b, nullptr);
-    if (n_launched) *n_launched = 1;
+    if (n_launched) *n_launched = 2;
     return cudaGetLastError();
   }
   cudaError_t e = cudaFuncSetAttribute(k_l1_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem);
@@ -601,6 +645,6 @@ cudaError_t mm_launch_l1(const mm_params &p, const mm_dev_index &ix, const mm_de
   if (e != cudaSuccess) return e;
   /* the general path reads its work count from counters[8] on the device: no host round trip in between */
   k_l1_cta<<<grid, 128, l1_cta_smem(p), st>>>(p, ix, b, slow_list);
-  if (n_launched) *n_launched = 2;
+  if (n_launched) *n_launched = 3;
   return cudaGetLastError();
 }
