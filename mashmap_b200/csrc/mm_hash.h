@@ -27,13 +27,78 @@
 
 MM_HD uint64_t mm_rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
 
+/* Building blocks of the hash. On the device they are spelled in 32-bit halves: a 64x64->64 multiply by a constant is
+ * one mul.wide + two mad.lo (nvcc's own expansion of `x * c` spends two extra adds per multiply), a rotate is two
+ * funnel shifts, `h*5 + c` is one mad.wide + one mad.lo. The per-base loop of the sketch kernel is issue-bound, so the
+ * instruction count is the throughput. Same results as the plain C expressions (tests/test_host_cpu.py checks the
+ * host spelling against the reference's getHash, the GPU sketch tests check the device spelling). */
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ uint64_t mm_pack64(uint32_t lo, uint32_t hi)
+{
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void mm_unpack64(uint64_t x, uint32_t &lo, uint32_t &hi)
+{
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(x));
+}
+/* x * C mod 2^64; NBYTES = number of low bytes of x that can be non-zero */
+template <uint64_t C, int NBYTES>
+__device__ __forceinline__ uint64_t mm_mulc(uint64_t x)
+{
+  uint32_t xl, xh, pl, ph;
+  uint64_t p;
+  mm_unpack64(x, xl, xh);
+  asm("mul.wide.u32 %0, %1, %2;" : "=l"(p) : "r"(xl), "n"((uint32_t)(C & 0xFFFFFFFFULL)));
+  mm_unpack64(p, pl, ph);
+  asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(ph) : "r"(xl), "n"((uint32_t)(C >> 32)));
+  if (NBYTES > 4) asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(ph) : "r"(xh), "n"((uint32_t)(C & 0xFFFFFFFFULL)));
+  return mm_pack64(pl, ph);
+}
+template <int R>
+__device__ __forceinline__ uint64_t mm_rotl(uint64_t x)
+{
+  uint32_t lo, hi;
+  mm_unpack64(x, lo, hi);
+  if (R < 32) return mm_pack64(__funnelshift_l(hi, lo, R), __funnelshift_l(lo, hi, R));
+  return mm_pack64(__funnelshift_l(lo, hi, R - 32), __funnelshift_l(hi, lo, R - 32));
+}
+/* x * 5 + A (A < 2^32) */
+template <uint32_t A>
+__device__ __forceinline__ uint64_t mm_mul5_add(uint64_t x)
+{
+  uint32_t xl, xh, pl, ph;
+  uint64_t p;
+  mm_unpack64(x, xl, xh);
+  asm("mad.wide.u32 %0, %1, 5, %2;" : "=l"(p) : "r"(xl), "l"((uint64_t)A));
+  mm_unpack64(p, pl, ph);
+  asm("mad.lo.u32 %0, %1, 5, %0;" : "+r"(ph) : "r"(xh));
+  return mm_pack64(pl, ph);
+}
+__device__ __forceinline__ uint64_t mm_xorshr33(uint64_t k)
+{ /* k ^ (k >> 33): only the low half changes */
+  uint32_t lo, hi;
+  mm_unpack64(k, lo, hi);
+  return mm_pack64(lo ^ (hi >> 1), hi);
+}
+#else
+template <uint64_t C, int NBYTES>
+MM_HD uint64_t mm_mulc(uint64_t x) { return x * C; }
+template <int R>
+MM_HD uint64_t mm_rotl(uint64_t x) { return mm_rotl64(x, R); }
+template <uint32_t A>
+MM_HD uint64_t mm_mul5_add(uint64_t x) { return x * 5 + A; }
+MM_HD uint64_t mm_xorshr33(uint64_t k) { return k ^ (k >> 33); }
+#endif
+
 MM_HD uint64_t mm_fmix64(uint64_t k)
 { /* murmur3.h fmix64 */
-  k ^= k >> 33;
-  k *= 0xff51afd7ed558ccdULL;
-  k ^= k >> 33;
-  k *= 0xc4ceb9fe1a85ec53ULL;
-  k ^= k >> 33;
+  k = mm_xorshr33(k);
+  k = mm_mulc<0xff51afd7ed558ccdULL, 8>(k);
+  k = mm_xorshr33(k);
+  k = mm_mulc<0xc4ceb9fe1a85ec53ULL, 8>(k);
+  k = mm_xorshr33(k);
   return k;
 }
 
@@ -52,24 +117,24 @@ MM_HD uint64_t mm_murmur3_k(const uint64_t *w)
 {
   constexpr int NB = K / 16;
   constexpr int TL = K & 15;
-  const uint64_t c1 = 0x87c37b91114253d5ULL;
-  const uint64_t c2 = 0x4cf5ad432745937fULL;
+  constexpr uint64_t c1 = 0x87c37b91114253d5ULL;
+  constexpr uint64_t c2 = 0x4cf5ad432745937fULL;
   uint64_t h1 = MM_SEED, h2 = MM_SEED;
 #pragma unroll
   for (int b = 0; b < NB; b++) {
     uint64_t k1 = w[2 * b], k2 = w[2 * b + 1];
-    k1 *= c1; k1 = mm_rotl64(k1, 31); k1 *= c2; h1 ^= k1;
-    h1 = mm_rotl64(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729;
-    k2 *= c2; k2 = mm_rotl64(k2, 33); k2 *= c1; h2 ^= k2;
-    h2 = mm_rotl64(h2, 31); h2 += h1; h2 = h2 * 5 + 0x38495ab5;
+    k1 = mm_mulc<c1, 8>(k1); k1 = mm_rotl<31>(k1); k1 = mm_mulc<c2, 8>(k1); h1 ^= k1;
+    h1 = mm_rotl<27>(h1); h1 += h2; h1 = mm_mul5_add<0x52dce729u>(h1);
+    k2 = mm_mulc<c2, 8>(k2); k2 = mm_rotl<33>(k2); k2 = mm_mulc<c1, 8>(k2); h2 ^= k2;
+    h2 = mm_rotl<31>(h2); h2 += h1; h2 = mm_mul5_add<0x38495ab5u>(h2);
   }
   if (TL > 8) {
     uint64_t k2 = w[2 * NB + 1];
-    k2 *= c2; k2 = mm_rotl64(k2, 33); k2 *= c1; h2 ^= k2;
+    k2 = mm_mulc<c2, (TL > 8 ? TL - 8 : 8)>(k2); k2 = mm_rotl<33>(k2); k2 = mm_mulc<c1, 8>(k2); h2 ^= k2;
   }
   if (TL > 0) {
     uint64_t k1 = w[2 * NB];
-    k1 *= c1; k1 = mm_rotl64(k1, 31); k1 *= c2; h1 ^= k1;
+    k1 = mm_mulc<c1, (TL > 8 ? 8 : (TL > 0 ? TL : 8))>(k1); k1 = mm_rotl<31>(k1); k1 = mm_mulc<c2, 8>(k1); h1 ^= k1;
   }
   h1 ^= (uint64_t)K; h2 ^= (uint64_t)K;
   h1 += h2; h2 += h1;
