@@ -54,6 +54,7 @@ struct mm_ctx {
   uint2 *d_l2_recs = nullptr; uint64_t l2_recs_cap = 0;
   void *d_scan_tmp = nullptr; size_t scan_tmp_bytes = 0;
   uint32_t *d_l1_slow = nullptr; uint64_t l1_slow_cap = 0;
+  void *d_l2_order = nullptr; size_t l2_order_bytes = 0; /* work area of the candidate ordering (mm_launch_l2_order) */
   int l1_warp = 1; /* 1 = warp-per-segment fast path + CTA path for big segments; 0 = CTA path only (MM_L1_CTA=1) */
   int l2_mode = 1; /* 1 = stream kernels (mm_l2_stream.cu), 0 = general kernel only (MM_L2_GENERAL=1) */
   bool batch_mapped = false;
@@ -285,6 +286,10 @@ int run_l2_stream(mm_ctx *c, uint32_t *h_cnt)
     CU(c, cudaMalloc((void **)&c->d_l2_rec_off, (c->l2_cand_cap + 1) * 8));
     c->scan_tmp_bytes = mm_l2_scan_tmp_bytes((uint32_t)c->l2_cand_cap);
     CU(c, cudaMalloc(&c->d_scan_tmp, c->scan_tmp_bytes + 256));
+    if (c->d_l2_order) cudaFree(c->d_l2_order);
+    c->d_l2_order = nullptr;
+    c->l2_order_bytes = mm_l2_order_bytes((uint32_t)c->l2_cand_cap);
+    CU(c, cudaMalloc(&c->d_l2_order, c->l2_order_bytes));
   }
   if (c->loci_cap < nc * LPC + 1024) {
     if (c->d_loci) cudaFree(c->d_loci);
@@ -317,8 +322,13 @@ int run_l2_stream(mm_ctx *c, uint32_t *h_cnt)
     CU(c, cudaEventRecord(c->ev[8], c->stream));
     CU(c, mm_launch_l2_prep(c->params, c->ix, b, (uint32_t)nc, c->stream, c->sm_count));
     CU(c, cudaEventRecord(c->ev[9], c->stream));
+    {
+      uint32_t *perm = nullptr;
+      CU(c, mm_launch_l2_order(b, (uint32_t)nc, c->d_l2_order, c->l2_order_bytes, &perm, c->stream));
+      b.l2_perm = perm;
+    }
     CU(c, mm_launch_l2_scan(c->params, c->ix, b, (uint32_t)nc, c->stream, c->sm_count));
-    c->launches += 4; /* ranges, scan (library), prep, scan */
+    c->launches += 6; /* ranges, prefix sum (library), prep, order keys, sort (library), scan */
     RD(c, c->d_counters, h_cnt, 16);
     uint64_t extent = nc * LPC;
     if (h_cnt[7] > 0) { /* candidates with more than LPC loci: general kernel, loci appended after the fixed slots */
@@ -498,7 +508,7 @@ int mm_ctx_destroy(mm_ctx *c)
   if (c->blob && c->blob_owned) cudaFree(c->blob);
   cudaFree(c->d_bases); cudaFree(c->d_segs); cudaFree(c->d_sk_hash); cudaFree(c->d_sk_val); cudaFree(c->d_sk_pos); cudaFree(c->d_sk_strand);
   cudaFree(c->d_seg_res); cudaFree(c->d_cands); cudaFree(c->d_loci); cudaFree(c->d_counters); cudaFree(c->d_scratch);
-  cudaFree(c->d_l1_slow); cudaFree(c->d_l2_ranges); cudaFree(c->d_l2_rec_off); cudaFree(c->d_l2_recs); cudaFree(c->d_scan_tmp);
+  cudaFree(c->d_l1_slow); cudaFree(c->d_l2_order); cudaFree(c->d_l2_ranges); cudaFree(c->d_l2_rec_off); cudaFree(c->d_l2_recs); cudaFree(c->d_scan_tmp);
   for (auto &ev : c->ev) cudaEventDestroy(ev);
   if (c->h_pub) cudaFreeHost(c->h_pub);
   cudaStreamDestroy(c->stream);

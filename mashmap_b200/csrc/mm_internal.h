@@ -98,6 +98,7 @@ struct mm_dev_batch {
   uint64_t *l2_rec_off;          /* per candidate (+1): first op record (exclusive prefix of the counts)   */
   uint2 *l2_recs;                /* op records {pos, info}                                                 */
   uint64_t l2_recs_cap;
+  const uint32_t *l2_perm;       /* order in which k_l2_scan takes the candidates (nullptr = identity)        */
   uint32_t l2_loci_per_cand;     /* fixed locus slots per candidate in `loci`; overflow -> general kernel  */
 };
 
@@ -130,6 +131,8 @@ cudaError_t mm_launch_l2(const mm_params &p, const mm_dev_index &ix, const mm_de
 cudaError_t mm_launch_l2_ranges(const mm_params &p, const mm_dev_index &ix, const mm_dev_batch &b, uint32_t n_cands,
                                 void *scan_tmp, size_t scan_tmp_bytes, cudaStream_t st);
 size_t mm_l2_scan_tmp_bytes(uint32_t n_cands);
+size_t mm_l2_order_bytes(uint32_t n_cands);
+cudaError_t mm_launch_l2_order(const mm_dev_batch &b, uint32_t n_cands, void *work, size_t work_bytes, uint32_t **perm, cudaStream_t st);
 cudaError_t mm_launch_l2_prep(const mm_params &p, const mm_dev_index &ix, const mm_dev_batch &b, uint32_t n_cands,
                               cudaStream_t st, int sm_count);
 cudaError_t mm_launch_l2_scan(const mm_params &p, const mm_dev_index &ix, const mm_dev_batch &b, uint32_t n_cands,

@@ -167,6 +167,53 @@ k_l2_prep(const mm_params prm, const mm_dev_index ix, const mm_dev_batch b, uint
   }
 }
 
+/* order of the scan: candidates sorted by their (post-compaction) operation count, longest first, so that the 32 lanes
+ * of a warp run scans of similar length */
+__global__ void k_l2_order_keys(const mm_dev_batch b, uint32_t n_cands, uint32_t *keys, uint32_t *vals)
+{
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_cands) return;
+  const mm_l2_range r = b.l2_ranges[c];
+  keys[c] = min(r.nI + r.nD, 0xFFFFu);
+  vals[c] = c;
+}
+
+/* One lane's sequential reader of 8-byte op records: the current 4 records and the next 4 live in registers (32-byte
+ * aligned chunks, two 16-byte loads each), the line after those is prefetched into L2. The scan consumes a record every
+ * few hundred cycles per lane and L1 is almost entirely given to shared memory, so a plain `rec = p[i]` per step would
+ * expose the full DRAM/L2 latency on every step. Reads run up to 8 records past the stream's end (the buffer has slack). */
+struct rec_stream {
+  const uint4 *next; /* chunk after `n0,n1` */
+  uint4 c0, c1, n0, n1;
+  uint32_t k;        /* record inside the current chunk, 0..3 */
+  __device__ __forceinline__ void open(const uint2 *base, uint64_t first)
+  {
+    const uint4 *p = (const uint4 *)(base + (first & ~3ULL));
+    k = (uint32_t)(first & 3ULL);
+    c0 = p[0]; c1 = p[1]; n0 = p[2]; n1 = p[3];
+    next = p + 4;
+  }
+  __device__ __forceinline__ uint2 at(uint32_t kk) const /* kk in 0..4: record kk of the current chunk / first of the next */
+  {
+    uint2 r;
+    r.x = kk == 0 ? c0.x : kk == 1 ? c0.z : kk == 2 ? c1.x : kk == 3 ? c1.z : n0.x;
+    r.y = kk == 0 ? c0.y : kk == 1 ? c0.w : kk == 2 ? c1.y : kk == 3 ? c1.w : n0.y;
+    return r;
+  }
+  __device__ __forceinline__ uint2 cur() const { return at(k); }
+  __device__ __forceinline__ uint32_t peek_x() const { return at(k + 1).x; }
+  __device__ __forceinline__ void advance()
+  {
+    if (++k == 4) {
+      k = 0;
+      c0 = n0; c1 = n1;
+      n0 = next[0]; n1 = next[1];
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(next + 8));
+      next += 2;
+    }
+  }
+};
+
 struct lane_locus {
   int start, end, mean, shared, strand;
 };
@@ -183,20 +230,17 @@ k_l2_scan(const mm_params prm, const mm_dev_index ix, const mm_dev_batch b, uint
   const int segL = prm.seg_length;
 
   for (uint32_t cbase = (blockIdx.x * L2C_WARPS + wid) * 32; cbase < n_cands; cbase += gridDim.x * L2C_WARPS * 32) {
-    const uint32_t c = cbase + lane;
-    const bool valid = c < n_cands;
+    const bool valid = cbase + lane < n_cands;
+    const uint32_t c = valid ? (b.l2_perm ? b.l2_perm[cbase + lane] : cbase + lane) : 0u;
     mm_l1_candidate cd;
     mm_l2_range r;
     r.nI = 0; r.nD = 0; r.it0 = 0; r.d0 = 0; r.next_wpos = 0;
     cd.seqId = 0; cd.rangeStartPos = 0; cd.rangeEndPos = 0; cd.segment = 0;
     int n = 0;
-    const uint2 *ins = nullptr, *del = nullptr;
     if (valid) {
       cd = b.cands[c];
       r = b.l2_ranges[c];
       n = b.seg_res[cd.segment].sketch_size;
-      ins = b.l2_recs + b.l2_rec_off[c];
-      del = ins + r.nI;
     }
     /* SlideMapper::init (slidingMap.hpp:104-121): every query slot counts itself once */
     int nmax = n;
@@ -231,11 +275,12 @@ k_l2_scan(const mm_params prm, const mm_dev_index ix, const mm_dev_batch b, uint
     };
 
     uint32_t i = 0, d = 0;
-    uint2 irec = make_uint2(0, 0), drec = make_uint2(0xFFFFFFFFu, 0);
-    if (r.nI > 0) irec = ins[0];
-    if (r.nD > 0) drec = del[0];
+    rec_stream is, ds;
+    is.open(b.l2_recs, valid ? b.l2_rec_off[c] : 0ULL);
+    ds.open(b.l2_recs, valid ? b.l2_rec_off[c] + r.nI : 0ULL);
     while (__any_sync(FULL, i < r.nI)) {
       if (i < r.nI) {
+        const uint2 irec = is.cur(), drec = ds.cur();
         const int ipos = (int)irec.x;
         const bool is_main = ipos >= cd.rangeStartPos;
         const bool do_del = is_main && d < r.nD && (int)drec.x <= ipos; /* evict while wpos_end <= wpos (:1344) */
@@ -244,50 +289,37 @@ k_l2_scan(const mm_params prm, const mm_dev_index ix, const mm_dev_batch b, uint
         const bool match = (info & MM_L2_MATCH) != 0;
         const int prev_votes = votes; /* computeMap.hpp:1342 (only read after an insert) */
         if (slot <= n) {
-          uint32_t w = words[slot * 32 + lane];
-          if (do_del) { /* delete_minmer (slidingMap.hpp:171-211) */
-            if (match) {
-              if (slot <= pivot) { shared--; votes -= w_sv(w); }
-              w = w_set_sv(w & ~W_ACT, 0);
-            } else {
-              w -= 1u;
-              if (slot <= pivot) pivRank--;
-              if (pivot < n) {
-                const uint32_t nx = (slot == pivot + 1) ? w : words[(pivot + 1) * 32 + lane];
-                if (pivRank + (int)(nx & W_NBI_MASK) <= n) {
-                  pivot++;
-                  shared += (nx & W_ACT) ? 1 : 0;
-                  votes += w_sv(nx);
-                  pivRank += (int)(nx & W_NBI_MASK);
-                }
-              }
-            }
-          } else { /* insert_minmer (slidingMap.hpp:125-165) */
-            if (match) {
-              int vote = (int)((info >> 17) & 3u);
-              vote = vote == 3 ? -1 : vote;
-              const int sv2 = w_sv(w) + vote;
-              w = w_set_sv(w | W_ACT, sv2);
-              if (slot <= pivot) { shared++; votes += sv2; }
-            } else {
-              w += 1u;
-              if (slot <= pivot) pivRank++;
-              if (pivRank > n) {
-                const uint32_t pw = (slot == pivot) ? w : words[pivot * 32 + lane];
-                shared -= (pw & W_ACT) ? 1 : 0;
-                votes -= w_sv(pw);
-                pivRank -= (int)(pw & W_NBI_MASK);
-                pivot--;
-              }
-            }
-          }
-          words[slot * 32 + lane] = (uint16_t)w;
+          /* insert_minmer / delete_minmer (slidingMap.hpp:125-165, :171-211) as one straight-line update: the four
+           * cases (insert/delete x hash in the query sketch or not) are selected with predicates, so the 32 candidates of
+           * the warp do not diverge. q is the slot whose membership in the pivot prefix may change: the pivot itself on
+           * an insert (it is popped when the rank overflows), the slot after it on a delete (it is pulled in when it
+           * fits). words[n+1] holds an unreachable count, which stands for the reference's `pivot != end` test. */
+          const uint32_t w = words[slot * 32 + lane];
+          const bool le = slot <= pivot;
+          const int sgn = do_del ? -1 : 1;
+          const int svw = w_sv(w);
+          int vote = (int)((info >> 17) & 3u);
+          vote = vote == 3 ? -1 : vote;
+          const int sv2 = do_del ? 0 : svw + vote;
+          const uint32_t w_match = w_set_sv(do_del ? (w & ~W_ACT) : (w | W_ACT), sv2);
+          const uint32_t w_plain = w + (uint32_t)sgn;
+          const int pr = pivRank + (le ? sgn : 0);
+          const int q = pivot + (do_del ? 1 : 0);
+          uint32_t x = words[q * 32 + lane];
+          if (q == slot) x = w_plain;
+          const int xn = (int)(x & W_NBI_MASK), xa = (x & W_ACT) ? 1 : 0, xs = w_sv(x);
+          const int mv = match ? 0 : (do_del ? ((pr + xn <= n) ? 1 : 0) : ((pr > n) ? -1 : 0));
+          shared += match ? (le ? sgn : 0) : mv * xa;
+          votes += match ? (le ? (do_del ? -svw : sv2) : 0) : mv * xs;
+          pivRank = match ? pivRank : pr + mv * xn;
+          pivot += mv;
+          words[slot * 32 + lane] = (uint16_t)(match ? w_match : w_plain);
         }
         if (do_del) {
           d++;
-          if (d < r.nD) drec = del[d];
+          ds.advance();
         } else {
-          const int npos = (i + 1 < r.nI) ? (int)ins[i + 1].x : r.next_wpos;
+          const int npos = (i + 1 < r.nI) ? (int)is.peek_x() : r.next_wpos;
           if (is_main) { /* region tracking (computeMap.hpp:1373-1430) */
             if (shared > best) {
               n_loci = 0; has_back = false; /* l2_vec_out.clear() */
@@ -310,7 +342,7 @@ k_l2_scan(const mm_params prm, const mm_dev_index ix, const mm_dev_batch b, uint
             }
           }
           i++;
-          if (i < r.nI) irec = ins[i];
+          is.advance();
         }
       }
     }
@@ -475,6 +507,28 @@ cudaError_t mm_launch_l2_ranges(const mm_params &p, const mm_dev_index &ix, cons
   if (e != cudaSuccess) return e;
   /* exclusive scan over n_cands+1 elements: the last one (written 0 by the caller) becomes the total */
   return cub::DeviceScan::ExclusiveSum(scan_tmp, scan_tmp_bytes, b.l2_rec_off, b.l2_rec_off, (int)n_cands + 1, st);
+}
+
+/* temp bytes needed by mm_launch_l2_order for n candidates (4 u32 arrays + the library's sort storage) */
+size_t mm_l2_order_bytes(uint32_t n_cands)
+{
+  size_t tmp = 0;
+  cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr,
+                                            (uint32_t *)nullptr, (int)n_cands, 0, 16);
+  return (size_t)n_cands * 16 + 1024 + tmp;
+}
+
+/* work: mm_l2_order_bytes(n_cands) bytes; returns the permutation (device pointer inside work) in *perm */
+cudaError_t mm_launch_l2_order(const mm_dev_batch &b, uint32_t n_cands, void *work, size_t work_bytes, uint32_t **perm, cudaStream_t st)
+{
+  uint32_t *k0 = (uint32_t *)work, *v0 = k0 + n_cands, *k1 = v0 + n_cands, *v1 = k1 + n_cands;
+  void *tmp = (void *)(((uintptr_t)(v1 + n_cands) + 255) & ~(uintptr_t)255);
+  size_t tmp_bytes = work_bytes - (size_t)((char *)tmp - (char *)work);
+  k_l2_order_keys<<<(n_cands + 255) / 256, 256, 0, st>>>(b, n_cands, k0, v0);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  *perm = v1;
+  return cub::DeviceRadixSort::SortPairsDescending(tmp, tmp_bytes, k0, k1, v0, v1, (int)n_cands, 0, 16, st);
 }
 
 static size_t l2_prep_smem(const mm_params &p) { return (size_t)L2S_WARPS * (size_t)(p.sketch_size + 2) * 9 + 16; }
