@@ -319,15 +319,24 @@ int run_l2_stream(mm_ctx *c, uint32_t *h_cnt)
     b = make_batch(c);
     ZERO_WORDS(c, c->d_counters + 1, 1);
     ZERO_WORDS(c, c->d_counters + 6, 2);
-    CU(c, cudaEventRecord(c->ev[8], c->stream));
-    CU(c, mm_launch_l2_prep(c->params, c->ix, b, (uint32_t)nc, c->stream, c->sm_count));
-    CU(c, cudaEventRecord(c->ev[9], c->stream));
+    /* the record-preparation kernel is the bandwidth-bound one: no PCIe upload next to it (MM_PHASE_L2) */
     {
+      struct phase_guard { /* the hook is always closed, whatever fails in between */
+        mm_ctx *c; bool open;
+        explicit phase_guard(mm_ctx *cc) : c(cc), open(cc->hook != nullptr) { if (open) c->hook(c->hook_user, MM_PHASE_L2, 1); }
+        void close() { if (open) { c->hook(c->hook_user, MM_PHASE_L2, 0); open = false; } }
+        ~phase_guard() { close(); }
+      } guard(c);
+      CU(c, cudaEventRecord(c->ev[8], c->stream));
+      CU(c, mm_launch_l2_prep(c->params, c->ix, b, (uint32_t)nc, c->stream, c->sm_count));
+      CU(c, cudaEventRecord(c->ev[9], c->stream));
       uint32_t *perm = nullptr;
       CU(c, mm_launch_l2_order(b, (uint32_t)nc, c->d_l2_order, c->l2_order_bytes, &perm, c->stream));
       b.l2_perm = perm;
+      CU(c, mm_launch_l2_scan(c->params, c->ix, b, (uint32_t)nc, c->stream, c->sm_count));
+      /* the scan is already queued behind it: waiting for the end of the preparation kernel costs no bubble */
+      if (guard.open) CU(c, cudaEventSynchronize(c->ev[9]));
     }
-    CU(c, mm_launch_l2_scan(c->params, c->ix, b, (uint32_t)nc, c->stream, c->sm_count));
     c->launches += 6; /* ranges, prefix sum (library), prep, order keys, sort (library), scan */
     RD(c, c->d_counters, h_cnt, 16);
     uint64_t extent = nc * LPC;
@@ -411,9 +420,7 @@ int run_pipeline(mm_ctx *c)
     c->n_cands = need_cands;
     /* K3 */
     if (c->l2_mode == 1) {
-      if (c->hook) c->hook(c->hook_user, MM_PHASE_L2, 1);
       int rc2 = run_l2_stream(c, h_cnt);
-      if (c->hook) c->hook(c->hook_user, MM_PHASE_L2, 0);
       if (rc2 == MM_OK) {
         cudaEventElapsedTime(&c->stage_ms[0], c->ev[0], c->ev[1]);
         cudaEventElapsedTime(&c->stage_ms[1], c->ev[1], c->ev[2]);
