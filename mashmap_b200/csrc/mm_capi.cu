@@ -251,11 +251,12 @@ __global__ void k_publish(const uint32_t *__restrict__ src, volatile uint32_t *d
 __global__ void k_set_u32(uint32_t *dst, uint32_t v) { *dst = v; }
 /* cudaMemsetAsync of a few words may be executed by a copy engine too: zero them with a kernel */
 __global__ void k_zero_words(uint32_t *dst, int n) { if ((int)threadIdx.x < n) dst[threadIdx.x] = 0; }
-#define ZERO_WORDS(c, ptr, n) do { k_zero_words<<<1, 32, 0, (c)->stream>>>((uint32_t *)(ptr), (n)); CU((c), cudaGetLastError()); } while (0)
+#define ZERO_WORDS(c, ptr, n) do { k_zero_words<<<1, 32, 0, (c)->stream>>>((uint32_t *)(ptr), (n)); (c)->launches++; CU((c), cudaGetLastError()); } while (0)
 
 int read_words(mm_ctx *c, const void *dev, uint32_t *out, int n_words)
 {
   k_publish<<<1, 32, 0, c->stream>>>((const uint32_t *)dev, c->h_pub, n_words);
+  c->launches++;
   CU(c, cudaGetLastError());
   CU(c, cudaStreamSynchronize(c->stream));
   for (int i = 0; i < n_words; i++) out[i] = c->h_pub[i];
@@ -337,12 +338,13 @@ int run_l2_stream(mm_ctx *c, uint32_t *h_cnt)
       /* the scan is already queued behind it: waiting for the end of the preparation kernel costs no bubble */
       if (guard.open) CU(c, cudaEventSynchronize(c->ev[9]));
     }
-    c->launches += 6; /* ranges, prefix sum (library), prep, order keys, sort (library), scan */
+    c->launches += 4; /* own kernels: ranges, prep, order keys, scan (the prefix sum and the sort are library calls, not counted) */
     RD(c, c->d_counters, h_cnt, 16);
     uint64_t extent = nc * LPC;
     if (h_cnt[7] > 0) { /* candidates with more than LPC loci: general kernel, loci appended after the fixed slots */
       const uint32_t base = (uint32_t)extent;
       k_set_u32<<<1, 1, 0, c->stream>>>(c->d_counters + 6, base);
+      c->launches++;
       CU(c, mm_launch_l2_overflow(c->params, c->ix, b, (uint32_t)nc, c->stream, c->sm_count));
       c->launches += 1;
       RD(c, c->d_counters, h_cnt, 16);
