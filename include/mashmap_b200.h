@@ -148,7 +148,8 @@ int mm_index_blob(mm_ctx *ctx, void **blob, uint64_t *n_bytes);
 int mm_index_blob_alloc(mm_ctx *ctx, uint64_t n_bytes, void **blob);
 int mm_index_adopt_blob(mm_ctx *ctx);
 /* A second context on the SAME device that reads the index image of `src` (not copied, not owned): lets a host
- * pipeline keep two batches in flight (copies of one overlapping the kernels of the other). `src` must outlive it. */
+ * pipeline keep several batches in flight (copies of one overlapping the kernels of another). `src` must outlive it;
+ * if `src` later gets a new image (another upload, an adopted blob, new tables) this context follows it. */
 int mm_ctx_share_index(mm_ctx *ctx, const mm_ctx *src);
 
 /* ---- the hot path ------------------------------------------------------------------------------ */

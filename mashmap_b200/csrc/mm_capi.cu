@@ -44,6 +44,7 @@ struct mm_ctx {
   mm_l1_candidate *d_cands = nullptr; uint64_t cand_cap = 0;
   mm_l2_locus *d_loci = nullptr; uint64_t loci_cap = 0;
   uint32_t *d_counters = nullptr;
+  const mm_ctx *share_src = nullptr; /* mm_ctx_share_index: the context whose index image this one reads */
   mm_phase_hook hook = nullptr;
   void *hook_user = nullptr;
   uint32_t *h_pub = nullptr; /* pinned, device-mapped: kernels publish counters here (no copy engine involved) */
@@ -143,6 +144,14 @@ int write_tables(mm_ctx *c)
 int check_ready(mm_ctx *c)
 {
   if (!c) return MM_EINVAL;
+  if (c->share_src) { /* follow the owner: its image may have been replaced since (new upload / adopted blob / new tables) */
+    const mm_ctx *s = c->share_src;
+    if (c->blob != s->blob || c->blob_bytes != s->blob_bytes || c->hdr.n_cutoffs != s->hdr.n_cutoffs ||
+        c->hdr.n_min_hits != s->hdr.n_min_hits || c->blob_ready != s->blob_ready) {
+      c->blob = s->blob; c->blob_bytes = s->blob_bytes; c->hdr = s->hdr; c->blob_ready = s->blob_ready;
+      resolve_index(c);
+    }
+  }
   if (!c->blob_ready) return fail(c, MM_ESTATE, "reference index not uploaded");
   if (c->hdr.n_cutoffs <= 0 || c->hdr.n_min_hits <= 0) return fail(c, MM_ESTATE, "threshold tables not uploaded");
   return MM_OK;
@@ -582,7 +591,7 @@ int mm_index_upload(mm_ctx *c, const mm_minmer *mi, uint64_t n_mi, const uint64_
   h.off_min_hits = place(TABLE_REGION_BYTES);
   h.total_bytes = o;
   CU(c, cudaMalloc((void **)&c->blob, o));
-  c->blob_bytes = o; c->blob_owned = true; c->hdr = h;
+  c->blob_bytes = o; c->blob_owned = true; c->hdr = h; c->share_src = nullptr;
 
   /* AoS records go up in chunks and are re-laid out on the device (SoA index, packed points, hash table) */
   {
@@ -672,7 +681,7 @@ int mm_index_blob_alloc(mm_ctx *c, uint64_t n_bytes, void **blob)
   if (c->blob && c->blob_owned) cudaFree(c->blob);
   c->blob = nullptr; c->blob_ready = false;
   CU(c, cudaMalloc((void **)&c->blob, n_bytes));
-  c->blob_bytes = n_bytes; c->blob_owned = true;
+  c->blob_bytes = n_bytes; c->blob_owned = true; c->share_src = nullptr;
   *blob = c->blob;
   return MM_OK;
 }
@@ -698,6 +707,7 @@ int mm_ctx_share_index(mm_ctx *c, const mm_ctx *src)
   c->blob = src->blob; c->blob_bytes = src->blob_bytes; c->blob_owned = false;
   c->hdr = src->hdr;
   c->cutoffs = src->cutoffs; c->min_hits = src->min_hits;
+  c->share_src = src;
   resolve_index(c);
   c->blob_ready = true;
   return MM_OK;
