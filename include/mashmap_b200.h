@@ -186,7 +186,7 @@ int mm_batch_fetch_sketch(mm_ctx *ctx, mm_minmer *out_sketch, int32_t *out_count
 
 /* Scheduling hook for host pipelines that keep several contexts in flight on one device. The library calls
  * hook(user, phase, 1) before and hook(user, phase, 0) after
- *   MM_PHASE_UPLOAD_CHUNK  each <= 64 MiB piece of a batch upload (mm_batch_upload / mm_map_segments), and
+ *   MM_PHASE_UPLOAD_CHUNK  each <= 16 MiB piece of a batch upload (mm_batch_upload / mm_map_segments), and
  *   MM_PHASE_L2            the L2 record-preparation kernel of mm_map_resident / mm_map_segments (bandwidth-bound:
  *                          measured 4x slower while another context's PCIe upload is writing HBM),
  * from the calling thread. A pipeline uses it to keep the two from overlapping (skch::BatchMapper does). NULL clears. */

@@ -3,6 +3,9 @@
  * the statistics tables, the host index builder, and the host tail fed with externally produced records.
  * Not part of the drop-in boundary (that is include/mashmap_b200.h + the skch:: classes).
  */
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <sstream>
 #include <string>
@@ -141,6 +144,7 @@ void *skch_bm_create(void *index_handle, float percentageIdentity, int device, i
   ih->p.threads = threads;
   ih->p.block_length = ih->p.segLength;
   ih->p.chain_gap = ih->p.segLength;
+  if (const char *e = getenv("MM_SUB_BATCH_BASES")) ih->p.sub_batch_bases = strtoull(e, nullptr, 10); /* tuning hook */
   BmHandle *h = new BmHandle();
   h->ih = ih;
   h->bm = new BatchMapper(ih->p, *ih->sk);
@@ -185,13 +189,19 @@ int skch_bm_map(void *hv, void *bv, uint64_t *paf_bytes, uint64_t *n_mapped_read
   BmHandle *h = (BmHandle *)hv;
   BmBatch *b = (BmBatch *)bv;
   const double d0 = h->bm->secondsDevice, t0 = h->bm->secondsHostTail;
+  const auto tm0 = std::chrono::steady_clock::now();
   h->bm->mapBatch(b->batch, h->results, &h->text, nullptr);
+  const auto tm1 = std::chrono::steady_clock::now();
   uint64_t bytes = 0, mapped = 0, maps = 0;
   for (size_t r = 0; r < h->results.size(); r++) {
     bytes += h->text[r].size();
     mapped += h->results[r].empty() ? 0 : 1;
     maps += h->results[r].size();
   }
+  if (getenv("MM_TRACE"))
+    fprintf(stderr, "[trace] skch_bm_map: mapBatch %.1f ms, result summary %.1f ms\n",
+            std::chrono::duration<double, std::milli>(tm1 - tm0).count(),
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tm1).count());
   if (paf_bytes) *paf_bytes = bytes;
   if (n_mapped_reads) *n_mapped_reads = mapped;
   if (n_mappings) *n_mappings = maps;

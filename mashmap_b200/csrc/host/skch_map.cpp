@@ -331,13 +331,23 @@ void BatchMapper::mapBatch(const ReadBatch &b, std::vector<MappingResultsVector_
         publish(i, 3);
       }
     });
+    const auto tp0 = Clock::now();
+    double waitUpload = 0, tFirst = 0, tLast = 0;
     for (size_t i = 0; i < np; i++) {  // kernels of successive parts run back to back from this thread
+      const auto tw = Clock::now();
       wait_for(i, 1);
+      waitUpload += since(tw);
+      if (i == 0) tFirst = since(tp0);
       laneCompute(lanes[i % NL]);
       publish(i, 2);
     }
+    tLast = since(tp0);
     uploader.join();
     finisher.join();
+    static const bool trace = getenv("MM_TRACE") != nullptr;
+    if (trace)
+      fprintf(stderr, "[trace] mapBatch: %zu parts; first kernels start at %.1f ms, last kernels end at %.1f ms, pipeline drained at %.1f ms; "
+              "compute thread waited %.1f ms for uploads\n", np, tFirst * 1e3, tLast * 1e3, since(tp0) * 1e3, waitUpload * 1e3);
   }
   memcpy(lastStageMs, lanes[0].stageMs, sizeof(lastStageMs));
   for (auto &ln : lanes) { secondsDevice += ln.secDevice; secondsHostTail += ln.secTail; }

@@ -198,7 +198,7 @@ int upload_batch(mm_ctx *c, const char *bases, uint64_t n_bases, const mm_segmen
   if (!c->hook) {
     CU(c, cudaMemcpyAsync(c->d_bases, bases, n_bases, cudaMemcpyHostToDevice, c->stream));
   } else { /* in pieces, so that the pipeline's scheduler can hold the upload back (MM_PHASE_UPLOAD_CHUNK) */
-    const uint64_t CH = 64ULL << 20;
+    const uint64_t CH = 16ULL << 20;
     for (uint64_t at = 0; at < n_bases; at += CH) {
       const uint64_t n = std::min(CH, n_bases - at);
       c->hook(c->hook_user, MM_PHASE_UPLOAD_CHUNK, 1);
