@@ -11,6 +11,7 @@
 #include <string>
 #include <vector>
 
+#include "skch_args.hpp"
 #include "skch_index.hpp"
 #include "skch_map.hpp"
 #include "skch_stats.hpp"
@@ -80,6 +81,22 @@ void *skch_index_build(const char *seqs, const uint64_t *offs, int n_contigs, in
   h->sk = new Sketch(h->p, meta, ptrs);
   return h;
 }
+
+/* skch::Sketch exactly as the driver program builds it: the reference's command line (reference
+ * parseCmdArgs.hpp) -> Parameters -> Sketch(param), including --saveIndex / --loadIndex. No device needed. */
+void *skch_index_from_cli(int argc, const char **argv)
+{
+  IndexHandle *h = new IndexHandle();
+  std::vector<std::string> store;
+  store.push_back("mashmap-b200");
+  for (int i = 0; i < argc; i++) store.push_back(argv[i]);
+  std::vector<char *> av;
+  for (auto &x : store) av.push_back(&x[0]);
+  parseandSave((int)av.size(), av.data(), h->p);
+  h->sk = new Sketch(h->p);
+  return h;
+}
+int skch_index_sketch_size(void *hv) { return ((IndexHandle *)hv)->p.sketchSize; }
 
 /* contig metadata only (ranks that receive the device index image by broadcast) */
 void *skch_index_metadata_only(int n_contigs, int contig_len, int k, int segLength, int sketchSize)

@@ -56,6 +56,8 @@ def lib():
         L.skch_index_from_minmers.restype = C.c_void_p
         L.skch_index_build.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float]
         L.skch_index_build.restype = C.c_void_p
+        L.skch_index_from_cli.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
+        L.skch_index_from_cli.restype = C.c_void_p
         L.skch_index_metadata_only.argtypes = [C.c_int] * 5
         L.skch_index_metadata_only.restype = C.c_void_p
         L.skch_index_destroy.argtypes = [C.c_void_p]
@@ -159,6 +161,13 @@ class HostIndex:
     @classmethod
     def metadata_only(cls, n_contigs, contig_len, k, seg_length, sketch_size):
         return cls(lib().skch_index_metadata_only(n_contigs, contig_len, k, seg_length, sketch_size))
+
+    @classmethod
+    def from_cli(cls, args):
+        """skch::Sketch built the way the driver program does it, from the reference's command-line options
+        (FASTA files, --saveIndex / --loadIndex ...). Host only."""
+        argv = (C.c_char_p * len(args))(*[a.encode() for a in args])
+        return cls(lib().skch_index_from_cli(len(args), argv))
 
     @classmethod
     def from_minmers(cls, minmers, n_contigs, kmer_pct_threshold=0.001):
