@@ -29,7 +29,10 @@
 
 namespace {
 
-constexpr int SK_THREADS = 128;
+#ifndef MM_SK_THREADS
+#define MM_SK_THREADS 128
+#endif
+constexpr int SK_THREADS = MM_SK_THREADS;
 constexpr int SK_BUCKETS = 256;
 constexpr uint64_t SK_EMPTY = ~0ULL;
 
@@ -102,14 +105,19 @@ __host__ __device__ inline sk_smem_layout sk_layout(int seg_length, int C)
   L.off_first = o; o += 4u * C;
   L.off_last = o; o += 4u * C;
   L.off_votes = o; o += 4u * C;
-  L.off_order = o; o += ((2u * C + 15) & ~15u);
-  L.off_bcnt = o; o += 4u * SK_BUCKETS;
-  L.off_bstart = o; o += 4u * SK_BUCKETS;
-  L.off_bfill = o; o += 4u * SK_BUCKETS;
   L.off_ctrl = o; o += (uint32_t)sizeof(sk_ctrl);
   o = (o + 15) & ~15u;
-  L.off_list_h = o; o += 8u * SK_WARPS * SK_LIST_PER_WARP;
-  L.off_list_m = o; o += 4u * SK_WARPS * SK_LIST_PER_WARP;
+  /* the per-warp survivor lists are dead once the table is built; the ordering scratch (order[] + bucket counters)
+   * lives in the same bytes -- 5 KB less per CTA is one more resident CTA per SM */
+  const uint32_t lists = (8u + 4u) * SK_WARPS * SK_LIST_PER_WARP;
+  const uint32_t ordering = ((2u * C + 15) & ~15u) + 3u * 4u * SK_BUCKETS;
+  L.off_list_h = o;
+  L.off_list_m = o + 8u * SK_WARPS * SK_LIST_PER_WARP;
+  L.off_order = o;
+  L.off_bcnt = o + ((2u * C + 15) & ~15u);
+  L.off_bstart = L.off_bcnt + 4u * SK_BUCKETS;
+  L.off_bfill = L.off_bstart + 4u * SK_BUCKETS;
+  o += lists > ordering ? lists : ordering;
   L.total = (o + 15) & ~15u;
   return L;
 }
@@ -228,7 +236,6 @@ k_sketch(const uint8_t *__restrict__ bases, const mm_segment *__restrict__ segs,
         last[i] = -1;
         votes[i] = 0;
       }
-      for (int i = tid; i < SK_BUCKETS; i += SK_THREADS) { bcnt[i] = 0; bfill[i] = 0; }
       if (tid == 0) {
         ctrl->distinct = 0; ctrl->overflow = 0; ctrl->above = 0; ctrl->has_max = 0;
         ctrl->max_first = 0x7fffffff; ctrl->max_last = -1; ctrl->max_votes = 0;
@@ -312,6 +319,8 @@ k_sketch(const uint8_t *__restrict__ bases, const mm_segment *__restrict__ segs,
 
     /* ---- order the survivors: counting sort on the leading bits, rank inside the bucket ---- */
     const int dt = ctrl->distinct; /* entries in the table (excludes the has_max entry) */
+    for (int i = tid; i < SK_BUCKETS; i += SK_THREADS) { bcnt[i] = 0; bfill[i] = 0; } /* aliases the (consumed) lists */
+    __syncthreads();
     const int sh = max(0, (64 - __clzll((long long)T)) - 8);
     for (int i = tid; i < C; i += SK_THREADS) {
       const uint64_t k = keys[i];
