@@ -87,10 +87,78 @@ __device__ __forceinline__ uint32_t group_exclusive_scan(uint32_t v, uint32_t *w
   return base + incl - v;
 }
 
+/* Bitonic sort of 32*E keys by one warp with the keys in registers: key i lives in lane i % 32, register i / 32.
+ * Exchanges at distance < 32 are warp shuffles, larger ones stay inside a lane; no shared-memory traffic and no
+ * barriers between the steps (the shared-memory version below spends a __syncwarp and two loads + two stores per
+ * compare-exchange). */
+template <int E, int JR>
+__device__ __forceinline__ void warp_sort_lane_step(uint64_t (&a)[E], int k)
+{ /* compare-exchange at distance 32*JR: both keys are in this lane (registers r and r | JR) */
+#pragma unroll
+  for (int r = 0; r < E; r++) {
+    if ((r & JR) == 0 && (r | JR) < E) {
+      const bool up = (r & (k >> 5)) == 0;
+      const uint64_t x = a[r], y = a[r | JR];
+      const bool sw = (x > y) == up;
+      a[r] = sw ? y : x;
+      a[r | JR] = sw ? x : y;
+    }
+  }
+}
+
+/* The step loops are NOT unrolled (fully unrolled, the five instantiations were 32 k instructions of straight-line code
+ * and the kernel became instruction-fetch bound); only the loops over the E registers of a lane are. */
+template <int E>
+__device__ __noinline__ void warp_sort_regs(uint64_t *keys)
+{
+  const int lane = threadIdx.x & 31;
+  uint64_t a[E];
+#pragma unroll
+  for (int r = 0; r < E; r++) a[r] = keys[r * 32 + lane];
+#pragma unroll 1
+  for (int k = 2; k <= 32 * E; k <<= 1) {
+#pragma unroll 1
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= 32) {
+        switch (j >> 5) {
+          case 1: warp_sort_lane_step<E, 1>(a, k); break;
+          case 2: warp_sort_lane_step<E, 2>(a, k); break;
+          case 4: warp_sort_lane_step<E, 4>(a, k); break;
+          default: warp_sort_lane_step<E, 8>(a, k); break;
+        }
+      } else {
+        const bool lower = (lane & j) == 0;
+        const bool up_lane = (lane & k) == 0;
+#pragma unroll
+        for (int r = 0; r < E; r++) {
+          const bool up = k < 32 ? up_lane : (r & (k >> 5)) == 0;
+          const uint64_t x = a[r];
+          const uint64_t y = __shfl_xor_sync(0xffffffffu, x, j);
+          a[r] = (lower == up) ? (x < y ? x : y) : (x < y ? y : x);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < E; r++) keys[r * 32 + lane] = a[r];
+}
+
 /* in-place bitonic sort of n (power of two) u64 keys by the group (shared or global memory) */
 template <int NT>
 __device__ void group_bitonic_sort(uint64_t *a, uint32_t n)
 {
+  if (NT == 32 && n >= 32 && n <= 512) { /* the warp path: n is 32..512 (the caller pads to at least 32) */
+    __syncwarp();
+    switch (n) {
+      case 32: warp_sort_regs<1>(a); break;
+      case 64: warp_sort_regs<2>(a); break;
+      case 128: warp_sort_regs<4>(a); break;
+      case 256: warp_sort_regs<8>(a); break;
+      default: warp_sort_regs<16>(a); break;
+    }
+    __syncwarp();
+    return;
+  }
   for (uint32_t k = 2; k <= n; k <<= 1) {
     for (uint32_t j = k >> 1; j > 0; j >>= 1) {
       for (uint32_t t = grp<NT>::tid(); t < (n >> 1); t += NT) {
@@ -147,49 +215,92 @@ __device__ __forceinline__ void l1_close_run(l1_walk_state &w, int seg_length, l
 }
 
 /* Executed by one warp. keys[0..n): sorted points of one reference group; ginfo[i] = O_g stored at
- * the last index of each group; head[i] = index of the group's first point. */
+ * the last index of each group; head[i] = index of the group's first point.
+ * Sweep #2 (computeMap.hpp:1009-1098) in data-parallel form, 32 points per step: every lane that ends a group knows
+ * whether its group is flagged, its contig and position and -- from the neighbouring group-ending lanes, found with
+ * ballots -- whether it starts or ends a run of consecutive flagged groups on one contig. The maximum overlap of a run
+ * is a segmented warp max-scan. Only the ends of runs (a handful per segment) go through the sequential join logic
+ * (:1102-1115); a run that is still open at the end of a step is carried to the next one. */
 __device__ void l1_walk(const uint64_t *keys, const uint32_t *ginfo, const uint32_t *head, uint32_t n, int mh,
                         int seg_length, l1_out_list &o)
 {
   const int lane = threadIdx.x & 31;
+  const uint32_t FULL = 0xffffffffu;
   l1_walk_state w;
   w.in_run = false; w.have_out = false; w.prev_group = -2;
   w.run_seq = w.run_start = w.run_end = w.run_isz = 0;
   w.out_seq = w.out_start = w.out_end = w.out_isz = 0;
-  int group_base = 0;
   for (uint32_t base = 0; base < n; base += 32) {
     const uint32_t i = base + lane;
     bool last_of_group = false, flagged = false;
-    uint32_t ov = 0;
+    int O = 0, seq = 0, pos = 0;
     if (i < n) {
       last_of_group = (i + 1 == n) || (mm_point_pos(keys[i + 1]) != mm_point_pos(keys[i]));
       if (last_of_group) {
-        ov = ginfo[i];
+        O = (int)ginfo[i];
         /* the last group is never tested (the test lags one group behind, :1026-1027,:1062) */
-        flagged = (i + 1 != n) && ((int)ov >= mh);
+        flagged = (i + 1 != n) && (O >= mh);
+        const uint64_t hk = keys[head[i]];
+        seq = mm_point_seq(hk); pos = mm_point_pos(hk);
       }
     }
-    const uint32_t glast = __ballot_sync(0xffffffffu, last_of_group);
-    uint32_t fl = __ballot_sync(0xffffffffu, flagged);
-    while (fl) {
-      const int l = __ffs(fl) - 1;
-      fl &= fl - 1;
-      const int g = group_base + __popc(glast & ((1u << l) - 1u));
-      const uint32_t idx = base + l;
-      const int O = (int)__shfl_sync(0xffffffffu, ov, l);
-      const uint64_t hk = keys[head[idx]];
-      const int seq = mm_point_seq(hk), pos = mm_point_pos(hk);
-      if (w.in_run && (g != w.prev_group + 1 || seq != w.run_seq)) l1_close_run(w, seg_length, o);
-      if (!w.in_run) {
-        w.in_run = true;
-        w.run_seq = seq; w.run_start = pos; w.run_end = pos; w.run_isz = O;
-      } else {
-        w.run_isz = max(w.run_isz, O); /* stage2_full_scan (:1077-1080) */
-        w.run_end = pos;
-      }
-      w.prev_group = g;
+    const uint32_t glast = __ballot_sync(FULL, last_of_group);
+    const uint32_t fl = __ballot_sync(FULL, flagged);
+    if (glast == 0) continue; /* no group ends in these 32 points: nothing changes */
+    if (fl == 0) {            /* only unflagged groups: an open run ends at the first of them */
+      l1_close_run(w, seg_length, o);
+      continue;
     }
-    group_base += __popc(glast);
+    /* the group before / after this lane's group (group-ending lanes below / above) */
+    const uint32_t below = glast & ((1u << lane) - 1u);
+    const int pl = below ? 31 - __clz(below) : 0;
+    const int pF_s = __shfl_sync(FULL, flagged ? 1 : 0, pl);
+    const int pSeq_s = __shfl_sync(FULL, seq, pl);
+    const bool prevF = below ? (pF_s != 0) : w.in_run;
+    const int prevSeq = below ? pSeq_s : w.run_seq;
+    const bool start = flagged && !(prevF && prevSeq == seq);
+    const uint32_t above = glast & ~((2u << lane) - 1u);
+    const int nl = above ? __ffs(above) - 1 : 0;
+    const int nF_s = __shfl_sync(FULL, flagged ? 1 : 0, nl);
+    const int nSeq_s = __shfl_sync(FULL, seq, nl);
+    const bool endf = flagged && above != 0 && !(nF_s != 0 && nSeq_s == seq);
+    /* segmented max of O over the run: segments begin at run starts and at unflagged groups */
+    const uint32_t rmask = __ballot_sync(FULL, start || (last_of_group && !flagged));
+    const uint32_t endmask = __ballot_sync(FULL, endf);
+    const uint32_t upto = rmask & ((2u << lane) - 1u);
+    const int hs = upto ? 31 - __clz(upto) : -1; /* first lane of this lane's segment; -1: it began in an earlier step */
+    int v = flagged ? O : 0;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int t = __shfl_up_sync(FULL, v, off);
+      if (lane >= off && lane - off >= hs) v = max(v, t);
+    }
+    const int sp_s = __shfl_sync(FULL, pos, hs < 0 ? 0 : hs);
+    const int rs = hs >= 0 ? sp_s : w.run_start;                 /* where this lane's run began */
+    const int vt = (hs < 0 && w.in_run) ? max(v, w.run_isz) : v; /* its maximum overlap so far */
+    /* does the run carried in from the previous step go on through the first group that ends here? */
+    const int f0 = __ffs(glast) - 1;
+    const int f0_cont = __shfl_sync(FULL, (flagged && !start) ? 1 : 0, f0);
+    if (w.in_run && !f0_cont) l1_close_run(w, seg_length, o);
+    for (uint32_t em = endmask; em; em &= em - 1) { /* runs that end in this step, in order */
+      const int e = __ffs(em) - 1;
+      w.in_run = true;
+      w.run_seq = __shfl_sync(FULL, seq, e);
+      w.run_start = __shfl_sync(FULL, rs, e);
+      w.run_end = __shfl_sync(FULL, pos, e);
+      w.run_isz = __shfl_sync(FULL, vt, e);
+      l1_close_run(w, seg_length, o);
+    }
+    /* carry: the last group that ends here leaves a run open iff it is flagged */
+    const int ll = 31 - __clz(glast);
+    const int c_seq = __shfl_sync(FULL, seq, ll), c_start = __shfl_sync(FULL, rs, ll), c_end = __shfl_sync(FULL, pos, ll),
+              c_isz = __shfl_sync(FULL, vt, ll);
+    if ((fl >> ll) & 1u) {
+      w.in_run = true;
+      w.run_seq = c_seq; w.run_start = c_start; w.run_end = c_end; w.run_isz = c_isz;
+    } else {
+      w.in_run = false;
+    }
   }
   l1_close_run(w, seg_length, o);
   if (w.have_out) l1_emit(o, w.out_seq, w.out_start, w.out_end, w.out_isz);
@@ -392,7 +503,7 @@ __device__ bool l1_segment(const mm_params &prm, const mm_dev_index &ix, const m
   grp<NT>::sync();
 
   /* ---- 2. gather the interval points (computeMap.hpp:887-907, order restored by the sort) ---- */
-  uint32_t n_pow2 = 1;
+  uint32_t n_pow2 = (NT == 32) ? 32 : 1; /* the warp path sorts in registers, 32 keys at least */
   while (n_pow2 < m) n_pow2 <<= 1;
   uint64_t *keys = skeys;
   uint32_t *copn = scopn, *head = shead, *ginfo = sginfo;
