@@ -3,6 +3,7 @@
  * the statistics tables, the host index builder, and the host tail fed with externally produced records.
  * Not part of the drop-in boundary (that is include/mashmap_b200.h + the skch:: classes).
  */
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -14,6 +15,7 @@
 #include "skch_args.hpp"
 #include "skch_index.hpp"
 #include "skch_map.hpp"
+#include "skch_seqio.hpp"
 #include "skch_stats.hpp"
 #include "skch_tail.hpp"
 
@@ -251,6 +253,32 @@ uint64_t skch_bm_results(void *hv, int32_t *out, uint64_t cap_rows)
       n++;
     }
   return n;
+}
+
+/* ---- input: the mapped-FASTA bulk reader against the line reader (tests) ----
+ * returns -1 if FastaFile declines the file, else the number of records that differ (name, length or bases) between
+ * the two readers; *n_records / *n_bases describe what the line reader saw */
+int64_t skch_fasta_readers_diff(const char *path, int threads, uint64_t *n_records, uint64_t *n_bases)
+{
+  std::vector<std::pair<std::string, std::string>> ref;
+  uint64_t bases = 0;
+  if (!seqio::for_each_seq_in_file(path, {}, "", [&](const std::string &name, const std::string &seq) {
+        ref.emplace_back(name, seq);
+        bases += seq.size();
+      }))
+    return -2;
+  if (n_records) *n_records = ref.size();
+  if (n_bases) *n_bases = bases;
+  seqio::FastaFile ff;
+  if (!ff.open(path, threads)) return -1;
+  const auto &recs = ff.records();
+  int64_t bad = recs.size() > ref.size() ? (int64_t)(recs.size() - ref.size()) : (int64_t)(ref.size() - recs.size());
+  for (size_t i = 0; i < std::min(recs.size(), ref.size()); i++) {
+    std::string seq(recs[i].seq_len, '\0');
+    ff.copy_bases(recs[i], &seq[0]);
+    if (ff.name(recs[i]) != ref[i].first || seq != ref[i].second) bad++;
+  }
+  return bad;
 }
 
 /* ---- host tail on caller-provided records ---- */

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <fstream>
 #include <iostream>
+#include <limits>
 #include <sstream>
 #include <thread>
 #include <tuple>
@@ -368,21 +369,41 @@ struct Map::Impl {
   MappingResultsVector_t allReadMappings;
   seqno_t totalReadsMapped = 0, totalReadsPicked = 0, seqCounter = 0;
 
-  Impl(const Parameters &p, const Sketch &s, PostProcessResultsFn_t f, Map &m)
+  // the batch being filled by the reader (`batch`) and the one being mapped by the worker thread (`inflight`)
+  ReadBatch inflight;
+  std::thread worker;
+  bool workerActive = false;
+  std::vector<MappingResultsVector_t> results;
+  std::vector<std::string> text;
+
+  Impl(const Parameters &p, const Sketch &s, PostProcessResultsFn_t f, Map &m, Clock::time_point tCtor = Clock::now())
       : param(p), refSketch(s), processMappingResults(f), self(m), bm(p, s)
   {
+    const double secIndex = since(tCtor);  // the default argument is evaluated before the members are constructed
+    auto t1 = Clock::now();
     batch.capacity = param.batch_bases + (uint64_t)param.segLength + 64;
     batch.bases = bm.allocBases(batch.capacity);
+    inflight.capacity = batch.capacity;
+    inflight.bases = bm.allocBases(inflight.capacity);
+    std::cerr << "[mashmap-b200::skch::Map] device contexts + index upload " << secIndex << " s, pinned batch buffers " << since(t1)
+              << " s" << std::endl;
   }
-  ~Impl() { bm.freeBases(batch.bases); }
-
-  void flushBatch()
+  ~Impl()
   {
-    if (batch.reads.empty()) return;
-    std::vector<MappingResultsVector_t> results;
-    std::vector<std::string> text;
+    waitWorker();
+    bm.freeBases(batch.bases);
+    bm.freeBases(inflight.bases);
+  }
+
+  void waitWorker()
+  {
+    if (workerActive) { worker.join(); workerActive = false; }
+  }
+
+  void mapAndWrite(ReadBatch &b)
+  {
     const bool report_now = param.filterMode != filter::ONETOONE;
-    bm.mapBatch(batch, results, report_now ? &text : nullptr, &qmetadata);
+    bm.mapBatch(b, results, report_now ? &text : nullptr, &qmetadata);
     for (size_t r = 0; r < results.size(); r++) {  // mapModuleHandleOutput (computeMap.hpp:724-747), in input order
       if (!results[r].empty()) totalReadsMapped++;
       if (!report_now) allReadMappings.insert(allReadMappings.end(), results[r].begin(), results[r].end());
@@ -392,7 +413,23 @@ struct Map::Impl {
           for (auto &e : results[r]) processMappingResults(e);
       }
     }
-    batch.clear();
+    b.clear();
+  }
+
+  /* hands the filled batch to the worker thread (mapping + output, in batch order) and goes on reading into the other
+   * buffer; one-to-one mode and user callbacks keep the reference's "everything from the calling thread" behaviour */
+  void flushBatch()
+  {
+    if (batch.reads.empty()) return;
+    waitWorker();
+    std::swap(batch, inflight);
+    const bool async = param.filterMode != filter::ONETOONE && processMappingResults == nullptr && !getenv("MM_SERIAL_INPUT");
+    if (async) {
+      worker = std::thread([this]() { mapAndWrite(inflight); });
+      workerActive = true;
+    } else {
+      mapAndWrite(inflight);
+    }
   }
 
   void onSequence(const std::string &name, const std::string &seq)
@@ -418,15 +455,82 @@ struct Map::Impl {
     seqCounter++;
   }
 
+  /* onSequence for every record of a mapped FASTA file; the bases go from the file mapping straight into the pinned
+   * batch buffer, copied by all host threads just before the batch is mapped */
+  void ingestMapped(const seqio::FastaFile &ff)
+  {
+    struct CopyJob { size_t rec; uint64_t dst; };
+    std::vector<CopyJob> jobs;
+    const auto &recs = ff.records();
+    auto runCopies = [&]() {
+      if (jobs.empty()) return;
+      const int T = std::max(1, std::min<int>(param.threads, (int)(jobs.size() / 16 + 1)));
+      std::atomic<size_t> next{0};
+      auto worker = [&]() {
+        while (true) {
+          const size_t b = next.fetch_add(64);
+          if (b >= jobs.size()) break;
+          const size_t e = std::min(jobs.size(), b + 64);
+          for (size_t j = b; j < e; j++) ff.copy_bases(recs[jobs[j].rec], batch.bases + jobs[j].dst);
+        }
+      };
+      if (T == 1) worker();
+      else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < T; t++) pool.emplace_back(worker);
+        for (auto &th : pool) th.join();
+      }
+      jobs.clear();
+    };
+    for (size_t i = 0; i < recs.size(); i++) {
+      const seqio::FastaRecord &r = recs[i];
+      if (r.seq_len > (uint64_t)std::numeric_limits<offset_t>::max()) {
+        std::cerr << "[mashmap-b200] ERROR: sequence " << ff.name(r) << " is longer than 2^31 bases" << std::endl;
+        exit(1);
+      }
+      const offset_t len = (offset_t)r.seq_len;
+      const std::string name = ff.name(r);
+      if (param.filterMode == filter::ONETOONE) qmetadata.push_back(ContigInfo{name, len});
+      if (len < param.kmerSize) {
+        std::cerr << std::endl << "WARNING, skch::Map::mapQuery, read " << name << " of " << len << "bp "
+                  << " is not long enough for mapping at segment length " << param.segLength << std::endl;
+      } else {
+        totalReadsPicked++;
+        if (batch.used + (uint64_t)len > param.batch_bases && !batch.reads.empty()) { runCopies(); flushBatch(); }
+        if ((uint64_t)len + 64 > batch.capacity) {
+          runCopies();
+          flushBatch();
+          bm.freeBases(batch.bases);
+          batch.capacity = (uint64_t)len + 64;
+          batch.bases = bm.allocBases(batch.capacity);
+        }
+        jobs.push_back(CopyJob{i, batch.used});
+        bm.addRead(batch, name, nullptr, len, seqCounter);
+        self.totalQueryBases += (uint64_t)len;
+      }
+      seqCounter++;
+    }
+    runCopies();
+  }
+
   void mapQuery()
   {  // computeMap.hpp:263-415
     outstrm.open(param.outFileName);
     auto t0 = Clock::now();
     for (const auto &fileName : param.querySequences) {
+      seqio::FastaFile ff;
+      if (!getenv("MM_SERIAL_INPUT") && ff.open(fileName, param.threads)) {  // plain FASTA: bulk path
+        ingestMapped(ff);
+        continue;
+      }
       bool ok = seqio::for_each_seq_in_file(fileName, {}, "", [&](const std::string &name, const std::string &seq) { onSequence(name, seq); });
       if (!ok) exit(1);
     }
+    const double secRead = since(t0);
     flushBatch();
+    waitWorker();
+    std::cerr << "[mashmap-b200::skch::Map::mapQuery] input read and handed over in " << secRead << " s, last batch done at "
+              << since(t0) << " s" << std::endl;
     self.secondsDevice = bm.secondsDevice;
     self.secondsHostTail = bm.secondsHostTail;
     self.secondsInput = since(t0) - self.secondsDevice - self.secondsHostTail;

@@ -1,9 +1,16 @@
 #include "skch_seqio.hpp"
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 
+#include <algorithm>
+#include <atomic>
 #include <cstring>
 #include <iostream>
+#include <thread>
 #include <vector>
 
 namespace skch {
@@ -103,6 +110,98 @@ bool for_each_seq_in_file(const std::string &filename, const std::unordered_set<
     }
   }
   return true;
+}
+
+/* ---- mapped FASTA ---- */
+
+FastaFile::~FastaFile()
+{
+  if (data_) munmap((void *)data_, size_);
+  if (fd_ >= 0) close(fd_);
+}
+
+bool FastaFile::open(const std::string &filename, int threads)
+{
+  fd_ = ::open(filename.c_str(), O_RDONLY);
+  if (fd_ < 0) return false;
+  struct stat st;
+  if (fstat(fd_, &st) != 0 || !S_ISREG(st.st_mode) || st.st_size < 2) return false;
+  size_ = (uint64_t)st.st_size;
+  void *m = mmap(nullptr, size_, PROT_READ, MAP_PRIVATE, fd_, 0);
+  if (m == MAP_FAILED) return false;
+  data_ = (const char *)m;
+  if (data_[0] != '>') return false; /* gzip magic, FASTQ, anything else: the line reader handles those */
+  madvise(m, size_, MADV_SEQUENTIAL);
+  const int T = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)std::max(1, threads), size_ / (1 << 20) + 1));
+  /* 1. record starts: '>' at the beginning of a line, found independently in T byte ranges */
+  std::vector<std::vector<uint64_t>> starts((size_t)T);
+  {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < T; t++) {
+      pool.emplace_back([&, t]() {
+        const uint64_t lo = size_ * (uint64_t)t / (uint64_t)T, hi = size_ * (uint64_t)(t + 1) / (uint64_t)T;
+        uint64_t p = lo;
+        while (p < hi) {
+          const char *q = (const char *)memchr(data_ + p, '>', hi - p);
+          if (!q) break;
+          p = (uint64_t)(q - data_);
+          if (p == 0 || data_[p - 1] == '\n') starts[(size_t)t].push_back(p);
+          p++;
+        }
+      });
+    }
+    for (auto &th : pool) th.join();
+  }
+  std::vector<uint64_t> all;
+  for (auto &v : starts) all.insert(all.end(), v.begin(), v.end());
+  /* 2. per record: header, sequence region, base count */
+  recs_.resize(all.size());
+  {
+    std::atomic<size_t> next{0};
+    std::vector<std::thread> pool;
+    for (int t = 0; t < T; t++) {
+      pool.emplace_back([&]() {
+        while (true) {
+          const size_t b = next.fetch_add(4096);
+          if (b >= all.size()) break;
+          const size_t e = std::min(all.size(), b + 4096);
+          for (size_t i = b; i < e; i++) {
+            const uint64_t p = all[i], end = i + 1 < all.size() ? all[i + 1] : size_;
+            const char *eol = (const char *)memchr(data_ + p, '\n', end - p);
+            const uint64_t hdr_end = eol ? (uint64_t)(eol - data_) : end;
+            const char *sp = (const char *)memchr(data_ + p + 1, ' ', hdr_end - (p + 1));
+            FastaRecord &r = recs_[i];
+            r.name_off = p + 1;
+            r.name_len = (uint32_t)((sp ? (uint64_t)(sp - data_) : hdr_end) - (p + 1));
+            r.seq_off = eol ? hdr_end + 1 : end;
+            r.raw_len = end - r.seq_off;
+            uint64_t nl = 0;
+            for (const char *c = data_ + r.seq_off, *ce = data_ + end; c < ce;) {
+              const char *q = (const char *)memchr(c, '\n', (size_t)(ce - c));
+              if (!q) break;
+              nl++;
+              c = q + 1;
+            }
+            r.seq_len = r.raw_len - nl;
+          }
+        }
+      });
+    }
+    for (auto &th : pool) th.join();
+  }
+  return true;
+}
+
+void FastaFile::copy_bases(const FastaRecord &r, char *dst) const
+{
+  const char *c = data_ + r.seq_off, *ce = c + r.raw_len;
+  while (c < ce) {
+    const char *q = (const char *)memchr(c, '\n', (size_t)(ce - c));
+    const size_t n = (size_t)((q ? q : ce) - c);
+    memcpy(dst, c, n);
+    dst += n;
+    c += n + 1;
+  }
 }
 
 }  // namespace seqio

@@ -8,9 +8,11 @@
 #ifndef SKCH_SEQIO_HPP
 #define SKCH_SEQIO_HPP
 
+#include <cstdint>
 #include <functional>
 #include <string>
 #include <unordered_set>
+#include <vector>
 
 namespace skch {
 namespace seqio {
@@ -20,6 +22,42 @@ typedef std::function<void(const std::string &name, const std::string &seq)> Seq
 /* returns false (after printing to stderr) if the file cannot be read or has an unknown format */
 bool for_each_seq_in_file(const std::string &filename, const std::unordered_set<std::string> &keep_seq,
                           const std::string &keep_prefix, const SeqCallback &func);
+
+/*
+ * Bulk view of a plain (uncompressed) FASTA file: the file is mapped and cut into records by all host threads, so that
+ * a caller can place the bases where it wants them (the pinned batch buffer) without going through one std::string per
+ * record on one thread -- at tens of Gbp/s of mapping, a serial parser is the bottleneck of the program.
+ * Same record semantics as for_each_seq_in_file: a record starts at a line whose first byte is '>', its name is the
+ * header up to the first space, its sequence is every following line up to the next record, concatenated (only the
+ * '\n' bytes are dropped).
+ */
+struct FastaRecord {
+  uint64_t name_off;  /* file offset of the first byte of the name */
+  uint32_t name_len;
+  uint64_t seq_off;   /* file offset of the first sequence line */
+  uint64_t raw_len;   /* bytes from seq_off to the next record (or EOF), newlines included */
+  uint64_t seq_len;   /* bases = raw_len minus the newlines */
+};
+
+class FastaFile {
+ public:
+  FastaFile() = default;
+  ~FastaFile();
+  FastaFile(const FastaFile &) = delete;
+  /* false if the file is not a plain FASTA file that can be mapped (gzip, FASTQ, pipe ...): use for_each_seq_in_file */
+  bool open(const std::string &filename, int threads);
+  const std::vector<FastaRecord> &records() const { return recs_; }
+  const char *data() const { return data_; }
+  std::string name(const FastaRecord &r) const { return std::string(data_ + r.name_off, r.name_len); }
+  /* copies the record's bases to dst (seq_len bytes) */
+  void copy_bases(const FastaRecord &r, char *dst) const;
+
+ private:
+  const char *data_ = nullptr;
+  uint64_t size_ = 0;
+  int fd_ = -1;
+  std::vector<FastaRecord> recs_;
+};
 
 }  // namespace seqio
 }  // namespace skch

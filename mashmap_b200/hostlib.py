@@ -52,6 +52,8 @@ def lib():
         L.skch_tail_map_read.argtypes = [C.c_void_p, C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                          C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
         L.skch_tail_map_read.restype = C.c_char_p
+        L.skch_fasta_readers_diff.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.skch_fasta_readers_diff.restype = C.c_int64
         L.skch_index_from_minmers.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_float]
         L.skch_index_from_minmers.restype = C.c_void_p
         L.skch_index_build.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float]
@@ -191,6 +193,14 @@ class HostIndex:
         if self.h:
             lib().skch_index_destroy(self.h)
             self.h = None
+
+
+def fasta_readers_diff(path, threads=4):
+    """(differences, records, bases): the mapped bulk FASTA reader against the line reader; differences = -1 if the bulk
+    reader declines the file (gzip, FASTQ ...)"""
+    nr, nb = C.c_uint64(), C.c_uint64()
+    d = lib().skch_fasta_readers_diff(path.encode(), threads, C.byref(nr), C.byref(nb))
+    return d, nr.value, nb.value
 
 
 def lookup_from_minmers(minmers, n_contigs, kmer_pct_threshold=0.001):
