@@ -87,78 +87,12 @@ __device__ __forceinline__ uint32_t group_exclusive_scan(uint32_t v, uint32_t *w
   return base + incl - v;
 }
 
-/* Bitonic sort of 32*E keys by one warp with the keys in registers: key i lives in lane i % 32, register i / 32.
- * Exchanges at distance < 32 are warp shuffles, larger ones stay inside a lane; no shared-memory traffic and no
- * barriers between the steps (the shared-memory version below spends a __syncwarp and two loads + two stores per
- * compare-exchange). */
-template <int E, int JR>
-__device__ __forceinline__ void warp_sort_lane_step(uint64_t (&a)[E], int k)
-{ /* compare-exchange at distance 32*JR: both keys are in this lane (registers r and r | JR) */
-#pragma unroll
-  for (int r = 0; r < E; r++) {
-    if ((r & JR) == 0 && (r | JR) < E) {
-      const bool up = (r & (k >> 5)) == 0;
-      const uint64_t x = a[r], y = a[r | JR];
-      const bool sw = (x > y) == up;
-      a[r] = sw ? y : x;
-      a[r | JR] = sw ? x : y;
-    }
-  }
-}
-
-/* The step loops are NOT unrolled (fully unrolled, the five instantiations were 32 k instructions of straight-line code
- * and the kernel became instruction-fetch bound); only the loops over the E registers of a lane are. */
-template <int E>
-__device__ __noinline__ void warp_sort_regs(uint64_t *keys)
-{
-  const int lane = threadIdx.x & 31;
-  uint64_t a[E];
-#pragma unroll
-  for (int r = 0; r < E; r++) a[r] = keys[r * 32 + lane];
-#pragma unroll 1
-  for (int k = 2; k <= 32 * E; k <<= 1) {
-#pragma unroll 1
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      if (j >= 32) {
-        switch (j >> 5) {
-          case 1: warp_sort_lane_step<E, 1>(a, k); break;
-          case 2: warp_sort_lane_step<E, 2>(a, k); break;
-          case 4: warp_sort_lane_step<E, 4>(a, k); break;
-          default: warp_sort_lane_step<E, 8>(a, k); break;
-        }
-      } else {
-        const bool lower = (lane & j) == 0;
-        const bool up_lane = (lane & k) == 0;
-#pragma unroll
-        for (int r = 0; r < E; r++) {
-          const bool up = k < 32 ? up_lane : (r & (k >> 5)) == 0;
-          const uint64_t x = a[r];
-          const uint64_t y = __shfl_xor_sync(0xffffffffu, x, j);
-          a[r] = (lower == up) ? (x < y ? x : y) : (x < y ? y : x);
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int r = 0; r < E; r++) keys[r * 32 + lane] = a[r];
-}
-
 /* in-place bitonic sort of n (power of two) u64 keys by the group (shared or global memory) */
 template <int NT>
 __device__ void group_bitonic_sort(uint64_t *a, uint32_t n)
 {
-  if (NT == 32 && n >= 32 && n <= 512) { /* the warp path: n is 32..512 (the caller pads to at least 32) */
-    __syncwarp();
-    switch (n) {
-      case 32: warp_sort_regs<1>(a); break;
-      case 64: warp_sort_regs<2>(a); break;
-      case 128: warp_sort_regs<4>(a); break;
-      case 256: warp_sort_regs<8>(a); break;
-      default: warp_sort_regs<16>(a); break;
-    }
-    __syncwarp();
-    return;
-  }
+  /* (a register-resident variant -- keys in lanes, exchanges by warp shuffle -- was measured slower than this one:
+   * 64-bit shuffles cost two SHFL each and the selects outweigh the saved shared-memory traffic) */
   for (uint32_t k = 2; k <= n; k <<= 1) {
     for (uint32_t j = k >> 1; j > 0; j >>= 1) {
       for (uint32_t t = grp<NT>::tid(); t < (n >> 1); t += NT) {
@@ -503,7 +437,7 @@ __device__ bool l1_segment(const mm_params &prm, const mm_dev_index &ix, const m
   grp<NT>::sync();
 
   /* ---- 2. gather the interval points (computeMap.hpp:887-907, order restored by the sort) ---- */
-  uint32_t n_pow2 = (NT == 32) ? 32 : 1; /* the warp path sorts in registers, 32 keys at least */
+  uint32_t n_pow2 = 1;
   while (n_pow2 < m) n_pow2 <<= 1;
   uint64_t *keys = skeys;
   uint32_t *copn = scopn, *head = shead, *ginfo = sginfo;
