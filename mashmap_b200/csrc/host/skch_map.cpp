@@ -9,6 +9,7 @@
 #include <mutex>
 #include <cstring>
 #include <fstream>
+#include <functional>
 #include <iostream>
 #include <limits>
 #include <sstream>
@@ -60,6 +61,62 @@ int BatchMapper::getRefGroup(const std::string &seqName) const
     if (queryPrefix == prefix(refSketch.metadata[i].name, param.prefix_delim)) return refIdGroup[i];
   return -1;
 }
+
+/* Persistent worker threads for the per-read host tail: a part's tail is a few milliseconds of work, creating a hundred
+ * threads for it costs as much again. One caller at a time. */
+class BatchMapper::WorkerPool {
+ public:
+  explicit WorkerPool(int n)
+  {
+    for (int i = 0; i < n; i++) threads_.emplace_back([this, i]() { loop(i); });
+  }
+  ~WorkerPool()
+  {
+    { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+    cvStart_.notify_all();
+    for (auto &t : threads_) t.join();
+  }
+  int size() const { return (int)threads_.size(); }
+  /* runs fn() on min(n, size()) workers and returns when all of them are back */
+  void run(int n, const std::function<void()> &fn)
+  {
+    n = std::min(n, size());
+    if (n <= 1) { fn(); return; }
+    std::unique_lock<std::mutex> lk(mu_);
+    fn_ = &fn; want_ = n; done_ = 0; gen_++;
+    cvStart_.notify_all();
+    cvDone_.wait(lk, [&] { return done_ == want_; });
+    fn_ = nullptr;
+  }
+
+ private:
+  void loop(int idx)
+  {
+    uint64_t seen = 0;
+    while (true) {
+      const std::function<void()> *fn = nullptr;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cvStart_.wait(lk, [&] { return stop_ || gen_ != seen; });
+        if (stop_) return;
+        seen = gen_;
+        if (idx < want_) fn = fn_;
+      }
+      if (fn) {
+        (*fn)();
+        std::lock_guard<std::mutex> lk(mu_);
+        if (++done_ == want_) cvDone_.notify_all();
+      }
+    }
+  }
+  std::vector<std::thread> threads_;
+  std::mutex mu_;
+  std::condition_variable cvStart_, cvDone_;
+  const std::function<void()> *fn_ = nullptr;
+  uint64_t gen_ = 0;
+  int want_ = 0, done_ = 0;
+  bool stop_ = false;
+};
 
 /* Upload chunks and the L2 phase exclude each other; a waiting L2 phase has priority over the next chunk. */
 struct BatchMapper::Gate {
@@ -124,6 +181,7 @@ BatchMapper::BatchMapper(const Parameters &p, const Sketch &refsketch) : param(p
   rc = mm_tables_upload(ctx, sketchCutoffs.data(), (int32_t)sketchCutoffs.size(), minHits.data(), (int32_t)minHits.size());
   if (rc != MM_OK) die(std::string("mm_tables_upload: ") + mm_last_error(ctx));
   tail_ = new MapTail(param, refSketch.metadata, refIdGroup);
+  tailPool = new WorkerPool(std::max(1, param.threads));
   // further contexts share the index image: one lane per pipeline stage in flight (upload / kernels / fetch + tail)
   lanes[0].ctx = ctx;
   nLanes = 1;
@@ -142,6 +200,7 @@ BatchMapper::BatchMapper(const Parameters &p, const Sketch &refsketch) : param(p
 
 BatchMapper::~BatchMapper()
 {
+  delete tailPool;
   delete tail_;
   for (int l = nLanes - 1; l >= 1; l--) mm_ctx_destroy(lanes[l].ctx);
   if (ctx) mm_ctx_destroy(ctx);
@@ -261,12 +320,7 @@ void BatchMapper::laneFinish(Lane &ln, const ReadBatch &b, std::vector<MappingRe
       }
     }
   };
-  if (nthreads == 1) worker();
-  else {
-    std::vector<std::thread> pool;
-    for (int t = 0; t < nthreads; t++) pool.emplace_back(worker);
-    for (auto &th : pool) th.join();
-  }
+  tailPool->run(nthreads, worker);
   ln.secTail += since(t0);
   static const bool trace = getenv("MM_TRACE") != nullptr;
   if (trace)

@@ -76,6 +76,8 @@ class BatchMapper {
   std::vector<int> contigNameId;
   mm_ctx *ctx = nullptr;   // owns the index image
   MapTail *tail_ = nullptr;
+  class WorkerPool;
+  WorkerPool *tailPool = nullptr;  // persistent threads of the per-read host tail
   struct Lane {  // per pipeline lane: device context (own stream + buffers) and its host-side record buffers
     mm_ctx *ctx = nullptr;
     std::vector<mm_segment> segs;
