@@ -4,6 +4,7 @@
 #include <atomic>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <fstream>
@@ -411,6 +412,13 @@ void Sketch::build()
  */
 void Sketch::index()
 {
+  static const bool trace = getenv("MM_TRACE") != nullptr;
+  auto tph = std::chrono::steady_clock::now();
+  auto phase = [&](const char *what) {
+    if (trace) std::cerr << "[trace] Sketch::index " << what << ": "
+                         << std::chrono::duration<double>(std::chrono::steady_clock::now() - tph).count() << " s" << std::endl;
+    tph = std::chrono::steady_clock::now();
+  };
   const size_t n = minmerIndex.size();
   lookupKeys.clear(); lookupOffsets.clear(); lookupPoints.clear(); lookupKeyIsFreq.clear();
   const int T = std::max(1, std::min(param.threads, 256));
@@ -439,101 +447,116 @@ void Sketch::index()
       });
     for (auto &th : pool) th.join();
   };
-  /* 1. counting partition: chunk c of the entries x part p */
+  /* Fresh memory is the expensive resource here (first touch of a page costs far more than copying it), so the pass
+   * allocates each big array once: one (hash, position) pair per entry, and the final arrays. */
+  /* 1. counting partition into (hash, index position) pairs: chunk c of the entries x part p */
   const size_t C = (size_t)T;
   const size_t chunk = (n + C - 1) / std::max<size_t>(C, 1);
-  std::vector<std::vector<uint64_t>> cnt(C, std::vector<uint64_t>(NP, 0));
-  std::vector<uint32_t> part_id(n);
+  std::vector<std::vector<uint64_t>> at(C, std::vector<uint64_t>(NP, 0));
   run_threads(C, [&](size_t c) {
     const size_t lo = std::min(n, c * chunk), hi = std::min(n, lo + chunk);
-    for (size_t i = lo; i < hi; i++) {
-      const uint32_t p = (uint32_t)part_of(minmerIndex[i].hash);
-      part_id[i] = p;
-      cnt[c][p]++;
-    }
+    for (size_t i = lo; i < hi; i++) at[c][part_of(minmerIndex[i].hash)]++;
   });
   std::vector<uint64_t> part_start(NP + 1, 0);
-  std::vector<std::vector<uint64_t>> at(C, std::vector<uint64_t>(NP, 0));
   {
     uint64_t run = 0;
     for (size_t p = 0; p < NP; p++) {
       part_start[p] = run;
-      for (size_t c = 0; c < C; c++) { at[c][p] = run; run += cnt[c][p]; }
+      for (size_t c = 0; c < C; c++) { const uint64_t k = at[c][p]; at[c][p] = run; run += k; }
     }
     part_start[NP] = run;
   }
-  std::vector<uint64_t> order(n);
+  typedef std::pair<hash_t, uint64_t> HashPos;
+  BigVec<HashPos> kv(n);
   run_threads(C, [&](size_t c) {
     const size_t lo = std::min(n, c * chunk), hi = std::min(n, lo + chunk);
     std::vector<uint64_t> &pos = at[c];
-    for (size_t i = lo; i < hi; i++) order[pos[part_id[i]]++] = i;
-  });
-  std::vector<uint32_t>().swap(part_id);
-  /* 2. per part: sort by hash (index order kept), emit keys / point counts / points */
-  struct PartOut {
-    std::vector<hash_t> keys;
-    std::vector<uint32_t> n_points;   /* per key */
-    std::vector<uint32_t> n_entries;  /* per key: minmer entries with that hash */
-    std::vector<IntervalPoint> points;
-  };
-  std::vector<PartOut> parts(NP);
-  run_threads(NP, [&](size_t p) {
-    uint64_t *b = order.data() + part_start[p], *e = order.data() + part_start[p + 1];
-    std::stable_sort(b, e, [this](uint64_t x, uint64_t y) { return minmerIndex[x].hash < minmerIndex[y].hash; });
-    PartOut &o = parts[p];
-    o.points.reserve((size_t)(e - b) * 2);
-    for (uint64_t *it = b; it != e;) {
-      const hash_t h = minmerIndex[*it].hash;
-      const size_t first_pt = o.points.size();
-      uint32_t ne = 0;
-      for (; it != e && minmerIndex[*it].hash == h; ++it, ++ne) {
-        const MinmerInfo &mi = minmerIndex[*it];
-        if (o.points.size() == first_pt || o.points.back().pos != mi.wpos) {
-          IntervalPoint a{}; a.pos = mi.wpos; a.hash = mi.hash; a.seqId = mi.seqId; a.side = side::OPEN;
-          IntervalPoint c2{}; c2.pos = mi.wpos_end; c2.hash = mi.hash; c2.seqId = mi.seqId; c2.side = side::CLOSE;
-          o.points.push_back(a);
-          o.points.push_back(c2);
-        } else {
-          o.points.back().pos = mi.wpos_end;
-        }
-      }
-      o.keys.push_back(h);
-      o.n_points.push_back((uint32_t)(o.points.size() - first_pt));
-      o.n_entries.push_back(ne);
+    for (size_t i = lo; i < hi; i++) {
+      const hash_t h = minmerIndex[i].hash;
+      kv[pos[part_of(h)]++] = HashPos(h, (uint64_t)i);
     }
   });
-  /* concatenate (parts are ascending hash ranges) */
-  std::vector<uint64_t> key_base(NP + 1, 0), pt_base(NP + 1, 0);
-  for (size_t p = 0; p < NP; p++) {
-    key_base[p + 1] = key_base[p] + parts[p].keys.size();
-    pt_base[p + 1] = pt_base[p] + parts[p].points.size();
-  }
-  lookupKeys.resize(key_base[NP]);
-  lookupOffsets.resize(key_base[NP] + 1);
-  lookupPoints.resize(pt_base[NP]);
-  lookupKeyIsFreq.assign(key_base[NP], 0);
+  phase("partition");
+  /* 2. per part: order by (hash, index position) and count keys and interval points (winSketch.hpp:383-396: an interval
+   *    that starts where the previous one of the same hash ended is fused into it -- whatever the contig) */
+  std::vector<uint64_t> n_keys(NP + 1, 0), n_pts(NP + 1, 0);
   run_threads(NP, [&](size_t p) {
-    const PartOut &o = parts[p];
-    if (!o.keys.empty()) memcpy(&lookupKeys[key_base[p]], o.keys.data(), o.keys.size() * sizeof(hash_t));
-    if (!o.points.empty()) memcpy(&lookupPoints[pt_base[p]], o.points.data(), o.points.size() * sizeof(IntervalPoint));
-    uint64_t run = pt_base[p];
-    for (size_t k = 0; k < o.keys.size(); k++) { lookupOffsets[key_base[p] + k] = run; run += o.n_points[k]; }
+    HashPos *b = kv.data() + part_start[p], *e = kv.data() + part_start[p + 1];
+    std::sort(b, e);
+    uint64_t keys = 0, pts = 0;
+    for (HashPos *it = b; it != e;) {
+      const hash_t h = it->first;
+      bool have = false;
+      offset_t last_pos = 0;
+      for (; it != e && it->first == h; ++it) {
+        const MinmerInfo &mi = minmerIndex[it->second];
+        if (!have || last_pos != mi.wpos) pts += 2;
+        have = true;
+        last_pos = mi.wpos_end;
+      }
+      keys++;
+    }
+    n_keys[p + 1] = keys; n_pts[p + 1] = pts;
   });
-  lookupOffsets[key_base[NP]] = pt_base[NP];
+  for (size_t p = 0; p < NP; p++) { n_keys[p + 1] += n_keys[p]; n_pts[p + 1] += n_pts[p]; }
+  phase("per-part sort + count");
+  /* 3. emit straight into the final arrays (parts are ascending hash ranges) */
+  lookupKeys.resize(n_keys[NP]);
+  lookupOffsets.resize(n_keys[NP] + 1);
+  lookupPoints.resize(n_pts[NP]);
+  lookupKeyIsFreq.resize(n_keys[NP]);
+  run_threads(NP, [&](size_t p) {
+    const HashPos *b = kv.data() + part_start[p], *e = kv.data() + part_start[p + 1];
+    uint64_t k = n_keys[p], w = n_pts[p];
+    for (const HashPos *it = b; it != e;) {
+      const hash_t h = it->first;
+      const uint64_t first_pt = w;
+      for (; it != e && it->first == h; ++it) {
+        const MinmerInfo &mi = minmerIndex[it->second];
+        if (w == first_pt || lookupPoints[w - 1].pos != mi.wpos) {
+          IntervalPoint a{}; a.pos = mi.wpos; a.hash = mi.hash; a.seqId = mi.seqId; a.side = side::OPEN;
+          IntervalPoint c2{}; c2.pos = mi.wpos_end; c2.hash = mi.hash; c2.seqId = mi.seqId; c2.side = side::CLOSE;
+          lookupPoints[w++] = a;
+          lookupPoints[w++] = c2;
+        } else {
+          lookupPoints[w - 1].pos = mi.wpos_end;
+        }
+      }
+      lookupKeys[k] = h;
+      lookupOffsets[k] = first_pt;
+      lookupKeyIsFreq[k] = 0;
+      k++;
+    }
+  });
+  lookupOffsets[n_keys[NP]] = n_pts[NP];
+  phase("emit keys / points");
   std::cerr << "[mashmap-b200::skch::Sketch::index] unique minmers = " << lookupKeys.size() << std::endl;
   if (saving_) return; /* the caller saves the un-filtered index first (winSketch.hpp:127-134) and calls again */
 
-  /* 3. frequency threshold (winSketch.hpp:410-453) */
+  /* 4. frequency threshold (winSketch.hpp:410-453) */
   if (lookupKeys.empty()) {
     std::cerr << "[mashmap-b200::skch::Sketch::computeFreqHist] No minmers." << std::endl;
     return;
   }
   std::map<int, int> hist;
-  for (size_t p = 0; p < NP; p++)
-    for (uint32_t c : parts[p].n_points) hist[(int)c] += 1;
+  {  // per-part counts first (one map update per key on one thread cost seconds at 140 M keys)
+    std::vector<std::vector<uint32_t>> ph(NP);
+    run_threads(NP, [&](size_t p) {
+      std::vector<uint32_t> &hh = ph[p];
+      for (uint64_t k = n_keys[p]; k < n_keys[p + 1]; k++) {
+        const uint64_t c = lookupOffsets[k + 1] - lookupOffsets[k];
+        if (c >= hh.size()) hh.resize((size_t)c + 1, 0);
+        hh[c]++;
+      }
+    });
+    for (size_t p = 0; p < NP; p++)
+      for (size_t c = 0; c < ph[p].size(); c++)
+        if (ph[p][c]) hist[(int)c] += (int)ph[p][c];
+  }
   std::cerr << "[mashmap-b200::skch::Sketch::computeFreqHist] Frequency histogram of minmer interval points = ("
             << hist.begin()->first << ", " << hist.begin()->second << ") ... (" << hist.rbegin()->first << ", "
             << hist.rbegin()->second << ")" << std::endl;
+  phase("histogram");
   int64_t totalUniqueMinmers = lookupKeys.size();
   int64_t minmerToIgnore = totalUniqueMinmers * param.kmer_pct_threshold / 100;
   int64_t sum = 0;
@@ -554,41 +577,33 @@ void Sketch::index()
   else
     std::cerr << "[mashmap-b200::skch::Sketch::computeFreqHist] With threshold " << param.kmer_pct_threshold
               << "%, consider all minmers during lookup." << std::endl;
-  /* 4. frequent seeds (:488-504): flag the keys, drop their entries from minmerIndex only */
+  /* 5. frequent seeds (:488-504): flag the keys, drop their entries from minmerIndex only */
   if (freqThreshold == std::numeric_limits<int>::max()) return;
-  std::vector<uint8_t> drop(n, 0);
-  std::atomic<uint64_t> n_drop{0};
+  std::vector<std::vector<uint64_t>> dropped(NP); /* index positions to remove (few: 0.001 % of the keys by default) */
   run_threads(NP, [&](size_t p) {
-    const PartOut &o = parts[p];
-    const uint64_t *it = order.data() + part_start[p];
-    uint64_t local = 0;
-    for (size_t k = 0; k < o.keys.size(); k++) {
-      const bool fr = (int64_t)o.n_points[k] >= (int64_t)freqThreshold;
-      if (fr) {
-        lookupKeyIsFreq[key_base[p] + k] = 1;
-        for (uint32_t j = 0; j < o.n_entries[k]; j++) drop[it[j]] = 1;
-        local += o.n_entries[k];
-      }
-      it += o.n_entries[k];
+    const HashPos *it = kv.data() + part_start[p];
+    for (uint64_t k = n_keys[p]; k < n_keys[p + 1]; k++) {
+      const hash_t h = lookupKeys[k];
+      const bool fr = (int64_t)(lookupOffsets[k + 1] - lookupOffsets[k]) >= (int64_t)freqThreshold;
+      if (fr) lookupKeyIsFreq[k] = 1;
+      for (; it != kv.data() + part_start[p + 1] && it->first == h; ++it)
+        if (fr) dropped[p].push_back(it->second);
     }
-    n_drop += local;
   });
-  if (n_drop.load() > 0) {
-    size_t w = 0;
-    for (size_t i = 0; i < n; i++)
-      if (!drop[i]) { if (w != i) minmerIndex[w] = minmerIndex[i]; w++; }
+  std::vector<uint64_t> drop;
+  for (auto &d : dropped) drop.insert(drop.end(), d.begin(), d.end());
+  phase("frequent flags");
+  if (!drop.empty()) {  // order-preserving removal in place: the runs between removed entries slide down
+    std::sort(drop.begin(), drop.end());
+    size_t w = drop[0];
+    for (size_t j = 0; j < drop.size(); j++) {
+      const size_t from = drop[j] + 1, to = j + 1 < drop.size() ? drop[j + 1] : n;
+      if (to > from) memmove(&minmerIndex[w], &minmerIndex[from], (to - from) * sizeof(MinmerInfo));
+      w += to - from;
+    }
     minmerIndex.resize(w);
   }
-}
-
-void Sketch::computeFreqHist() {}  /* folded into index() */
-void Sketch::dropFreqSeedSet() {}  /* folded into index() */
-
-bool Sketch::isFreqSeed(hash_t h) const
-{
-  auto it = std::lower_bound(lookupKeys.begin(), lookupKeys.end(), h);
-  if (it == lookupKeys.end() || *it != h) return false;
-  return lookupKeyIsFreq[(size_t)(it - lookupKeys.begin())] != 0;
+  phase("compaction");
 }
 
 void Sketch::saveIndexTSV(const std::string &path) const

@@ -16,12 +16,25 @@
 #define SKCH_INDEX_HPP
 
 #include <limits>
+#include <memory>
 #include <string>
+#include <type_traits>
+#include <utility>
 #include <vector>
 
 #include "skch_types.hpp"
 
 namespace skch {
+
+template <class T>
+struct default_init_allocator : std::allocator<T> {
+  template <class U> struct rebind { typedef default_init_allocator<U> other; };
+  default_init_allocator() = default;
+  template <class U> default_init_allocator(const default_init_allocator<U> &) {}
+  template <class U> void construct(U *p) noexcept(std::is_nothrow_default_constructible<U>::value) { ::new ((void *)p) U; }
+  template <class U, class... A> void construct(U *p, A &&...a) { ::new ((void *)p) U(std::forward<A>(a)...); }
+};
+template <class T> using BigVec = std::vector<T, default_init_allocator<T>>;
 
 namespace CommonFunc {
 /* commonFunc.hpp:301-570 */
@@ -47,9 +60,11 @@ class Sketch {
 
   // minmerPosLookupIndex (winSketch.hpp:101), flattened: keys ascending; points of keys[i] are
   // lookupPoints[lookupOffsets[i] .. lookupOffsets[i+1]) in reference per-key order
-  std::vector<hash_t> lookupKeys;
-  std::vector<uint64_t> lookupOffsets;
-  std::vector<IntervalPoint> lookupPoints;
+  // (BigVec: resize() leaves trivially-constructible elements uninitialised -- these arrays are filled by all threads
+  //  right away, and zero-filling 12 GB of points on one thread first cost seconds at 3 Gbp)
+  BigVec<hash_t> lookupKeys;
+  BigVec<uint64_t> lookupOffsets;
+  BigVec<IntervalPoint> lookupPoints;
   std::vector<uint8_t> lookupKeyIsFreq;      // frequentSeeds membership per key (winSketch.hpp:488-495)
 
   int getFreqThreshold() const { return freqThreshold; }   // winSketch.hpp:483-486
