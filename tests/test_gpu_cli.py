@@ -120,3 +120,39 @@ def test_small_batches_and_threads_do_not_change_output(workdir):
         outs.append(open(o).read())
     assert outs[0] == outs[1] == outs[2] == outs[3]
     assert len(outs[0]) > 0
+
+
+def test_fastq_gz_and_multiple_query_files(workdir):
+    """gzip'ed FASTQ and several query files go through the line reader; plain FASTA through the mapped bulk reader:
+    same PAF as the reference on the same files, and the same as the single plain FASTA file"""
+    import gzip
+
+    d = datasets.make_panel_set(workdir, tag="clip")
+    names, seqs = [], []
+    for line in open(d["qry"]):
+        if line.startswith(">"):
+            names.append(line[1:].strip()); seqs.append("")
+        else:
+            seqs[-1] += line.strip()
+    half = len(names) // 2
+    fq = os.path.join(workdir, "q_first.fq.gz")
+    with gzip.open(fq, "wt") as f:
+        for n, s_ in zip(names[:half], seqs[:half]):
+            f.write(f"@{n} extra words\n{s_}\n+\n{'I' * len(s_)}\n")
+    fa2 = os.path.join(workdir, "q_second.fa")
+    with open(fa2, "w") as f:
+        for n, s_ in zip(names[half:], seqs[half:]):
+            f.write(f">{n}\n")
+            for o in range(0, len(s_), 70):
+                f.write(s_[o : o + 70] + "\n")
+    args = ["-s", "5000", "--pi", "85", "-t", "4"]
+    ref_out, got_out, one_out = (os.path.join(workdir, x) for x in ("mq_ref.paf", "mq_got.paf", "mq_one.paf"))
+    ql = os.path.join(workdir, "queries.txt")
+    with open(ql, "w") as f:
+        f.write(fq + "\n" + fa2 + "\n")
+    run([refh.REF_BIN, "-r", d["ref"], "--ql", ql, "-o", ref_out] + args)
+    run([hostlib.CLI_PATH, "-r", d["ref"], "--ql", ql, "-o", got_out] + args)
+    run([hostlib.CLI_PATH, "-r", d["ref"], "-q", d["qry"], "-o", one_out] + args)
+    n_equal, tolerated, problems = compare_paf(parse(ref_out), parse(got_out), 5000)
+    assert not problems and n_equal > 0
+    assert open(got_out).read() == open(one_out).read()
