@@ -102,6 +102,25 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_cpu_info():
+    """what the host side really has: visible CPUs, affinity, cgroup quota (a container can show 128 CPUs and be allowed a
+    fraction of them) -- reported next to cpu_baseline.cores, which is the number of threads used"""
+    info = {"visible": os.cpu_count(), "affinity": len(os.sched_getaffinity(0))}
+    try:
+        q = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q and q[0] != "max":
+            info["cgroup_quota_cpus"] = round(int(q[0]) / int(q[1]), 2)
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                info["cgroup_quota_cpus"] = round(q / per, 2)
+        except Exception:
+            pass
+    return info
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -335,10 +354,14 @@ def cpu_baseline(args, hi, batch, S, threads=None, n_reads=None):
         rate = pilot / max(time.time() - t0, 1e-3)
         n_reads = int(min(total_reads, max(pilot, rate * 4.0)))  # the pilot over-estimates the sustained rate ~4x
     t0 = time.time()
+    c0 = os.times()
     n_map = L.orc_map_reads_mt(O.h, batch.bases.ctypes.data, n_reads, READ_LEN, 0, threads, C.byref(mapped))
     dt = time.time() - t0
+    c1 = os.times()
     O.close()
+    busy = ((c1.user - c0.user) + (c1.system - c0.system)) / max(dt, 1e-9)  # CPUs actually kept busy by the threads
     return {"value": n_reads * READ_LEN / dt / 1e9, "unit": "Gbp/s", "cores": threads, "kind": "port",
+            "cpus_busy": round(busy, 1), "host": host_cpu_info(),
             "sample": f"first {n_reads} reads of the batch ({n_reads * READ_LEN / 1e6:.0f} Mbp), oracle/libmm_oracle.so mapModule per read "
                       f"on {threads} threads, {dt:.1f} s; {mapped.value} reads mapped, {n_map} mappings"}
 
