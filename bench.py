@@ -308,6 +308,7 @@ def gpu_arm(args):
                          "frac": achieved / peak,
                          "traffic": (traffic["k_sketch_dram_bytes_per_segment"] * n_segs if "k_sketch_dram_bytes_per_segment" in traffic else None),
                          "peak_source": peak_src, "algorithmic_bytes_per_segment": b1,
+                         "instruction_roofline": _instruction_roofline(n_segs, k1_ms, clocks, torch.cuda.get_device_properties(local_rank).multi_processor_count),
                          "note": "bit-exact Murmur3 makes K1 INT-ALU bound (SURVEY 8(d)); see DESIGN.md for the instruction roofline"},
         }
         if not args.no_cpu_baseline and world == 1:
@@ -316,6 +317,20 @@ def gpu_arm(args):
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+K1_INSTR_PER_POSITION = 236  # executed SASS instructions per k-mer position in k_sketch's loop (scripts/sass_loops.py)
+
+
+def _instruction_roofline(n_segs, k1_ms, clocks, sm_count):
+    """K1 is bound by instruction issue, not by HBM: positions hashed per second against one instruction per cycle per
+    scheduler (4 per SM) at the SM clock sampled during the run"""
+    positions = n_segs * (SEG - K + 1)
+    achieved = positions / (k1_ms * 1e-3) / 1e9
+    mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    peak = sm_count * 4 * mhz * 1e6 / K1_INSTR_PER_POSITION / 1e9
+    return {"unit": "G k-mer positions/s", "achieved": achieved, "peak": peak, "frac": achieved / peak,
+            "instructions_per_position": K1_INSTR_PER_POSITION}
 
 
 def _accuracy(res, truth, contig_len, first_counter):
