@@ -341,14 +341,25 @@ void BatchMapper::mapBatch(const ReadBatch &b, std::vector<MappingResultsVector_
   double d0 = 0, t0 = 0;
   for (auto &ln : lanes) { d0 += ln.secDevice; t0 += ln.secTail; }
   // parts of ~SUB bases (a read is never split across parts)
+  // A large batch starts and ends with smaller parts: the first upload (nothing to hide it behind) and the last
+  // fetch + host tail (nothing left to hide it) are the exposed ends of the pipeline.
   const uint64_t SUB = std::max<uint64_t>(param.sub_batch_bases, 1);
+  std::vector<uint64_t> targets;
+  if (b.used >= 4 * SUB) {
+    uint64_t left = b.used;
+    for (uint64_t t : {SUB / 4, SUB / 2}) { targets.push_back(std::max<uint64_t>(t, 1)); left -= std::min(left, t); }
+    while (left > SUB + SUB / 2 + SUB / 4) { targets.push_back(SUB); left -= SUB; }
+    targets.push_back(std::max<uint64_t>(left * 4 / 7, 1));  // the rest in two parts, the last one the smaller
+    targets.push_back(~0ULL);
+  }
   std::vector<std::pair<size_t, size_t>> parts;
   {
     size_t r0 = 0;
     uint64_t acc = 0;
     for (size_t r = 0; r < nreads; r++) {
       acc += (uint64_t)b.reads[r].len;
-      if (acc >= SUB || r + 1 == nreads) { parts.emplace_back(r0, r + 1); r0 = r + 1; acc = 0; }
+      const uint64_t want = parts.size() < targets.size() ? targets[parts.size()] : SUB;
+      if (acc >= want || r + 1 == nreads) { parts.emplace_back(r0, r + 1); r0 = r + 1; acc = 0; }
     }
   }
   const size_t np = parts.size();
