@@ -328,7 +328,7 @@ def _instruction_roofline(n_segs, k1_ms, clocks, sm_count):
     positions = n_segs * (SEG - K + 1)
     achieved = positions / (k1_ms * 1e-3) / 1e9
     mhz = (clocks or {}).get("sm_mhz") or 1965.0
-    peak = sm_count * 4 * mhz * 1e6 / K1_INSTR_PER_POSITION / 1e9
+    peak = sm_count * 4 * mhz * 1e6 * 32 / K1_INSTR_PER_POSITION / 1e9  # a warp instruction serves 32 positions
     return {"unit": "G k-mer positions/s", "achieved": achieved, "peak": peak, "frac": achieved / peak,
             "instructions_per_position": K1_INSTR_PER_POSITION}
 

@@ -225,6 +225,7 @@ class Context:
         bases = np.ascontiguousarray(bases, dtype=np.uint8)
         segments = _c(segments, segment_dtype)
         n = len(segments)
+        self._n_segs = n
         seg_res = np.zeros(n, dtype=segres_dtype)
         cap_c, cap_l = 2 * n + 1024, 4 * n + 2048
         while True:

@@ -341,13 +341,13 @@ void BatchMapper::mapBatch(const ReadBatch &b, std::vector<MappingResultsVector_
   double d0 = 0, t0 = 0;
   for (auto &ln : lanes) { d0 += ln.secDevice; t0 += ln.secTail; }
   // parts of ~SUB bases (a read is never split across parts)
-  // A large batch starts and ends with smaller parts: the first upload (nothing to hide it behind) and the last
-  // fetch + host tail (nothing left to hide it) are the exposed ends of the pipeline.
+  // A large batch ends with smaller parts: the last fetch + host tail has nothing left to hide behind. (Smaller FIRST
+  // parts were tried too and lost: the upload runs barely faster than the kernels, so a short first part only makes the
+  // compute thread wait for the second upload.)
   const uint64_t SUB = std::max<uint64_t>(param.sub_batch_bases, 1);
   std::vector<uint64_t> targets;
   if (b.used >= 4 * SUB) {
     uint64_t left = b.used;
-    for (uint64_t t : {SUB / 4, SUB / 2}) { targets.push_back(std::max<uint64_t>(t, 1)); left -= std::min(left, t); }
     while (left > SUB + SUB / 2 + SUB / 4) { targets.push_back(SUB); left -= SUB; }
     targets.push_back(std::max<uint64_t>(left * 4 / 7, 1));  // the rest in two parts, the last one the smaller
     targets.push_back(~0ULL);

@@ -122,7 +122,6 @@ def test_small_batches_and_threads_do_not_change_output(workdir):
     assert len(outs[0]) > 0
 
 
-@pytest.mark.skipif(not os.environ.get("MM_UNVERIFIED"), reason="written while the GPU pool was busy: enabled once it has passed on a B200")
 def test_fastq_gz_and_multiple_query_files(workdir):
     """gzip'ed FASTQ and several query files go through the line reader; plain FASTA through the mapped bulk reader:
     same PAF as the reference on the same files, and the same as the single plain FASTA file"""

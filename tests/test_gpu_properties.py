@@ -9,8 +9,7 @@ import pytest
 
 from conftest import have_gpu
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not have_gpu(), reason="no GPU"),
-              pytest.mark.skipif(not os.environ.get("MM_UNVERIFIED"), reason="written while the GPU pool was busy: enabled once it has passed on a B200")]
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not have_gpu(), reason="no GPU")]
 
 K, SEG, S, PI = 19, 5000, 220, 0.85
 N_READS, READ_LEN, N_CONTIGS, CONTIG_LEN = 60_000, 10_000, 16, 6_250_000
