@@ -121,6 +121,15 @@ def host_cpu_info():
     return info
 
 
+def usable_cpus():
+    """CPUs this process can really use: visible CPUs, limited by the affinity mask and the cgroup CPU quota"""
+    info = host_cpu_info()
+    n = min(info["visible"] or 8, info["affinity"])
+    if "cgroup_quota_cpus" in info:
+        n = min(n, max(1, int(info["cgroup_quota_cpus"])))
+    return max(1, n)
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -195,14 +204,14 @@ def gpu_arm(args):
     from mashmap_b200 import capi, hostlib
     from mashmap_b200 import dist as mdist
 
-    host_threads = max(1, (os.cpu_count() or 8) // max(1, world))
+    host_threads = max(1, usable_cpus() // max(1, world))  # sized to the CPU quota: more threads than CPUs only adds throttling
     wl = setup_workload(args, rank, world, device)
     S = wl["sketch"]
 
     # ---- index: built on the host by rank 0, uploaded; other ranks receive the device image over NCCL ----
     t_index = time.time()
     if rank == 0:
-        hi = build_index(args, wl, os.cpu_count() or 8)
+        hi = build_index(args, wl, os.cpu_count() or 8)  # memory-latency-bound tasks: oversubscription is harmless here
     else:
         hi = hostlib.HostIndex.metadata_only(args.contigs, wl["contig_len"], K, SEG, S)  # the index arrives by broadcast
     bm = hostlib.BatchMapper(hi, pi=PI, device=local_rank, threads=host_threads)
@@ -349,7 +358,7 @@ def cpu_baseline(args, hi, batch, S, threads=None, n_reads=None):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_py
 
-    threads = threads or (os.cpu_count() or 8)
+    threads = threads or usable_cpus()
     mi, keys, offs, pts, fr = hi.arrays()
     O = oracle_py.Oracle(K, SEG, S, PI)
     O.set_index(mi, keys, offs, pts, fr, np.full(args.contigs, args.ref_bp // args.contigs, dtype=np.int32))
@@ -395,7 +404,7 @@ def cpu_arm(args):
     from mashmap_b200 import hostlib
 
     device = torch.device("cuda:0") if torch.cuda.is_available() else torch.device("cpu")
-    threads = os.cpu_count() or 8
+    threads = usable_cpus()
     sample = args.cpu_sample_reads or 1500 * threads  # ~15 s per step at ~0.1 Gbp/s on 128 cores
     a2 = argparse.Namespace(**vars(args))
     a2.reads = sample
