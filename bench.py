@@ -160,19 +160,22 @@ def setup_workload(args, rank, world, device):
     contig_len = args.ref_bp // args.contigs
     t0 = time.time()
     ref = synth_gpu.random_reference(args.contigs, contig_len, seed=1, device=device)
-    torch.cuda.synchronize()
+    if device.type == "cuda":
+        torch.cuda.synchronize()
     log(f"rank {rank}: reference {args.contigs} x {contig_len} bp generated in {time.time() - t0:.1f} s")
     sketch = args.sketch or int(hostlib.lib().skch_recommended_sketch_size(K, PI, SEG, int(args.ref_bp * REF_FASTA_BYTES_PER_BASE) + 16 * args.contigs))
     t0 = time.time()
     reads_dev, truth = synth_gpu.simulate_reads(ref, args.reads, READ_LEN, 0.02, 0.14, seed=2 + rank, chunk=8192)
-    torch.cuda.synchronize()
+    if device.type == "cuda":
+        torch.cuda.synchronize()
     log(f"rank {rank}: {args.reads} reads simulated in {time.time() - t0:.1f} s; sketch size {sketch}")
     ref_host = None
     if rank == 0:
         ref_host = ref.cpu().numpy().reshape(-1)
     contig_of, start_of, strand_of = truth["contig"].cpu().numpy(), truth["start"].cpu().numpy(), truth["strand"].cpu().numpy()
     del ref
-    torch.cuda.empty_cache()
+    if device.type == "cuda":
+        torch.cuda.empty_cache()
     return dict(ref_host=ref_host, contig_len=contig_len, sketch=sketch, reads_dev=reads_dev,
                 truth=(contig_of, start_of, strand_of))
 
@@ -371,12 +374,8 @@ def cpu_baseline(args, hi, batch, S, threads=None, n_reads=None):
     total_reads = len(batch.bases) // READ_LEN
     if not n_reads:
         n_reads = args.cpu_sample_reads
-    if not n_reads:  # pilot run, then a sample sized for about 15 s of wall time on all cores
-        pilot = min(total_reads, 4 * threads)
-        t0 = time.time()
-        L.orc_map_reads_mt(O.h, batch.bases.ctypes.data, pilot, READ_LEN, 0, threads, C.byref(mapped))
-        rate = pilot / max(time.time() - t0, 1e-3)
-        n_reads = int(min(total_reads, max(pilot, rate * 4.0)))  # the pilot over-estimates the sustained rate ~4x
+    if not n_reads:  # about 15 s of wall time: the port maps ~1,100 reads (11 Mbp) per second per CPU on this workload
+        n_reads = int(min(total_reads, 17000 * threads))
     t0 = time.time()
     c0 = os.times()
     n_map = L.orc_map_reads_mt(O.h, batch.bases.ctypes.data, n_reads, READ_LEN, 0, threads, C.byref(mapped))
@@ -405,7 +404,7 @@ def cpu_arm(args):
 
     device = torch.device("cuda:0") if torch.cuda.is_available() else torch.device("cpu")
     threads = usable_cpus()
-    sample = args.cpu_sample_reads or 1500 * threads  # ~15 s per step at ~0.1 Gbp/s on 128 cores
+    sample = args.cpu_sample_reads or min(args.reads, 17000 * threads)  # ~15 s per step (~1,100 reads/s per CPU)
     a2 = argparse.Namespace(**vars(args))
     a2.reads = sample
     wl = setup_workload(a2, 0, 1, device)
