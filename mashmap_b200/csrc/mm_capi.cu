@@ -44,6 +44,8 @@ struct mm_ctx {
   mm_l1_candidate *d_cands = nullptr; uint64_t cand_cap = 0;
   mm_l2_locus *d_loci = nullptr; uint64_t loci_cap = 0;
   uint32_t *d_counters = nullptr;
+  bool blocking_wait = false;       /* MM_BLOCKING_WAIT=1: host waits block on an event instead of spinning (experiment) */
+  cudaEvent_t ev_wait = nullptr;
   const mm_ctx *share_src = nullptr; /* mm_ctx_share_index: the context whose index image this one reads */
   mm_phase_hook hook = nullptr;
   void *hook_user = nullptr;
@@ -141,6 +143,15 @@ int write_tables(mm_ctx *c)
   return MM_OK;
 }
 
+/* wait for the context's stream. Default: cudaStreamSynchronize (spins, lowest latency). With MM_BLOCKING_WAIT=1 the
+ * thread sleeps on a blocking event instead -- for hosts with fewer usable CPUs than pipeline threads. */
+cudaError_t wait_stream(mm_ctx *c)
+{
+  if (!c->blocking_wait) return cudaStreamSynchronize(c->stream);
+  const cudaError_t e = cudaEventRecord(c->ev_wait, c->stream);
+  return e != cudaSuccess ? e : cudaEventSynchronize(c->ev_wait);
+}
+
 int check_ready(mm_ctx *c)
 {
   if (!c) return MM_EINVAL;
@@ -203,7 +214,7 @@ int upload_batch(mm_ctx *c, const char *bases, uint64_t n_bases, const mm_segmen
       const uint64_t n = std::min(CH, n_bases - at);
       c->hook(c->hook_user, MM_PHASE_UPLOAD_CHUNK, 1);
       cudaError_t e = cudaMemcpyAsync(c->d_bases + at, bases + at, n, cudaMemcpyHostToDevice, c->stream);
-      if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+      if (e == cudaSuccess) e = wait_stream(c);
       c->hook(c->hook_user, MM_PHASE_UPLOAD_CHUNK, 0);
       CU(c, e);
     }
@@ -267,7 +278,7 @@ int read_words(mm_ctx *c, const void *dev, uint32_t *out, int n_words)
   k_publish<<<1, 32, 0, c->stream>>>((const uint32_t *)dev, c->h_pub, n_words);
   c->launches++;
   CU(c, cudaGetLastError());
-  CU(c, cudaStreamSynchronize(c->stream));
+  CU(c, wait_stream(c));
   for (int i = 0; i < n_words; i++) out[i] = c->h_pub[i];
   return MM_OK;
 }
@@ -282,7 +293,7 @@ int run_l2_stream(mm_ctx *c, uint32_t *h_cnt)
   CU(c, cudaEventRecord(c->ev[3], c->stream));
   if (nc == 0) {
     CU(c, cudaEventRecord(c->ev[4], c->stream));
-    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, wait_stream(c));
     c->n_loci = 0;
     return MM_OK;
   }
@@ -367,7 +378,7 @@ int run_l2_stream(mm_ctx *c, uint32_t *h_cnt)
       extent = h_cnt[6];
     }
     CU(c, cudaEventRecord(c->ev[4], c->stream));
-    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, wait_stream(c));
     cudaEventElapsedTime(&c->stage_ms[6], c->ev[8], c->ev[9]); /* k_l2_prep */
     cudaEventElapsedTime(&c->stage_ms[7], c->ev[9], c->ev[4]); /* k_l2_scan (+ overflow kernel) */
     c->n_loci = extent;
@@ -511,6 +522,10 @@ int mm_ctx_create(int device, const mm_params *params, mm_ctx **out)
     delete c;
     return fail(nullptr, MM_ENOMEM, "cannot allocate the pinned counter page");
   }
+  if (const char *g = getenv("MM_BLOCKING_WAIT")) {
+    if (g[0] == '1' && cudaEventCreateWithFlags(&c->ev_wait, cudaEventBlockingSync | cudaEventDisableTiming) == cudaSuccess)
+      c->blocking_wait = true;
+  }
   if (const char *g = getenv("MM_L2_GENERAL")) c->l2_mode = (g[0] == '1') ? 0 : 1; /* test hook: general kernel only */
   if (const char *g = getenv("MM_L1_CTA")) c->l1_warp = (g[0] == '1') ? 0 : 1; /* test hook: general L1 path only */
   if (params->sketch_size > 1000) c->l2_mode = 0; /* the stream kernel packs its counters in 11 bits */
@@ -529,6 +544,7 @@ int mm_ctx_destroy(mm_ctx *c)
   cudaFree(c->d_l1_slow); cudaFree(c->d_l2_order); cudaFree(c->d_l2_ranges); cudaFree(c->d_l2_rec_off); cudaFree(c->d_l2_recs); cudaFree(c->d_scan_tmp);
   for (auto &ev : c->ev) cudaEventDestroy(ev);
   if (c->h_pub) cudaFreeHost(c->h_pub);
+  if (c->ev_wait) cudaEventDestroy(c->ev_wait);
   cudaStreamDestroy(c->stream);
   delete c;
   return MM_OK;
@@ -718,7 +734,7 @@ int mm_batch_upload(mm_ctx *c, const char *bases, uint64_t n_bases, const mm_seg
   if (!c || (!bases && n_bases) || (!segs && n_segs)) return fail(c, MM_EINVAL, "null argument");
   int rc = upload_batch(c, bases, n_bases, segs, n_segs);
   if (rc) return rc;
-  CU(c, cudaStreamSynchronize(c->stream));
+  CU(c, wait_stream(c));
   cudaEventElapsedTime(&c->stage_ms[3], c->ev[6], c->ev[7]);
   return MM_OK;
 }
@@ -744,7 +760,7 @@ int mm_batch_fetch(mm_ctx *c, mm_segment_result *seg_results, mm_l1_candidate *c
   if (cands && c->n_cands) CU(c, cudaMemcpyAsync(cands, c->d_cands, c->n_cands * sizeof(mm_l1_candidate), cudaMemcpyDeviceToHost, c->stream));
   if (loci && c->n_loci) CU(c, cudaMemcpyAsync(loci, c->d_loci, c->n_loci * sizeof(mm_l2_locus), cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaEventRecord(c->ev[6], c->stream));
-  CU(c, cudaStreamSynchronize(c->stream));
+  CU(c, wait_stream(c));
   cudaEventElapsedTime(&c->stage_ms[4], c->ev[5], c->ev[6]);
   return MM_OK;
 }
