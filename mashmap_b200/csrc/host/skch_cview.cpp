@@ -100,6 +100,34 @@ void *skch_index_from_cli(int argc, const char **argv)
 }
 int skch_index_sketch_size(void *hv) { return ((IndexHandle *)hv)->p.sketchSize; }
 
+/* the Parameters the command line produced, in the field order of the oracle's orc_params (tests/refh.py OrcParams) */
+struct skch_params_view {
+  int32_t kmerSize, segLength, sketchSize, alphabetSize;
+  float percentageIdentity;
+  int32_t filterMode, numMappingsForSegment, numMappingsForShortSequence, block_length, chain_gap, split, mergeMappings,
+      stage1_topANI_filter;
+  float ANIDiff, ANIDiffConf;
+  int32_t stage2_full_scan, keep_low_pct_id;
+  float kmer_pct_threshold, kmerComplexityThreshold;
+  int32_t skip_self, skip_prefix, prefix_delim, lower_triangular, filterLengthMismatches, legacy_output, report_ANI_percentage;
+  uint64_t sparsity_hash_threshold, referenceSize;
+};
+void skch_index_params(void *hv, skch_params_view *o)
+{
+  const Parameters &p = ((IndexHandle *)hv)->p;
+  memset(o, 0, sizeof(*o));
+  o->kmerSize = p.kmerSize; o->segLength = p.segLength; o->sketchSize = p.sketchSize; o->alphabetSize = p.alphabetSize;
+  o->percentageIdentity = p.percentageIdentity; o->filterMode = p.filterMode;
+  o->numMappingsForSegment = (int32_t)p.numMappingsForSegment; o->numMappingsForShortSequence = (int32_t)p.numMappingsForShortSequence;
+  o->block_length = p.block_length; o->chain_gap = p.chain_gap; o->split = p.split; o->mergeMappings = p.mergeMappings;
+  o->stage1_topANI_filter = p.stage1_topANI_filter; o->ANIDiff = p.ANIDiff; o->ANIDiffConf = p.ANIDiffConf;
+  o->stage2_full_scan = p.stage2_full_scan; o->keep_low_pct_id = p.keep_low_pct_id; o->kmer_pct_threshold = p.kmer_pct_threshold;
+  o->kmerComplexityThreshold = p.kmerComplexityThreshold; o->skip_self = p.skip_self; o->skip_prefix = p.skip_prefix;
+  o->prefix_delim = p.prefix_delim; o->lower_triangular = p.lower_triangular; o->filterLengthMismatches = p.filterLengthMismatches;
+  o->legacy_output = p.legacy_output; o->report_ANI_percentage = p.report_ANI_percentage;
+  o->sparsity_hash_threshold = p.sparsity_hash_threshold; o->referenceSize = p.referenceSize;
+}
+
 /* contig metadata only (ranks that receive the device index image by broadcast) */
 void *skch_index_metadata_only(int n_contigs, int contig_len, int k, int segLength, int sketchSize)
 {

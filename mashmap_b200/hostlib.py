@@ -60,6 +60,7 @@ def lib():
         L.skch_index_build.restype = C.c_void_p
         L.skch_index_from_cli.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
         L.skch_index_from_cli.restype = C.c_void_p
+        L.skch_index_params.argtypes = [C.c_void_p, C.c_void_p]
         L.skch_index_metadata_only.argtypes = [C.c_int] * 5
         L.skch_index_metadata_only.restype = C.c_void_p
         L.skch_index_destroy.argtypes = [C.c_void_p]
@@ -170,6 +171,11 @@ class HostIndex:
         (FASTA files, --saveIndex / --loadIndex ...). Host only."""
         argv = (C.c_char_p * len(args))(*[a.encode() for a in args])
         return cls(lib().skch_index_from_cli(len(args), argv))
+
+    def params_into(self, struct):
+        """fills a ctypes structure laid out like tests/refh.py::OrcParams with the parsed skch::Parameters"""
+        lib().skch_index_params(self.h, C.byref(struct))
+        return struct
 
     @classmethod
     def from_minmers(cls, minmers, n_contigs, kmer_pct_threshold=0.001):
