@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-reads", type=int, default=0, help="reads per CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sketch", type=int, default=0, help="sketch size override (0 = the reference's automatic choice)")
+    ap.add_argument("--as-rank", type=int, default=-1, help="debug: generate the reads rank R of a multi-GPU run would get (read seed 2 + R)")
     return ap.parse_args()
 
 
@@ -165,7 +166,7 @@ def setup_workload(args, rank, world, device):
     log(f"rank {rank}: reference {args.contigs} x {contig_len} bp generated in {time.time() - t0:.1f} s")
     sketch = args.sketch or int(hostlib.lib().skch_recommended_sketch_size(K, PI, SEG, int(args.ref_bp * REF_FASTA_BYTES_PER_BASE) + 16 * args.contigs))
     t0 = time.time()
-    reads_dev, truth = synth_gpu.simulate_reads(ref, args.reads, READ_LEN, 0.02, 0.14, seed=2 + rank, chunk=8192)
+    reads_dev, truth = synth_gpu.simulate_reads(ref, args.reads, READ_LEN, 0.02, 0.14, seed=2 + (args.as_rank if args.as_rank >= 0 else rank), chunk=8192)
     if device.type == "cuda":
         torch.cuda.synchronize()
     log(f"rank {rank}: {args.reads} reads simulated in {time.time() - t0:.1f} s; sketch size {sketch}")

@@ -115,7 +115,7 @@ void parseandSave(int argc, char **argv, Parameters &parameters)
 
   if (found("ref")) parameters.refSequences.push_back(opt["ref"]);
   else parseFileList(opt["refList"], parameters.refSequences);
-  parameters.referenceSize = CommonFunc::getReferenceSize(parameters.refSequences);
+  parameters.referenceSize = (offset_t)CommonFunc::getReferenceSize(parameters.refSequences);  // truncates like the reference (:304)
 
   if (found("query")) parameters.querySequences.push_back(opt["query"]);
   else if (found("queryList")) parseFileList(opt["queryList"], parameters.querySequences);

@@ -98,6 +98,18 @@ void *skch_index_from_cli(int argc, const char **argv)
   h->sk = new Sketch(h->p);
   return h;
 }
+/* command line -> Parameters only (no Sketch): for option-parser tests that must not read the reference file */
+void *skch_params_from_cli(int argc, const char **argv)
+{
+  IndexHandle *h = new IndexHandle();
+  std::vector<std::string> store;
+  store.push_back("mashmap-b200");
+  for (int i = 0; i < argc; i++) store.push_back(argv[i]);
+  std::vector<char *> av;
+  for (auto &x : store) av.push_back(&x[0]);
+  parseandSave((int)av.size(), av.data(), h->p);
+  return h;
+}
 int skch_index_sketch_size(void *hv) { return ((IndexHandle *)hv)->p.sketchSize; }
 
 /* the Parameters the command line produced, in the field order of the oracle's orc_params (tests/refh.py OrcParams) */
@@ -125,7 +137,7 @@ void skch_index_params(void *hv, skch_params_view *o)
   o->kmerComplexityThreshold = p.kmerComplexityThreshold; o->skip_self = p.skip_self; o->skip_prefix = p.skip_prefix;
   o->prefix_delim = p.prefix_delim; o->lower_triangular = p.lower_triangular; o->filterLengthMismatches = p.filterLengthMismatches;
   o->legacy_output = p.legacy_output; o->report_ANI_percentage = p.report_ANI_percentage;
-  o->sparsity_hash_threshold = p.sparsity_hash_threshold; o->referenceSize = p.referenceSize;
+  o->sparsity_hash_threshold = p.sparsity_hash_threshold; o->referenceSize = (uint64_t)p.referenceSize; /* sign-extends, as the reference's use does */
 }
 
 /* contig metadata only (ranks that receive the device index image by broadcast) */
@@ -147,6 +159,7 @@ void skch_index_destroy(void *hv)
 void skch_index_sizes(void *hv, uint64_t *n_minmers, uint64_t *n_keys, uint64_t *n_points, int32_t *freq_threshold)
 {
   Sketch *s = ((IndexHandle *)hv)->sk;
+  if (!s) { *n_minmers = *n_keys = *n_points = 0; *freq_threshold = 0; return; } /* parameters-only handle */
   *n_minmers = s->minmerIndex.size(); *n_keys = s->lookupKeys.size(); *n_points = s->lookupPoints.size();
   *freq_threshold = s->getFreqThreshold();
 }

@@ -75,7 +75,8 @@ struct Parameters {
   offset_t block_length = 5000;
   offset_t chain_gap = 5000;
   int alphabetSize = 4;
-  uint64_t referenceSize = 0;
+  offset_t referenceSize = 0;  // map_parameters.hpp:41: offset_t (int32): a file size >= 2 GiB wraps, and the wrapped value is
+                               // sign-extended into recommendedSketchSize's uint64 parameter (parseCmdArgs.hpp:304,639) -- kept
   float percentageIdentity = 0.85f;
   bool stage2_full_scan = true;
   bool stage1_topANI_filter = true;

@@ -60,6 +60,8 @@ def lib():
         L.skch_index_build.restype = C.c_void_p
         L.skch_index_from_cli.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
         L.skch_index_from_cli.restype = C.c_void_p
+        L.skch_params_from_cli.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
+        L.skch_params_from_cli.restype = C.c_void_p
         L.skch_index_params.argtypes = [C.c_void_p, C.c_void_p]
         L.skch_index_metadata_only.argtypes = [C.c_int] * 5
         L.skch_index_metadata_only.restype = C.c_void_p
@@ -171,6 +173,12 @@ class HostIndex:
         (FASTA files, --saveIndex / --loadIndex ...). Host only."""
         argv = (C.c_char_p * len(args))(*[a.encode() for a in args])
         return cls(lib().skch_index_from_cli(len(args), argv))
+
+    @classmethod
+    def params_from_cli(cls, args):
+        """command line -> skch::Parameters only (no Sketch is built, the reference file is not read)"""
+        argv = (C.c_char_p * len(args))(*[a.encode() for a in args])
+        return cls(lib().skch_params_from_cli(len(args), argv))
 
     def params_into(self, struct):
         """fills a ctypes structure laid out like tests/refh.py::OrcParams with the parsed skch::Parameters"""

@@ -119,6 +119,20 @@ void *refh_open(int argc, const char **argv)
   return h;
 }
 
+/* parse only: Parameters from the command line, no Sketch / Map (the reference file is not read) */
+void *refh_parse(int argc, const char **argv)
+{
+  std::vector<char *> av;
+  static char prog[] = "mashmap";
+  av.push_back(prog);
+  for (int i = 0; i < argc; i++) av.push_back(const_cast<char *>(argv[i]));
+  CommandLineProcessing::ArgvParser cmd;
+  skch::initCmdParser(cmd);
+  Handle *h = new Handle();
+  skch::parseandSave((int)av.size(), av.data(), cmd, h->params);
+  return h;
+}
+
 void refh_close(void *hv)
 {
   Handle *h = (Handle *)hv;

@@ -145,6 +145,19 @@ def add_minmers(seq, k, w, s, seq_id=0):
         cap = -n + 16
 
 
+def parse_only(args):
+    """skch::Parameters the reference's own parseandSave produces for a command line (no Sketch, the files are not read)"""
+    L = lib()
+    L.refh_parse.restype = C.c_void_p
+    L.refh_parse.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
+    argv = (C.c_char_p * len(args))(*[a.encode() for a in args])
+    h = L.refh_parse(len(args), argv)
+    p = OrcParams()
+    L.refh_params(C.c_void_p(h), C.byref(p))
+    L.refh_close(C.c_void_p(h))
+    return p
+
+
 class RefSession:
     """The reference's Sketch + Map built from a FASTA, with stage-level access."""
 

@@ -45,3 +45,21 @@ def test_parameters_equal_reference(d, opts, with_query):
         ours.close()
     finally:
         R.close()
+
+
+@pytest.mark.parametrize("size", [2**31 - 1000, 2**31 + 1000, 3_100_000_000, 5_000_000_000, 2**32 + 4096])
+def test_reference_size_wraps_like_the_reference(tmp_path, size):
+    """map_parameters.hpp:41 keeps referenceSize in an offset_t (int32): for files >= 2 GiB the value wraps and is
+    sign-extended into recommendedSketchSize (parseCmdArgs.hpp:304,639), so the automatic sketch size differs from the
+    one the formula gives for the true size. The product reproduces that (a sparse file stands in for the FASTA)."""
+    f = tmp_path / "big.fa"
+    with open(f, "wb") as fh:
+        fh.write(b">c\nACGT\n")
+        fh.truncate(size)
+    args = ["-r", str(f), "-q", str(f), "-s", "5000", "--pi", "85"]
+    ref = refh.parse_only(args)
+    ours = hostlib.HostIndex.params_from_cli(args)
+    p = ours.params_into(refh.OrcParams())
+    ours.close()
+    assert p.referenceSize == ref.referenceSize
+    assert p.sketchSize == ref.sketchSize
