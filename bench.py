@@ -192,12 +192,67 @@ def build_index(args, wl, threads):
     return hi
 
 
-def gpu_arm(args):
-    import torch
+def host_memory_info():
+    """memory this process group may use: cgroup limit / current use, MemTotal / MemAvailable, the locked-memory ulimit"""
+    info = {}
+    for name, path in (("cgroup_max", "/sys/fs/cgroup/memory.max"), ("cgroup_current", "/sys/fs/cgroup/memory.current"),
+                       ("cgroup_v1_limit", "/sys/fs/cgroup/memory/memory.limit_in_bytes")):
+        try:
+            v = open(path).read().strip()
+            info[name] = v if v == "max" else round(int(v) / 2**30, 1)
+        except Exception:
+            pass
+    try:
+        for line in open("/proc/meminfo"):
+            f = line.split()
+            if f[0] in ("MemTotal:", "MemAvailable:"):
+                info[f[0][:-1]] = round(int(f[1]) / 2**20, 1)
+    except Exception:
+        pass
+    try:
+        import resource
 
+        soft, _ = resource.getrlimit(resource.RLIMIT_MEMLOCK)
+        info["memlock"] = "unlimited" if soft == resource.RLIM_INFINITY else round(soft / 2**30, 2)
+    except Exception:
+        pass
+    return info
+
+
+def rss_gb():
+    try:
+        for line in open("/proc/self/status"):
+            if line.startswith("VmRSS:"):
+                return round(int(line.split()[1]) / 2**20, 1)
+    except Exception:
+        pass
+    return None
+
+
+def keep_rank_stderr(rank):
+    """every rank's stderr also goes to its own file (MM_BENCH_LOGDIR, default gpurun_out/ when that directory exists):
+    torchrun only shows the tail of the merged stream, and a rank that dies with exit(1) must leave its reason behind"""
+    d = os.environ.get("MM_BENCH_LOGDIR") or (os.path.join(ROOT, "gpurun_out") if os.path.isdir(os.path.join(ROOT, "gpurun_out")) else None)
+    if not d:
+        return
+    try:
+        os.makedirs(d, exist_ok=True)
+        path = os.path.join(d, f"bench_rank{rank}.log")
+        tee = subprocess.Popen(["tee", "-a", path], stdin=subprocess.PIPE, stdout=sys.stderr.fileno())
+        os.dup2(tee.stdin.fileno(), 2)
+    except Exception as e:  # never fatal
+        print(f"[bench] rank {rank}: cannot keep a per-rank log: {e}", file=sys.stderr)
+
+
+def gpu_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        keep_rank_stderr(rank)
+    import torch
+
+    log(f"rank {rank}/{world}: host memory {host_memory_info()}, cpus {host_cpu_info()}")
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -229,6 +284,7 @@ def gpu_arm(args):
     wl["ref_host"] = None
 
     # ---- the batch: pinned host copy (e2e) and device-resident copy (value) ----
+    log(f"rank {rank}: index ready, rss {rss_gb()} GB, {host_memory_info()}")
     batch = bm.make_batch(args.reads, READ_LEN, first_seq_counter=rank * args.reads)
     torch.from_numpy(batch.bases).copy_(wl["reads_dev"].reshape(-1))
     del wl["reads_dev"]
@@ -236,6 +292,7 @@ def gpu_arm(args):
     n_bases = args.reads * READ_LEN
     n_segs = len(batch.segments)
     ctx.batch_upload(batch.bases, batch.segments)
+    log(f"rank {rank}: batch resident, rss {rss_gb()} GB")
 
     def barrier():
         if dist is not None:
@@ -263,6 +320,7 @@ def gpu_arm(args):
     clocks = sampler.stop(t0, t1)
     wall_ms = (t1 - t0) * 1e3
     seg_res, cands, loci = ctx.batch_fetch()
+    log(f"rank {rank}: value phase done ({ev_ms / args.steps:.1f} ms/step), rss {rss_gb()} GB")
 
     # ---- e2e: host buffers -> C ABI -> records -> host tail -> PAF text ----
     for _ in range(min(args.warmup, 1)):
@@ -277,6 +335,7 @@ def gpu_arm(args):
             _, gathered = mdist.gather_records(dist, torch.from_numpy(bm.results()).to(device), world)
     barrier()
     e2e_ms = (time.time() - t0) * 1e3
+    log(f"rank {rank}: e2e phase done ({e2e_ms / args.steps:.1f} ms/step), rss {rss_gb()} GB")
     h2d = n_bases + n_segs * capi.segment_dtype.itemsize
     d2h = n_segs * capi.segres_dtype.itemsize + len(cands) * capi.l1_dtype.itemsize + len(loci) * capi.l2_dtype.itemsize
 
@@ -325,7 +384,9 @@ def gpu_arm(args):
                          "note": "bit-exact Murmur3 makes K1 INT-ALU bound (SURVEY 8(d)); see DESIGN.md for the instruction roofline"},
         }
         if not args.no_cpu_baseline and world == 1:
-            out["cpu_baseline"] = cpu_baseline(args, hi, batch, S)
+            cb = cpu_baseline(args, hi, batch, S, gpu_rows=res, first_counter=rank * args.reads)
+            out["parity"] = cb.pop("parity")  # GPU mappings of the sampled reads == the CPU port's, at bench scale
+            out["cpu_baseline"] = cb
         print(json.dumps(out), flush=True)
     if dist is not None:
         dist.barrier()
@@ -356,9 +417,31 @@ def _accuracy(res, truth, contig_len, first_counter):
     return {"mapped": float(mapped), "correct": float(ok.mean())}
 
 
-def cpu_baseline(args, hi, batch, S, threads=None, n_reads=None):
+def _parity_diff(cpu_rows, gpu_rows):
+    """full-scale parity of what was timed: the mappings of the sampled reads from the CPU port of the reference path against
+    the GPU product's (rows: query id, query start/end, ref id, ref start/end, strand, conserved sketches, block length,
+    identity * 1e6). Coordinates / strand / counts exact, identity within 1e-4 (north_star)."""
+    def order(r):
+        return r[np.lexsort(tuple(r[:, c] for c in range(8, -1, -1)))] if len(r) else r
+
+    a, b = order(cpu_rows), order(gpu_rows)
+    out = {"mappings_cpu": int(len(a)), "mappings_gpu": int(len(b))}
+    if len(a) == len(b) and np.array_equal(a[:, :9], b[:, :9]):
+        d = np.abs(a[:, 9].astype(np.int64) - b[:, 9]) if len(a) else np.zeros(0, np.int64)
+        out["mismatches"] = int((d > 100).sum())
+        out["max_identity_diff"] = float(d.max() / 1e6) if len(d) else 0.0
+    else:  # count rows (exact integer columns) present on one side only
+        ka = {tuple(x) for x in a[:, :9].tolist()}
+        kb = {tuple(x) for x in b[:, :9].tolist()}
+        out["mismatches"] = len(ka ^ kb) + abs(len(a) - len(ka)) + abs(len(b) - len(kb))
+        out["examples"] = [list(map(int, x)) for x in list(ka ^ kb)[:4]]
+    return out
+
+
+def cpu_baseline(args, hi, batch, S, threads=None, n_reads=None, gpu_rows=None, first_counter=0):
     """The oracle port of the reference path (oracle/libmm_oracle.so, mapModule per read, one task per read on
-    all host threads) on a bounded sample of the same batch, with the same index content."""
+    all host threads) on a bounded sample of the same batch, with the same index content. With gpu_rows (the
+    product's mappings of the whole batch) the port's mappings of the sampled reads are diffed against them."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_py
 
@@ -370,7 +453,8 @@ def cpu_baseline(args, hi, batch, S, threads=None, n_reads=None):
     import ctypes as C
 
     L.orc_map_reads_mt.restype = C.c_int64
-    L.orc_map_reads_mt.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64)]
+    L.orc_map_reads_mt.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64),
+                                   C.c_void_p, C.c_int64]
     mapped = C.c_int64()
     total_reads = len(batch.bases) // READ_LEN
     if not n_reads:
@@ -379,12 +463,18 @@ def cpu_baseline(args, hi, batch, S, threads=None, n_reads=None):
         n_reads = int(min(total_reads, 17000 * threads))
     t0 = time.time()
     c0 = os.times()
-    n_map = L.orc_map_reads_mt(O.h, batch.bases.ctypes.data, n_reads, READ_LEN, 0, threads, C.byref(mapped))
+    rows = np.zeros((4 * n_reads + 16, 10), dtype=np.int32) if gpu_rows is not None else None
+    n_map = L.orc_map_reads_mt(O.h, batch.bases.ctypes.data, n_reads, READ_LEN, first_counter, threads, C.byref(mapped),
+                               rows.ctypes.data if rows is not None else None, len(rows) if rows is not None else 0)
     dt = time.time() - t0
     c1 = os.times()
     O.close()
     busy = ((c1.user - c0.user) + (c1.system - c0.system)) / max(dt, 1e-9)  # CPUs actually kept busy by the threads
-    return {"value": n_reads * READ_LEN / dt / 1e9, "unit": "Gbp/s", "cores": threads, "kind": "port",
+    parity = None
+    if gpu_rows is not None:
+        sel = (gpu_rows[:, 0] - first_counter < n_reads) if len(gpu_rows) else np.zeros(0, bool)
+        parity = {"reads": int(n_reads), **_parity_diff(rows[: min(n_map, len(rows))], gpu_rows[sel])}
+    return {"parity": parity, "value": n_reads * READ_LEN / dt / 1e9, "unit": "Gbp/s", "cores": threads, "kind": "port",
             "cpus_busy": round(busy, 1), "host": host_cpu_info(),
             "sample": f"first {n_reads} reads of the batch ({n_reads * READ_LEN / 1e6:.0f} Mbp), oracle/libmm_oracle.so mapModule per read "
                       f"on {threads} threads, {dt:.1f} s; {mapped.value} reads mapped, {n_map} mappings"}
@@ -421,6 +511,7 @@ def cpu_arm(args):
     times, last = [], None
     for i in range(args.warmup + args.steps):
         last = cpu_baseline(a2, hi, b, S, threads=threads, n_reads=sample)
+        last.pop("parity", None)
         if i >= args.warmup:
             times.append(sample * READ_LEN / last["value"] / 1e9)
     dt = sum(times)

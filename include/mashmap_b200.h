@@ -118,6 +118,15 @@ const char *mm_last_error(const mm_ctx *ctx); /* ctx may be NULL: error of the l
 /* Number of CUDA kernels this context has launched so far (bench.py's gpu_launches). */
 uint64_t mm_kernel_launches(const mm_ctx *ctx);
 
+/* Cumulative counts of the rare paths this context has taken (test / diagnostics only; nothing in the reference):
+ * out[MM_DIAG_*]. */
+#define MM_DIAG_L1_CTA_SEGMENTS 0  /* segments with more interval points than the warp path holds (CTA path)        */
+#define MM_DIAG_L1_POOL_REGROW 1   /* L1 re-runs because the bump-allocated point pool was exhausted                  */
+#define MM_DIAG_CAND_REGROW 2      /* re-runs because the candidate buffer was too small                              */
+#define MM_DIAG_L2_GENERAL_CANDS 3 /* candidates redone by the general L2 kernel (more loci than the fixed slots / counter range) */
+#define MM_DIAG_L2_LOCI_REGROW 4   /* L2 re-runs because the locus buffer was too small                               */
+int mm_ctx_diag(const mm_ctx *ctx, uint64_t out[8]);
+
 /* ---- reference index -> device (replaces the in-memory members of skch::Sketch) ---------------- */
 
 /* minmerIndex (winSketch.hpp:102, after dropFreqSeedSet :497-504), sorted by (seqId, wpos) as the

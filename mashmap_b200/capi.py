@@ -77,6 +77,7 @@ def lib():
         L.mm_last_error.restype = C.c_char_p
         L.mm_kernel_launches.argtypes = [vp]
         L.mm_kernel_launches.restype = u64
+        L.mm_ctx_diag.argtypes = [vp, C.POINTER(u64 * 8)]
         L.mm_index_upload.argtypes = [vp, vp, u64, vp, vp, u64, vp, u64, vp, vp, vp, vp, i32]
         L.mm_tables_upload.argtypes = [vp, vp, i32, vp, i32]
         L.mm_index_blob.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
@@ -97,7 +98,7 @@ def lib():
 
 
 EXPORTED_SYMBOLS = [
-    "mm_ctx_create", "mm_ctx_destroy", "mm_last_error", "mm_kernel_launches", "mm_index_upload",
+    "mm_ctx_create", "mm_ctx_destroy", "mm_last_error", "mm_kernel_launches", "mm_ctx_diag", "mm_index_upload",
     "mm_tables_upload", "mm_index_blob", "mm_index_blob_alloc", "mm_index_adopt_blob", "mm_ctx_share_index", "mm_sketch_segments",
     "mm_map_segments", "mm_batch_upload", "mm_map_resident", "mm_batch_fetch", "mm_batch_fetch_sketch",
     "mm_last_stage_ms", "mm_ctx_set_phase_hook", "mm_host_alloc", "mm_host_free",
@@ -174,6 +175,14 @@ class Context:
     def _check(self, rc):
         if rc != MM_OK:
             raise MashmapError(rc, self._L.mm_last_error(self._h).decode())
+
+    DIAG_NAMES = ("l1_cta_segments", "l1_pool_regrow", "cand_regrow", "l2_general_cands", "l2_loci_regrow")
+
+    def diag(self):
+        """how often the rare paths ran (mm_ctx_diag), by name"""
+        out = (C.c_uint64 * 8)()
+        self._check(self._L.mm_ctx_diag(self._h, C.byref(out)))
+        return {n: int(out[i]) for i, n in enumerate(self.DIAG_NAMES)}
 
     @property
     def kernel_launches(self):

@@ -26,6 +26,7 @@ struct mm_ctx {
   cudaStream_t stream = nullptr;
   std::string error;
   uint64_t launches = 0;
+  uint64_t diag[8] = {0}; /* mm_ctx_diag: how often the rare paths ran (cumulative) */
 
   /* index blob */
   unsigned char *blob = nullptr;
@@ -362,6 +363,7 @@ int run_l2_stream(mm_ctx *c, uint32_t *h_cnt)
     RD(c, c->d_counters, h_cnt, 16);
     uint64_t extent = nc * LPC;
     if (h_cnt[7] > 0) { /* candidates with more than LPC loci: general kernel, loci appended after the fixed slots */
+      c->diag[MM_DIAG_L2_GENERAL_CANDS] += h_cnt[7];
       const uint32_t base = (uint32_t)extent;
       k_set_u32<<<1, 1, 0, c->stream>>>(c->d_counters + 6, base);
       c->launches++;
@@ -370,6 +372,7 @@ int run_l2_stream(mm_ctx *c, uint32_t *h_cnt)
       RD(c, c->d_counters, h_cnt, 16);
       if (h_cnt[1] == 2) return fail(c, MM_ECUDA, "L2 live-set overflow in the general kernel");
       if (h_cnt[1] == 1 || h_cnt[6] > c->loci_cap) { /* grow and redo prep+scan+overflow */
+        c->diag[MM_DIAG_L2_LOCI_REGROW]++;
         cudaFree(c->d_loci); c->d_loci = nullptr;
         c->loci_cap = (uint64_t)h_cnt[6] + h_cnt[6] / 4 + 1024;
         CU(c, cudaMalloc((void **)&c->d_loci, c->loci_cap * sizeof(mm_l2_locus)));
@@ -426,13 +429,16 @@ int run_pipeline(mm_ctx *c)
     RD(c, c->d_counters, h_cnt, 16);
     const uint64_t need_cands = h_cnt[0];
     bool retry = false;
+    c->diag[MM_DIAG_L1_CTA_SEGMENTS] += h_cnt[8];
     if (h_cnt[3] || need_cands > c->cand_cap) {
+      c->diag[MM_DIAG_CAND_REGROW]++;
       cudaFree(c->d_cands); c->d_cands = nullptr;
       c->cand_cap = need_cands + need_cands / 4 + 1024;
       CU(c, cudaMalloc((void **)&c->d_cands, c->cand_cap * sizeof(mm_l1_candidate)));
       retry = true;
     }
     if (h_cnt[2]) { /* scratch pool exhausted: quadruple it */
+      c->diag[MM_DIAG_L1_POOL_REGROW]++;
       const uint64_t pool = c->scratch_cap - c->scratch_pool;
       cudaFree(c->d_scratch); c->d_scratch = nullptr; c->scratch_cap = 0;
       if ((rc = ensure_scratch(c, pool * 4))) return rc;
@@ -551,6 +557,12 @@ int mm_ctx_destroy(mm_ctx *c)
 }
 
 const char *mm_last_error(const mm_ctx *c) { return c ? c->error.c_str() : g_create_error.c_str(); }
+int mm_ctx_diag(const mm_ctx *ctx, uint64_t out[8])
+{
+  if (!ctx || !out) return MM_EINVAL;
+  memcpy(out, ctx->diag, sizeof(ctx->diag));
+  return MM_OK;
+}
 uint64_t mm_kernel_launches(const mm_ctx *c) { return c ? c->launches : 0; }
 
 int mm_index_upload(mm_ctx *c, const mm_minmer *mi, uint64_t n_mi, const uint64_t *keys, const uint64_t *offsets,

@@ -41,6 +41,11 @@ def broadcast_index(dist, ctx, rank: int, device):
         ptr = ctx.index_blob_alloc(n)
     blob = wrap_device_memory(ptr, n, device)
     dist.broadcast(blob, 0)
+    # the collective runs on the process group's own stream and the C ABI context reads the image on ITS stream: wait for
+    # the device before adopting (without this, ranks far down the broadcast tree read a stale header -- the round-1
+    # 8-GPU failure "blob header mismatch")
+    if getattr(device, "type", str(device)) == "cuda":
+        torch.cuda.synchronize(device)
     if rank != 0:
         ctx.index_adopt_blob()
     return n

@@ -1023,11 +1023,14 @@ ORC_API int orc_map_fragment(void *cv, const char *seq, int len, int fullLen, in
  * `threads` worker threads, one read per task like the reference's pool (ThreadPool.hpp:176-215; mapModule is the
  * task, computeMap.hpp:275,340). Returns the number of mappings; *mapped_reads = reads with >= 1 mapping. */
 ORC_API int64_t orc_map_reads_mt(void *cv, const char *bases, int64_t n_reads, int read_len, int first_seq_counter, int threads,
-                                 int64_t *mapped_reads)
+                                 int64_t *mapped_reads, int32_t *rows_out, int64_t cap_rows)
 {
   Ctx &c0 = *(Ctx *)cv;
   for (int s = 1; s <= c0.p.sketchSize; s++) minimumHitsFor(c0, s); /* fill the memo before the threads read it */
   std::atomic<int64_t> next{0}, total{0}, mapped{0};
+  /* optional copy of the mappings for the full-scale parity diff of bench.py: kept per read (read order is the
+   * reference's output order), flattened after the threads have finished */
+  std::vector<std::vector<orc_mapping>> keep(rows_out ? (size_t)n_reads : 0);
   auto work = [&]() {
     std::vector<orc_mapping> res;
     while (true) {
@@ -1037,12 +1040,26 @@ ORC_API int64_t orc_map_reads_mt(void *cv, const char *bases, int64_t n_reads, i
       mapModule(c0, bases + i * (int64_t)read_len, read_len, first_seq_counter + (int)i, -1, -1, res);
       total += (int64_t)res.size();
       if (!res.empty()) mapped++;
+      if (rows_out) keep[(size_t)i] = res;
     }
   };
   std::vector<std::thread> pool;
   for (int t = 0; t < std::max(1, threads); t++) pool.emplace_back(work);
   for (auto &th : pool) th.join();
   if (mapped_reads) *mapped_reads = mapped.load();
+  if (rows_out) { /* same row layout as the product's skch_bm_results */
+    int64_t n = 0;
+    for (auto &v : keep)
+      for (auto &m : v) {
+        if (n < cap_rows) {
+          int32_t *r = rows_out + n * 10;
+          r[0] = m.querySeqId; r[1] = m.queryStartPos; r[2] = m.queryEndPos; r[3] = m.refSeqId; r[4] = m.refStartPos;
+          r[5] = m.refEndPos; r[6] = m.strand; r[7] = m.conservedSketches; r[8] = m.blockLength;
+          r[9] = (int32_t)(m.nucIdentity * 1e6f);
+        }
+        n++;
+      }
+  }
   return total.load();
 }
 
