@@ -182,10 +182,24 @@ int mm_map_segments(mm_ctx *ctx, const char *bases, uint64_t n_bases,
                     mm_l1_candidate *candidates, uint64_t cand_cap, uint64_t *n_candidates,
                     mm_l2_locus *loci, uint64_t loci_cap, uint64_t *n_loci);
 
+/* The same with the bases already in the device's own input format, ONE NIBBLE PER BASE: base i of the batch is
+ * (nibbles[i / 2] >> (4 * (i & 1))) & 15 = 2-bit code (A 0, C 1, T 2, G 3 = bits 1-2 of the upper-cased letter) | 8 for
+ * every byte that is not ACGT after upper-casing -- makeUpperCaseAndValidDNA (commonFunc.hpp:75-107) folded into the
+ * encoding. A host that touches every base anyway while it parses (skch::BatchMapper does) halves the PCIe traffic this
+ * way; mm_map_segments does the same conversion on the device (kernel k_pack_bases). segments[i].offset counts BASES.
+ * n_bases bases = (n_bases + 1) / 2 bytes. */
+int mm_map_segments_packed(mm_ctx *ctx, const uint8_t *nibbles, uint64_t n_bases,
+                           const mm_segment *segments, uint64_t n_segments,
+                           mm_segment_result *seg_results,
+                           mm_l1_candidate *candidates, uint64_t cand_cap, uint64_t *n_candidates,
+                           mm_l2_locus *loci, uint64_t loci_cap, uint64_t *n_loci);
+
 /* Same computation with the batch already resident in HBM (bench.py `value`):
  * upload once, run many times, fetch once. */
 int mm_batch_upload(mm_ctx *ctx, const char *bases, uint64_t n_bases,
                     const mm_segment *segments, uint64_t n_segments);
+int mm_batch_upload_packed(mm_ctx *ctx, const uint8_t *nibbles, uint64_t n_bases,
+                           const mm_segment *segments, uint64_t n_segments);
 int mm_map_resident(mm_ctx *ctx, uint64_t *n_candidates, uint64_t *n_loci);
 int mm_batch_fetch(mm_ctx *ctx, mm_segment_result *seg_results,
                    mm_l1_candidate *candidates, uint64_t cand_cap,
@@ -209,6 +223,9 @@ int mm_ctx_set_phase_hook(mm_ctx *ctx, mm_phase_hook hook, void *user);
  * [5] first kernel launch -> last kernel end (events on the launching stream; includes the two counter
  *     read-backs between kernels)  [6] L2 record-preparation kernel  [7] L2 scan kernel(s). */
 int mm_last_stage_ms(const mm_ctx *ctx, float ms[8]);
+/* ... and of the base-packing kernel that runs in front of the sketch kernel when the batch came in as text (0 for a
+ * batch uploaded as nibbles). It is inside [5], not inside [0]. */
+int mm_last_pack_ms(const mm_ctx *ctx, float *ms);
 
 /* Pinned host memory for the caller's batch buffers (so the copies inside mm_map_segments run at full
  * PCIe rate). Plain malloc'ed buffers work too, only slower. */

@@ -87,6 +87,9 @@ def lib():
         L.mm_sketch_segments.argtypes = [vp, vp, u64, vp, u64, vp, vp]
         L.mm_map_segments.argtypes = [vp, vp, u64, vp, u64, vp, vp, u64, C.POINTER(u64), vp, u64, C.POINTER(u64)]
         L.mm_batch_upload.argtypes = [vp, vp, u64, vp, u64]
+        L.mm_batch_upload_packed.argtypes = [vp, vp, u64, vp, u64]
+        L.mm_map_segments_packed.argtypes = [vp, vp, u64, vp, u64, vp, vp, u64, C.POINTER(u64), vp, u64, C.POINTER(u64)]
+        L.mm_last_pack_ms.argtypes = [vp, C.POINTER(C.c_float)]
         L.mm_map_resident.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
         L.mm_batch_fetch.argtypes = [vp, vp, vp, u64, vp, u64]
         L.mm_batch_fetch_sketch.argtypes = [vp, vp, vp]
@@ -100,7 +103,7 @@ def lib():
 EXPORTED_SYMBOLS = [
     "mm_ctx_create", "mm_ctx_destroy", "mm_last_error", "mm_kernel_launches", "mm_ctx_diag", "mm_index_upload",
     "mm_tables_upload", "mm_index_blob", "mm_index_blob_alloc", "mm_index_adopt_blob", "mm_ctx_share_index", "mm_sketch_segments",
-    "mm_map_segments", "mm_batch_upload", "mm_map_resident", "mm_batch_fetch", "mm_batch_fetch_sketch",
+    "mm_map_segments", "mm_map_segments_packed", "mm_batch_upload", "mm_batch_upload_packed", "mm_last_pack_ms", "mm_map_resident", "mm_batch_fetch", "mm_batch_fetch_sketch",
     "mm_last_stage_ms", "mm_ctx_set_phase_hook", "mm_host_alloc", "mm_host_free",
 ]
 
@@ -112,6 +115,23 @@ def _ptr(a):
 def _c(a, dtype):
     a = np.ascontiguousarray(a, dtype=dtype)
     return a
+
+
+_NIB = np.full(256, 8, dtype=np.uint8)
+for _ch, _code in ((b"A", 0), (b"C", 1), (b"T", 2), (b"G", 3)):
+    _NIB[_ch[0]] = _code
+    _NIB[_ch.lower()[0]] = _code
+
+
+def pack_bases(ascii_bases):
+    """numpy statement of the device input format (include/mashmap_b200.h, mm_map_segments_packed): one nibble per base,
+    2-bit code (A 0, C 1, T 2, G 3) | 8 for anything that is not ACGT after upper-casing; base i in byte i // 2, low
+    nibble first. Used by the tests; the product packs in C++ (skch::BatchMapper) or on the device (k_pack_bases)."""
+    a = np.ascontiguousarray(ascii_bases, dtype=np.uint8)
+    n = _NIB[a]
+    if len(n) & 1:
+        n = np.concatenate([n, np.array([8], dtype=np.uint8)])
+    return (n[0::2] | (n[1::2] << 4)).astype(np.uint8)
 
 
 class PinnedBuffer:
@@ -254,6 +274,39 @@ class Context:
         segments = _c(segments, segment_dtype)
         self._n_segs = len(segments)
         self._check(self._L.mm_batch_upload(self._h, _ptr(bases), len(bases), _ptr(segments), len(segments)))
+
+    def batch_upload_packed(self, nibbles, n_bases, segments):
+        """the batch as one nibble per base (see pack_bases): mm_batch_upload_packed"""
+        nibbles = np.ascontiguousarray(nibbles, dtype=np.uint8)
+        assert len(nibbles) >= (n_bases + 1) // 2
+        segments = _c(segments, segment_dtype)
+        self._n_segs = len(segments)
+        self._check(self._L.mm_batch_upload_packed(self._h, _ptr(nibbles), int(n_bases), _ptr(segments), len(segments)))
+
+    def map_segments_packed(self, nibbles, n_bases, segments):
+        nibbles = np.ascontiguousarray(nibbles, dtype=np.uint8)
+        segments = _c(segments, segment_dtype)
+        n = len(segments)
+        self._n_segs = n
+        seg_res = np.zeros(n, dtype=segres_dtype)
+        cand_cap, loci_cap = max(4 * n, 1024), max(8 * n, 2048)
+        while True:
+            cands = np.zeros(cand_cap, dtype=l1_dtype)
+            loci = np.zeros(loci_cap, dtype=l2_dtype)
+            nc, nl = C.c_uint64(), C.c_uint64()
+            rc = self._L.mm_map_segments_packed(self._h, _ptr(nibbles), int(n_bases), _ptr(segments), n, _ptr(seg_res),
+                                                _ptr(cands), cand_cap, C.byref(nc), _ptr(loci), loci_cap, C.byref(nl))
+            if rc == MM_ECAPACITY:
+                cand_cap, loci_cap = max(cand_cap, nc.value), max(loci_cap, nl.value)
+                continue
+            self._check(rc)
+            self._nc, self._nl = nc.value, nl.value
+            return seg_res, cands[: nc.value], loci[: nl.value]
+
+    def pack_ms(self):
+        v = C.c_float()
+        self._L.mm_last_pack_ms(self._h, C.byref(v))
+        return float(v.value)
 
     def map_resident(self):
         nc, nl = C.c_uint64(), C.c_uint64()

@@ -4,7 +4,9 @@
  * Not part of the drop-in boundary (that is include/mashmap_b200.h + the skch:: classes).
  */
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -217,19 +219,50 @@ void skch_bm_destroy(void *hv)
 }
 mm_ctx *skch_bm_ctx(void *hv) { return ((BmHandle *)hv)->bm->context(); }
 
-/* n_reads reads of read_len bases each, laid out back to back in a pinned buffer the caller fills */
+/* n_reads reads of read_len bases each in a pinned batch buffer (nibbles, every read at a multiple of 32 bases);
+ * skch_bm_batch_fill packs the caller's text into it */
 void *skch_bm_batch_create(void *hv, uint64_t n_reads, int32_t read_len, int32_t first_seq_counter)
 {
   BmHandle *h = (BmHandle *)hv;
   BmBatch *b = new BmBatch();
   b->owner = h;
-  b->batch.capacity = n_reads * (uint64_t)read_len + 64;
+  const uint64_t A = ReadBatch::READ_ALIGN;
+  b->batch.capacity = n_reads * (((uint64_t)read_len + A - 1) / A * A) + 64;
   b->batch.bases = h->bm->allocBases(b->batch.capacity);
+  memset(b->batch.bases, 0x88, b->batch.capacity / 2 + 256);
   for (uint64_t i = 0; i < n_reads; i++)
     h->bm->addRead(b->batch, "read" + std::to_string(first_seq_counter + (int64_t)i), nullptr, read_len, (seqno_t)(first_seq_counter + i));
   return b;
 }
-char *skch_bm_batch_bases(void *bv) { return ((BmBatch *)bv)->batch.bases; }
+/* what a reader does while it parses: `ascii` holds the batch's reads back to back as text (read r at r * read_len);
+ * every read is packed to nibbles at its place in the batch, on `threads` threads. Returns the seconds it took. */
+double skch_bm_batch_fill(void *bv, const char *ascii, int threads)
+{
+  BmBatch *b = (BmBatch *)bv;
+  const auto t0 = std::chrono::steady_clock::now();
+  const size_t n = b->batch.reads.size();
+  std::atomic<size_t> next{0};
+  auto work = [&]() {
+    while (true) {
+      const size_t lo = next.fetch_add(64);
+      if (lo >= n) break;
+      const size_t hi = std::min(n, lo + 64);
+      for (size_t r = lo; r < hi; r++) {
+        const ReadRec &rd = b->batch.reads[r];
+        seqio::pack_bases(ascii + r * (size_t)rd.len, (uint64_t)rd.len, b->batch.nibbles(b->batch.segs[rd.first_seg].offset));
+      }
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < std::max(1, threads); t++) pool.emplace_back(work);
+  work();
+  for (auto &th : pool) th.join();
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+/* bytes of the batch that cross PCIe per mapping pass (nibbles of the used part of the buffer) */
+uint64_t skch_bm_batch_bytes(void *bv) { return (((BmBatch *)bv)->batch.used + 1) / 2; }
+/* the host packer by itself (tests): n text bases -> (n + 1) / 2 bytes */
+void skch_pack_bases(const char *ascii, uint64_t n, uint8_t *out) { seqio::pack_bases(ascii, n, out); }
 uint64_t skch_bm_batch_segments(void *bv, const mm_segment **segs)
 {
   BmBatch *b = (BmBatch *)bv;
@@ -317,7 +350,13 @@ int64_t skch_fasta_readers_diff(const char *path, int threads, uint64_t *n_recor
   for (size_t i = 0; i < std::min(recs.size(), ref.size()); i++) {
     std::string seq(recs[i].seq_len, '\0');
     ff.copy_bases(recs[i], &seq[0]);
-    if (ff.name(recs[i]) != ref[i].first || seq != ref[i].second) bad++;
+    if (ff.name(recs[i]) != ref[i].first || seq != ref[i].second) { bad++; continue; }
+    /* the packing variant of the same copy: nibbles straight from the file mapping == nibbles of the text */
+    std::vector<uint8_t> a((recs[i].seq_len + 1) / 2 + 1, 0), b((recs[i].seq_len + 1) / 2 + 1, 0);
+    ff.pack_bases(recs[i], a.data());
+    seqio::pack_bases(seq.data(), seq.size(), b.data());
+    if (recs[i].seq_len & 1) { a[recs[i].seq_len / 2] |= 0xF0; b[recs[i].seq_len / 2] |= 0xF0; }  /* unused nibble */
+    if (a != b) bad++;
   }
   return bad;
 }

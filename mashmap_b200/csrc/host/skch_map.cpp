@@ -207,10 +207,12 @@ BatchMapper::~BatchMapper()
   delete gate;
 }
 
-char *BatchMapper::allocBases(uint64_t bytes)
+char *BatchMapper::allocBases(uint64_t n_bases)
 {
   char *p = nullptr;
-  if (mm_host_alloc((void **)&p, bytes) != MM_OK) die("cannot allocate the pinned batch buffer");
+  const uint64_t bytes = n_bases / 2 + 256;
+  if (mm_host_alloc((void **)&p, bytes) != MM_OK)
+    die("cannot allocate the pinned batch buffer (" + std::to_string(bytes >> 20) + " MiB)");
   return p;
 }
 void BatchMapper::freeBases(char *p) { if (p) mm_host_free(p); }
@@ -225,7 +227,7 @@ void BatchMapper::addRead(ReadBatch &b, const std::string &name, const char *seq
     auto it = refNameId.find(name);
     if (it != refNameId.end()) name_id = it->second;
   }
-  if (seq) memcpy(b.bases + b.used, seq, (size_t)len);
+  if (seq) seqio::pack_bases(seq, (uint64_t)len, b.nibbles(b.used));
   auto push = [&](offset_t start, offset_t flen) {
     mm_segment s;
     s.offset = b.used + (uint64_t)start; s.length = flen; s.seq_counter = seqCounter; s.name_id = name_id; s.ref_group = rd.refGroup;
@@ -238,7 +240,7 @@ void BatchMapper::addRead(ReadBatch &b, const std::string &name, const char *seq
     if (len % param.segLength != 0) push(len - param.segLength, param.segLength);  // :644-671
   }
   rd.n_seg = (uint32_t)(b.segs.size() - rd.first_seg);
-  b.used += (uint64_t)len;
+  b.used += ((uint64_t)len + ReadBatch::READ_ALIGN - 1) / ReadBatch::READ_ALIGN * ReadBatch::READ_ALIGN;
   b.reads.push_back(std::move(rd));
 }
 
@@ -251,9 +253,8 @@ void BatchMapper::laneUpload(Lane &ln, const ReadBatch &b, size_t r0, size_t r1)
   ln.r0 = r0; ln.r1 = r1;
   ln.s0 = b.reads[r0].first_seg;
   const size_t s1 = b.reads[r1 - 1].first_seg + b.reads[r1 - 1].n_seg;
-  const uint64_t b0 = b.segs[ln.s0].offset;  // a read's first fragment starts at the read's first base
-  uint64_t b1 = b0;
-  for (size_t r = r0; r < r1; r++) b1 += (uint64_t)b.reads[r].len;
+  const uint64_t b0 = b.segs[ln.s0].offset;  // a read's first fragment starts at the read's first base (a multiple of READ_ALIGN)
+  const uint64_t b1 = r1 < b.reads.size() ? b.segs[b.reads[r1].first_seg].offset : b.used;
   const mm_segment *segp = b.segs.data() + ln.s0;
   if (b0 != 0) {  // fragment offsets are relative to the buffer handed to the device call
     ln.segs.assign(b.segs.begin() + ln.s0, b.segs.begin() + s1);
@@ -261,8 +262,8 @@ void BatchMapper::laneUpload(Lane &ln, const ReadBatch &b, size_t r0, size_t r1)
     segp = ln.segs.data();
   }
   ln.nseg = s1 - ln.s0;
-  int rc = mm_batch_upload(ln.ctx, b.bases + b0, b1 - b0, segp, ln.nseg);
-  if (rc != MM_OK) die(std::string("mm_batch_upload: ") + mm_last_error(ln.ctx));
+  int rc = mm_batch_upload_packed(ln.ctx, b.nibbles(b0), b1 - b0, segp, ln.nseg);
+  if (rc != MM_OK) die(std::string("mm_batch_upload_packed: ") + mm_last_error(ln.ctx));
   ln.msUpload = since(t0) * 1e3;
   ln.secDevice += since(t0);
 }
@@ -536,7 +537,7 @@ struct Map::Impl {
           const size_t b = next.fetch_add(64);
           if (b >= jobs.size()) break;
           const size_t e = std::min(jobs.size(), b + 64);
-          for (size_t j = b; j < e; j++) ff.copy_bases(recs[jobs[j].rec], batch.bases + jobs[j].dst);
+          for (size_t j = b; j < e; j++) ff.pack_bases(recs[jobs[j].rec], batch.nibbles(jobs[j].dst));
         }
       };
       if (T == 1) worker();

@@ -37,8 +37,13 @@ namespace skch {
 
 /* one device batch of reads */
 struct ReadBatch {
-  char *bases = nullptr;  // pinned host memory (BatchMapper::allocBases)
+  /* pinned host memory (BatchMapper::allocBases) holding the reads in the device's input format: ONE NIBBLE PER BASE
+   * (seqio::pack_bases; base i of the batch in byte i / 2). capacity / used count BASES; every read starts at a multiple
+   * of READ_ALIGN bases, so two threads packing neighbouring reads never share a byte (or a cache line's word). */
+  static constexpr uint64_t READ_ALIGN = 32;
+  char *bases = nullptr;
   uint64_t capacity = 0, used = 0;
+  uint8_t *nibbles(uint64_t base_offset) const { return (uint8_t *)bases + (base_offset >> 1); }
   std::vector<mm_segment> segs;
   std::vector<ReadRec> reads;
   void clear() { used = 0; segs.clear(); reads.clear(); }
@@ -50,10 +55,11 @@ class BatchMapper {
   ~BatchMapper();
   BatchMapper(const BatchMapper &) = delete;
 
-  char *allocBases(uint64_t bytes);
+  char *allocBases(uint64_t n_bases);  // room for n_bases bases (n_bases / 2 bytes + slack)
   void freeBases(char *p);
   /* mapModule's fragmenting (computeMap.hpp:587-671): appends the read's fragments to the batch.
-   * `seq` may be nullptr when the bases are already in place at batch.bases + batch.used. */
+   * `seq` (text) is packed into the batch; nullptr = the caller packs the bases itself at b.nibbles(offset of the read's
+   * first fragment) (the bulk FASTA path does that from all host threads). */
   void addRead(ReadBatch &b, const std::string &name, const char *seq, offset_t len, seqno_t seqCounter) const;
   /* one device call + the host tail; results[r] = final mappings of batch.reads[r]; text[r] = their PAF lines */
   void mapBatch(const ReadBatch &b, std::vector<MappingResultsVector_t> &results, std::vector<std::string> *text,

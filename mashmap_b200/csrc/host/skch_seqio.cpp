@@ -5,6 +5,9 @@
 #include <sys/stat.h>
 #include <unistd.h>
 #include <zlib.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 #include <algorithm>
 #include <atomic>
@@ -202,6 +205,85 @@ void FastaFile::copy_bases(const FastaRecord &r, char *dst) const
     dst += n;
     c += n + 1;
   }
+}
+
+namespace {
+
+struct NibTable {
+  uint8_t t[256];
+  NibTable()
+  {
+    for (int i = 0; i < 256; i++) t[i] = 8;
+    t[(int)'A'] = t[(int)'a'] = 0; t[(int)'C'] = t[(int)'c'] = 1; t[(int)'T'] = t[(int)'t'] = 2; t[(int)'G'] = t[(int)'g'] = 3;
+  }
+};
+const NibTable NIB;
+
+void pack_scalar(const uint8_t *src, uint64_t n, uint8_t *dst)
+{
+  uint64_t i = 0;
+  for (; i + 1 < n; i += 2) dst[i >> 1] = (uint8_t)(NIB.t[src[i]] | (NIB.t[src[i + 1]] << 4));
+  if (i < n) dst[i >> 1] = (uint8_t)(NIB.t[src[i]] | 0x80);
+}
+
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) void pack_avx2(const uint8_t *src, uint64_t n, uint8_t *dst)
+{
+  const __m256i up = _mm256_set1_epi8((char)0xDF), three = _mm256_set1_epi8(3), eight = _mm256_set1_epi8(8);
+  const __m256i cA = _mm256_set1_epi8('A'), cC = _mm256_set1_epi8('C'), cG = _mm256_set1_epi8('G'), cT = _mm256_set1_epi8('T');
+  const __m256i mul = _mm256_set1_epi16(0x1001); /* low byte * 1 + high byte * 16 */
+  uint64_t i = 0;
+  for (; i + 32 <= n; i += 32) {
+    const __m256i v = _mm256_loadu_si256((const __m256i *)(src + i));
+    const __m256i x = _mm256_and_si256(v, up);
+    const __m256i code = _mm256_and_si256(_mm256_srli_epi16(x, 1), three);
+    const __m256i ok = _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi8(x, cA), _mm256_cmpeq_epi8(x, cC)),
+                                       _mm256_or_si256(_mm256_cmpeq_epi8(x, cG), _mm256_cmpeq_epi8(x, cT)));
+    const __m256i nib = _mm256_blendv_epi8(eight, code, ok);
+    const __m256i w = _mm256_maddubs_epi16(nib, mul);                 /* 16 x (n0 + 16 n1) */
+    const __m256i b = _mm256_packus_epi16(w, w);                      /* per 128-bit lane: 8 bytes, twice */
+    const __m256i q = _mm256_permute4x64_epi64(b, 0x08);              /* lanes' low halves next to each other */
+    _mm_storeu_si128((__m128i *)(dst + (i >> 1)), _mm256_castsi256_si128(q));
+  }
+  pack_scalar(src + i, n - i, dst + (i >> 1));
+}
+bool have_avx2()
+{
+  static const bool v = __builtin_cpu_supports("avx2");
+  return v;
+}
+#endif
+
+}  // namespace
+
+void pack_bases(const char *src, uint64_t n, uint8_t *dst)
+{
+#if defined(__x86_64__)
+  if (have_avx2()) { pack_avx2((const uint8_t *)src, n, dst); return; }
+#endif
+  pack_scalar((const uint8_t *)src, n, dst);
+}
+
+void FastaFile::pack_bases(const FastaRecord &r, uint8_t *dst) const
+{
+  /* lines are gathered into an even-sized stretch of text first (a line may have an odd length; nibble pairs must not
+   * straddle two pack calls), then packed: the stretch stays in the L1/L2 cache */
+  char buf[8192 + 64];
+  size_t fill = 0;
+  const char *c = data_ + r.seq_off, *ce = c + r.raw_len;
+  while (c < ce) {
+    const char *q = (const char *)memchr(c, '\n', (size_t)(ce - c));
+    size_t n = (size_t)((q ? q : ce) - c);
+    const char *next = c + n + 1;
+    while (n) {
+      const size_t take = std::min(n, (size_t)8192 - fill);
+      memcpy(buf + fill, c, take);
+      fill += take; c += take; n -= take;
+      if (fill == 8192) { seqio::pack_bases(buf, fill, dst); dst += fill / 2; fill = 0; }
+    }
+    c = next;
+  }
+  if (fill) seqio::pack_bases(buf, fill, dst);
 }
 
 }  // namespace seqio

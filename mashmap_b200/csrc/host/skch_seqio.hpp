@@ -51,6 +51,8 @@ class FastaFile {
   std::string name(const FastaRecord &r) const { return std::string(data_ + r.name_off, r.name_len); }
   /* copies the record's bases to dst (seq_len bytes) */
   void copy_bases(const FastaRecord &r, char *dst) const;
+  /* the record's bases as nibbles (pack_bases below) to dst ((seq_len + 1) / 2 bytes), newlines dropped on the way */
+  void pack_bases(const FastaRecord &r, uint8_t *dst) const;
 
  private:
   const char *data_ = nullptr;
@@ -58,6 +60,16 @@ class FastaFile {
   int fd_ = -1;
   std::vector<FastaRecord> recs_;
 };
+
+/*
+ * The device's input format (include/mashmap_b200.h, mm_map_segments_packed): one nibble per base, base i of the
+ * sequence in byte i / 2 (low nibble first); nibble = 2-bit code (A 0, C 1, T 2, G 3: bits 1-2 of the upper-cased
+ * letter) | 8 for every byte that is not ACGT after upper-casing -- makeUpperCaseAndValidDNA (reference
+ * commonFunc.hpp:75-107) folded into the encoding. The parser touches every base once anyway; writing 4 bits instead of
+ * 8 halves what crosses PCIe afterwards. dst gets (n + 1) / 2 bytes; an odd n leaves an 'N' nibble in the last byte.
+ * AVX2 where the CPU has it (32 bases per step), plain C otherwise.
+ */
+void pack_bases(const char *src, uint64_t n, uint8_t *dst);
 
 }  // namespace seqio
 }  // namespace skch

@@ -39,6 +39,10 @@ struct mm_ctx {
 
   /* batch */
   uint8_t *d_bases = nullptr; uint64_t bases_cap = 0; uint64_t n_bases = 0;
+  uint8_t *d_packed = nullptr; uint64_t packed_cap = 0; /* nibbles, bytes */
+  bool batch_is_ascii = false; /* the resident batch came in as text: K0 (pack) runs in front of K1 */
+  cudaEvent_t ev_pack = nullptr;
+  float pack_ms = 0;
   mm_segment *d_segs = nullptr; uint64_t segs_cap = 0; uint64_t n_segs = 0;
   uint64_t *d_sk_hash = nullptr; uint64_t *d_sk_val = nullptr; int2 *d_sk_pos = nullptr; int8_t *d_sk_strand = nullptr; uint64_t sk_cap = 0;
   mm_segment_result *d_seg_res = nullptr;
@@ -182,12 +186,19 @@ int validate_segments(mm_ctx *c, const mm_segment *segs, uint64_t n_segs, uint64
   return MM_OK;
 }
 
-int upload_batch(mm_ctx *c, const char *bases, uint64_t n_bases, const mm_segment *segs, uint64_t n_segs)
+/* batch buffers that do not depend on the input format */
+int prepare_batch_buffers(mm_ctx *c, uint64_t n_bases, uint64_t n_segs)
 {
-  int rc = validate_segments(c, segs, n_segs, n_bases);
-  if (rc) return rc;
-  CU(c, cudaSetDevice(c->device));
-  if ((rc = grow(c, c->d_bases, c->bases_cap, n_bases, 256))) return rc;
+  int rc;
+  /* nibbles: n_bases/2 rounded up to 8-byte groups of 16 bases, + 256 so that the 16-byte-granular bulk copies of the
+   * sketch kernel never leave the allocation */
+  const uint64_t pbytes = (n_bases + 15) / 16 * 8;
+  if (pbytes + 256 > c->packed_cap || !c->d_packed) {
+    if (c->d_packed) { cudaFree(c->d_packed); c->d_packed = nullptr; c->packed_cap = 0; }
+    CU(c, cudaMalloc((void **)&c->d_packed, pbytes + 256));
+    c->packed_cap = pbytes + 256;
+    CU(c, cudaMemsetAsync(c->d_packed, 0x88, c->packed_cap, c->stream));
+  }
   if ((rc = grow(c, c->d_segs, c->segs_cap, n_segs, 1))) return rc;
   const uint64_t S = (uint64_t)c->params.sketch_size;
   if (n_segs * S + 1 > c->sk_cap || !c->d_sk_hash) {
@@ -206,33 +217,68 @@ int upload_batch(mm_ctx *c, const char *bases, uint64_t n_bases, const mm_segmen
     c->sk_cap = n;
   }
   if (!c->d_counters) CU(c, cudaMalloc((void **)&c->d_counters, 64));
-  CU(c, cudaEventRecord(c->ev[6], c->stream));
+  return MM_OK;
+}
+
+/* host -> device copy of `bytes` bytes, in <= 16 MiB pieces when a phase hook is installed (MM_PHASE_UPLOAD_CHUNK) */
+int copy_in(mm_ctx *c, uint8_t *dst, const void *src, uint64_t bytes)
+{
   if (!c->hook) {
-    CU(c, cudaMemcpyAsync(c->d_bases, bases, n_bases, cudaMemcpyHostToDevice, c->stream));
-  } else { /* in pieces, so that the pipeline's scheduler can hold the upload back (MM_PHASE_UPLOAD_CHUNK) */
-    const uint64_t CH = 16ULL << 20;
-    for (uint64_t at = 0; at < n_bases; at += CH) {
-      const uint64_t n = std::min(CH, n_bases - at);
-      c->hook(c->hook_user, MM_PHASE_UPLOAD_CHUNK, 1);
-      cudaError_t e = cudaMemcpyAsync(c->d_bases + at, bases + at, n, cudaMemcpyHostToDevice, c->stream);
-      if (e == cudaSuccess) e = wait_stream(c);
-      c->hook(c->hook_user, MM_PHASE_UPLOAD_CHUNK, 0);
-      CU(c, e);
-    }
+    CU(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    return MM_OK;
   }
-  CU(c, cudaMemsetAsync(c->d_bases + n_bases, 'N', 256, c->stream));
+  const uint64_t CH = 16ULL << 20;
+  for (uint64_t at = 0; at < bytes; at += CH) {
+    const uint64_t n = std::min(CH, bytes - at);
+    c->hook(c->hook_user, MM_PHASE_UPLOAD_CHUNK, 1);
+    cudaError_t e = cudaMemcpyAsync(dst + at, (const uint8_t *)src + at, n, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = wait_stream(c);
+    c->hook(c->hook_user, MM_PHASE_UPLOAD_CHUNK, 0);
+    CU(c, e);
+  }
+  return MM_OK;
+}
+
+/* packed != 0: `bases` holds nibbles (mm_batch_upload_packed) */
+int upload_batch(mm_ctx *c, const void *bases, uint64_t n_bases, const mm_segment *segs, uint64_t n_segs, int packed)
+{
+  int rc = validate_segments(c, segs, n_segs, n_bases);
+  if (rc) return rc;
+  CU(c, cudaSetDevice(c->device));
+  if ((rc = prepare_batch_buffers(c, n_bases, n_segs))) return rc;
+  CU(c, cudaEventRecord(c->ev[6], c->stream));
+  if (packed) {
+    const uint64_t pbytes = (n_bases + 1) / 2;
+    if ((rc = copy_in(c, c->d_packed, bases, pbytes))) return rc;
+    CU(c, cudaMemsetAsync(c->d_packed + pbytes, 0x88, 64, c->stream));
+    if (n_bases & 1) { /* the unused high nibble of the last byte is whatever the caller had there: irrelevant (never a k-mer) */ }
+  } else {
+    if ((rc = grow(c, c->d_bases, c->bases_cap, n_bases, 256))) return rc;
+    if ((rc = copy_in(c, c->d_bases, bases, n_bases))) return rc;
+    CU(c, cudaMemsetAsync(c->d_bases + n_bases, 'N', 256, c->stream));
+  }
   CU(c, cudaMemcpyAsync(c->d_segs, segs, n_segs * sizeof(mm_segment), cudaMemcpyHostToDevice, c->stream));
   CU(c, cudaEventRecord(c->ev[7], c->stream));
   c->n_bases = n_bases;
   c->n_segs = n_segs;
+  c->batch_is_ascii = !packed;
   c->batch_mapped = false;
+  return MM_OK;
+}
+
+/* K0 in front of K1 when the resident batch is text */
+int launch_pack_if_ascii(mm_ctx *c)
+{
+  if (!c->batch_is_ascii) { c->pack_ms = 0; return MM_OK; }
+  CU(c, mm_launch_pack_bases(c->d_bases, c->d_packed, c->n_bases, c->stream, c->sm_count));
+  c->launches++;
   return MM_OK;
 }
 
 mm_dev_batch make_batch(mm_ctx *c)
 {
   mm_dev_batch b{};
-  b.bases = c->d_bases; b.segs = c->d_segs; b.n_segs = (uint32_t)c->n_segs;
+  b.bases = c->d_bases; b.packed = c->d_packed; b.segs = c->d_segs; b.n_segs = (uint32_t)c->n_segs;
   b.sk_hash = c->d_sk_hash; b.sk_val = c->d_sk_val; b.sk_pos = c->d_sk_pos; b.sk_strand = c->d_sk_strand;
   b.seg_res = c->d_seg_res;
   b.cands = c->d_cands; b.cand_cap = (uint32_t)std::min<uint64_t>(c->cand_cap, 0xffffffffu);
@@ -407,7 +453,9 @@ int run_pipeline(mm_ctx *c)
     c->loci_cap = 2 * c->cand_cap;
     CU(c, cudaMalloc((void **)&c->d_loci, c->loci_cap * sizeof(mm_l2_locus)));
   }
-  if ((rc = ensure_scratch(c, c->scratch_cap ? c->scratch_cap - c->scratch_pool : (32ULL << 20)))) return rc;
+  uint64_t pool0 = 32ULL << 20; /* interval points the bump pool holds at first (grown on demand below) */
+  if (const char *e = getenv("MM_L1_POOL_ELEMS")) pool0 = std::max<uint64_t>(1024, strtoull(e, nullptr, 10)); /* tests: force the regrow path */
+  if ((rc = ensure_scratch(c, c->scratch_cap ? c->scratch_cap - c->scratch_pool : pool0))) return rc;
   if (c->l1_slow_cap < n_segs + 1) {
     if (c->d_l1_slow) cudaFree(c->d_l1_slow);
     c->d_l1_slow = nullptr;
@@ -420,6 +468,8 @@ int run_pipeline(mm_ctx *c)
     mm_dev_batch b = make_batch(c);
     ZERO_WORDS(c, c->d_counters, 16);
     CU(c, cudaEventRecord(c->ev[0], c->stream));
+    if ((rc = launch_pack_if_ascii(c))) return rc;
+    CU(c, cudaEventRecord(c->ev_pack, c->stream));
     CU(c, mm_launch_sketch(c->params, b, c->stream, c->sm_count));
     CU(c, cudaEventRecord(c->ev[1], c->stream));
     int l1_launches = 0;
@@ -450,7 +500,8 @@ int run_pipeline(mm_ctx *c)
     if (c->l2_mode == 1) {
       int rc2 = run_l2_stream(c, h_cnt);
       if (rc2 == MM_OK) {
-        cudaEventElapsedTime(&c->stage_ms[0], c->ev[0], c->ev[1]);
+        cudaEventElapsedTime(&c->pack_ms, c->ev[0], c->ev_pack);
+        cudaEventElapsedTime(&c->stage_ms[0], c->ev_pack, c->ev[1]);
         cudaEventElapsedTime(&c->stage_ms[1], c->ev[1], c->ev[2]);
         cudaEventElapsedTime(&c->stage_ms[2], c->ev[3], c->ev[4]);
         cudaEventElapsedTime(&c->stage_ms[5], c->ev[0], c->ev[4]);
@@ -479,7 +530,8 @@ int run_pipeline(mm_ctx *c)
         continue;
       }
       c->n_loci = h_cnt[6];
-      cudaEventElapsedTime(&c->stage_ms[0], c->ev[0], c->ev[1]);
+      cudaEventElapsedTime(&c->pack_ms, c->ev[0], c->ev_pack);
+      cudaEventElapsedTime(&c->stage_ms[0], c->ev_pack, c->ev[1]);
       cudaEventElapsedTime(&c->stage_ms[1], c->ev[1], c->ev[2]);
       cudaEventElapsedTime(&c->stage_ms[2], c->ev[3], c->ev[4]);
       cudaEventElapsedTime(&c->stage_ms[5], c->ev[0], c->ev[4]); /* first launch -> last kernel end, incl. host gaps */
@@ -511,7 +563,7 @@ int mm_ctx_create(int device, const mm_params *params, mm_ctx **out)
     return fail(nullptr, MM_EINVAL, "k-mer size %d is not compiled in", params->kmer_size);
   if (params->sketch_size < 1 || params->seg_length < params->kmer_size)
     return fail(nullptr, MM_EINVAL, "bad sketch_size / seg_length");
-  if (mm_sketch_smem_bytes(params->seg_length, params->sketch_size, nullptr) == 0)
+  if (mm_sketch_smem_bytes(params->seg_length, params->sketch_size, params->kmer_size, nullptr, nullptr) == 0)
     return fail(nullptr, MM_EINVAL, "seg_length %d / sketch_size %d exceed the shared-memory budget of the sketch kernel",
                 params->seg_length, params->sketch_size);
   mm_ctx *c = new mm_ctx();
@@ -523,6 +575,7 @@ int mm_ctx_create(int device, const mm_params *params, mm_ctx **out)
     return fail(nullptr, MM_ECUDA, "cannot create stream");
   }
   for (auto &ev : c->ev) cudaEventCreate(&ev);
+  cudaEventCreate(&c->ev_pack);
   if (cudaHostAlloc((void **)&c->h_pub, 256, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
     cudaStreamDestroy(c->stream);
     delete c;
@@ -545,7 +598,7 @@ int mm_ctx_destroy(mm_ctx *c)
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   if (c->blob && c->blob_owned) cudaFree(c->blob);
-  cudaFree(c->d_bases); cudaFree(c->d_segs); cudaFree(c->d_sk_hash); cudaFree(c->d_sk_val); cudaFree(c->d_sk_pos); cudaFree(c->d_sk_strand);
+  cudaFree(c->d_bases); cudaFree(c->d_packed); cudaFree(c->d_segs); cudaFree(c->d_sk_hash); cudaFree(c->d_sk_val); cudaFree(c->d_sk_pos); cudaFree(c->d_sk_strand);
   cudaFree(c->d_seg_res); cudaFree(c->d_cands); cudaFree(c->d_loci); cudaFree(c->d_counters); cudaFree(c->d_scratch);
   cudaFree(c->d_l1_slow); cudaFree(c->d_l2_order); cudaFree(c->d_l2_ranges); cudaFree(c->d_l2_rec_off); cudaFree(c->d_l2_recs); cudaFree(c->d_scan_tmp);
   for (auto &ev : c->ev) cudaEventDestroy(ev);
@@ -741,14 +794,22 @@ int mm_ctx_share_index(mm_ctx *c, const mm_ctx *src)
   return MM_OK;
 }
 
-int mm_batch_upload(mm_ctx *c, const char *bases, uint64_t n_bases, const mm_segment *segs, uint64_t n_segs)
+static int batch_upload_any(mm_ctx *c, const void *bases, uint64_t n_bases, const mm_segment *segs, uint64_t n_segs, int packed)
 {
   if (!c || (!bases && n_bases) || (!segs && n_segs)) return fail(c, MM_EINVAL, "null argument");
-  int rc = upload_batch(c, bases, n_bases, segs, n_segs);
+  int rc = upload_batch(c, bases, n_bases, segs, n_segs, packed);
   if (rc) return rc;
   CU(c, wait_stream(c));
   cudaEventElapsedTime(&c->stage_ms[3], c->ev[6], c->ev[7]);
   return MM_OK;
+}
+int mm_batch_upload(mm_ctx *c, const char *bases, uint64_t n_bases, const mm_segment *segs, uint64_t n_segs)
+{
+  return batch_upload_any(c, bases, n_bases, segs, n_segs, 0);
+}
+int mm_batch_upload_packed(mm_ctx *c, const uint8_t *nibbles, uint64_t n_bases, const mm_segment *segs, uint64_t n_segs)
+{
+  return batch_upload_any(c, nibbles, n_bases, segs, n_segs, 1);
 }
 
 int mm_map_resident(mm_ctx *c, uint64_t *n_candidates, uint64_t *n_loci)
@@ -808,9 +869,10 @@ int mm_sketch_segments(mm_ctx *c, const char *bases, uint64_t n_bases, const mm_
                        mm_minmer *out, int32_t *out_count)
 {
   if (!c || !out || !out_count) return fail(c, MM_EINVAL, "null argument");
-  int rc = upload_batch(c, bases, n_bases, segs, n_segs);
+  int rc = upload_batch(c, bases, n_bases, segs, n_segs, 0);
   if (rc) return rc;
   mm_dev_batch b = make_batch(c);
+  if ((rc = launch_pack_if_ascii(c))) return rc;
   CU(c, cudaEventRecord(c->ev[0], c->stream));
   CU(c, mm_launch_sketch(c->params, b, c->stream, c->sm_count));
   CU(c, cudaEventRecord(c->ev[1], c->stream));
@@ -823,12 +885,12 @@ int mm_sketch_segments(mm_ctx *c, const char *bases, uint64_t n_bases, const mm_
   return rc;
 }
 
-int mm_map_segments(mm_ctx *c, const char *bases, uint64_t n_bases, const mm_segment *segs, uint64_t n_segs,
-                    mm_segment_result *seg_results, mm_l1_candidate *cands, uint64_t cand_cap, uint64_t *n_candidates,
-                    mm_l2_locus *loci, uint64_t loci_cap, uint64_t *n_loci)
+static int map_segments_any(mm_ctx *c, const void *bases, uint64_t n_bases, const mm_segment *segs, uint64_t n_segs,
+                            mm_segment_result *seg_results, mm_l1_candidate *cands, uint64_t cand_cap, uint64_t *n_candidates,
+                            mm_l2_locus *loci, uint64_t loci_cap, uint64_t *n_loci, int packed)
 {
   if (!c || !seg_results || !n_candidates || !n_loci) return fail(c, MM_EINVAL, "null argument");
-  int rc = upload_batch(c, bases, n_bases, segs, n_segs);
+  int rc = upload_batch(c, bases, n_bases, segs, n_segs, packed);
   if (rc) return rc;
   if ((rc = run_pipeline(c))) return rc;
   cudaEventElapsedTime(&c->stage_ms[3], c->ev[6], c->ev[7]);
@@ -836,6 +898,18 @@ int mm_map_segments(mm_ctx *c, const char *bases, uint64_t n_bases, const mm_seg
   *n_loci = c->n_loci;
   if (cand_cap < c->n_cands || loci_cap < c->n_loci) return fail(c, MM_ECAPACITY, "need %llu candidates, %llu loci", (unsigned long long)c->n_cands, (unsigned long long)c->n_loci);
   return mm_batch_fetch(c, seg_results, cands, cand_cap, loci, loci_cap);
+}
+int mm_map_segments(mm_ctx *c, const char *bases, uint64_t n_bases, const mm_segment *segs, uint64_t n_segs,
+                    mm_segment_result *seg_results, mm_l1_candidate *cands, uint64_t cand_cap, uint64_t *n_candidates,
+                    mm_l2_locus *loci, uint64_t loci_cap, uint64_t *n_loci)
+{
+  return map_segments_any(c, bases, n_bases, segs, n_segs, seg_results, cands, cand_cap, n_candidates, loci, loci_cap, n_loci, 0);
+}
+int mm_map_segments_packed(mm_ctx *c, const uint8_t *nibbles, uint64_t n_bases, const mm_segment *segs, uint64_t n_segs,
+                           mm_segment_result *seg_results, mm_l1_candidate *cands, uint64_t cand_cap, uint64_t *n_candidates,
+                           mm_l2_locus *loci, uint64_t loci_cap, uint64_t *n_loci)
+{
+  return map_segments_any(c, nibbles, n_bases, segs, n_segs, seg_results, cands, cand_cap, n_candidates, loci, loci_cap, n_loci, 1);
 }
 
 int mm_ctx_set_phase_hook(mm_ctx *c, mm_phase_hook hook, void *user)
@@ -849,6 +923,12 @@ int mm_last_stage_ms(const mm_ctx *c, float ms[8])
 {
   if (!c || !ms) return MM_EINVAL;
   for (int i = 0; i < 8; i++) ms[i] = c->stage_ms[i];
+  return MM_OK;
+}
+int mm_last_pack_ms(const mm_ctx *c, float *ms)
+{
+  if (!c || !ms) return MM_EINVAL;
+  *ms = c->pack_ms;
   return MM_OK;
 }
 

@@ -83,6 +83,8 @@ __device__ __forceinline__ uint64_t mm_xorshr33(uint64_t k)
   return mm_pack64(lo ^ (hi >> 1), hi);
 }
 #else
+MM_HD uint64_t mm_pack64(uint32_t lo, uint32_t hi) { return (uint64_t)lo | ((uint64_t)hi << 32); }
+MM_HD void mm_unpack64(uint64_t x, uint32_t &lo, uint32_t &hi) { lo = (uint32_t)x; hi = (uint32_t)(x >> 32); }
 template <uint64_t C, int NBYTES>
 MM_HD uint64_t mm_mulc(uint64_t x) { return x * C; }
 template <int R>
@@ -124,7 +126,11 @@ MM_HD uint64_t mm_murmur3_k(const uint64_t *w)
   for (int b = 0; b < NB; b++) {
     uint64_t k1 = w[2 * b], k2 = w[2 * b + 1];
     k1 = mm_mulc<c1, 8>(k1); k1 = mm_rotl<31>(k1); k1 = mm_mulc<c2, 8>(k1); h1 ^= k1;
-    h1 = mm_rotl<27>(h1); h1 += h2; h1 = mm_mul5_add<0x52dce729u>(h1);
+    if (b == 0) { /* h2 is still the seed: (x + seed) * 5 + c = x * 5 + (c + 5 * seed), two instructions fewer */
+      h1 = mm_rotl<27>(h1); h1 = mm_mul5_add<0x52dce729u + 5u * (uint32_t)MM_SEED>(h1);
+    } else {
+      h1 = mm_rotl<27>(h1); h1 += h2; h1 = mm_mul5_add<0x52dce729u>(h1);
+    }
     k2 = mm_mulc<c2, 8>(k2); k2 = mm_rotl<33>(k2); k2 = mm_mulc<c1, 8>(k2); h2 ^= k2;
     h2 = mm_rotl<31>(h2); h2 += h1; h2 = mm_mul5_add<0x38495ab5u>(h2);
   }

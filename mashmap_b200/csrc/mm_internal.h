@@ -71,7 +71,9 @@ struct mm_dev_index {
 
 /* Per-batch device buffers. */
 struct mm_dev_batch {
-  const uint8_t *bases;       /* padded by >= 64 bytes                                          */
+  const uint8_t *bases;       /* ASCII bases (only when the batch came in as text), padded by 256 bytes          */
+  const uint8_t *packed;      /* one nibble per base (2-bit code | 8 = not ACGT), base i in byte i/2, low nibble first; */
+                              /* what the sketch kernel reads; padded by 256 bytes                                 */
   const mm_segment *segs;
   uint32_t n_segs;
   /* query sketches, slot seg*S + j (ascending hash); compacted in place by the L1 kernel      */
@@ -123,6 +125,8 @@ MM_HD uint32_t mm_tab_slot_of(uint64_t key, int log2)
 
 /* launchers implemented in the .cu files; all return cudaError_t from the launch */
 cudaError_t mm_launch_sketch(const mm_params &p, const mm_dev_batch &b, cudaStream_t st, int sm_count);
+/* K0: ASCII -> nibbles (makeUpperCaseAndValidDNA as a format change); both buffers padded to a multiple of 16 bases */
+cudaError_t mm_launch_pack_bases(const uint8_t *ascii, uint8_t *packed, uint64_t n_bases, cudaStream_t st, int sm_count);
 cudaError_t mm_launch_l1(const mm_params &p, const mm_dev_index &ix, const mm_dev_batch &b,
                          cudaStream_t st, int sm_count, uint32_t *slow_list, int use_warp_path, int *n_launched);
 cudaError_t mm_launch_l2(const mm_params &p, const mm_dev_index &ix, const mm_dev_batch &b,
@@ -151,7 +155,7 @@ cudaError_t mm_build_death_order(const uint64_t *idx_hash, const int32_t *idx_we
                                  int32_t n_contigs, uint64_t n, uint64_t *idx2_hash, int32_t *idx2_wend, cudaStream_t st);
 uint32_t mm_l1_grid_size(const mm_params &p, int sm_count);
 int mm_sketch_kmer_supported(int k);
-/* dynamic shared memory the sketch kernel needs for (seg_length, sketch_size); 0 if unsupported */
-size_t mm_sketch_smem_bytes(int seg_length, int sketch_size, int *table_cap);
+/* dynamic shared memory the sketch kernel needs for (seg_length, sketch_size, kmer_size); 0 if unsupported */
+size_t mm_sketch_smem_bytes(int seg_length, int sketch_size, int kmer_size, int *table_cap, int *list_cap);
 
 #endif

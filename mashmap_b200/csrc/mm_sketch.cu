@@ -1,5 +1,5 @@
 /*
- * mm_sketch.cu -- K1: bottom-s MinHash sketch of every query segment.
+ * mm_sketch.cu -- K0 (base packing) and K1: bottom-s MinHash sketch of every query segment.
  *
  * Replaces CommonFunc::sketchSequence (reference src/map/include/commonFunc.hpp:182-288) as
  * called from Map::getSeedHits (computeMap.hpp:817-843), i.e. rows a1-a3 of SURVEY 8(a):
@@ -10,20 +10,27 @@
  *   vote sum (:242-286), ascending by hash.
  * sketchSequence is a pure set function (the heap top only decreases once full, so
  * every occurrence of a surviving hash is seen), so any selection that yields that set is
- * bit-exact. This kernel does it without a heap:
+ * bit-exact. This file does it without a heap:
  *
- *   one CTA per segment (persistent grid), segment bytes staged HBM -> shared memory with a 1-D
- *   TMA bulk copy (cp.async.bulk + mbarrier, double buffered across segments);
- *   each thread slides forward / reverse-complement k-mer windows in registers over a contiguous
- *   run of positions and evaluates both Murmur3 hashes (INT-ALU bound: ~10 64-bit multiplies each);
- *   canonical hashes <= T (T ~ c*s/n * 2^64) are inserted into a shared-memory open-addressing
- *   table keyed by hash (atomicCAS), accumulating min position / max position / vote sum
- *   (atomicMin / atomicMax / atomicAdd) -- this de-duplicates before any sorting;
- *   if fewer than s distinct hashes survived although larger ones exist, or the table overflowed,
- *   T is raised / lowered / bisected and the pass is redone (rare; always terminates because
- *   distinct-count(T) grows by at most one per unit of T);
- *   the <= C survivors are ordered with a 256-bucket counting sort on the leading bits plus
- *   in-bucket ranking, and the first s are written out.
+ *   K0 k_pack_bases: makeUpperCaseAndValidDNA (commonFunc.hpp:97-107) as a format change -- every base becomes one
+ *     nibble: 2-bit code (A=0 C=1 T=2 G=3: bits 1-2 of the upper-cased letter) | 8 for anything that is not ACGT.
+ *     HBM-bound (1 B read + 0.5 B written per base). Hosts that pack while they parse (skch::BatchMapper) upload the
+ *     nibbles directly and skip it.
+ *   K1 k_sketch: one CTA per segment (persistent grid); the segment's nibbles are staged HBM -> shared memory with a
+ *     1-D TMA bulk copy (cp.async.bulk + mbarrier, double buffered across segments). Each thread owns a contiguous run of
+ *     k-mer positions, four per step: the ASCII bytes of the forward k-mers and of their reverse complements are
+ *     rebuilt in registers from the nibbles with byte permutes (PRMT: a 4-entry lookup per nibble, then one permute per
+ *     32-bit window word per position), so no base is decoded one at a time. Both Murmur3 evaluations run on those
+ *     words (INT-ALU bound: ~10 64-bit multiplies each). A position whose smaller hash has a leading word <= T's
+ *     (T ~ c*s/n * 2^64) is kept, raw, in a per-thread list in shared memory; after the run every thread inserts its own
+ *     list into a shared-memory open-addressing table keyed by hash (atomicCAS) that accumulates first position / last
+ *     position / vote sum (atomicMin / atomicMax / atomicAdd) -- de-duplication before any sorting. If fewer than s
+ *     distinct hashes survived although larger ones exist, or the table overflowed, T is raised / lowered / bisected and
+ *     the pass is redone (rare; always terminates because distinct-count(T) grows by at most one per unit of T). The
+ *     <= C survivors are ordered with a 256-bucket counting sort on the leading bits plus in-bucket ranking, and the
+ *     first s are written out.
+ *   A thread whose stretch of the segment contains an N (nibble bit 3) takes the same loop with the run-length test
+ *   of commonFunc.hpp:207-223 compiled in; all others skip it.
  */
 #include "mm_internal.h"
 
@@ -35,6 +42,8 @@ namespace {
 constexpr int SK_THREADS = MM_SK_THREADS;
 constexpr int SK_BUCKETS = 256;
 constexpr uint64_t SK_EMPTY = ~0ULL;
+constexpr uint32_t SK_POOL_FWD = 0x47544341u;  /* ASCII by code: A C T G */
+constexpr uint32_t SK_POOL_COMP = 0x43414754u; /* ASCII of the complement by code: T G A C */
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
@@ -76,7 +85,44 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
       "r"(parity)
       : "memory");
 }
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+  return r;
+}
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * K0: ASCII -> nibbles. 16 bases per thread and step (one 16-byte load, one 8-byte store).
+ * ------------------------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ uint32_t pack4(uint32_t w)
+{ /* 4 ASCII bytes -> 4 nibbles in the low 16 bits (base 0 in bits 0-3) */
+  const uint32_t x = w & 0xDFDFDFDFu;                 /* a-z -> A-Z (commonFunc.hpp:100-101) */
+  uint32_t code = (x >> 1) & 0x03030303u;             /* A=0 C=1 T=2 G=3 */
+  const uint32_t t = code | (code >> 4);              /* byte0 = c0|c1<<4, byte2 = c2|c3<<4 */
+  const uint32_t sel = prmt(t, 0u, 0x4420u);          /* the four codes as PRMT selector nibbles */
+  const uint32_t diff = prmt(SK_POOL_FWD, 0u, sel) ^ x; /* zero byte <=> the byte is exactly A, C, G or T */
+  const uint32_t nz = (((diff & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | diff) & 0x80808080u; /* bit 7 of every non-zero byte */
+  const uint32_t inv = nz >> 7;                       /* 0/1 per byte: not ACGT -> N (commonFunc.hpp:103-105) */
+  code = (code & ~(inv * 3u)) | (inv << 3);
+  const uint32_t n = code | (code >> 4);
+  return prmt(n, 0u, 0x4420u);
+}
+__global__ void __launch_bounds__(256) k_pack_bases(const uint4 *__restrict__ in, uint2 *__restrict__ out, uint64_t n16)
+{
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+    const uint4 v = in[i];
+    uint2 o;
+    o.x = pack4(v.x) | (pack4(v.y) << 16);
+    o.y = pack4(v.z) | (pack4(v.w) << 16);
+    out[i] = o;
+  }
+}
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * K1
+ * ------------------------------------------------------------------------------------------------------------- */
 struct sk_ctrl {
   int distinct;
   int overflow;
@@ -86,19 +132,18 @@ struct sk_ctrl {
   int _pad;
 };
 
-constexpr int SK_WARPS = SK_THREADS / 32;
-constexpr int SK_LIST_PER_WARP = 128; /* survivors buffered per warp before they are inserted into the table */
-
 struct sk_smem_layout {
   uint32_t stage_bytes;  /* per staging buffer */
   uint32_t off_bar, off_keys, off_first, off_last, off_votes, off_order, off_bcnt, off_bstart, off_bfill,
-      off_ctrl, off_list_h, off_list_m, total;
+      off_ctrl, off_list_h, off_list_p, total;
 };
 
-__host__ __device__ inline sk_smem_layout sk_layout(int seg_length, int C)
+/* CAP = entries of the per-thread candidate list */
+__host__ __device__ inline sk_smem_layout sk_layout(int seg_length, int C, int CAP)
 {
   sk_smem_layout L;
-  L.stage_bytes = (uint32_t)(((seg_length + 15) & ~15) + 32);
+  /* nibbles of one segment + 16 (alignment of the bulk copy) + 64 (the last threads read a few words past the end) */
+  L.stage_bytes = (uint32_t)((((seg_length + 1) / 2 + 15) & ~15) + 16 + 64);
   uint32_t o = 2 * L.stage_bytes;
   L.off_bar = o; o += 16;
   L.off_keys = o; o += 8u * C;
@@ -107,12 +152,12 @@ __host__ __device__ inline sk_smem_layout sk_layout(int seg_length, int C)
   L.off_votes = o; o += 4u * C;
   L.off_ctrl = o; o += (uint32_t)sizeof(sk_ctrl);
   o = (o + 15) & ~15u;
-  /* the per-warp survivor lists are dead once the table is built; the ordering scratch (order[] + bucket counters)
-   * lives in the same bytes -- 5 KB less per CTA is one more resident CTA per SM */
-  const uint32_t lists = (8u + 4u) * SK_WARPS * SK_LIST_PER_WARP;
+  /* the per-thread candidate lists are dead once the table is built; the ordering scratch (order[] + bucket counters)
+   * lives in the same bytes */
+  const uint32_t lists = (16u + 4u) * SK_THREADS * (uint32_t)CAP;
   const uint32_t ordering = ((2u * C + 15) & ~15u) + 3u * 4u * SK_BUCKETS;
-  L.off_list_h = o;
-  L.off_list_m = o + 8u * SK_WARPS * SK_LIST_PER_WARP;
+  L.off_list_h = o;                                     /* uint4 {hf, hb} [CAP][SK_THREADS] */
+  L.off_list_p = o + 16u * SK_THREADS * (uint32_t)CAP;  /* u32 position   [CAP][SK_THREADS] */
   L.off_order = o;
   L.off_bcnt = o + ((2u * C + 15) & ~15u);
   L.off_bstart = L.off_bcnt + 4u * SK_BUCKETS;
@@ -156,14 +201,163 @@ __device__ __forceinline__ void sk_insert(unsigned long long *keys, int *first, 
   ctrl->overflow = 1;
 }
 
+/* one raw candidate (both hashes of a position) -> the table, if it is a valid k-mer with canonical hash <= T */
+__device__ __forceinline__ void sk_take(unsigned long long *keys, int *first, int *last, int *votes, uint32_t mask,
+                                        int limit, sk_ctrl *ctrl, uint64_t hf, uint64_t hb, int pos, uint64_t T, bool &above)
+{
+  if (hf == hb) return; /* commonFunc.hpp:234 */
+  const bool fwd = hf < hb;
+  const uint64_t h = fwd ? hf : hb; /* :237 */
+  if (h > T) { above = true; return; }
+  sk_insert(keys, first, last, votes, mask, limit, ctrl, h, pos, fwd ? 1 : -1); /* :240 */
+}
+
+/* Geometry of the k-mer windows in 32-bit words (see the loop below) */
+template <int K>
+struct sk_geom {
+  static constexpr int NH = (K + 3) / 4;        /* 32-bit words holding K bytes                          */
+  static constexpr int TB = K - 4 * (NH - 1);   /* bytes used in the last of them (1..4)                 */
+  static constexpr int NWIN = (K + 6) / 4;      /* words spanning the 4 k-mers of one step (K + 3 bytes) */
+  static constexpr int ROFF = 4 * NWIN - K;     /* byte offset of the reverse-complement k-mer of d = 0  */
+};
+
+/* words [OFF, OFF + K) of the byte string held little-endian in A[0..NWIN): out[j] = bytes OFF+4j.. ; the unused
+ * bytes of the last word are zero (PRMT selector 8 = sign of byte 0 replicated; every byte here is ASCII or 0) */
+template <int K, int OFF>
+__device__ __forceinline__ void sk_extract(const uint32_t (&A)[sk_geom<K>::NWIN], uint32_t (&out)[sk_geom<K>::NH])
+{
+  constexpr int NH = sk_geom<K>::NH, TB = sk_geom<K>::TB, NWIN = sk_geom<K>::NWIN;
+#pragma unroll
+  for (int j = 0; j < NH; j++) {
+    const int b = OFF + 4 * j, wi = b >> 2, bo = b & 3;
+    const int nb = (j == NH - 1) ? TB : 4;
+    if (bo == 0 && nb == 4) {
+      out[j] = A[wi];
+    } else {
+      uint32_t sel = 0;
+#pragma unroll
+      for (int t = 0; t < 4; t++) sel |= (uint32_t)(t < nb ? bo + t : 8) << (4 * t);
+      const int w2 = (bo + nb > 4 && wi + 1 < NWIN) ? wi + 1 : wi;
+      out[j] = prmt(A[wi], A[w2], sel);
+    }
+  }
+}
+
+template <int K>
+__device__ __forceinline__ uint64_t sk_hash_words(const uint32_t (&h)[sk_geom<K>::NH])
+{
+  constexpr int NW = mm_kmer_words<K>::NW;
+  uint64_t w[NW];
+#pragma unroll
+  for (int i = 0; i < NW; i++) w[i] = mm_pack64(h[2 * i], (2 * i + 1 < sk_geom<K>::NH) ? h[2 * i + 1] : 0u);
+  return mm_murmur3_k<K>(w);
+}
+
+/* per-segment state handed to the hashing loop */
+struct sk_run {
+  const uint32_t *nib;  /* staged nibbles as aligned 32-bit words (8 bases each) */
+  uint32_t b0;          /* base index (within the stage) of this thread's first position */
+  int p0, p1;           /* this thread's positions [p0, p1) */
+  uint32_t T_hi;
+  uint4 *list_h;        /* this thread's column of the candidate list */
+  uint32_t *list_p;
+  int cap;
+};
+
+/* The hashing loop of one thread. CHECK_N: the stretch contains an N -> per-position validity (run of non-N bases >= K).
+ * Returns the number of candidates stored (<= cap); candidates beyond cap go straight into the table. */
+template <int K, bool CHECK_N>
+__device__ __forceinline__ int sk_hash_run(const sk_run &r, uint32_t &amax, unsigned long long *keys, int *first, int *last,
+                                           int *votes, uint32_t mask, int limit, sk_ctrl *ctrl, uint64_t T, bool &above)
+{
+  constexpr int NH = sk_geom<K>::NH, NWIN = sk_geom<K>::NWIN, ROFF = sk_geom<K>::ROFF;
+  /* F[m] = ASCII of bases 4m..4m+3 after the current step base; C[t] = complement of F-word (NWIN-1-t), byte-reversed,
+   * so that C[0] || C[1] || ... is the reverse complement of the NWIN*4 bases read backwards */
+  uint32_t F[NWIN], C[NWIN];
+  const uint32_t sh = (r.b0 & 7u) * 4u;
+  uint32_t wq = r.b0 >> 3;
+  uint32_t lo = r.nib[wq], hi = r.nib[wq + 1];
+  uint32_t sel = __funnelshift_r(lo, hi, sh); /* the next 8 nibbles, base 0 in bits 0-3 */
+  int have = 8;                               /* unused nibbles left in sel */
+  auto next_word = [&](uint32_t &f, uint32_t &c) {
+    if (have == 0) {
+      wq++;
+      lo = hi; hi = r.nib[wq + 1];
+      sel = __funnelshift_r(lo, hi, sh);
+      have = 8;
+    }
+    f = prmt(SK_POOL_FWD, 0u, sel);                      /* N nibbles (bit 3) give a zero byte */
+    c = prmt(prmt(SK_POOL_COMP, 0u, sel), 0u, 0x0123u);  /* complement, bytes reversed */
+    sel >>= 16;
+    have -= 4;
+  };
+#pragma unroll
+  for (int m = 0; m < NWIN; m++) next_word(F[m], C[NWIN - 1 - m]);
+
+  int run = 0; /* CHECK_N: consecutive non-N bases ending at base (position + K - 2) */
+  if (CHECK_N) {
+#pragma unroll
+    for (int j = 0; j < K - 1; j++) {
+      const uint32_t byte = (F[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+      run = byte ? run + 1 : 0;
+    }
+  }
+  int cnt = 0;
+  uint32_t lofs = 0; /* cnt * SK_THREADS */
+
+  auto position = [&](const uint32_t (&fw)[NH], const uint32_t (&rw)[NH], int pos, uint32_t last_byte) {
+    const uint64_t hf = sk_hash_words<K>(fw);
+    const uint64_t hb = sk_hash_words<K>(rw);
+    bool ok = pos < r.p1;
+    if (CHECK_N) {
+      run = last_byte ? run + 1 : 0;
+      ok = ok && run >= K;
+    }
+    const uint32_t mh = min((uint32_t)(hf >> 32), (uint32_t)(hb >> 32));
+    if (ok) amax = max(amax, mh);
+    if (ok && mh <= r.T_hi) {
+      if (cnt < r.cap) {
+        uint32_t fl, fh, bl, bh;
+        mm_unpack64(hf, fl, fh);
+        mm_unpack64(hb, bl, bh);
+        r.list_h[lofs] = make_uint4(fl, fh, bl, bh);
+        r.list_p[lofs] = (uint32_t)pos;
+        lofs += SK_THREADS;
+        cnt++;
+      } else {
+        sk_take(keys, first, last, votes, mask, limit, ctrl, hf, hb, pos, T, above);
+      }
+    }
+  };
+
+#pragma unroll 1
+  for (int p = r.p0; p < r.p1; p += 4) {
+    uint32_t fw[NH], rw[NH];
+    /* last byte of the forward k-mer of offset d = byte K-1+d of F */
+#define SK_LASTB(d) ((F[(K - 1 + (d)) >> 2] >> (8 * ((K - 1 + (d)) & 3))) & 0xFFu)
+    sk_extract<K, 0>(F, fw); sk_extract<K, ROFF - 0>(C, rw); position(fw, rw, p + 0, CHECK_N ? SK_LASTB(0) : 1u);
+    sk_extract<K, 1>(F, fw); sk_extract<K, ROFF - 1>(C, rw); position(fw, rw, p + 1, CHECK_N ? SK_LASTB(1) : 1u);
+    sk_extract<K, 2>(F, fw); sk_extract<K, ROFF - 2>(C, rw); position(fw, rw, p + 2, CHECK_N ? SK_LASTB(2) : 1u);
+    sk_extract<K, 3>(F, fw); sk_extract<K, ROFF - 3>(C, rw); position(fw, rw, p + 3, CHECK_N ? SK_LASTB(3) : 1u);
+#undef SK_LASTB
+    /* slide by one word */
+#pragma unroll
+    for (int m = 0; m < NWIN - 1; m++) F[m] = F[m + 1];
+#pragma unroll
+    for (int t = NWIN - 1; t > 0; t--) C[t] = C[t - 1];
+    next_word(F[NWIN - 1], C[0]);
+  }
+  return cnt;
+}
+
 template <int K>
 __global__ void __launch_bounds__(SK_THREADS)
-k_sketch(const uint8_t *__restrict__ bases, const mm_segment *__restrict__ segs, uint32_t n_segs, int S,
-         int seg_length, int C, uint64_t *__restrict__ sk_hash, int2 *__restrict__ sk_pos,
+k_sketch(const uint8_t *__restrict__ packed, const mm_segment *__restrict__ segs, uint32_t n_segs, int S,
+         int seg_length, int C, int CAP, uint64_t *__restrict__ sk_hash, int2 *__restrict__ sk_pos,
          int8_t *__restrict__ sk_strand, mm_segment_result *__restrict__ seg_res)
 {
   extern __shared__ __align__(16) unsigned char smem[];
-  const sk_smem_layout L = sk_layout(seg_length, C);
+  const sk_smem_layout L = sk_layout(seg_length, C, CAP);
   uint64_t *bars = (uint64_t *)(smem + L.off_bar);
   unsigned long long *keys = (unsigned long long *)(smem + L.off_keys);
   int *first = (int *)(smem + L.off_first);
@@ -174,11 +368,10 @@ k_sketch(const uint8_t *__restrict__ bases, const mm_segment *__restrict__ segs,
   uint32_t *bstart = (uint32_t *)(smem + L.off_bstart);
   uint32_t *bfill = (uint32_t *)(smem + L.off_bfill);
   sk_ctrl *ctrl = (sk_ctrl *)(smem + L.off_ctrl);
-  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint64_t *list_h = (uint64_t *)(smem + L.off_list_h) + (size_t)wid * SK_LIST_PER_WARP;
-  uint32_t *list_m = (uint32_t *)(smem + L.off_list_m) + (size_t)wid * SK_LIST_PER_WARP;
-
   const int tid = threadIdx.x;
+  uint4 *list_h = (uint4 *)(smem + L.off_list_h) + tid;
+  uint32_t *list_p = (uint32_t *)(smem + L.off_list_p) + tid;
+
   const uint32_t mask = (uint32_t)C - 1;
   const int limit = C / 2;
 
@@ -189,13 +382,14 @@ k_sketch(const uint8_t *__restrict__ bases, const mm_segment *__restrict__ segs,
   }
   __syncthreads();
 
+  /* nibble bytes of segment seg: [off/2, (off+len+1)/2), copied from the 16-byte floor */
   auto issue = [&](uint32_t seg, int stage) {
     const uint64_t off = segs[seg].offset;
     const int len = segs[seg].length;
-    const uint64_t g0 = off & ~15ULL;
-    const uint32_t bytes = (uint32_t)(((off + (uint64_t)len + 15ULL) & ~15ULL) - g0);
+    const uint64_t g0 = (off >> 1) & ~15ULL;
+    const uint32_t bytes = (uint32_t)(((((off + (uint64_t)len + 1ULL) >> 1) + 15ULL) & ~15ULL) - g0);
     mbar_expect_tx(&bars[stage], bytes);
-    bulk_g2s(smem + (size_t)stage * L.stage_bytes, bases + g0, bytes, &bars[stage]);
+    bulk_g2s(smem + (size_t)stage * L.stage_bytes, packed + g0, bytes, &bars[stage]);
   };
 
   uint32_t it = 0;
@@ -210,13 +404,18 @@ k_sketch(const uint8_t *__restrict__ bases, const mm_segment *__restrict__ segs,
     }
     const uint64_t off = segs[seg].offset;
     const int len = segs[seg].length;
-    const uint8_t *s = smem + (size_t)stage * L.stage_bytes + (off & 15ULL);
-    mbar_wait(&bars[stage], (it >> 1) & 1);
+    const uint32_t skew = (uint32_t)(off - (((off >> 1) & ~15ULL) << 1)); /* bases between the copy's start and the segment */
 
     const int n = len - K + 1; /* number of k-mer positions (commonFunc.hpp:217) */
-    const int P = n > 0 ? (n + SK_THREADS - 1) / SK_THREADS : 0;
-    const int p0 = tid * P;
-    const int p1 = min(n, p0 + P);
+    /* positions in steps of four; every thread gets a whole number of steps */
+    const int P = n > 0 ? 4 * ((((n + 3) >> 2) + SK_THREADS - 1) / SK_THREADS) : 0;
+    sk_run r;
+    r.nib = (const uint32_t *)(smem + (size_t)stage * L.stage_bytes);
+    r.p0 = tid * P;
+    r.p1 = min(n, r.p0 + P);
+    r.b0 = skew + (uint32_t)r.p0;
+    r.list_h = list_h; r.list_p = list_p; r.cap = CAP;
+    const bool has_work = r.p0 < r.p1;
 
     /* initial threshold: expect c*S distinct survivors, c = 1.1 + 6/sqrt(S). The canonical hash is the MIN of two
      * uniform hashes, so P(canonical <= t) = 1 - (1-t)^2: solve that for the wanted fraction f = c*S/n. */
@@ -228,78 +427,52 @@ k_sketch(const uint8_t *__restrict__ bases, const mm_segment *__restrict__ segs,
     }
     uint64_t lo = 0, hi = 0;
     bool have_lo = false, have_hi = false;
+    bool waited = false;
+    bool any_n = false;
 
     while (true) {
-      for (int i = tid; i < C; i += SK_THREADS) {
-        keys[i] = SK_EMPTY;
-        first[i] = 0x7fffffff;
-        last[i] = -1;
-        votes[i] = 0;
+      { /* reset the table: 16-byte stores */
+        uint4 *k4 = (uint4 *)keys;
+        for (int i = tid; i < C / 2; i += SK_THREADS) k4[i] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+        int4 *f4 = (int4 *)first, *l4 = (int4 *)last, *v4 = (int4 *)votes;
+        for (int i = tid; i < C / 4; i += SK_THREADS) {
+          f4[i] = make_int4(0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff);
+          l4[i] = make_int4(-1, -1, -1, -1);
+          v4[i] = make_int4(0, 0, 0, 0);
+        }
       }
       if (tid == 0) {
         ctrl->distinct = 0; ctrl->overflow = 0; ctrl->above = 0; ctrl->has_max = 0;
         ctrl->max_first = 0x7fffffff; ctrl->max_last = -1; ctrl->max_votes = 0;
       }
+      if (!waited) {
+        mbar_wait(&bars[stage], (it >> 1) & 1);
+        waited = true;
+        if (has_work) { /* any N (nibble bit 3) in the words this thread will read? (a few bases too many: harmless) */
+          const uint32_t w0 = r.b0 >> 3, w1 = (r.b0 + (uint32_t)(r.p1 - r.p0) + (uint32_t)K + 6u) >> 3;
+          uint32_t acc = 0;
+          for (uint32_t w = w0; w <= w1; w++) acc |= r.nib[w];
+          any_n = (acc & 0x88888888u) != 0;
+        }
+      }
       __syncthreads();
 
-      /* Hashing pass. Survivors (canonical hash <= T) are appended to this warp's list -- ballot + popc, no atomics --
-       * and inserted into the table afterwards by all threads, so that the rare insert path (7 % of the positions, but
-       * some lane of almost every warp iteration) does not serialise the hashing loop. */
-      uint32_t wcount = 0; /* warp-uniform */
-      {
-        mm_kmer_window<K> w;
-        w.reset();
-        int run = 0; /* consecutive non-N bases ending at the current byte */
-        bool above = false;
-        const bool has_work = p0 < p1;
-        if (has_work) {
-#pragma unroll 1
-          for (int j = 0; j < K - 1; j++) {
-            bool isn;
-            const uint32_t code = mm_base_code(s[p0 + j], isn);
-            run = isn ? 0 : run + 1;
-            w.push(code);
-          }
-        }
-#pragma unroll 1
-        for (int jj = 0; jj < P; jj++) {
-          const int i = p0 + jj;
-          bool surv = false;
-          uint64_t h = 0;
-          uint32_t meta = 0;
-          if (i < p1) {
-            bool isn;
-            const uint32_t code = mm_base_code(s[i + K - 1], isn);
-            run = isn ? 0 : run + 1;
-            w.push(code);
-            const uint64_t hf = w.hash_fwd();
-            const uint64_t hb = w.hash_rev();
-            if (run >= K && hf != hb) { /* commonFunc.hpp:234 */
-              h = hf < hb ? hf : hb;
-              meta = ((uint32_t)i << 1) | (hf < hb ? 1u : 0u);
-              if (h <= T) surv = true; else above = true;
-            }
-          }
-          const uint32_t sm = __ballot_sync(0xffffffffu, surv);
-          if (sm) {
-            const uint32_t idx = wcount + __popc(sm & ((1u << lane) - 1u));
-            if (surv) {
-              if (idx < (uint32_t)SK_LIST_PER_WARP) { list_h[idx] = h; list_m[idx] = meta; }
-              else sk_insert(keys, first, last, votes, mask, limit, ctrl, h, (int)(meta >> 1), (meta & 1u) ? 1 : -1);
-            }
-            wcount += __popc(sm);
-          }
-        }
-        if (above) ctrl->above = 1;
+      r.T_hi = (uint32_t)(T >> 32);
+      bool above = false;
+      uint32_t amax = 0;
+      int cnt = 0;
+      if (has_work) {
+        if (any_n) cnt = sk_hash_run<K, true>(r, amax, keys, first, last, votes, mask, limit, ctrl, T, above);
+        else cnt = sk_hash_run<K, false>(r, amax, keys, first, last, votes, mask, limit, ctrl, T, above);
       }
-      __syncwarp();
-      {
-        const uint32_t nl = min(wcount, (uint32_t)SK_LIST_PER_WARP);
-        for (uint32_t q = lane; q < nl; q += 32) {
-          const uint32_t meta = list_m[q];
-          sk_insert(keys, first, last, votes, mask, limit, ctrl, list_h[q], (int)(meta >> 1), (meta & 1u) ? 1 : -1);
-        }
+      if (amax > r.T_hi) above = true; /* a valid position whose smaller hash is certainly > T */
+      /* every thread inserts its own candidates */
+      for (int q = 0; q < cnt; q++) {
+        const uint4 e = list_h[(size_t)q * SK_THREADS];
+        const int pos = (int)list_p[(size_t)q * SK_THREADS];
+        sk_take(keys, first, last, votes, mask, limit, ctrl, mm_pack64(e.x, e.y), mm_pack64(e.z, e.w), pos, T, above);
       }
+      if (above) ctrl->above = 1;
       __syncthreads();
       const int d = ctrl->distinct + ctrl->has_max;
       const int ovf = ctrl->overflow;
@@ -379,20 +552,42 @@ k_sketch(const uint8_t *__restrict__ bases, const mm_segment *__restrict__ segs,
         count = dt + 1;
       }
       if (count > S) count = S;
-      mm_segment_result r;
-      r.sketch_max_hash = 0; /* filled by the L1 kernel from sk_hash[count-1] */
-      r.sketch_raw_count = count;
-      r.sketch_size = count;
-      r.n_points = 0; r.minimum_hits = 0; r.best_intersection = 0;
-      r.first_candidate = 0; r.n_candidates = 0; r._pad = 0;
-      seg_res[seg] = r;
+      mm_segment_result res;
+      res.sketch_max_hash = 0; /* filled by the L1 kernel from sk_hash[count-1] */
+      res.sketch_raw_count = count;
+      res.sketch_size = count;
+      res.n_points = 0; res.minimum_hits = 0; res.best_intersection = 0;
+      res.first_candidate = 0; res.n_candidates = 0; res._pad = 0;
+      seg_res[seg] = res;
     }
     __syncthreads(); /* all reads of the staging buffer and of the table are done */
   }
 }
 
+/* table capacity and candidate-list capacity for (seg_length, sketch_size) */
+void sk_sizes(int seg_length, int sketch_size, int kmer_size, int *C_out, int *CAP_out)
+{
+  /* survivors ~ c*S with c = 1.1 + 6/sqrt(S); the table may be half full at most */
+  const double c = 1.1 + 6.0 / sqrt((double)sketch_size);
+  const double want = 2.0 * (c * sketch_size + 8.0 * sqrt(c * sketch_size) + 16.0);
+  int C = 512;
+  while (C < want) C <<= 1;
+  /* candidates per thread ~ Poisson(mu): mu + 2 sqrt(mu) + 1 entries hold all but a few per cent of the threads'
+   * lists; the rest go straight to the table (correct, just slower) */
+  const int n = seg_length - kmer_size + 1 > 0 ? seg_length - kmer_size + 1 : 1;
+  const int P = 4 * ((((n + 3) >> 2) + SK_THREADS - 1) / SK_THREADS);
+  double f = c * (double)sketch_size / (double)n;
+  if (f > 1.0) f = 1.0;
+  const double mu = f * P;
+  int CAP = (int)ceil(mu + 2.0 * sqrt(mu) + 1.0);
+  if (CAP < 4) CAP = 4;
+  if (CAP > 24) CAP = 24;
+  *C_out = C;
+  *CAP_out = CAP;
+}
+
 template <int K>
-cudaError_t launch_k(const mm_params &p, const mm_dev_batch &b, cudaStream_t st, int sm_count, int C, size_t smem)
+cudaError_t launch_k(const mm_params &p, const mm_dev_batch &b, cudaStream_t st, int sm_count, int C, int CAP, size_t smem)
 {
   cudaError_t e = cudaFuncSetAttribute(k_sketch<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -403,14 +598,16 @@ cudaError_t launch_k(const mm_params &p, const mm_dev_batch &b, cudaStream_t st,
   uint32_t grid = (uint32_t)sm_count * (uint32_t)occ; /* persistent: a whole number of CTAs per SM */
   if (grid > b.n_segs) grid = b.n_segs;
   if (grid == 0) return cudaSuccess;
-  k_sketch<K><<<grid, SK_THREADS, smem, st>>>(b.bases, b.segs, b.n_segs, p.sketch_size, p.seg_length, C, b.sk_hash,
+  k_sketch<K><<<grid, SK_THREADS, smem, st>>>(b.packed, b.segs, b.n_segs, p.sketch_size, p.seg_length, C, CAP, b.sk_hash,
                                               b.sk_pos, b.sk_strand, b.seg_res);
   return cudaGetLastError();
 }
 
 } // namespace
 
-#define MM_FOR_EACH_K(X) X(11) X(13) X(15) X(16) X(17) X(19) X(21) X(23) X(25) X(27) X(29) X(31) X(32)
+#define MM_FOR_EACH_K(X) \
+  X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16) X(17) X(18) X(19) X(20) X(21) X(22) X(23) X(24) X(25) X(26) X(27) \
+  X(28) X(29) X(30) X(31) X(32)
 
 int mm_sketch_kmer_supported(int k)
 {
@@ -423,27 +620,40 @@ int mm_sketch_kmer_supported(int k)
   }
 }
 
-size_t mm_sketch_smem_bytes(int seg_length, int sketch_size, int *table_cap)
+size_t mm_sketch_smem_bytes(int seg_length, int sketch_size, int kmer_size, int *table_cap, int *list_cap)
 {
-  /* survivors ~ c*S with c = 1.1 + 6/sqrt(S); the table may be half full at most */
-  const double c = 1.1 + 6.0 / sqrt((double)sketch_size);
-  const double want = 2.0 * (c * sketch_size + 8.0 * sqrt(c * sketch_size) + 16.0);
-  int C = 512;
-  while (C < want) C <<= 1;
+  int C = 0, CAP = 0;
+  sk_sizes(seg_length, sketch_size, kmer_size, &C, &CAP);
   if (C > 32768) return 0; /* order[] holds 16-bit slots */
-  if (table_cap) *table_cap = C;
-  const sk_smem_layout L = sk_layout(seg_length, C);
+  sk_smem_layout L = sk_layout(seg_length, C, CAP);
+  while (L.total > 227u * 1024u && CAP > 4) { /* long segments: a shorter list before giving up */
+    CAP--;
+    L = sk_layout(seg_length, C, CAP);
+  }
   if (L.total > 227u * 1024u) return 0;
+  if (table_cap) *table_cap = C;
+  if (list_cap) *list_cap = CAP;
   return L.total;
+}
+
+cudaError_t mm_launch_pack_bases(const uint8_t *ascii, uint8_t *packed, uint64_t n_bases, cudaStream_t st, int sm_count)
+{
+  const uint64_t n16 = (n_bases + 15) / 16; /* both buffers are padded to a multiple of 16 bases */
+  if (n16 == 0) return cudaSuccess;
+  uint64_t grid = (n16 + 255) / 256;
+  const uint64_t cap = (uint64_t)sm_count * 16;
+  if (grid > cap) grid = cap;
+  k_pack_bases<<<(uint32_t)grid, 256, 0, st>>>((const uint4 *)ascii, (uint2 *)packed, n16);
+  return cudaGetLastError();
 }
 
 cudaError_t mm_launch_sketch(const mm_params &p, const mm_dev_batch &b, cudaStream_t st, int sm_count)
 {
-  int C = 0;
-  const size_t smem = mm_sketch_smem_bytes(p.seg_length, p.sketch_size, &C);
+  int C = 0, CAP = 0;
+  const size_t smem = mm_sketch_smem_bytes(p.seg_length, p.sketch_size, p.kmer_size, &C, &CAP);
   if (smem == 0) return cudaErrorInvalidValue;
   switch (p.kmer_size) {
-#define X(KK) case KK: return launch_k<KK>(p, b, st, sm_count, C, smem);
+#define X(KK) case KK: return launch_k<KK>(p, b, st, sm_count, C, CAP, smem);
     MM_FOR_EACH_K(X)
 #undef X
     default: return cudaErrorInvalidValue;

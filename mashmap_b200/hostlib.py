@@ -78,8 +78,11 @@ def lib():
         L.skch_bm_ctx.restype = vp
         L.skch_bm_batch_create.argtypes = [vp, C.c_uint64, C.c_int32, C.c_int32]
         L.skch_bm_batch_create.restype = vp
-        L.skch_bm_batch_bases.argtypes = [vp]
-        L.skch_bm_batch_bases.restype = vp
+        L.skch_bm_batch_fill.argtypes = [vp, vp, C.c_int]
+        L.skch_bm_batch_fill.restype = C.c_double
+        L.skch_bm_batch_bytes.argtypes = [vp]
+        L.skch_bm_batch_bytes.restype = C.c_uint64
+        L.skch_pack_bases.argtypes = [vp, C.c_uint64, vp]
         L.skch_bm_batch_segments.argtypes = [vp, C.POINTER(vp)]
         L.skch_bm_batch_segments.restype = C.c_uint64
         L.skch_bm_batch_destroy.argtypes = [vp]
@@ -133,17 +136,35 @@ class ReadBatch:
     def __init__(self, bm, n_reads, read_len, first_seq_counter):
         self.h = lib().skch_bm_batch_create(bm.h, n_reads, read_len, first_seq_counter)
         self.n_reads, self.read_len = n_reads, read_len
-        ptr = lib().skch_bm_batch_bases(self.h)
-        self.bases = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(n_reads * read_len,))
         sp = C.c_void_p()
         ns = lib().skch_bm_batch_segments(self.h, C.byref(sp))
         buf = (C.c_char * (ns * capi.segment_dtype.itemsize)).from_address(sp.value)
         self.segments = np.frombuffer(buf, dtype=capi.segment_dtype, count=ns)
 
+    def fill(self, ascii_reads, threads=8):
+        """packs the reads (text, read r at r * read_len) into the pinned batch buffer as nibbles -- what the FASTA
+        reader of skch::Map does while it parses. Returns the seconds the packing took."""
+        a = np.ascontiguousarray(ascii_reads, dtype=np.uint8).reshape(-1)
+        assert len(a) == self.n_reads * self.read_len
+        return float(lib().skch_bm_batch_fill(self.h, a.ctypes.data, int(threads)))
+
+    @property
+    def h2d_bytes(self):
+        """bytes of bases that cross PCIe per mapping pass"""
+        return int(lib().skch_bm_batch_bytes(self.h))
+
     def close(self):
         if self.h:
             lib().skch_bm_batch_destroy(self.h)
             self.h = None
+
+
+def pack_bases(ascii_bases):
+    """the host library's packer (seqio::pack_bases, AVX2): text -> one nibble per base"""
+    a = np.ascontiguousarray(ascii_bases, dtype=np.uint8)
+    out = np.zeros((len(a) + 1) // 2, dtype=np.uint8)
+    lib().skch_pack_bases(a.ctypes.data, len(a), out.ctypes.data)
+    return out
 
 
 class HostIndex:

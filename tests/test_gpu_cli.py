@@ -83,12 +83,21 @@ CONFIGS = [
     ("panel", ["-s", "3000", "--pi", "90", "-f", "one-to-one", "-X"]),
     ("panel", ["-s", "5000", "--pi", "90", "--lowerTriangular", "-n", "2"]),
     ("panel", ["-s", "2000", "--pi", "90", "-J", "25", "--noHgFilter", "-k", "16"]),
+    ("panel", ["-s", "5000", "--pi", "85", "--kmerThreshold", "5"]),          # frequent seeds dropped on the device
+    ("panel", ["-s", "3000", "--pi", "90", "-k", "14", "-J", "40"]),          # a k-mer size outside round 1's list
+    ("assembly", ["-s", "10000", "--pi", "90", "-f", "one-to-one"]),          # BASELINE config 5 shape
+    ("hifi", ["-s", "5000", "--pi", "95", "-J", "20", "-f", "one-to-one"]),   # BASELINE config 4 shape
+    ("repeat", ["-s", "5000", "--pi", "85"]),                                 # L1 bump pool
+    ("repeat", ["-s", "5000", "--pi", "85", "--noHgFilter", "-n", "4"]),      # > 2 loci per candidate
 ]
+MAKERS = {"random": ("cli", datasets.make_random_set), "panel": ("clip", datasets.make_panel_set),
+          "assembly": ("clia", datasets.make_assembly_set), "hifi": ("clih", datasets.make_hifi_set),
+          "repeat": ("clir", datasets.make_repeat_set)}
 
 
 @pytest.mark.parametrize("which,args", CONFIGS)
 def test_paf_matches_reference_cli(workdir, which, args):
-    d = datasets.make_random_set(workdir, tag="cli") if which == "random" else datasets.make_panel_set(workdir, tag="clip")
+    d = MAKERS[which][1](workdir, tag=MAKERS[which][0])
     tag = "_".join(a.strip("-#") for a in args)
     ref_out = os.path.join(workdir, f"ref_{which}_{tag}.paf")
     got_out = os.path.join(workdir, f"got_{which}_{tag}.paf")
@@ -156,3 +165,46 @@ def test_fastq_gz_and_multiple_query_files(workdir):
     n_equal, tolerated, problems = compare_paf(parse(ref_out), parse(got_out), 5000)
     assert not problems and n_equal > 0
     assert open(got_out).read() == open(one_out).read()
+
+
+YEAST = os.path.join(os.path.dirname(refh.REF_BIN), "data", "scerevisiae8.fa.gz")
+
+
+@pytest.mark.skipif(not os.path.exists(YEAST), reason="oracle/_ref/data/scerevisiae8.fa.gz not staged (make -C oracle ref)")
+def test_yeast_selfmap_config1(workdir):
+    """BASELINE config 1: the reference's own fixture (8 yeast genomes, 136 contigs, 96 Mbp, gzip'ed), self-map
+    -s 5000 --pi 85. The PAF of the product equals the reference CLI's line by line, and the reference CLI's output is
+    the one SURVEY 8(c) pinned (1019 lines, md5 f6d55572...)."""
+    import hashlib
+
+    ref_out, got_out = os.path.join(workdir, "yeast_ref.paf"), os.path.join(workdir, "yeast_got.paf")
+    run([refh.REF_BIN, "-r", YEAST, "-q", YEAST, "-s", "5000", "--pi", "85", "-t", "16", "-o", ref_out])
+    run([hostlib.CLI_PATH, "-r", YEAST, "-q", YEAST, "-s", "5000", "--pi", "85", "-t", "16", "-o", got_out])
+    ref_rows, got_rows = parse(ref_out), parse(got_out)
+    assert len(ref_rows) == 1019
+    assert hashlib.md5(open(ref_out, "rb").read()).hexdigest() == "f6d55572af77fb8b2ee74fe452f2129c"
+    n_equal, tolerated, problems = compare_paf(ref_rows, got_rows, 5000)
+    print(f"yeast: reference {len(ref_rows)} lines, ours {len(got_rows)}, equal {n_equal}, tolerated {tolerated}, problems {len(problems)}")
+    for p in problems[:8]:
+        print("  ", p)
+    assert not problems
+    if tolerated == 0:
+        assert open(ref_out).read() == open(got_out).read() or [r[:12] for r in ref_rows] == [g[:12] for g in got_rows]
+
+
+def test_maps_from_an_index_the_reference_saved(workdir):
+    """SURVEY 8(f)-4 on the GPU: the reference CLI writes PREFIX.index / PREFIX.map (--saveIndex, winSketch.hpp:270-315),
+    the product loads them (--loadIndex) instead of building, maps on the device and prints the reference's PAF; and
+    the other way round (the reference maps from the files the product saved)."""
+    d = datasets.make_panel_set(workdir, tag="clip")
+    args = ["-r", d["ref"], "-q", d["qry"], "-s", "5000", "--pi", "85", "-t", "4"]
+    ref_prefix, our_prefix = os.path.join(workdir, "gpu_ref_saved"), os.path.join(workdir, "gpu_our_saved")
+    ref_paf, got_paf, got2_paf, ref2_paf = (os.path.join(workdir, x) for x in ("ld_ref.paf", "ld_got.paf", "ld_got2.paf", "ld_ref2.paf"))
+    run([refh.REF_BIN] + args + ["--saveIndex", ref_prefix, "-o", ref_paf])
+    run([hostlib.CLI_PATH] + args + ["--loadIndex", ref_prefix, "-o", got_paf])
+    n_equal, tolerated, problems = compare_paf(parse(ref_paf), parse(got_paf), 5000)
+    assert not problems and n_equal > 0
+    run([hostlib.CLI_PATH] + args + ["--saveIndex", our_prefix, "-o", got2_paf])
+    assert open(got2_paf).read() == open(got_paf).read()
+    run([refh.REF_BIN] + args + ["--loadIndex", our_prefix, "-o", ref2_paf])
+    assert open(ref2_paf).read() == open(ref_paf).read()

@@ -42,7 +42,7 @@ def map_all(world, env):
     try:
         bm = hostlib.BatchMapper(world["hi"], pi=PI, device=0, threads=min(32, os.cpu_count() or 8))
         batch = bm.make_batch(N_READS, READ_LEN)
-        batch.bases[:] = world["reads"].reshape(-1)
+        batch.fill(world["reads"].reshape(-1), threads=min(32, os.cpu_count() or 8))
         info = bm.map(batch)
         res, paf = bm.results(), bm.paf()
         info2 = bm.map(batch)  # the same batch again on the warm pipeline

@@ -157,7 +157,9 @@ def kernel_paths(request, monkeypatch):
     return request.param
 
 
-def run_stage_parity(d, args, seg_length, **ctx_kw):
+def run_stage_parity(d, args, seg_length, expect_diag=(), expect_freq_seeds=False, **ctx_kw):
+    """expect_diag: names of mm_ctx_diag counters that must be non-zero afterwards (the rare path really ran);
+    expect_freq_seeds: the reference must have flagged frequent seeds and some query sketch must have lost hashes to them"""
     from mashmap_b200 import capi
 
     R = refh.RefSession(args)
@@ -191,6 +193,16 @@ def run_stage_parity(d, args, seg_length, **ctx_kw):
                 O.close()
 
         bad = compare_stages(ctx, R, d, ridx, start, length, seg_res2, cands2, loci2, dev_sketch, dev_count, diag=diag)
+        dg = ctx.diag()
+        print("rare paths taken:", dg)
+        for name in expect_diag:
+            assert dg[name] > 0, f"the test data no longer reaches the {name} path: {dg}"
+        if expect_freq_seeds:
+            fr = R.lookup()[3]
+            removed = int((seg_res2["sketch_raw_count"] - seg_res2["sketch_size"]).sum())
+            print(f"frequent seeds: threshold {R.freq_threshold()}, {int(np.asarray(fr).sum())} keys flagged, "
+                  f"{removed} hashes removed from the query sketches on the device")
+            assert np.asarray(fr).sum() > 0 and removed > 0
         ctx.close()
         return bad
     finally:
@@ -218,4 +230,129 @@ def test_stages_panel_selfmap(panel_set, kernel_paths):
 def test_stages_panel_no_hg_filter_small_sketch(panel_set, kernel_paths):
     d = panel_set
     bad = run_stage_parity(d, ["-r", d["ref"], "-q", d["qry"], "-s", "2000", "--pi", "90", "-J", "25", "--noHgFilter", "-t", "4"], 2000)
+    assert not bad
+
+
+def test_packed_input_equals_text_input(random_set):
+    """mm_map_segments_packed (one nibble per base, the format a packing host uploads) == mm_map_segments (text, packed
+    on the device by k_pack_bases): lower case, IUPAC codes, N runs and an all-N read are in the set"""
+    from mashmap_b200 import capi
+
+    d = random_set
+    R = refh.RefSession(["-r", d["ref"], "-q", d["qry"], "-s", "5000", "--pi", "85", "-t", "4"])
+    try:
+        ctx = capi.Context(kmer_size=R.p.kmerSize, seg_length=R.p.segLength, sketch_size=R.p.sketchSize)
+        upload_reference_index(ctx, R)
+        bases, segs, ridx, start, length = build_segments(d, R.p.segLength, R.p.kmerSize)
+        a = ctx.map_segments(bases, segs)
+        sk_a = ctx.batch_fetch_sketch() if False else None
+        b = ctx.map_segments_packed(capi.pack_bases(bases), len(bases), segs)
+        for x, y in zip(a, b):
+            assert x.tobytes() == y.tobytes()
+        assert ctx.pack_ms() == 0.0  # the packed batch skipped the device packing kernel
+        # odd segment offsets / an odd number of bases: shift everything by one base
+        bases1 = np.concatenate([np.frombuffer(b"G", np.uint8), bases])
+        segs1 = segs.copy()
+        segs1["offset"] += 1
+        c = ctx.map_segments_packed(capi.pack_bases(bases1), len(bases1), segs1)
+        for x, y in zip(a, c):
+            assert x.tobytes() == y.tobytes()
+        ctx.close()
+    finally:
+        R.close()
+
+
+@pytest.mark.parametrize("k", list(range(8, 33)))
+def test_sketch_every_kmer_size(random_set, k):
+    """the reference accepts any -k (parseCmdArgs.hpp:435-443); every k-mer length from 8 to 32 is compiled in"""
+    from mashmap_b200 import capi
+
+    d = random_set
+    s = 60
+    ctx = capi.Context(kmer_size=k, seg_length=3000, sketch_size=s)
+    sub = dict(reads=d["reads"][:6] + d["reads"][-5:], rnames=d["rnames"][:6] + d["rnames"][-5:])
+    bases, segs, ridx, start, length = build_segments(sub, 3000, k)
+    out, cnt = ctx.sketch_segments(bases, segs)
+    for i in range(len(segs)):
+        seg = sub["reads"][ridx[i]][start[i] : start[i] + length[i]]
+        ref = refh.sketch_sequence(seg, k, s, seq_id=int(ridx[i]))
+        dev = out[i][: cnt[i]]
+        assert len(ref) == len(dev), (k, i, len(ref), len(dev))
+        for f in ("hash", "wpos", "wpos_end", "strand"):
+            assert np.array_equal(ref[f], dev[f]), (k, i, f)
+    ctx.close()
+
+
+def test_stages_frequent_seeds_removed_on_device(panel_set, kernel_paths):
+    """--kmerThreshold high enough that the reference reports "ignore minmers occurring >= N": Sketch::isFreqSeed hashes are
+    dropped from the query sketch on the device (table value bit 0; computeMap.hpp:834-839) and Q.sketchSize shrinks"""
+    d = panel_set
+    bad = run_stage_parity(d, ["-r", d["ref"], "-q", d["qry"], "-s", "5000", "--pi", "85", "--kmerThreshold", "5", "-t", "4"], 5000,
+                           expect_freq_seeds=True)
+    assert not bad
+
+
+@pytest.fixture(scope="module")
+def assembly_set(workdir):
+    return datasets.make_assembly_set(workdir)
+
+
+@pytest.fixture(scope="module")
+def hifi_set(workdir):
+    return datasets.make_hifi_set(workdir)
+
+
+@pytest.fixture(scope="module")
+def big_random_set(workdir):
+    return datasets.make_big_random_set(workdir)
+
+
+@pytest.fixture(scope="module")
+def repeat_set(workdir):
+    return datasets.make_repeat_set(workdir)
+
+
+def test_stages_config5_shape_assembly_s10000(assembly_set, kernel_paths):
+    """BASELINE config 5 shape: assembly vs assembly, -s 10000 --pi 90 -f one-to-one (10 kb fragments, automatic sketch)"""
+    d = assembly_set
+    bad = run_stage_parity(d, ["-r", d["ref"], "-q", d["qry"], "-s", "10000", "--pi", "90", "-f", "one-to-one", "-t", "4"], 10000)
+    assert not bad
+
+
+def test_stages_config4_shape_hifi_sketch20(hifi_set, kernel_paths):
+    """BASELINE config 4 shape: 20 kb HiFi-like reads, --pi 95, sketch size 20 (what the reference picks for a 3 Gbp file)"""
+    d = hifi_set
+    bad = run_stage_parity(d, ["-r", d["ref"], "-q", d["qry"], "-s", "5000", "--pi", "95", "-J", "20", "-f", "one-to-one", "-t", "4"], 5000)
+    assert not bad
+
+
+def test_stages_config3_shape_dense_pi95_32mbp(big_random_set):
+    """BASELINE config 3 shape: --dense --pi 95 (s = 199) on a 32 Mbp reference"""
+    d = big_random_set
+    bad = run_stage_parity(d, ["-r", d["ref"], "-q", d["qry"], "-s", "5000", "--pi", "95", "--dense", "-t", "8"], 5000)
+    assert not bad
+
+
+def test_stages_config2_shape_pi85_32mbp(big_random_set):
+    d = big_random_set
+    bad = run_stage_parity(d, ["-r", d["ref"], "-q", d["qry"], "-s", "5000", "--pi", "85", "-J", "220", "-t", "8"], 5000)
+    assert not bad
+
+
+def test_stages_repeat_dense_l1_pool(repeat_set, monkeypatch):
+    """fragments with 60-110 thousand interval points: more than the warp path (512), the CTA's shared memory (2048) and
+    its global slice (65,536) hold -> bump-allocated pool; with a pool of 4,096 points the host has to grow it and re-run"""
+    monkeypatch.setenv("MM_L1_POOL_ELEMS", "4096")
+    d = repeat_set
+    bad = run_stage_parity(d, ["-r", d["ref"], "-q", d["qry"], "-s", "5000", "--pi", "85", "-t", "4"], 5000,
+                           expect_diag=("l1_cta_segments", "l1_pool_regrow"))
+    assert not bad
+
+
+def test_stages_repeat_dense_many_loci_per_candidate(repeat_set, kernel_paths):
+    """without the hypergeometric filter one L1 candidate spans the whole tandem array and L2 returns six equally good loci
+    (two fixed slots in the stream kernel -> general L2 kernel); the interspersed-repeat fragments scan a 2 Mbp range"""
+    d = repeat_set
+    bad = run_stage_parity(d, ["-r", d["ref"], "-q", d["qry"], "-s", "5000", "--pi", "85", "--noHgFilter", "-t", "4"], 5000,
+                           expect_diag=("l2_general_cands",) if kernel_paths == "fast-paths" else ())
     assert not bad

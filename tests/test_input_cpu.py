@@ -57,3 +57,21 @@ def test_bulk_reader_declines_gzip_and_fastq(tmp_path):
     fq = write(str(tmp_path / "x.fq"), b"@r1\nACGT\n+\nIIII\n@r2\nGG\n+\nII\n")
     assert hostlib.fasta_readers_diff(gz)[0] == -1 and hostlib.fasta_readers_diff(gz)[1] == 2
     assert hostlib.fasta_readers_diff(fq)[0] == -1 and hostlib.fasta_readers_diff(fq)[1] == 2
+
+
+def test_host_packer_matches_the_format_statement():
+    """seqio::pack_bases (AVX2 + scalar tail) == the numpy statement of the nibble format (capi.pack_bases): every byte
+    value, lower case, IUPAC codes, odd lengths, lengths around the 32-byte vector width"""
+    import numpy as np
+
+    from mashmap_b200 import capi
+
+    rng = np.random.default_rng(3)
+    allbytes = np.arange(256, dtype=np.uint8)
+    dna = np.frombuffer(b"ACGTacgtNnRYKM", dtype=np.uint8)[rng.integers(0, 14, size=5000)]
+    for seq in (allbytes, dna, dna[:31], dna[:32], dna[:33], dna[:63], dna[:64], dna[:65], dna[:1], dna[:4999]):
+        want = capi.pack_bases(seq)
+        got = hostlib.pack_bases(seq)
+        if len(seq) & 1:  # the unused high nibble of the last byte is an N in both
+            assert want[-1] >> 4 == 8 and got[-1] >> 4 == 8
+        assert np.array_equal(want, got), len(seq)
