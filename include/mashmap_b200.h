@@ -115,6 +115,7 @@ typedef struct mm_ctx mm_ctx;
 int mm_ctx_create(int device, const mm_params *params, mm_ctx **out);
 int mm_ctx_destroy(mm_ctx *ctx);
 const char *mm_last_error(const mm_ctx *ctx); /* ctx may be NULL: error of the last failed create */
+int mm_ctx_device(const mm_ctx *ctx); /* the CUDA device the context lives on (-1 for NULL) */
 /* Number of CUDA kernels this context has launched so far (bench.py's gpu_launches). */
 uint64_t mm_kernel_launches(const mm_ctx *ctx);
 
@@ -125,6 +126,7 @@ uint64_t mm_kernel_launches(const mm_ctx *ctx);
 #define MM_DIAG_CAND_REGROW 2      /* re-runs because the candidate buffer was too small                              */
 #define MM_DIAG_L2_GENERAL_CANDS 3 /* candidates redone by the general L2 kernel (more loci than the fixed slots / counter range) */
 #define MM_DIAG_L2_LOCI_REGROW 4   /* L2 re-runs because the locus buffer was too small                               */
+#define MM_DIAG_SKETCH_GENERAL_SEGMENTS 5 /* segments the fast sketch kernel handed to the general one (repeats, N-rich ...) */
 int mm_ctx_diag(const mm_ctx *ctx, uint64_t out[8]);
 
 /* ---- reference index -> device (replaces the in-memory members of skch::Sketch) ---------------- */

@@ -73,6 +73,7 @@ def lib():
         vp, u64, i32 = C.c_void_p, C.c_uint64, C.c_int32
         L.mm_ctx_create.argtypes = [C.c_int, C.POINTER(Params), C.POINTER(vp)]
         L.mm_ctx_destroy.argtypes = [vp]
+        L.mm_ctx_device.argtypes = [vp]
         L.mm_last_error.argtypes = [vp]
         L.mm_last_error.restype = C.c_char_p
         L.mm_kernel_launches.argtypes = [vp]
@@ -101,7 +102,7 @@ def lib():
 
 
 EXPORTED_SYMBOLS = [
-    "mm_ctx_create", "mm_ctx_destroy", "mm_last_error", "mm_kernel_launches", "mm_ctx_diag", "mm_index_upload",
+    "mm_ctx_create", "mm_ctx_destroy", "mm_ctx_device", "mm_last_error", "mm_kernel_launches", "mm_ctx_diag", "mm_index_upload",
     "mm_tables_upload", "mm_index_blob", "mm_index_blob_alloc", "mm_index_adopt_blob", "mm_ctx_share_index", "mm_sketch_segments",
     "mm_map_segments", "mm_map_segments_packed", "mm_batch_upload", "mm_batch_upload_packed", "mm_last_pack_ms", "mm_map_resident", "mm_batch_fetch", "mm_batch_fetch_sketch",
     "mm_last_stage_ms", "mm_ctx_set_phase_hook", "mm_host_alloc", "mm_host_free",
@@ -196,7 +197,7 @@ class Context:
         if rc != MM_OK:
             raise MashmapError(rc, self._L.mm_last_error(self._h).decode())
 
-    DIAG_NAMES = ("l1_cta_segments", "l1_pool_regrow", "cand_regrow", "l2_general_cands", "l2_loci_regrow")
+    DIAG_NAMES = ("l1_cta_segments", "l1_pool_regrow", "cand_regrow", "l2_general_cands", "l2_loci_regrow", "sketch_general_segments")
 
     def diag(self):
         """how often the rare paths ran (mm_ctx_diag), by name"""

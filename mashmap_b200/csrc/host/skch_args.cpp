@@ -32,7 +32,7 @@ const OptDef kOptions[] = {
     {"sparsifyMappings", "x", true}, {"filter_mode", "f", true}, {"noMerge", "M", false}, {"legacy", nullptr, false},
     {"reportPercentage", nullptr, false},
     // B200-specific
-    {"device", nullptr, true}, {"batchBases", nullptr, true}, {"subBatchBases", nullptr, true},
+    {"device", nullptr, true}, {"devices", nullptr, true}, {"batchBases", nullptr, true}, {"subBatchBases", nullptr, true},
 };
 
 [[noreturn]] void usage_error(const std::string &msg)
@@ -108,7 +108,7 @@ void parseandSave(int argc, char **argv, Parameters &parameters)
 
   if (found("version")) { std::cerr << fixed::VERSION << std::endl; exit(0); }
   if (found("help")) {
-    std::cerr << "mashmap-b200 -r ref.fa -q seq.fq [OPTIONS]   (options as in MashMap v3.1.3, plus --device N, --batchBases N)" << std::endl;
+    std::cerr << "mashmap-b200 -r ref.fa -q seq.fq [OPTIONS]   (options as in MashMap v3.1.3, plus --device N | --devices 0-7, --batchBases N)" << std::endl;
     exit(0);
   }
   if (!found("ref") && !found("refList")) usage_error("ERROR, skch::parseandSave, Provide reference file(s)");
@@ -234,6 +234,19 @@ void parseandSave(int argc, char **argv, Parameters &parameters)
   parameters.legacy_output = found("legacy");
   parameters.report_ANI_percentage = found("reportPercentage");
   if (found("device")) parameters.device = to<int>(opt["device"]);
+  if (found("devices")) {  // "0-7", "0,2,5", "1": the GPUs this process drives; reads are sharded across them by batch parts
+    parameters.devices.clear();
+    std::stringstream ss(opt["devices"]);
+    std::string item;
+    while (std::getline(ss, item, ',')) {
+      const size_t dash = item.find('-');
+      if (dash == std::string::npos) parameters.devices.push_back(to<int>(item));
+      else
+        for (int d = to<int>(item.substr(0, dash)); d <= to<int>(item.substr(dash + 1)); d++) parameters.devices.push_back(d);
+    }
+    if (parameters.devices.empty()) usage_error("ERROR, --devices needs a list such as 0-7 or 0,2,5");
+    parameters.device = parameters.devices[0];
+  }
   if (found("batchBases")) parameters.batch_bases = to<uint64_t>(opt["batchBases"]);
   if (found("subBatchBases")) parameters.sub_batch_bases = to<uint64_t>(opt["subBatchBases"]);
 

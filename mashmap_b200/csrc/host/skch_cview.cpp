@@ -198,10 +198,20 @@ struct BmBatch {
   ReadBatch batch;
 };
 
+void *skch_bm_create_ex(void *index_handle, float percentageIdentity, int device, int threads, int filter_mode, const int *devices,
+                        int n_devices);
 void *skch_bm_create(void *index_handle, float percentageIdentity, int device, int threads)
+{
+  return skch_bm_create_ex(index_handle, percentageIdentity, device, threads, filter::MAP, nullptr, 0);
+}
+/* filter_mode: 1 map, 2 one-to-one, 3 none (map_parameters.hpp); devices: the GPUs this one process drives (--devices) */
+void *skch_bm_create_ex(void *index_handle, float percentageIdentity, int device, int threads, int filter_mode, const int *devices,
+                        int n_devices)
 {
   IndexHandle *ih = (IndexHandle *)index_handle;
   ih->p.percentageIdentity = percentageIdentity;
+  ih->p.filterMode = filter_mode;
+  ih->p.devices.assign(devices, devices + (devices ? n_devices : 0));
   ih->p.device = device;
   ih->p.threads = threads;
   ih->p.block_length = ih->p.segLength;
@@ -303,6 +313,42 @@ int skch_bm_map(void *hv, void *bv, uint64_t *paf_bytes, uint64_t *n_mapped_read
   if (sec_tail) *sec_tail = h->bm->secondsHostTail - t0;
   return 0;
 }
+/* the mappings of the last skch_bm_map as raw skch::MappingResult records (a POD, base_types.hpp:152-153): what a rank
+ * hands to mm_records_allgather */
+uint32_t skch_mapping_record_bytes() { return (uint32_t)sizeof(MappingResult); }
+uint64_t skch_bm_results_raw(void *hv, void *out, uint64_t cap)
+{
+  BmHandle *h = (BmHandle *)hv;
+  uint64_t n = 0;
+  MappingResult *o = (MappingResult *)out;
+  for (auto &v : h->results)
+    for (auto &m : v) {
+      if (o && n < cap) o[n] = m;
+      n++;
+    }
+  return n;
+}
+/* -f one-to-one, the run-wide step (computeMap.hpp:358-405) over `n` raw records of any origin (one rank's, or all ranks'
+ * after the all-gather): reference-axis plane sweep + sort + PAF text (kept in the handle, see skch_bm_paf_final). Queries
+ * are the reads "read<i>" of query_len bases, i in [0, n_queries). Returns the number of mappings kept. */
+uint64_t skch_bm_one_to_one(void *hv, const void *recs, uint64_t n, int32_t n_queries, int32_t query_len)
+{
+  BmHandle *h = (BmHandle *)hv;
+  MappingResultsVector_t all((const MappingResult *)recs, (const MappingResult *)recs + n);
+  std::vector<ContigInfo> q((size_t)n_queries);
+  for (int32_t i = 0; i < n_queries; i++) q[(size_t)i] = ContigInfo{"read" + std::to_string(i), query_len};
+  h->paf.clear();
+  h->bm->finalizeOneToOne(all, q, h->paf);
+  return all.size();
+}
+const char *skch_bm_paf_final(void *hv, uint64_t *n)
+{
+  BmHandle *h = (BmHandle *)hv;
+  if (n) *n = h->paf.size();
+  return h->paf.c_str();
+}
+int skch_bm_device_count(void *hv) { return ((BmHandle *)hv)->bm->deviceCount(); }
+
 /* the PAF text of the last skch_bm_map, concatenated in read order */
 const char *skch_bm_paf(void *hv, uint64_t *n)
 {

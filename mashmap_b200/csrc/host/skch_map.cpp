@@ -16,6 +16,7 @@
 #include <thread>
 #include <tuple>
 
+#include "../../../include/mashmap_b200_nccl.h"
 #include "skch_seqio.hpp"
 #include "skch_stats.hpp"
 
@@ -181,30 +182,59 @@ BatchMapper::BatchMapper(const Parameters &p, const Sketch &refsketch) : param(p
   rc = mm_tables_upload(ctx, sketchCutoffs.data(), (int32_t)sketchCutoffs.size(), minHits.data(), (int32_t)minHits.size());
   if (rc != MM_OK) die(std::string("mm_tables_upload: ") + mm_last_error(ctx));
   tail_ = new MapTail(param, refSketch.metadata, refIdGroup);
-  tailPool = new WorkerPool(std::max(1, param.threads));
-  // further contexts share the index image: one lane per pipeline stage in flight (upload / kernels / fetch + tail)
-  lanes[0].ctx = ctx;
-  nLanes = 1;
-  for (int l = 1; l < MAX_LANES; l++) {
-    mm_ctx *c2 = nullptr;
-    if (mm_ctx_create(param.device, &mp, &c2) != MM_OK) break;
-    if (mm_ctx_share_index(c2, ctx) != MM_OK) { mm_ctx_destroy(c2); break; }
-    lanes[l].ctx = c2;
-    nLanes = l + 1;
+  // one group per device; the first one owns the uploaded image, the others receive a copy over NVLink
+  std::vector<int> devs = param.devices.empty() ? std::vector<int>{param.device} : param.devices;
+  std::vector<mm_ctx *> others;
+  for (size_t d = 0; d < devs.size(); d++) {
+    DeviceGroup *g = new DeviceGroup();
+    g->device = devs[d];
+    if (d == 0) g->owner = ctx;
+    else {
+      rc = mm_ctx_create(devs[d], &mp, &g->owner);
+      if (rc != MM_OK) die(std::string("mm_ctx_create (device ") + std::to_string(devs[d]) + "): " + mm_last_error(nullptr));
+      others.push_back(g->owner);
+    }
+    groups.push_back(g);
   }
-  if (nLanes > 1 && !getenv("MM_NO_GATE")) {
-    gate = new Gate();
-    for (int l = 0; l < nLanes; l++) mm_ctx_set_phase_hook(lanes[l].ctx, &BatchMapper::phaseHook, gate);
+  if (!others.empty()) {
+    auto t0 = Clock::now();
+    rc = mm_index_replicate(ctx, others.data(), (int)others.size());
+    if (rc != MM_OK) die(std::string("mm_index_replicate: ") + mm_comm_last_error(nullptr));
+    std::cerr << "[mashmap-b200::skch::BatchMapper] index image replicated to " << others.size() << " more device(s) in " << since(t0)
+              << " s (one grouped NCCL broadcast)" << std::endl;
+  }
+  const int G = (int)groups.size();
+  for (DeviceGroup *g : groups) {
+    g->tailThreads = std::max(1, param.threads / G);
+    g->tailPool = new WorkerPool(g->tailThreads);
+    // further contexts share the device's index image: one lane per pipeline stage in flight (upload / kernels / fetch + tail)
+    g->lanes[0].ctx = g->owner;
+    g->nLanes = 1;
+    for (int l = 1; l < MAX_LANES; l++) {
+      mm_ctx *c2 = nullptr;
+      if (mm_ctx_create(g->device, &mp, &c2) != MM_OK) break;
+      if (mm_ctx_share_index(c2, g->owner) != MM_OK) { mm_ctx_destroy(c2); break; }
+      g->lanes[l].ctx = c2;
+      g->nLanes = l + 1;
+    }
+    if (g->nLanes > 1 && !getenv("MM_NO_GATE")) {
+      g->gate = new Gate();
+      for (int l = 0; l < g->nLanes; l++) mm_ctx_set_phase_hook(g->lanes[l].ctx, &BatchMapper::phaseHook, g->gate);
+    }
   }
 }
 
 BatchMapper::~BatchMapper()
 {
-  delete tailPool;
+  for (DeviceGroup *g : groups) {
+    delete g->tailPool;
+    for (int l = g->nLanes - 1; l >= 1; l--) mm_ctx_destroy(g->lanes[l].ctx);
+    if (g->owner && g->owner != ctx) mm_ctx_destroy(g->owner);
+    delete g->gate;
+    delete g;
+  }
   delete tail_;
-  for (int l = nLanes - 1; l >= 1; l--) mm_ctx_destroy(lanes[l].ctx);
   if (ctx) mm_ctx_destroy(ctx);
-  delete gate;
 }
 
 char *BatchMapper::allocBases(uint64_t n_bases)
@@ -244,6 +274,36 @@ void BatchMapper::addRead(ReadBatch &b, const std::string &name, const char *seq
   b.reads.push_back(std::move(rd));
 }
 
+void BatchMapper::finalizeOneToOne(MappingResultsVector_t &allReadMappings, const std::vector<ContigInfo> &qmetadata, std::string &paf) const
+{  // computeMap.hpp:358-405
+  const int n_mappings = param.numMappingsForSegment - 1;
+  auto sb = allReadMappings.begin(), se = allReadMappings.begin();
+  MappingResultsVector_t tmp, filtered;
+  while (se != allReadMappings.end()) {
+    if (param.skip_prefix) {
+      const int g = getRefGroup(qmetadata[sb->querySeqId].name);
+      se = std::find_if_not(sb, allReadMappings.end(),
+                            [&](const MappingResult &c) { return g == getRefGroup(qmetadata[c.querySeqId].name); });
+    } else {
+      se = allReadMappings.end();
+    }
+    tmp.insert(tmp.end(), std::make_move_iterator(sb), std::make_move_iterator(se));
+    tail_->filterByGroup(tmp, filtered, n_mappings, true);
+    tmp.clear();
+    sb = se;
+  }
+  allReadMappings = std::move(filtered);
+  std::sort(allReadMappings.begin(), allReadMappings.end(), [](const MappingResult &a, const MappingResult &b) {
+    return std::tie(a.querySeqId, a.queryStartPos, a.refSeqId, a.refStartPos) <
+           std::tie(b.querySeqId, b.queryStartPos, b.refSeqId, b.refStartPos);
+  });
+  std::ostringstream os;
+  MapTail t(param, refSketch.metadata, refIdGroup);
+  t.qmetadata = &qmetadata;
+  t.formatMappings(allReadMappings, "", os);
+  paf = os.str();
+}
+
 /* The three stages of one part (reads [r0, r1) of the batch) on one lane (= one device context with its own stream
  * and buffers). mapBatch runs them as a pipeline: uploads on one thread, kernels on another, fetch + host tail on a
  * third, so that the PCIe copy of part i+1 and the host tail of part i-1 are hidden behind the kernels of part i. */
@@ -277,9 +337,10 @@ void BatchMapper::laneCompute(Lane &ln)
   ln.secDevice += since(t0);
 }
 
-void BatchMapper::laneFinish(Lane &ln, const ReadBatch &b, std::vector<MappingResultsVector_t> &results,
-                             std::vector<std::string> *text, const std::vector<ContigInfo> *qmetadata, int tail_threads)
+void BatchMapper::laneFinish(DeviceGroup &g, Lane &ln, const ReadBatch &b, std::vector<MappingResultsVector_t> &results,
+                             std::vector<std::string> *text, const std::vector<ContigInfo> *qmetadata)
 {
+  const int tail_threads = g.tailThreads;
   auto t0 = Clock::now();
   const size_t r0 = ln.r0, r1 = ln.r1;
   if (ln.segRes.size() < ln.nseg) ln.segRes.resize(ln.nseg);
@@ -321,12 +382,12 @@ void BatchMapper::laneFinish(Lane &ln, const ReadBatch &b, std::vector<MappingRe
       }
     }
   };
-  tailPool->run(nthreads, worker);
+  g.tailPool->run(nthreads, worker);
   ln.secTail += since(t0);
   static const bool trace = getenv("MM_TRACE") != nullptr;
   if (trace)
     fprintf(stderr, "[trace] lane %d reads %zu-%zu segs %zu: upload %.2f ms (h2d %.2f) compute %.2f ms (kernels %.2f [k1 %.2f k2 %.2f k3 %.2f: prep %.2f scan %.2f]) "
-            "fetch %.2f ms (d2h %.2f) tail %.2f ms (%d threads)\n", (int)(&ln - lanes), r0, r1, ln.nseg, ln.msUpload, ln.stageMs[3],
+            "fetch %.2f ms (d2h %.2f) tail %.2f ms (%d threads)\n", (int)(&ln - g.lanes), r0, r1, ln.nseg, ln.msUpload, ln.stageMs[3],
             ln.msCompute, ln.stageMs[5], ln.stageMs[0], ln.stageMs[1], ln.stageMs[2], ln.stageMs[6], ln.stageMs[7], msFetch, ln.stageMs[4], since(t0) * 1e3, nthreads);
 }
 
@@ -340,12 +401,15 @@ void BatchMapper::mapBatch(const ReadBatch &b, std::vector<MappingResultsVector_
   if (text) text->resize(nreads);
   if (nreads == 0) return;
   double d0 = 0, t0 = 0;
-  for (auto &ln : lanes) { d0 += ln.secDevice; t0 += ln.secTail; }
+  for (DeviceGroup *g : groups)
+    for (auto &ln : g->lanes) { d0 += ln.secDevice; t0 += ln.secTail; }
   // parts of ~SUB bases (a read is never split across parts)
   // A large batch ends with smaller parts: the last fetch + host tail has nothing left to hide behind. (Smaller FIRST
   // parts were tried too and lost: the upload runs barely faster than the kernels, so a short first part only makes the
   // compute thread wait for the second upload.)
-  const uint64_t SUB = std::max<uint64_t>(param.sub_batch_bases, 1);
+  uint64_t SUB = std::max<uint64_t>(param.sub_batch_bases, 1);
+  if (groups.size() > 1)  // several devices: enough parts for every device's three lanes
+    SUB = std::max<uint64_t>(std::min<uint64_t>(SUB, b.used / (3 * groups.size()) + 1), (uint64_t)param.segLength);
   std::vector<uint64_t> targets;
   if (b.used >= 4 * SUB) {
     uint64_t left = b.used;
@@ -363,12 +427,38 @@ void BatchMapper::mapBatch(const ReadBatch &b, std::vector<MappingResultsVector_
       if (acc >= want || r + 1 == nreads) { parts.emplace_back(r0, r + 1); r0 = r + 1; acc = 0; }
     }
   }
+  const size_t G = groups.size();
+  if (G == 1) {
+    runGroup(*groups[0], b, parts, 0, 1, results, text, qmetadata);
+  } else {  // parts dealt round robin to the devices, every device runs its own pipeline
+    std::vector<std::thread> drivers;
+    for (size_t g = 1; g < G; g++)
+      drivers.emplace_back([&, g] { runGroup(*groups[g], b, parts, g, G, results, text, qmetadata); });
+    runGroup(*groups[0], b, parts, 0, G, results, text, qmetadata);
+    for (auto &t : drivers) t.join();
+  }
+  memcpy(lastStageMs, groups[0]->lanes[0].stageMs, sizeof(lastStageMs));
+  for (DeviceGroup *g : groups)
+    for (auto &ln : g->lanes) { secondsDevice += ln.secDevice; secondsHostTail += ln.secTail; }
+  secondsDevice -= d0; secondsHostTail -= t0;
+}
+
+/* the parts first, first + step, ... of the batch through the three-stage pipeline of one device */
+void BatchMapper::runGroup(DeviceGroup &g, const ReadBatch &b, const std::vector<std::pair<size_t, size_t>> &all_parts, size_t first,
+                           size_t step, std::vector<MappingResultsVector_t> &results, std::vector<std::string> *text,
+                           const std::vector<ContigInfo> *qmetadata)
+{
+  std::vector<std::pair<size_t, size_t>> parts;
+  for (size_t i = first; i < all_parts.size(); i += step) parts.push_back(all_parts[i]);
   const size_t np = parts.size();
+  if (np == 0) return;
+  Lane *lanes = g.lanes;
+  const int nLanes = g.nLanes;
   if (np < 2 || nLanes < 2) {
     for (auto &p : parts) {
       laneUpload(lanes[0], b, p.first, p.second);
       laneCompute(lanes[0]);
-      laneFinish(lanes[0], b, results, text, qmetadata, param.threads);
+      laneFinish(g, lanes[0], b, results, text, qmetadata);
     }
   } else {
     // part i lives on lane i % nLanes; state: 0 waiting, 1 uploaded, 2 computed, 3 finished (its lane is free again)
@@ -394,7 +484,7 @@ void BatchMapper::mapBatch(const ReadBatch &b, std::vector<MappingResultsVector_
     std::thread finisher([&] {
       for (size_t i = 0; i < np; i++) {
         wait_for(i, 2);
-        laneFinish(lanes[i % NL], b, results, text, qmetadata, param.threads);
+        laneFinish(g, lanes[i % NL], b, results, text, qmetadata);
         publish(i, 3);
       }
     });
@@ -413,12 +503,9 @@ void BatchMapper::mapBatch(const ReadBatch &b, std::vector<MappingResultsVector_
     finisher.join();
     static const bool trace = getenv("MM_TRACE") != nullptr;
     if (trace)
-      fprintf(stderr, "[trace] mapBatch: %zu parts; first kernels start at %.1f ms, last kernels end at %.1f ms, pipeline drained at %.1f ms; "
-              "compute thread waited %.1f ms for uploads\n", np, tFirst * 1e3, tLast * 1e3, since(tp0) * 1e3, waitUpload * 1e3);
+      fprintf(stderr, "[trace] device %d: %zu parts; first kernels start at %.1f ms, last kernels end at %.1f ms, pipeline drained at %.1f ms; "
+              "compute thread waited %.1f ms for uploads\n", g.device, np, tFirst * 1e3, tLast * 1e3, since(tp0) * 1e3, waitUpload * 1e3);
   }
-  memcpy(lastStageMs, lanes[0].stageMs, sizeof(lastStageMs));
-  for (auto &ln : lanes) { secondsDevice += ln.secDevice; secondsHostTail += ln.secTail; }
-  secondsDevice -= d0; secondsHostTail -= t0;
 }
 
 /* ------------------------------------------------------------------------------------------------------ */
@@ -602,31 +689,9 @@ struct Map::Impl {
     self.secondsInput = since(t0) - self.secondsDevice - self.secondsHostTail;
 
     if (param.filterMode == filter::ONETOONE) {  // :358-405
-      const int n_mappings = param.numMappingsForSegment - 1;
-      auto sb = allReadMappings.begin(), se = allReadMappings.begin();
-      MappingResultsVector_t tmp, filtered;
-      while (se != allReadMappings.end()) {
-        if (param.skip_prefix) {
-          const int g = bm.getRefGroup(qmetadata[sb->querySeqId].name);
-          se = std::find_if_not(sb, allReadMappings.end(),
-                                [&](const MappingResult &c) { return g == bm.getRefGroup(qmetadata[c.querySeqId].name); });
-        } else {
-          se = allReadMappings.end();
-        }
-        tmp.insert(tmp.end(), std::make_move_iterator(sb), std::make_move_iterator(se));
-        bm.tail().filterByGroup(tmp, filtered, n_mappings, true);
-        tmp.clear();
-        sb = se;
-      }
-      allReadMappings = std::move(filtered);
-      std::sort(allReadMappings.begin(), allReadMappings.end(), [](const MappingResult &a, const MappingResult &b) {
-        return std::tie(a.querySeqId, a.queryStartPos, a.refSeqId, a.refStartPos) <
-               std::tie(b.querySeqId, b.queryStartPos, b.refSeqId, b.refStartPos);
-      });
-      std::ostringstream os;
-      const_cast<MapTail &>(bm.tail()).qmetadata = &qmetadata;
-      bm.tail().formatMappings(allReadMappings, "", os);
-      outstrm << os.str();
+      std::string paf;
+      bm.finalizeOneToOne(allReadMappings, qmetadata, paf);
+      outstrm << paf;
       if (processMappingResults != nullptr)
         for (auto &e : allReadMappings) processMappingResults(e);
     }

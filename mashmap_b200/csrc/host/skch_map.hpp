@@ -65,10 +65,17 @@ class BatchMapper {
   void mapBatch(const ReadBatch &b, std::vector<MappingResultsVector_t> &results, std::vector<std::string> *text,
                 const std::vector<ContigInfo> *qmetadata);
 
+  /* -f one-to-one, the run-wide step of mapQuery (computeMap.hpp:358-405): all mappings of all reads go through the
+   * reference-axis plane sweep together (per query prefix group with -Y), are sorted by (query id, query start, ref id,
+   * ref start) and formatted. Works on whatever set the caller hands over -- the mappings of one process, or the
+   * records gathered from all ranks (MappingResult is a POD, base_types.hpp:152-153). */
+  void finalizeOneToOne(MappingResultsVector_t &allReadMappings, const std::vector<ContigInfo> &qmetadata, std::string &paf) const;
+
   int getRefGroup(const std::string &seqName) const;  // computeMap.hpp:164-177
   const std::vector<int> &refGroups() const { return refIdGroup; }
   const MapTail &tail() const { return *tail_; }
   mm_ctx *context() const { return ctx; }
+  int deviceCount() const { return (int)groups.size(); }
   double secondsDevice = 0, secondsHostTail = 0;
   float lastStageMs[8] = {0};
 
@@ -80,10 +87,9 @@ class BatchMapper {
   std::vector<int> minHits;        // estimateMinimumHitsRelaxed by Q.sketchSize (computeMap.hpp:1144)
   std::unordered_map<std::string, int> refNameId;
   std::vector<int> contigNameId;
-  mm_ctx *ctx = nullptr;   // owns the index image
+  mm_ctx *ctx = nullptr;   // the first device's context: owns the index image that was uploaded
   MapTail *tail_ = nullptr;
   class WorkerPool;
-  WorkerPool *tailPool = nullptr;  // persistent threads of the per-read host tail
   struct Lane {  // per pipeline lane: device context (own stream + buffers) and its host-side record buffers
     mm_ctx *ctx = nullptr;
     std::vector<mm_segment> segs;
@@ -97,16 +103,29 @@ class BatchMapper {
   };
   // scheduler state of the phase hook: batch uploads wait while the L2 kernels of another lane run
   struct Gate;
-  Gate *gate = nullptr;
   static void phaseHook(void *user, int phase, int begin);
   static constexpr int MAX_LANES = 3;
-  Lane lanes[MAX_LANES];
-  int nLanes = 1;
+  /* One group per GPU this process drives (--devices): its own index image (replicated from the first device with one
+   * grouped NCCL broadcast, mm_index_replicate), its own three pipeline lanes and gate, its own share of the host-tail
+   * threads. The parts of a batch are dealt to the groups round robin (a read lives in one part, so output order and
+   * content do not depend on the number of devices). */
+  struct DeviceGroup {
+    int device = 0;
+    mm_ctx *owner = nullptr;  // holds this device's index image
+    Lane lanes[MAX_LANES];
+    int nLanes = 1;
+    Gate *gate = nullptr;
+    WorkerPool *tailPool = nullptr;  // persistent threads of the per-read host tail
+    int tailThreads = 1;
+  };
+  std::vector<DeviceGroup *> groups;
   void setRefGroups();
   void laneUpload(Lane &ln, const ReadBatch &b, size_t r0, size_t r1);
   void laneCompute(Lane &ln);
-  void laneFinish(Lane &ln, const ReadBatch &b, std::vector<MappingResultsVector_t> &results, std::vector<std::string> *text,
-                  const std::vector<ContigInfo> *qmetadata, int tail_threads);
+  void laneFinish(DeviceGroup &g, Lane &ln, const ReadBatch &b, std::vector<MappingResultsVector_t> &results,
+                  std::vector<std::string> *text, const std::vector<ContigInfo> *qmetadata);
+  void runGroup(DeviceGroup &g, const ReadBatch &b, const std::vector<std::pair<size_t, size_t>> &parts, size_t first, size_t step,
+                std::vector<MappingResultsVector_t> &results, std::vector<std::string> *text, const std::vector<ContigInfo> *qmetadata);
 };
 
 class Map {

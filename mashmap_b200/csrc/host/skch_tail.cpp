@@ -217,7 +217,7 @@ void MapTail::filterByGroup(MappingResultsVector_t &unfiltered, MappingResultsVe
       std::sort(tmp.begin(), tmp.end(), [](const MappingResult &a, const MappingResult &b) {
         return std::tie(a.queryStartPos, a.refSeqId, a.refStartPos) < std::tie(b.queryStartPos, b.refSeqId, b.refStartPos);
       });
-      if (filter_ref) Filter::ref::filterMappings(tmp, metadata, (uint16_t)n_mappings);
+      if (filter_ref) Filter::ref::filterMappingsParallel(tmp, metadata, (uint16_t)n_mappings, param.threads);
       else Filter::query::filterMappings(tmp, (uint16_t)n_mappings);
       filtered.insert(filtered.end(), std::make_move_iterator(tmp.begin()), std::make_move_iterator(tmp.end()));
       tmp.clear();

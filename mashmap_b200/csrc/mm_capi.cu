@@ -46,6 +46,8 @@ struct mm_ctx {
   mm_segment *d_segs = nullptr; uint64_t segs_cap = 0; uint64_t n_segs = 0;
   uint64_t *d_sk_hash = nullptr; uint64_t *d_sk_val = nullptr; int2 *d_sk_pos = nullptr; int8_t *d_sk_strand = nullptr; uint64_t sk_cap = 0;
   mm_segment_result *d_seg_res = nullptr;
+  uint32_t *d_sk_reject = nullptr;
+  int sk_mode = 0; /* 0 = fast sketch kernel + general kernel over its rejects; 1 = general kernel only (MM_SKETCH_TABLE=1) */
   mm_l1_candidate *d_cands = nullptr; uint64_t cand_cap = 0;
   mm_l2_locus *d_loci = nullptr; uint64_t loci_cap = 0;
   uint32_t *d_counters = nullptr;
@@ -207,6 +209,8 @@ int prepare_batch_buffers(mm_ctx *c, uint64_t n_bases, uint64_t n_segs)
     if (c->d_sk_pos) cudaFree(c->d_sk_pos);
     if (c->d_sk_strand) cudaFree(c->d_sk_strand);
     if (c->d_seg_res) cudaFree(c->d_seg_res);
+    if (c->d_sk_reject) cudaFree(c->d_sk_reject);
+    c->d_sk_reject = nullptr;
     c->d_sk_hash = nullptr; c->d_sk_val = nullptr; c->d_sk_pos = nullptr; c->d_sk_strand = nullptr; c->d_seg_res = nullptr; c->sk_cap = 0;
     const uint64_t n = n_segs * S + 1;
     CU(c, cudaMalloc((void **)&c->d_sk_hash, n * 8));
@@ -214,6 +218,7 @@ int prepare_batch_buffers(mm_ctx *c, uint64_t n_bases, uint64_t n_segs)
     CU(c, cudaMalloc((void **)&c->d_sk_pos, n * 8));
     CU(c, cudaMalloc((void **)&c->d_sk_strand, n));
     CU(c, cudaMalloc((void **)&c->d_seg_res, (n_segs + 1) * sizeof(mm_segment_result)));
+    CU(c, cudaMalloc((void **)&c->d_sk_reject, (n_segs + 1) * 4));
     c->sk_cap = n;
   }
   if (!c->d_counters) CU(c, cudaMalloc((void **)&c->d_counters, 64));
@@ -280,7 +285,7 @@ mm_dev_batch make_batch(mm_ctx *c)
   mm_dev_batch b{};
   b.bases = c->d_bases; b.packed = c->d_packed; b.segs = c->d_segs; b.n_segs = (uint32_t)c->n_segs;
   b.sk_hash = c->d_sk_hash; b.sk_val = c->d_sk_val; b.sk_pos = c->d_sk_pos; b.sk_strand = c->d_sk_strand;
-  b.seg_res = c->d_seg_res;
+  b.seg_res = c->d_seg_res; b.sk_reject = c->d_sk_reject;
   b.cands = c->d_cands; b.cand_cap = (uint32_t)std::min<uint64_t>(c->cand_cap, 0xffffffffu);
   b.loci = c->d_loci; b.loci_cap = (uint32_t)std::min<uint64_t>(c->loci_cap, 0xffffffffu);
   b.counters = c->d_counters;
@@ -470,16 +475,17 @@ int run_pipeline(mm_ctx *c)
     CU(c, cudaEventRecord(c->ev[0], c->stream));
     if ((rc = launch_pack_if_ascii(c))) return rc;
     CU(c, cudaEventRecord(c->ev_pack, c->stream));
-    CU(c, mm_launch_sketch(c->params, b, c->stream, c->sm_count));
+    CU(c, mm_launch_sketch(c->params, b, c->stream, c->sm_count, c->sk_mode));
     CU(c, cudaEventRecord(c->ev[1], c->stream));
     int l1_launches = 0;
     CU(c, mm_launch_l1(c->params, c->ix, b, c->stream, c->sm_count, c->d_l1_slow, c->l1_warp, &l1_launches));
     CU(c, cudaEventRecord(c->ev[2], c->stream));
-    c->launches += 1 + (uint64_t)l1_launches;
+    c->launches += (c->sk_mode ? 1 : 2) + (uint64_t)l1_launches;
     RD(c, c->d_counters, h_cnt, 16);
     const uint64_t need_cands = h_cnt[0];
     bool retry = false;
     c->diag[MM_DIAG_L1_CTA_SEGMENTS] += h_cnt[8];
+    c->diag[MM_DIAG_SKETCH_GENERAL_SEGMENTS] += h_cnt[9];
     if (h_cnt[3] || need_cands > c->cand_cap) {
       c->diag[MM_DIAG_CAND_REGROW]++;
       cudaFree(c->d_cands); c->d_cands = nullptr;
@@ -500,7 +506,7 @@ int run_pipeline(mm_ctx *c)
     if (c->l2_mode == 1) {
       int rc2 = run_l2_stream(c, h_cnt);
       if (rc2 == MM_OK) {
-        cudaEventElapsedTime(&c->pack_ms, c->ev[0], c->ev_pack);
+        if (c->batch_is_ascii) cudaEventElapsedTime(&c->pack_ms, c->ev[0], c->ev_pack);
         cudaEventElapsedTime(&c->stage_ms[0], c->ev_pack, c->ev[1]);
         cudaEventElapsedTime(&c->stage_ms[1], c->ev[1], c->ev[2]);
         cudaEventElapsedTime(&c->stage_ms[2], c->ev[3], c->ev[4]);
@@ -530,7 +536,7 @@ int run_pipeline(mm_ctx *c)
         continue;
       }
       c->n_loci = h_cnt[6];
-      cudaEventElapsedTime(&c->pack_ms, c->ev[0], c->ev_pack);
+      if (c->batch_is_ascii) cudaEventElapsedTime(&c->pack_ms, c->ev[0], c->ev_pack);
       cudaEventElapsedTime(&c->stage_ms[0], c->ev_pack, c->ev[1]);
       cudaEventElapsedTime(&c->stage_ms[1], c->ev[1], c->ev[2]);
       cudaEventElapsedTime(&c->stage_ms[2], c->ev[3], c->ev[4]);
@@ -586,6 +592,7 @@ int mm_ctx_create(int device, const mm_params *params, mm_ctx **out)
       c->blocking_wait = true;
   }
   if (const char *g = getenv("MM_L2_GENERAL")) c->l2_mode = (g[0] == '1') ? 0 : 1; /* test hook: general kernel only */
+  if (const char *g = getenv("MM_SKETCH_TABLE")) c->sk_mode = (g[0] == '1') ? 1 : 0; /* test hook: general sketch kernel only */
   if (const char *g = getenv("MM_L1_CTA")) c->l1_warp = (g[0] == '1') ? 0 : 1; /* test hook: general L1 path only */
   if (params->sketch_size > 1000) c->l2_mode = 0; /* the stream kernel packs its counters in 11 bits */
   *out = c;
@@ -598,7 +605,7 @@ int mm_ctx_destroy(mm_ctx *c)
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   if (c->blob && c->blob_owned) cudaFree(c->blob);
-  cudaFree(c->d_bases); cudaFree(c->d_packed); cudaFree(c->d_segs); cudaFree(c->d_sk_hash); cudaFree(c->d_sk_val); cudaFree(c->d_sk_pos); cudaFree(c->d_sk_strand);
+  cudaFree(c->d_bases); cudaFree(c->d_packed); cudaFree(c->d_sk_reject); cudaFree(c->d_segs); cudaFree(c->d_sk_hash); cudaFree(c->d_sk_val); cudaFree(c->d_sk_pos); cudaFree(c->d_sk_strand);
   cudaFree(c->d_seg_res); cudaFree(c->d_cands); cudaFree(c->d_loci); cudaFree(c->d_counters); cudaFree(c->d_scratch);
   cudaFree(c->d_l1_slow); cudaFree(c->d_l2_order); cudaFree(c->d_l2_ranges); cudaFree(c->d_l2_rec_off); cudaFree(c->d_l2_recs); cudaFree(c->d_scan_tmp);
   for (auto &ev : c->ev) cudaEventDestroy(ev);
@@ -616,6 +623,7 @@ int mm_ctx_diag(const mm_ctx *ctx, uint64_t out[8])
   memcpy(out, ctx->diag, sizeof(ctx->diag));
   return MM_OK;
 }
+int mm_ctx_device(const mm_ctx *c) { return c ? c->device : -1; }
 uint64_t mm_kernel_launches(const mm_ctx *c) { return c ? c->launches : 0; }
 
 int mm_index_upload(mm_ctx *c, const mm_minmer *mi, uint64_t n_mi, const uint64_t *keys, const uint64_t *offsets,
@@ -873,12 +881,17 @@ int mm_sketch_segments(mm_ctx *c, const char *bases, uint64_t n_bases, const mm_
   if (rc) return rc;
   mm_dev_batch b = make_batch(c);
   if ((rc = launch_pack_if_ascii(c))) return rc;
+  ZERO_WORDS(c, c->d_counters, 16);
   CU(c, cudaEventRecord(c->ev[0], c->stream));
-  CU(c, mm_launch_sketch(c->params, b, c->stream, c->sm_count));
+  CU(c, mm_launch_sketch(c->params, b, c->stream, c->sm_count, c->sk_mode));
   CU(c, cudaEventRecord(c->ev[1], c->stream));
-  c->launches += 1;
+  c->launches += c->sk_mode ? 1 : 2;
   CU(c, cudaStreamSynchronize(c->stream));
   cudaEventElapsedTime(&c->stage_ms[0], c->ev[0], c->ev[1]);
+  {
+    uint32_t h9 = 0;
+    if (cudaMemcpy(&h9, c->d_counters + 9, 4, cudaMemcpyDeviceToHost) == cudaSuccess) c->diag[MM_DIAG_SKETCH_GENERAL_SEGMENTS] += h9;
+  }
   c->batch_mapped = true; /* sketches only; fetch_sketch reads sketch_size == raw count */
   rc = mm_batch_fetch_sketch(c, out, out_count);
   c->batch_mapped = false;
@@ -936,7 +949,7 @@ int mm_last_pack_ms(const mm_ctx *c, float *ms)
 int mm_host_alloc(void **ptr, uint64_t bytes)
 {
   if (!ptr) return MM_EINVAL;
-  return cudaHostAlloc(ptr, bytes, cudaHostAllocDefault) == cudaSuccess ? MM_OK : MM_ENOMEM;
+  return cudaHostAlloc(ptr, bytes, cudaHostAllocPortable) == cudaSuccess ? MM_OK : MM_ENOMEM; /* pinned for every device of the process */
 }
 int mm_host_free(void *ptr) { return cudaFreeHost(ptr) == cudaSuccess ? MM_OK : MM_ECUDA; }
 

@@ -82,6 +82,7 @@ struct mm_dev_batch {
   int2 *sk_pos;               /* (first position, last position)                                */
   int8_t *sk_strand;
   mm_segment_result *seg_res;
+  uint32_t *sk_reject;        /* work list of the general sketch kernel: segments the fast kernel handed over (count in counters[9]) */
   mm_l1_candidate *cands;
   uint32_t cand_cap;
   mm_l2_locus *loci;
@@ -89,7 +90,8 @@ struct mm_dev_batch {
   uint32_t *counters;         /* [0] candidates needed, [1] loci overflow (1) / live-set overflow (2), */
                               /* [2] scratch overflow, [3] candidate overflow,                         */
                               /* [4..5] u64 bump pointer into the scratch pool, [6] loci needed,       */
-                              /* [7] L2 candidates to redo, [8] segments handed to the general L1 path */
+                              /* [7] L2 candidates to redo, [8] segments handed to the general L1 path, */
+                              /* [9] segments handed to the general sketch kernel                     */
   uint64_t *scratch;          /* global-memory work area for segments with many interval points:       */
                               /* one slice per CTA of the L1 grid, then a bump-allocated pool          */
   uint64_t scratch_slice;     /* u64 elements per CTA slice                                            */
@@ -124,7 +126,7 @@ MM_HD uint32_t mm_tab_slot_of(uint64_t key, int log2)
 }
 
 /* launchers implemented in the .cu files; all return cudaError_t from the launch */
-cudaError_t mm_launch_sketch(const mm_params &p, const mm_dev_batch &b, cudaStream_t st, int sm_count);
+cudaError_t mm_launch_sketch(const mm_params &p, const mm_dev_batch &b, cudaStream_t st, int sm_count, int mode);
 /* K0: ASCII -> nibbles (makeUpperCaseAndValidDNA as a format change); both buffers padded to a multiple of 16 bases */
 cudaError_t mm_launch_pack_bases(const uint8_t *ascii, uint8_t *packed, uint64_t n_bases, cudaStream_t st, int sm_count);
 cudaError_t mm_launch_l1(const mm_params &p, const mm_dev_index &ix, const mm_dev_batch &b,

@@ -266,9 +266,31 @@ struct sk_run {
 
 /* The hashing loop of one thread. CHECK_N: the stretch contains an N -> per-position validity (run of non-N bases >= K).
  * Returns the number of candidates stored (<= cap); candidates beyond cap go straight into the table. */
-template <int K, bool CHECK_N>
-__device__ __forceinline__ int sk_hash_run(const sk_run &r, uint32_t &amax, unsigned long long *keys, int *first, int *last,
-                                           int *votes, uint32_t mask, int limit, sk_ctrl *ctrl, uint64_t T, bool &above)
+/* what the hashing loop does with a candidate that no longer fits in the thread's list */
+struct sk_spill_table { /* general kernel: straight into the table */
+  unsigned long long *keys; int *first, *last, *votes; uint32_t mask; int limit; sk_ctrl *ctrl; uint64_t T; bool *above;
+  __device__ __forceinline__ void operator()(uint64_t hf, uint64_t hb, int pos) const
+  {
+    sk_take(keys, first, last, votes, mask, limit, ctrl, hf, hb, pos, T, *above);
+  }
+};
+struct sk_spill_list { /* fast kernel: a small CTA-wide list; when that is full too the segment goes to the general kernel */
+  uint4 *h; uint32_t *p; int *n; int cap;
+  __device__ __forceinline__ void operator()(uint64_t hf, uint64_t hb, int pos) const
+  {
+    const int at = atomicAdd(n, 1);
+    if (at < cap) {
+      uint32_t fl, fh, bl, bh;
+      mm_unpack64(hf, fl, fh);
+      mm_unpack64(hb, bl, bh);
+      h[at] = make_uint4(fl, fh, bl, bh);
+      p[at] = (uint32_t)pos;
+    }
+  }
+};
+
+template <int K, bool CHECK_N, bool TRACK_ABOVE, typename Spill>
+__device__ __forceinline__ int sk_hash_run(const sk_run &r, uint32_t &amax, const Spill &spill)
 {
   constexpr int NH = sk_geom<K>::NH, NWIN = sk_geom<K>::NWIN, ROFF = sk_geom<K>::ROFF;
   /* F[m] = ASCII of bases 4m..4m+3 after the current step base; C[t] = complement of F-word (NWIN-1-t), byte-reversed,
@@ -314,7 +336,7 @@ __device__ __forceinline__ int sk_hash_run(const sk_run &r, uint32_t &amax, unsi
       ok = ok && run >= K;
     }
     const uint32_t mh = min((uint32_t)(hf >> 32), (uint32_t)(hb >> 32));
-    if (ok) amax = max(amax, mh);
+    if (TRACK_ABOVE && ok) amax = max(amax, mh);
     if (ok && mh <= r.T_hi) {
       if (cnt < r.cap) {
         uint32_t fl, fh, bl, bh;
@@ -325,7 +347,7 @@ __device__ __forceinline__ int sk_hash_run(const sk_run &r, uint32_t &amax, unsi
         lofs += SK_THREADS;
         cnt++;
       } else {
-        sk_take(keys, first, last, votes, mask, limit, ctrl, hf, hb, pos, T, above);
+        spill(hf, hb, pos);
       }
     }
   };
@@ -350,13 +372,18 @@ __device__ __forceinline__ int sk_hash_run(const sk_run &r, uint32_t &amax, unsi
   return cnt;
 }
 
+/* The general kernel: handles every input (any number of repeated k-mers, fewer than s distinct k-mers, thresholds that
+ * have to be re-estimated). work_list == nullptr: all n_segs segments; else the segments listed there, *work_count of them
+ * (the fast kernel's rejects; the count is read on the device, no host round trip). */
 template <int K>
 __global__ void __launch_bounds__(SK_THREADS)
-k_sketch(const uint8_t *__restrict__ packed, const mm_segment *__restrict__ segs, uint32_t n_segs, int S,
-         int seg_length, int C, int CAP, uint64_t *__restrict__ sk_hash, int2 *__restrict__ sk_pos,
-         int8_t *__restrict__ sk_strand, mm_segment_result *__restrict__ seg_res)
+k_sketch_table(const uint8_t *__restrict__ packed, const mm_segment *__restrict__ segs, uint32_t n_segs_all,
+               const uint32_t *__restrict__ work_list, const uint32_t *__restrict__ work_count, int S,
+               int seg_length, int C, int CAP, uint64_t *__restrict__ sk_hash, int2 *__restrict__ sk_pos,
+               int8_t *__restrict__ sk_strand, mm_segment_result *__restrict__ seg_res)
 {
   extern __shared__ __align__(16) unsigned char smem[];
+  const uint32_t n_segs = work_list ? *work_count : n_segs_all;
   const sk_smem_layout L = sk_layout(seg_length, C, CAP);
   uint64_t *bars = (uint64_t *)(smem + L.off_bar);
   unsigned long long *keys = (unsigned long long *)(smem + L.off_keys);
@@ -393,14 +420,15 @@ k_sketch(const uint8_t *__restrict__ packed, const mm_segment *__restrict__ segs
   };
 
   uint32_t it = 0;
-  if (tid == 0 && blockIdx.x < n_segs) issue(blockIdx.x, 0);
+  if (tid == 0 && blockIdx.x < n_segs) issue(work_list ? work_list[blockIdx.x] : blockIdx.x, 0);
 
-  for (uint32_t seg = blockIdx.x; seg < n_segs; seg += gridDim.x, it++) {
+  for (uint32_t wi = blockIdx.x; wi < n_segs; wi += gridDim.x, it++) {
+    const uint32_t seg = work_list ? work_list[wi] : wi;
     const int stage = it & 1;
-    const uint32_t next = seg + gridDim.x;
+    const uint32_t next = wi + gridDim.x;
     if (tid == 0 && next < n_segs) {
       fence_proxy_async(); /* generic-proxy reads of that buffer (previous iteration) before the async write */
-      issue(next, stage ^ 1);
+      issue(work_list ? work_list[next] : next, stage ^ 1);
     }
     const uint64_t off = segs[seg].offset;
     const int len = segs[seg].length;
@@ -462,8 +490,9 @@ k_sketch(const uint8_t *__restrict__ packed, const mm_segment *__restrict__ segs
       uint32_t amax = 0;
       int cnt = 0;
       if (has_work) {
-        if (any_n) cnt = sk_hash_run<K, true>(r, amax, keys, first, last, votes, mask, limit, ctrl, T, above);
-        else cnt = sk_hash_run<K, false>(r, amax, keys, first, last, votes, mask, limit, ctrl, T, above);
+        const sk_spill_table spill{keys, first, last, votes, mask, limit, ctrl, T, &above};
+        if (any_n) cnt = sk_hash_run<K, true, true>(r, amax, spill);
+        else cnt = sk_hash_run<K, false, true>(r, amax, spill);
       }
       if (amax > r.T_hi) above = true; /* a valid position whose smaller hash is certainly > T */
       /* every thread inserts its own candidates */
@@ -564,6 +593,303 @@ k_sketch(const uint8_t *__restrict__ packed, const mm_segment *__restrict__ segs
   }
 }
 
+
+/* ---- the fast kernel ------------------------------------------------------------------------------------------
+ * One pass per segment, no table, no atomics on the hot path, no threshold loop:
+ *   hashing loop (as above) -> per-thread candidate lists;
+ *   compaction: every thread filters its own candidates exactly (valid k-mer, canonical hash <= T) and writes them to a
+ *     dense array at an offset from a CTA-wide prefix sum;
+ *   256-bucket counting sort on the leading bits of the hash (bucket sizes ~1.3);
+ *   inside its bucket every candidate finds out whether it is the first occurrence of its hash and, if so, gathers
+ *     first position / last position / vote sum of the occurrences and its rank among the bucket's distinct hashes;
+ *   a prefix sum over the buckets' distinct counts turns that into the global rank; ranks < s are written out.
+ * Anything unusual -- more candidates than the dense array holds, a bucket with more than SKF_BUCKET_MAX entries (heavily
+ * repeated k-mers), fewer than s distinct hashes below T -- sends the segment to the general kernel through a device
+ * work list. On random or genomic sequence that is a fraction of a per cent of the segments.
+ */
+constexpr int SKF_SPILL = 64;       /* CTA-wide list for candidates that did not fit a thread's own list */
+constexpr int SKF_BUCKET_MAX = 24;
+
+struct skf_layout {
+  uint32_t stage_bytes, off_bar, off_ctrl, off_list_h, off_list_p, off_spill_h, off_spill_p, off_cand_h, off_cand_m, off_order,
+      off_bcnt, off_bstart, off_bfill, off_dcnt, off_dstart, off_flag, total;
+};
+struct skf_ctrl {
+  int n_spill, n_cand, reject, warp_tot[SK_THREADS / 32];
+};
+__host__ __device__ inline skf_layout skf_make_layout(int seg_length, int NC, int CAP)
+{
+  skf_layout L;
+  L.stage_bytes = (uint32_t)((((seg_length + 1) / 2 + 15) & ~15) + 16 + 64);
+  uint32_t o = 2 * L.stage_bytes;
+  L.off_bar = o; o += 16;
+  L.off_ctrl = o; o += 2 * 32; /* two copies, used alternately (see the kernel) */
+  L.off_spill_h = o; o += 16u * SKF_SPILL;
+  L.off_spill_p = o; o += 4u * SKF_SPILL;
+  L.off_cand_h = o; o += 8u * NC;   /* canonical hash */
+  L.off_cand_m = o; o += 4u * NC;   /* position << 1 | (forward hash was the smaller one) */
+  /* the per-thread lists are dead after the compaction: order[], the bucket counters and the first-occurrence flags
+   * live in the same bytes */
+  const uint32_t lists = (16u + 4u) * SK_THREADS * (uint32_t)CAP;
+  const uint32_t sorting = ((2u * NC + 15) & ~15u) + 5u * 4u * SK_BUCKETS + (((uint32_t)NC + 15) & ~15u);
+  L.off_list_h = o;
+  L.off_list_p = o + 16u * SK_THREADS * (uint32_t)CAP;
+  L.off_order = o;
+  L.off_bcnt = o + ((2u * NC + 15) & ~15u);
+  L.off_bstart = L.off_bcnt + 4u * SK_BUCKETS;
+  L.off_bfill = L.off_bstart + 4u * SK_BUCKETS;
+  L.off_dcnt = L.off_bfill + 4u * SK_BUCKETS;
+  L.off_dstart = L.off_dcnt + 4u * SK_BUCKETS;
+  L.off_flag = L.off_dstart + 4u * SK_BUCKETS;
+  o += lists > sorting ? lists : sorting;
+  L.total = (o + 15) & ~15u;
+  return L;
+}
+
+/* exclusive prefix over SK_BUCKETS counters by warp 0 */
+__device__ __forceinline__ void skf_bucket_prefix(const uint32_t *cnt, uint32_t *start, int tid)
+{
+  if (tid < 32) {
+    uint32_t loc[SK_BUCKETS / 32];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int j = 0; j < SK_BUCKETS / 32; j++) { loc[j] = sum; sum += cnt[tid * (SK_BUCKETS / 32) + j]; }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (tid >= o) incl += v;
+    }
+    const uint32_t excl = incl - sum;
+#pragma unroll
+    for (int j = 0; j < SK_BUCKETS / 32; j++) start[tid * (SK_BUCKETS / 32) + j] = excl + loc[j];
+  }
+}
+
+template <int K>
+__global__ void __launch_bounds__(SK_THREADS)
+k_sketch(const uint8_t *__restrict__ packed, const mm_segment *__restrict__ segs, uint32_t n_segs, int S, int seg_length,
+         int NC, int CAP, uint64_t *__restrict__ sk_hash, int2 *__restrict__ sk_pos, int8_t *__restrict__ sk_strand,
+         mm_segment_result *__restrict__ seg_res, uint32_t *__restrict__ reject_list, uint32_t *__restrict__ reject_count)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  const skf_layout L = skf_make_layout(seg_length, NC, CAP);
+  uint64_t *bars = (uint64_t *)(smem + L.off_bar);
+  skf_ctrl *ctrl2 = (skf_ctrl *)(smem + L.off_ctrl);
+  static_assert(sizeof(skf_ctrl) <= 32, "skf_ctrl");
+  uint4 *spill_h = (uint4 *)(smem + L.off_spill_h);
+  uint32_t *spill_p = (uint32_t *)(smem + L.off_spill_p);
+  uint64_t *cand_h = (uint64_t *)(smem + L.off_cand_h);
+  uint32_t *cand_m = (uint32_t *)(smem + L.off_cand_m);
+  uint16_t *order = (uint16_t *)(smem + L.off_order);
+  uint32_t *bcnt = (uint32_t *)(smem + L.off_bcnt);
+  uint32_t *bstart = (uint32_t *)(smem + L.off_bstart);
+  uint32_t *bfill = (uint32_t *)(smem + L.off_bfill);
+  uint32_t *dcnt = (uint32_t *)(smem + L.off_dcnt);
+  uint32_t *dstart = (uint32_t *)(smem + L.off_dstart);
+  uint8_t *flag = (uint8_t *)(smem + L.off_flag);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  uint4 *list_h = (uint4 *)(smem + L.off_list_h) + tid;
+  uint32_t *list_p = (uint32_t *)(smem + L.off_list_p) + tid;
+
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_proxy_async();
+    ctrl2[0].n_spill = 0; ctrl2[0].reject = 0;
+    ctrl2[1].n_spill = 0; ctrl2[1].reject = 0;
+  }
+  __syncthreads();
+
+  auto issue = [&](uint32_t seg, int stage) {
+    const uint64_t off = segs[seg].offset;
+    const int len = segs[seg].length;
+    const uint64_t g0 = (off >> 1) & ~15ULL;
+    const uint32_t bytes = (uint32_t)(((((off + (uint64_t)len + 1ULL) >> 1) + 15ULL) & ~15ULL) - g0);
+    mbar_expect_tx(&bars[stage], bytes);
+    bulk_g2s(smem + (size_t)stage * L.stage_bytes, packed + g0, bytes, &bars[stage]);
+  };
+
+  uint32_t it = 0;
+  if (tid == 0 && blockIdx.x < n_segs) issue(blockIdx.x, 0);
+
+  for (uint32_t seg = blockIdx.x; seg < n_segs; seg += gridDim.x, it++) {
+    const int stage = it & 1;
+    /* the spill counter / reject flag are written during one segment's hashing loop by threads that may be a whole
+     * phase ahead of thread 0: two copies used alternately, the idle one is cleared in the middle of the other's turn */
+    skf_ctrl *ctrl = ctrl2 + (it & 1), *ctrl_next = ctrl2 + ((it + 1) & 1);
+    const uint32_t next = seg + gridDim.x;
+    if (tid == 0 && next < n_segs) {
+      fence_proxy_async();
+      issue(next, stage ^ 1);
+    }
+    const uint64_t off = segs[seg].offset;
+    const int len = segs[seg].length;
+    const uint32_t skew = (uint32_t)(off - (((off >> 1) & ~15ULL) << 1));
+    const int n = len - K + 1;
+    const int P = n > 0 ? 4 * ((((n + 3) >> 2) + SK_THREADS - 1) / SK_THREADS) : 0;
+    sk_run r;
+    r.nib = (const uint32_t *)(smem + (size_t)stage * L.stage_bytes);
+    r.p0 = tid * P;
+    r.p1 = min(n, r.p0 + P);
+    r.b0 = skew + (uint32_t)r.p0;
+    r.list_h = list_h; r.list_p = list_p; r.cap = CAP;
+    const bool has_work = r.p0 < r.p1;
+    uint64_t T = SK_EMPTY;
+    if (n > 0) {
+      const double c = 1.1 + 6.0 / sqrt((double)S);
+      const double f = c * (double)S / (double)n;
+      if (f < 1.0) T = (uint64_t)((1.0 - sqrt(1.0 - f)) * 18446744073709551616.0);
+    }
+    r.T_hi = (uint32_t)(T >> 32);
+
+    mbar_wait(&bars[stage], (it >> 1) & 1);
+    int cnt = 0;
+    if (has_work) {
+      const uint32_t w0 = r.b0 >> 3, w1 = (r.b0 + (uint32_t)(r.p1 - r.p0) + (uint32_t)K + 6u) >> 3;
+      uint32_t acc = 0;
+      for (uint32_t w = w0; w <= w1; w++) acc |= r.nib[w];
+      uint32_t amax = 0;
+      const sk_spill_list spill{spill_h, spill_p, &ctrl->n_spill, SKF_SPILL};
+      if (acc & 0x88888888u) cnt = sk_hash_run<K, true, false>(r, amax, spill);
+      else cnt = sk_hash_run<K, false, false>(r, amax, spill);
+    }
+
+    /* ---- compaction: exact filter, CTA-wide prefix sum, dense (hash, position|strand) array ---- */
+    int keep = 0;
+    uint32_t keep_mask = 0;
+    for (int q = 0; q < cnt; q++) {
+      const uint4 e = list_h[(size_t)q * SK_THREADS];
+      const uint64_t hf = mm_pack64(e.x, e.y), hb = mm_pack64(e.z, e.w);
+      const uint64_t h = hf < hb ? hf : hb;
+      if (hf != hb && h <= T) { keep++; keep_mask |= 1u << q; }
+    }
+    int incl = keep;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) ctrl->warp_tot[wid] = incl;
+    __syncthreads();
+    if (tid == 0) { ctrl_next->n_spill = 0; ctrl_next->reject = 0; } /* nobody is in the next segment's loop yet, nobody in the last one's */
+    int base = incl - keep;
+    for (int w = 0; w < wid; w++) base += ctrl->warp_tot[w];
+    int total = 0;
+#pragma unroll
+    for (int w = 0; w < SK_THREADS / 32; w++) total += ctrl->warp_tot[w];
+    const int n_spill = min(ctrl->n_spill, SKF_SPILL);
+    const bool spill_over = ctrl->n_spill > SKF_SPILL;
+    /* the lists are read and the dense array is written in the same pass; the dense array does not alias the lists */
+    if (total + n_spill <= NC) {
+      int at = base;
+      for (int q = 0; q < cnt; q++) {
+        if (keep_mask & (1u << q)) {
+          const uint4 e = list_h[(size_t)q * SK_THREADS];
+          const uint64_t hf = mm_pack64(e.x, e.y), hb = mm_pack64(e.z, e.w);
+          const bool fwd = hf < hb;
+          cand_h[at] = fwd ? hf : hb;
+          cand_m[at] = (list_p[(size_t)q * SK_THREADS] << 1) | (fwd ? 1u : 0u);
+          at++;
+        }
+      }
+    }
+    __syncthreads(); /* lists consumed: their bytes become order[] / counters / flags */
+    bool reject = spill_over || total + n_spill > NC;
+    int nc = total;
+    if (!reject) {
+      /* spilled candidates (rare): thread 0 appends them */
+      if (n_spill) {
+        if (tid == 0) {
+          int at = total;
+          for (int q = 0; q < n_spill; q++) {
+            const uint4 e = spill_h[q];
+            const uint64_t hf = mm_pack64(e.x, e.y), hb = mm_pack64(e.z, e.w);
+            const bool fwd = hf < hb;
+            const uint64_t h = fwd ? hf : hb;
+            if (hf != hb && h <= T) { cand_h[at] = h; cand_m[at] = (spill_p[q] << 1) | (fwd ? 1u : 0u); at++; }
+          }
+          ctrl->n_cand = at;
+        }
+      }
+      for (int i = tid; i < SK_BUCKETS; i += SK_THREADS) { bcnt[i] = 0; bfill[i] = 0; dcnt[i] = 0; }
+      __syncthreads();
+      if (n_spill) nc = ctrl->n_cand;
+      const int sh = max(0, (64 - __clzll((long long)T)) - 8);
+      for (int i = tid; i < nc; i += SK_THREADS) atomicAdd(&bcnt[(uint32_t)(cand_h[i] >> sh)], 1u);
+      __syncthreads();
+      skf_bucket_prefix(bcnt, bstart, tid);
+      __syncthreads();
+      for (int i = tid; i < nc; i += SK_THREADS) {
+        const uint32_t b = (uint32_t)(cand_h[i] >> sh);
+        order[bstart[b] + atomicAdd(&bfill[b], 1u)] = (uint16_t)i;
+      }
+      __syncthreads();
+      /* first occurrence of its hash? (among equal hashes: the smallest position) */
+      bool big_bucket = false;
+      for (int i = tid; i < nc; i += SK_THREADS) {
+        const uint64_t h = cand_h[i];
+        const uint32_t b = (uint32_t)(h >> sh);
+        const uint32_t bs = bstart[b], bn = bcnt[b];
+        if (bn > (uint32_t)SKF_BUCKET_MAX) { big_bucket = true; continue; }
+        const uint32_t pos = cand_m[i] >> 1;
+        bool is_first = true;
+        for (uint32_t q = bs; q < bs + bn; q++) {
+          const uint32_t j = order[q];
+          if (cand_h[j] == h && (cand_m[j] >> 1) < pos) is_first = false;
+        }
+        flag[i] = is_first ? 1 : 0;
+        if (is_first) atomicAdd(&dcnt[b], 1u);
+      }
+      if (big_bucket) ctrl->reject = 1;
+      __syncthreads();
+      skf_bucket_prefix(dcnt, dstart, tid);
+      __syncthreads();
+      int distinct = (int)(dstart[SK_BUCKETS - 1] + dcnt[SK_BUCKETS - 1]);
+      reject = ctrl->reject != 0 || (distinct < S && T != SK_EMPTY);
+      if (!reject) {
+        const size_t obase = (size_t)seg * (size_t)S;
+        for (int i = tid; i < nc; i += SK_THREADS) {
+          if (!flag[i]) continue;
+          const uint64_t h = cand_h[i];
+          const uint32_t b = (uint32_t)(h >> sh);
+          const uint32_t bs = bstart[b], bn = bcnt[b];
+          uint32_t rank = dstart[b];
+          int first = 0x7fffffff, last = -1, votes = 0;
+          for (uint32_t q = bs; q < bs + bn; q++) {
+            const uint32_t j = order[q];
+            const uint64_t hj = cand_h[j];
+            if (hj == h) {
+              const uint32_t m = cand_m[j];
+              const int pj = (int)(m >> 1);
+              first = min(first, pj); last = max(last, pj); votes += (m & 1u) ? 1 : -1;
+            } else if (hj < h && flag[j]) {
+              rank++;
+            }
+          }
+          if ((int)rank < S) {
+            sk_hash[obase + rank] = h;
+            sk_pos[obase + rank] = make_int2(first, last);
+            sk_strand[obase + rank] = (int8_t)(votes > 0 ? 1 : (votes == 0 ? 0 : -1)); /* commonFunc.hpp:282 */
+          }
+        }
+        if (tid == 0) {
+          const int count = min(distinct, S);
+          mm_segment_result res;
+          res.sketch_max_hash = 0; /* filled by the L1 kernel from sk_hash[count-1] */
+          res.sketch_raw_count = count;
+          res.sketch_size = count;
+          res.n_points = 0; res.minimum_hits = 0; res.best_intersection = 0;
+          res.first_candidate = 0; res.n_candidates = 0; res._pad = 0;
+          seg_res[seg] = res;
+        }
+      }
+    }
+    if (reject && tid == 0) reject_list[atomicAdd(reject_count, 1u)] = seg; /* the general kernel takes it */
+    __syncthreads(); /* everything read; the staging buffer, lists and counters may be overwritten */
+  }
+}
+
 /* table capacity and candidate-list capacity for (seg_length, sketch_size) */
 void sk_sizes(int seg_length, int sketch_size, int kmer_size, int *C_out, int *CAP_out)
 {
@@ -586,20 +912,56 @@ void sk_sizes(int seg_length, int sketch_size, int kmer_size, int *C_out, int *C
   *CAP_out = CAP;
 }
 
-template <int K>
-cudaError_t launch_k(const mm_params &p, const mm_dev_batch &b, cudaStream_t st, int sm_count, int C, int CAP, size_t smem)
+/* dense-array capacity of the fast kernel: the expected number of candidates + 6 sigma, at least 256 */
+int skf_cand_cap(int seg_length, int sketch_size, int kmer_size)
 {
-  cudaError_t e = cudaFuncSetAttribute(k_sketch<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const double c = 1.1 + 6.0 / sqrt((double)sketch_size);
+  const int n = seg_length - kmer_size + 1 > 0 ? seg_length - kmer_size + 1 : 1;
+  double want = c * sketch_size;
+  if (want > n) want = n;
+  int NC = (int)(want + 6.0 * sqrt(want) + 32.0);
+  NC = (NC + 63) & ~63;
+  return NC < 256 ? 256 : NC;
+}
+
+template <int K>
+cudaError_t launch_k(const mm_params &p, const mm_dev_batch &b, cudaStream_t st, int sm_count, int C, int CAP, size_t smem,
+                     int mode)
+{
+  /* general kernel: over everything (mode 1, MM_SKETCH_TABLE=1) or over the fast kernel's rejects (mode 0) */
+  cudaError_t e = cudaFuncSetAttribute(k_sketch_table<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int occ = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sketch<K>, SK_THREADS, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sketch_table<K>, SK_THREADS, smem);
   if (e != cudaSuccess) return e;
   if (occ < 1) occ = 1;
-  uint32_t grid = (uint32_t)sm_count * (uint32_t)occ; /* persistent: a whole number of CTAs per SM */
-  if (grid > b.n_segs) grid = b.n_segs;
-  if (grid == 0) return cudaSuccess;
-  k_sketch<K><<<grid, SK_THREADS, smem, st>>>(b.packed, b.segs, b.n_segs, p.sketch_size, p.seg_length, C, CAP, b.sk_hash,
-                                              b.sk_pos, b.sk_strand, b.seg_res);
+  const uint32_t full = (uint32_t)sm_count * (uint32_t)occ;
+  if (b.n_segs == 0) return cudaSuccess;
+  const int NC = skf_cand_cap(p.seg_length, p.sketch_size, K);
+  const skf_layout FL = skf_make_layout(p.seg_length, NC, CAP);
+  if (mode == 1 || NC > 65535 || FL.total > 227u * 1024u) {
+    const uint32_t grid = full > b.n_segs ? b.n_segs : full;
+    k_sketch_table<K><<<grid, SK_THREADS, smem, st>>>(b.packed, b.segs, b.n_segs, nullptr, nullptr, p.sketch_size, p.seg_length, C,
+                                                      CAP, b.sk_hash, b.sk_pos, b.sk_strand, b.seg_res);
+    return cudaGetLastError();
+  }
+  e = cudaFuncSetAttribute(k_sketch<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FL.total);
+  if (e != cudaSuccess) return e;
+  int focc = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&focc, k_sketch<K>, SK_THREADS, FL.total);
+  if (e != cudaSuccess) return e;
+  if (focc < 1) focc = 1;
+  uint32_t fgrid = (uint32_t)sm_count * (uint32_t)focc; /* persistent: a whole number of CTAs per SM */
+  if (fgrid > b.n_segs) fgrid = b.n_segs;
+  k_sketch<K><<<fgrid, SK_THREADS, FL.total, st>>>(b.packed, b.segs, b.n_segs, p.sketch_size, p.seg_length, NC, CAP, b.sk_hash, b.sk_pos,
+                                                   b.sk_strand, b.seg_res, b.sk_reject, b.counters + 9);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  /* the rejects: the count is read on the device; a grid of one CTA per SM is enough for a fraction of a per cent */
+  uint32_t rgrid = (uint32_t)sm_count;
+  if (rgrid > b.n_segs) rgrid = b.n_segs;
+  k_sketch_table<K><<<rgrid, SK_THREADS, smem, st>>>(b.packed, b.segs, b.n_segs, b.sk_reject, b.counters + 9, p.sketch_size, p.seg_length,
+                                                     C, CAP, b.sk_hash, b.sk_pos, b.sk_strand, b.seg_res);
   return cudaGetLastError();
 }
 
@@ -647,13 +1009,15 @@ cudaError_t mm_launch_pack_bases(const uint8_t *ascii, uint8_t *packed, uint64_t
   return cudaGetLastError();
 }
 
-cudaError_t mm_launch_sketch(const mm_params &p, const mm_dev_batch &b, cudaStream_t st, int sm_count)
+/* mode 0: fast kernel + general kernel over its rejects (2 launches); mode 1: general kernel over everything (1 launch).
+ * b.counters[9] must be 0 and b.sk_reject must hold n_segs entries. */
+cudaError_t mm_launch_sketch(const mm_params &p, const mm_dev_batch &b, cudaStream_t st, int sm_count, int mode)
 {
   int C = 0, CAP = 0;
   const size_t smem = mm_sketch_smem_bytes(p.seg_length, p.sketch_size, p.kmer_size, &C, &CAP);
   if (smem == 0) return cudaErrorInvalidValue;
   switch (p.kmer_size) {
-#define X(KK) case KK: return launch_k<KK>(p, b, st, sm_count, C, CAP, smem);
+#define X(KK) case KK: return launch_k<KK>(p, b, st, sm_count, C, CAP, smem, mode);
     MM_FOR_EACH_K(X)
 #undef X
     default: return cudaErrorInvalidValue;

@@ -93,10 +93,14 @@ def panel_set(workdir):
     return datasets.make_panel_set(workdir)
 
 
+@pytest.mark.parametrize("mode", ["fast+general", "general-only"])
 @pytest.mark.parametrize("k,s", [(19, 130), (16, 40), (21, 250), (32, 17)])
-def test_sketch_matches_reference(random_set, k, s):
+def test_sketch_matches_reference(random_set, k, s, mode, monkeypatch):
+    """both sketch kernels: the one-pass fast kernel (its rejects go to the general kernel) and the general kernel alone"""
     from mashmap_b200 import capi
 
+    if mode == "general-only":
+        monkeypatch.setenv("MM_SKETCH_TABLE", "1")
     d = random_set
     ctx = capi.Context(kmer_size=k, seg_length=5000, sketch_size=s)
     bases, segs, ridx, start, length = build_segments(d, 5000, k)
@@ -145,6 +149,10 @@ def test_sketch_degenerate_inputs():
         assert len(ref) == len(dev), (i, len(ref), len(dev))
         for f in ("hash", "wpos", "wpos_end", "strand"):
             assert np.array_equal(ref[f], dev[f]), (i, f)
+    # homopolymers, tandem repeats, all-N, fewer than s distinct k-mers: the fast kernel must have handed them over
+    dg = ctx.diag()
+    print("rare paths taken:", dg)
+    assert dg["sketch_general_segments"] >= 4
     ctx.close()
 
 
@@ -152,6 +160,7 @@ def test_sketch_degenerate_inputs():
 def kernel_paths(request, monkeypatch):
     """the warp-per-segment L1 + stream L2 kernels (default), or the general CTA / warp-per-candidate kernels alone"""
     if request.param == "general-kernels":
+        monkeypatch.setenv("MM_SKETCH_TABLE", "1")
         monkeypatch.setenv("MM_L1_CTA", "1")
         monkeypatch.setenv("MM_L2_GENERAL", "1")
     return request.param
@@ -244,19 +253,30 @@ def test_packed_input_equals_text_input(random_set):
         ctx = capi.Context(kmer_size=R.p.kmerSize, seg_length=R.p.segLength, sketch_size=R.p.sketchSize)
         upload_reference_index(ctx, R)
         bases, segs, ridx, start, length = build_segments(d, R.p.segLength, R.p.kmerSize)
-        a = ctx.map_segments(bases, segs)
-        sk_a = ctx.batch_fetch_sketch() if False else None
-        b = ctx.map_segments_packed(capi.pack_bases(bases), len(bases), segs)
-        for x, y in zip(a, b):
-            assert x.tobytes() == y.tobytes()
+        def canon(res):
+            """per segment: (sketch size, points, minimum hits, candidates with their loci) -- the position of a segment's
+            candidate slice in the batch-wide arrays depends on the order the CTAs reserved them in"""
+            seg_res, cands, loci = res
+            out = []
+            for sr in seg_res:
+                c = cands[sr["first_candidate"] : sr["first_candidate"] + sr["n_candidates"]]
+                cl = [(tuple(int(x[f]) for f in ("seqId", "rangeStartPos", "rangeEndPos", "intersectionSize")),
+                       loci[x["first_locus"] : x["first_locus"] + x["n_loci"]].tobytes()) for x in c]
+                out.append((int(sr["sketch_max_hash"]), int(sr["sketch_raw_count"]), int(sr["sketch_size"]), int(sr["n_points"]),
+                            int(sr["minimum_hits"]), int(sr["best_intersection"]), cl))
+            return out
+
+        a = canon(ctx.map_segments(bases, segs))
+        assert ctx.pack_ms() > 0.0    # text input: packed on the device
+        b = canon(ctx.map_segments_packed(capi.pack_bases(bases), len(bases), segs))
+        assert a == b
         assert ctx.pack_ms() == 0.0  # the packed batch skipped the device packing kernel
         # odd segment offsets / an odd number of bases: shift everything by one base
         bases1 = np.concatenate([np.frombuffer(b"G", np.uint8), bases])
         segs1 = segs.copy()
         segs1["offset"] += 1
-        c = ctx.map_segments_packed(capi.pack_bases(bases1), len(bases1), segs1)
-        for x, y in zip(a, c):
-            assert x.tobytes() == y.tobytes()
+        c = canon(ctx.map_segments_packed(capi.pack_bases(bases1), len(bases1), segs1))
+        assert a == c
         ctx.close()
     finally:
         R.close()

@@ -27,6 +27,22 @@ def test_c_abi_library_loads_and_exports_every_symbol():
     assert declared == set(capi.EXPORTED_SYMBOLS)
 
 
+def test_nccl_library_loads_and_exports_every_symbol():
+    """include/mashmap_b200_nccl.h (multi-GPU entry points) vs libmashmap_nccl.so: loads without a GPU, exports every
+    declared function"""
+    import os
+    import re
+
+    from mashmap_b200 import nccl
+
+    L = nccl.lib()
+    hdr = open(os.path.join(os.path.dirname(capi._HERE), "include", "mashmap_b200_nccl.h")).read()
+    declared = set(re.findall(r"\b(mm_[a-z_0-9]+)\s*\(", hdr))
+    for sym in declared:
+        assert hasattr(L, sym), f"{sym} declared in the header but not exported"
+    assert declared == set(nccl.EXPORTED_SYMBOLS)
+
+
 def test_no_cpu_fallback_without_device():
     from conftest import have_gpu
 
