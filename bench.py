@@ -32,9 +32,20 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-K, SEG, PI = 19, 5000, 0.85
-READ_LEN = 10_000
+K = 19
 REF_FASTA_BYTES_PER_BASE = 81.0 / 80.0  # 80-column FASTA: what recommendedSketchSize is fed (file size in bytes)
+
+# BASELINE.json configs[1..4] (configs[0], the yeast self-map, is the reference's own CPU-runnable case: tests/test_gpu_cli.py)
+CONFIGS = {
+    2: dict(tag="configs[1]", kind="reads", reads=1_000_000, read_len=10_000, err=(0.02, 0.14), seg=5000, pi=0.85, dense=False,
+            filt="map", scaling="weak", what="synthetic ONT reads"),
+    3: dict(tag="configs[2]", kind="reads", reads=1_000_000, read_len=10_000, err=(0.02, 0.14), seg=5000, pi=0.95, dense=True,
+            filt="map", scaling="weak", what="synthetic ONT reads"),
+    4: dict(tag="configs[3]", kind="reads", reads=100_000, read_len=20_000, err=(0.004, 0.006), seg=5000, pi=0.95, dense=False,
+            filt="one-to-one", scaling="strong", what="synthetic HiFi-like reads"),
+    5: dict(tag="configs[4]", kind="assembly", seg=10_000, pi=0.90, dense=False, filt="one-to-one", scaling="strong",
+            snp=0.03, indel=0.003, inversions=100, translocations=100, what="contigs of a second synthetic assembly"),
+}
 
 
 def log(*a):
@@ -47,8 +58,10 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json configuration (2 = configs[1], the "
+                    "one the metric is quoted on; 3 = --dense --pi 95; 4 = HiFi one-to-one, strong scaling; 5 = assembly vs assembly)")
     # workload overrides (tests / quick runs only; the defaults are the BASELINE configuration)
-    ap.add_argument("--reads", type=int, default=1_000_000)
+    ap.add_argument("--reads", type=int, default=0, help="0 = the configuration's own number of reads")
     ap.add_argument("--ref-bp", type=int, default=3_000_000_000)
     ap.add_argument("--contigs", type=int, default=256)
     ap.add_argument("--cpu-sample-reads", type=int, default=0, help="reads per CPU-baseline sample (0 = auto)")
@@ -152,51 +165,21 @@ def roofline_traffic():
     return {}
 
 
-def setup_workload(args, rank, world, device):
-    """reference on the GPU -> host index (rank 0) -> device; reads generated on the GPU"""
-    import torch
-
-    from mashmap_b200 import hostlib, synth_gpu
-
-    contig_len = args.ref_bp // args.contigs
-    t0 = time.time()
-    ref = synth_gpu.random_reference(args.contigs, contig_len, seed=1, device=device)
-    if device.type == "cuda":
-        torch.cuda.synchronize()
-    log(f"rank {rank}: reference {args.contigs} x {contig_len} bp generated in {time.time() - t0:.1f} s")
-    sketch = args.sketch or int(hostlib.lib().skch_recommended_sketch_size(K, PI, SEG, int(args.ref_bp * REF_FASTA_BYTES_PER_BASE) + 16 * args.contigs))
-    t0 = time.time()
-    reads_dev, truth = synth_gpu.simulate_reads(ref, args.reads, READ_LEN, 0.02, 0.14, seed=2 + (args.as_rank if args.as_rank >= 0 else rank), chunk=8192)
-    if device.type == "cuda":
-        torch.cuda.synchronize()
-    log(f"rank {rank}: {args.reads} reads simulated in {time.time() - t0:.1f} s; sketch size {sketch}")
-    ref_host = None
-    if rank == 0:
-        ref_host = ref.cpu().numpy().reshape(-1)
-    contig_of, start_of, strand_of = truth["contig"].cpu().numpy(), truth["start"].cpu().numpy(), truth["strand"].cpu().numpy()
-    del ref
-    if device.type == "cuda":
-        torch.cuda.empty_cache()
-    return dict(ref_host=ref_host, contig_len=contig_len, sketch=sketch, reads_dev=reads_dev,
-                truth=(contig_of, start_of, strand_of))
-
-
-def build_index(args, wl, threads):
-    from mashmap_b200 import hostlib
-
-    t0 = time.time()
-    offs = np.arange(args.contigs + 1, dtype=np.uint64) * np.uint64(wl["contig_len"])
-    hi = hostlib.HostIndex.build(wl["ref_host"], offs, K, SEG, wl["sketch"], threads=threads)
-    log(f"host index: {hi.n_minmers} minmers, {hi.n_keys} keys, {hi.n_points} points, freq threshold {hi.freq_threshold} "
-        f"in {time.time() - t0:.1f} s ({threads} threads)")
-    return hi
+def issue_peak():
+    """measured INT32 issue rates (mashmap_b200/mm_issue_peak on this pool's B200), if committed"""
+    p = os.path.join(ROOT, "profiles", "issue_peak.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            return None
+    return None
 
 
 def host_memory_info():
     """memory this process group may use: cgroup limit / current use, MemTotal / MemAvailable, the locked-memory ulimit"""
     info = {}
-    for name, path in (("cgroup_max", "/sys/fs/cgroup/memory.max"), ("cgroup_current", "/sys/fs/cgroup/memory.current"),
-                       ("cgroup_v1_limit", "/sys/fs/cgroup/memory/memory.limit_in_bytes")):
+    for name, path in (("cgroup_max", "/sys/fs/cgroup/memory.max"), ("cgroup_current", "/sys/fs/cgroup/memory.current")):
         try:
             v = open(path).read().strip()
             info[name] = v if v == "max" else round(int(v) / 2**30, 1)
@@ -207,13 +190,6 @@ def host_memory_info():
             f = line.split()
             if f[0] in ("MemTotal:", "MemAvailable:"):
                 info[f[0][:-1]] = round(int(f[1]) / 2**20, 1)
-    except Exception:
-        pass
-    try:
-        import resource
-
-        soft, _ = resource.getrlimit(resource.RLIMIT_MEMLOCK)
-        info["memlock"] = "unlimited" if soft == resource.RLIM_INFINITY else round(soft / 2**30, 2)
     except Exception:
         pass
     return info
@@ -244,15 +220,145 @@ def keep_rank_stderr(rank):
         print(f"[bench] rank {rank}: cannot keep a per-rank log: {e}", file=sys.stderr)
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """CPU affinity (and with it first-touch memory placement) of this rank = the NUMA node its GPU hangs off: the pinned
+    batch buffer and the host tail then stay on the socket whose PCIe root the copies use"""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        node = None
+        try:
+            node = pynvml.nvmlDeviceGetNumaNodeId(h)
+        except Exception:
+            pass
+        if node is None or node < 0:
+            bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+            bus = bus.decode() if isinstance(bus, bytes) else bus
+            node = int(open(f"/sys/bus/pci/devices/{bus[-12:].lower()}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        cpus = sorted(set(cpus) & os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node, len(cpus)
+    except Exception as e:
+        log(f"NUMA binding skipped: {e}")
+    return None
+
+
+def config_of(args):
+    cfg = dict(CONFIGS[args.config])
+    if cfg["kind"] == "reads":
+        if args.reads:
+            cfg["reads"] = args.reads
+    else:  # assembly: the queries are the contigs of the second genome, cut to one common length
+        contig_len = args.ref_bp // args.contigs
+        cfg["reads"] = args.contigs
+        cfg["read_len"] = contig_len - max(64, contig_len // 100)
+    return cfg
+
+
+def sketch_size_of(args, cfg):
+    from mashmap_b200 import hostlib
+
+    if args.sketch:
+        return args.sketch
+    if cfg["dense"]:  # parseCmdArgs.hpp:626-631
+        return int(0.02 * (1 + (1 - cfg["pi"]) / 0.05) * (cfg["seg"] - K))
+    # the reference's automatic choice for a file of this size (SURVEY 8(a) table: 220 / 20 / 70). A file >= 2 GiB would in
+    # fact wrap the reference's int32 referenceSize (310 for this one, see DESIGN.md); --sketch 310 measures that variant.
+    return int(hostlib.lib().skch_recommended_sketch_size(K, cfg["pi"], cfg["seg"], int(args.ref_bp * REF_FASTA_BYTES_PER_BASE) + 16 * args.contigs))
+
+
+def workload_text(args, cfg, S):
+    n, L = cfg["reads"], cfg["read_len"]
+    if cfg["kind"] == "reads":
+        q = f"{n} {cfg['what']} x {L} bp (err U[{cfg['err'][0] * 100:g}%,{cfg['err'][1] * 100:g}%])"
+    else:
+        q = (f"{n} contigs x {L} bp of a second assembly ({cfg['snp'] * 100:g}% SNPs, {cfg['indel'] * 100:g}% indels, "
+             f"{cfg['inversions']} inversions, {cfg['translocations']} translocations)")
+    opts = f"-s {cfg['seg']} --pi {int(cfg['pi'] * 100)}" + (" --dense" if cfg["dense"] else "") + (f" -f {cfg['filt']}" if cfg["filt"] != "map" else "")
+    return (f"{q} vs {args.ref_bp / 1e9:.2f} Gbp uniform-random reference ({args.contigs} contigs), {opts}, k={K}, sketch={S} "
+            f"(BASELINE.json {cfg['tag']})")
+
+
+def make_queries(args, cfg, ref, seed_rank):
+    """all queries of one step of this rank's workload as text on the device: [n, read_len] uint8 (+ truth for reads)"""
+    from mashmap_b200 import synth_gpu
+
+    if cfg["kind"] == "reads":
+        return synth_gpu.simulate_reads(ref, cfg["reads"], cfg["read_len"], cfg["err"][0], cfg["err"][1], seed=2 + seed_rank, chunk=8192)
+    q = synth_gpu.mutated_genome(ref, cfg["read_len"], cfg["snp"], cfg["indel"], cfg["inversions"], cfg["translocations"], seed=4)
+    return q, None
+
+
+def setup_workload(args, cfg, rank, world, device):
+    """reference on the GPU -> host copy for the index builder (rank 0); this rank's queries generated on the GPU.
+    weak scaling: every rank its own cfg.reads reads (seed 2 + rank); strong scaling: ONE set, rank r takes its block."""
+    import torch
+
+    from mashmap_b200 import dist as mdist
+    from mashmap_b200 import synth_gpu
+
+    contig_len = args.ref_bp // args.contigs
+    t0 = time.time()
+    ref = synth_gpu.random_reference(args.contigs, contig_len, seed=1, device=device)
+    S = sketch_size_of(args, cfg)
+    strong = cfg["scaling"] == "strong"
+    seed_rank = 0 if strong else (args.as_rank if args.as_rank >= 0 else rank)
+    q, truth = make_queries(args, cfg, ref, seed_rank)
+    lo, hi = (mdist.shard_reads(cfg["reads"], rank, world) if strong else (0, cfg["reads"]))
+    first_counter = lo if strong else rank * cfg["reads"]
+    if device.type == "cuda":
+        torch.cuda.synchronize()
+    log(f"rank {rank}: reference {args.contigs} x {contig_len} bp and {cfg['reads']} queries x {cfg['read_len']} bp generated in "
+        f"{time.time() - t0:.1f} s; sketch size {S}; this rank maps queries [{lo}, {hi})")
+    ref_host = ref.cpu().numpy().reshape(-1) if rank == 0 else None
+    t = None
+    if truth is not None:
+        t = tuple(truth[k].cpu().numpy() for k in ("contig", "start", "strand"))
+    all_q = q  # strong scaling keeps the whole set on rank 0 for the single-GPU comparison
+    del ref
+    return dict(ref_host=ref_host, contig_len=contig_len, sketch=S, queries=q[lo:hi], all_queries=all_q if (strong and rank == 0) else None,
+                truth=t, lo=lo, hi=hi, first_counter=first_counter)
+
+
+def build_index(args, cfg, wl, threads):
+    from mashmap_b200 import hostlib
+
+    t0 = time.time()
+    offs = np.arange(args.contigs + 1, dtype=np.uint64) * np.uint64(wl["contig_len"])
+    hi = hostlib.HostIndex.build(wl["ref_host"], offs, K, cfg["seg"], wl["sketch"], threads=threads)
+    log(f"host index: {hi.n_minmers} minmers, {hi.n_keys} keys, {hi.n_points} points, freq threshold {hi.freq_threshold} "
+        f"in {time.time() - t0:.1f} s ({threads} threads)")
+    return hi
+
+
+def text_segments(batch, read_len):
+    """the batch's fragments with offsets into the plain text layout (read r at r * read_len) instead of the packed one"""
+    seg = batch.segments.copy()
+    stride = (read_len + 31) // 32 * 32  # reads sit at multiples of 32 bases in the packed batch
+    rd = seg["offset"] // stride
+    seg["offset"] = rd * read_len + (seg["offset"] - rd * stride)
+    return seg
+
+
 def gpu_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         keep_rank_stderr(rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     import torch
 
-    log(f"rank {rank}/{world}: host memory {host_memory_info()}, cpus {host_cpu_info()}")
+    log(f"rank {rank}/{world}: host memory {host_memory_info()}, cpus {host_cpu_info()}, bound to NUMA node {numa}")
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -261,46 +367,47 @@ def gpu_arm(args):
     torch.cuda.set_device(local_rank)
     device = torch.device(f"cuda:{local_rank}")
     from mashmap_b200 import capi, hostlib
-    from mashmap_b200 import dist as mdist
+    from mashmap_b200 import nccl as mnccl
 
+    cfg = config_of(args)
     host_threads = max(1, usable_cpus() // max(1, world))  # sized to the CPU quota: more threads than CPUs only adds throttling
-    wl = setup_workload(args, rank, world, device)
-    S = wl["sketch"]
+    wl = setup_workload(args, cfg, rank, world, device)
+    S, L, SEG, PI = wl["sketch"], cfg["read_len"], cfg["seg"], cfg["pi"]
+    one_to_one = cfg["filt"] == "one-to-one"
+    strong = cfg["scaling"] == "strong"
 
-    # ---- index: built on the host by rank 0, uploaded; other ranks receive the device image over NCCL ----
+    # ---- index: built on the host by rank 0, uploaded; other ranks receive the device image with ONE NCCL broadcast ----
+    comm = mnccl.create_with_torch(dist, rank, world, local_rank) if world > 1 else None  # the product's own communicator
     t_index = time.time()
     if rank == 0:
-        hi = build_index(args, wl, os.cpu_count() or 8)  # memory-latency-bound tasks: oversubscription is harmless here
+        hi = build_index(args, cfg, wl, usable_cpus())
     else:
         hi = hostlib.HostIndex.metadata_only(args.contigs, wl["contig_len"], K, SEG, S)  # the index arrives by broadcast
-    bm = hostlib.BatchMapper(hi, pi=PI, device=local_rank, threads=host_threads)
+    bm = hostlib.BatchMapper(hi, pi=PI, device=local_rank, threads=host_threads, filter_mode=cfg["filt"])
     ctx = capi.Context.from_handle(bm.ctx_handle, S, device=local_rank)
-    if world > 1:
+    if comm is not None:
         t0 = time.time()
-        n = mdist.broadcast_index(dist, ctx, rank, device)
-        torch.cuda.synchronize()
-        log(f"rank {rank}: index image {n / 1e9:.2f} GB broadcast in {time.time() - t0:.2f} s")
+        n = comm.index_broadcast(bm.ctx_handle, root=0)  # mm_index_broadcast (include/mashmap_b200_nccl.h)
+        log(f"rank {rank}: index image {n / 1e9:.2f} GB received/sent in {time.time() - t0:.2f} s (includes waiting for rank 0's build)")
     index_seconds = time.time() - t_index
     wl["ref_host"] = None
 
     # ---- the batch: pinned host copy (e2e) and device-resident copy (value) ----
-    log(f"rank {rank}: index ready, rss {rss_gb()} GB, {host_memory_info()}")
-    ascii_reads = wl["reads_dev"].reshape(-1).cpu().numpy()  # the reads as text (what the reference's path consumes)
-    del wl["reads_dev"]
+    n_local = wl["hi"] - wl["lo"]
+    ascii_reads = wl["queries"].reshape(-1).cpu().numpy()  # the queries as text (what the reference's path consumes)
+    wl["queries"] = None
     torch.cuda.empty_cache()
-    n_bases = args.reads * READ_LEN
+    n_bases = n_local * L
     # e2e input: the pinned batch buffer of skch::BatchMapper, filled the way its FASTA reader fills it -- every read
     # packed to one nibble per base while it is copied in (outside the timed region, like parsing is)
-    batch = bm.make_batch(args.reads, READ_LEN, first_seq_counter=rank * args.reads)
+    batch = bm.make_batch(n_local, L, first_seq_counter=wl["first_counter"])
     pack_seconds = batch.fill(ascii_reads, threads=host_threads)
     n_segs = len(batch.segments)
     # value input: the same reads resident in HBM as TEXT; the packing kernel (K0) is then part of every timed step
-    seg_text = batch.segments.copy()
-    stride = (READ_LEN + 31) // 32 * 32  # reads sit at multiples of 32 bases in the packed batch
-    rd = seg_text["offset"] // stride
-    seg_text["offset"] = rd * READ_LEN + (seg_text["offset"] - rd * stride)
+    seg_text = text_segments(batch, L)
     ctx.batch_upload(ascii_reads, seg_text)
-    log(f"rank {rank}: batch resident, rss {rss_gb()} GB; host packing {n_bases / pack_seconds / 1e9:.1f} Gbases/s on {host_threads} threads")
+    log(f"rank {rank}: batch resident ({n_local} queries, {n_segs} fragments), rss {rss_gb()} GB; host packing "
+        f"{n_bases / max(pack_seconds, 1e-9) / 1e9:.1f} Gbases/s on {host_threads} threads")
 
     def barrier():
         if dist is not None:
@@ -328,35 +435,61 @@ def gpu_arm(args):
     clocks = sampler.stop(t0, t1)
     wall_ms = (t1 - t0) * 1e3
     seg_res, cands, loci = ctx.batch_fetch()
-    log(f"rank {rank}: value phase done ({ev_ms / args.steps:.1f} ms/step), rss {rss_gb()} GB")
+    diag = ctx.diag()
+    log(f"rank {rank}: value phase done ({ev_ms / args.steps:.1f} ms/step), rare paths {diag}")
 
-    # ---- e2e: host buffers -> C ABI -> records -> host tail -> PAF text ----
+    # ---- e2e: host buffers -> C ABI -> records -> host tail -> (all-gather, one-to-one sweep) -> PAF text ----
+    n_q_global = cfg["reads"] if strong else cfg["reads"] * world
+
+    def e2e_step():
+        info = bm.map(batch)
+        gathered, final = 0, None
+        if comm is not None or one_to_one:
+            raw = bm.results_raw()
+            if comm is not None:  # all ranks' mapping records on every rank: mm_records_allgather
+                raw, counts = comm.records_allgather(raw)
+                gathered = int(counts.sum())
+            if one_to_one and rank == 0:  # the run-wide reference-axis sweep + sort (computeMap.hpp:358-405) over ALL records
+                kept, paf = bm.one_to_one(raw, n_q_global, L)
+                final = (kept, paf)
+        return info, gathered, final
+
     for _ in range(min(args.warmup, 1)):
-        bm.map(batch)
+        e2e_step()
     barrier()
     t0 = time.time()
-    e2e_info = None
-    gathered = 0
+    e2e_info, gathered, final = None, 0, None
     for _ in range(args.steps):
-        e2e_info = bm.map(batch)
-        if dist is not None:  # all ranks' mapping records on rank 0
-            _, gathered = mdist.gather_records(dist, torch.from_numpy(bm.results()).to(device), world)
+        e2e_info, gathered, final = e2e_step()
     barrier()
     e2e_ms = (time.time() - t0) * 1e3
     log(f"rank {rank}: e2e phase done ({e2e_ms / args.steps:.1f} ms/step), rss {rss_gb()} GB")
     h2d = batch.h2d_bytes + n_segs * capi.segment_dtype.itemsize
     d2h = n_segs * capi.segres_dtype.itemsize + len(cands) * capi.l1_dtype.itemsize + len(loci) * capi.l2_dtype.itemsize
 
-    # ---- correctness of what was timed: reads land on their true locus ----
+    # ---- correctness of what was timed ----
     res = bm.results()
-    acc = _accuracy(res, wl["truth"], wl["contig_len"], rank * args.reads)
+    acc = _accuracy(res, wl["truth"], wl["contig_len"], wl["first_counter"], wl["lo"]) if wl["truth"] is not None else None
+    sharded_check = None
+    if strong and world > 1 and rank == 0 and one_to_one:
+        # the same queries on this one GPU alone: the sharded run's final PAF must be the single-GPU PAF
+        import hashlib
+
+        full = bm.make_batch(cfg["reads"], L, first_seq_counter=0)
+        full.fill(wl["all_queries"].reshape(-1).cpu().numpy(), threads=host_threads)
+        bm.map(full)
+        kept1, paf1 = bm.one_to_one(bm.results_raw(), cfg["reads"], L)
+        full.close()
+        sharded_check = {"paf_equal_to_single_gpu": bool(paf1 == final[1]), "mappings": int(final[0]), "single_gpu_mappings": int(kept1),
+                         "paf_md5": hashlib.md5(final[1]).hexdigest()}
+        bm.map(batch)  # results() below refer to this rank's own shard again
 
     # max over ranks
     times = torch.tensor([ev_ms, wall_ms, e2e_ms], dtype=torch.float64, device=device)
     if dist is not None:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     ev_ms, wall_ms, e2e_ms = [float(x) for x in times.tolist()]
-    total_bases = n_bases * world * args.steps
+    total_bases = (cfg["reads"] * L if strong else n_bases * world) * args.steps
 
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -364,27 +497,32 @@ def gpu_arm(args):
         k1_ms = k_ms[0] / args.steps
         achieved = b1 * n_segs / (k1_ms * 1e-3) / 1e9
         traffic = roofline_traffic()
+        sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
         out = {
             "metric": "mapped query Gbp/s", "value": total_bases / (ev_ms * 1e-3) / 1e9, "unit": "Gbp/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ev_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": f"{args.reads} synthetic ONT reads x {READ_LEN} bp (err U[2%,14%]) vs {args.ref_bp / 1e9:.2f} Gbp "
-                                   f"uniform-random reference ({args.contigs} contigs), -s {SEG} --pi {int(PI * 100)}, k={K}, sketch={S} "
-                                   "(BASELINE.json configs[1])",
-                       "segments_per_step": n_segs * world, "l2_policy": "inputs (10 GB reads + index) larger than L2, no flush",
+            "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": workload_text(args, cfg, S),
+                       "segments_per_step": n_segs * world if not strong else int(cfg["reads"]) * (L // SEG + (1 if L % SEG else 0)),
+                       "l2_policy": "inputs (reads + index) larger than L2, no flush",
+                       "timing": "CUDA events on the launching stream, first kernel launch -> last kernel end, max over ranks",
                        "value_input": "reads resident in HBM as text (1 B/base); the packing kernel K0 runs inside every timed step",
                        "e2e_input": f"skch::BatchMapper's pinned batch buffer: one nibble per base, packed by the host reader at "
-                                    f"ingest ({n_bases / pack_seconds / 1e9:.1f} Gbases/s on {host_threads} threads, outside the timed region)",
-                       "timing": "CUDA events on the launching stream, first kernel launch -> last kernel end, max over ranks",
+                                    f"ingest ({n_bases / max(pack_seconds, 1e-9) / 1e9:.1f} Gbases/s on {host_threads} threads, outside the timed region)",
+                       "multi_gpu": (None if world == 1 else "one process per GPU; index image by ONE mm_index_broadcast (NCCL), reads "
+                                     "sharded by rank, mapping records by mm_records_allgather every e2e step"
+                                     + ("; run-wide one-to-one sweep + sort on rank 0" if one_to_one else "")),
                        "wall_ms_per_step": wall_ms / args.steps, "index_build_seconds": index_seconds,
                        "index": {"minmers": hi.n_minmers, "keys": hi.n_keys, "points": hi.n_points},
-                       "candidates": int(nc), "loci": int(nl), "host_threads": host_threads,
-                       "mapped_read_fraction": acc["mapped"], "true_locus_fraction": acc["correct"]},
+                       "candidates": int(nc), "loci": int(nl), "host_threads": host_threads, "rare_paths": diag,
+                       "mapped_read_fraction": None if acc is None else acc["mapped"],
+                       "true_locus_fraction": None if acc is None else acc["correct"]},
             "clocks": clocks,
             "e2e": {"value": total_bases / (e2e_ms * 1e-3) / 1e9, "unit": "Gbp/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps,
                     "stage_seconds_last_step": {"device_call": e2e_info["sec_device"], "host_tail": e2e_info["sec_tail"]},
-                    "paf_bytes_per_step": int(e2e_info["paf_bytes"]), "records_gathered_on_rank0": int(gathered)},
+                    "paf_bytes_per_step": int(len(final[1]) if final else e2e_info["paf_bytes"]), "records_gathered": int(gathered),
+                    "efficiency_note": "e2e includes the all-gather" + (" and the run-wide one-to-one sweep" if one_to_one else "")},
             "gpu_launches": int(launches),
             "kernel_ms_per_step": {"pack": k_ms[3] / args.steps, "sketch": k_ms[0] / args.steps, "l1": k_ms[1] / args.steps,
                                    "l2": k_ms[2] / args.steps},
@@ -392,41 +530,55 @@ def gpu_arm(args):
                          "frac": achieved / peak,
                          "traffic": (traffic["k_sketch_dram_bytes_per_segment"] * n_segs if "k_sketch_dram_bytes_per_segment" in traffic else None),
                          "peak_source": peak_src, "algorithmic_bytes_per_segment": b1,
-                         "instruction_roofline": _instruction_roofline(n_segs, k1_ms, clocks, torch.cuda.get_device_properties(local_rank).multi_processor_count),
+                         "instruction_roofline": _instruction_roofline(n_segs, SEG, k1_ms, clocks, sm_count),
                          "note": "bit-exact Murmur3 makes K1 INT-ALU bound (SURVEY 8(d)); see DESIGN.md for the instruction roofline"},
         }
+        if sharded_check is not None:
+            out["sharded_check"] = sharded_check
         if not args.no_cpu_baseline and world == 1:
-            cb = cpu_baseline(args, hi, argparse.Namespace(bases=ascii_reads), S, gpu_rows=res, first_counter=rank * args.reads)
+            cb = cpu_baseline(args, cfg, hi, ascii_reads, S, gpu_rows=res, first_counter=wl["first_counter"])
             out["parity"] = cb.pop("parity")  # GPU mappings of the sampled reads == the CPU port's, at bench scale
             out["cpu_baseline"] = cb
         print(json.dumps(out), flush=True)
     if dist is not None:
         dist.barrier()
+        if comm is not None:
+            comm.close()
         dist.destroy_process_group()
 
 
-K1_INSTR_PER_POSITION = 236  # executed SASS instructions per k-mer position in k_sketch's loop (scripts/sass_loops.py)
-
-
-def _instruction_roofline(n_segs, k1_ms, clocks, sm_count):
-    """K1 is bound by instruction issue, not by HBM: positions hashed per second against one instruction per cycle per
-    scheduler (4 per SM) at the SM clock sampled during the run"""
-    positions = n_segs * (SEG - K + 1)
+def _instruction_roofline(n_segs, seg, k1_ms, clocks, sm_count):
+    """K1 is bound by instruction issue, not by HBM: every k-mer position costs two bit-exact MurmurHash3_x64_128
+    evaluations. Peak = the MEASURED rate at which this GPU runs that hash alone (mashmap_b200/mm_issue_peak: mm_hash.h's
+    own device code on register-resident data, every lane busy, no memory, no selection; profiles/issue_peak.json), two
+    hashes per position. What K1 loses against it is everything that is not hashing."""
+    positions = n_segs * (seg - K + 1)
     achieved = positions / (k1_ms * 1e-3) / 1e9
     mhz = (clocks or {}).get("sm_mhz") or 1965.0
-    peak = sm_count * 4 * mhz * 1e6 * 32 / K1_INSTR_PER_POSITION / 1e9  # a warp instruction serves 32 positions
-    return {"unit": "G k-mer positions/s", "achieved": achieved, "peak": peak, "frac": achieved / peak,
-            "instructions_per_position": K1_INSTR_PER_POSITION}
+    ip = issue_peak() or {}
+    per_clk = ip.get("hash19_per_clk_per_sm")
+    if per_clk:
+        peak = per_clk * sm_count * mhz * 1e6 * 32 / 2 / 1e9
+        src = "measured: standalone Murmur3 (k=19) rate of mm_hash.h on this GPU (profiles/issue_peak.json), 2 hashes per position"
+    else:  # no measurement committed: one instruction per clock per scheduler over the loop's SASS instruction count
+        peak = sm_count * 4.0 * mhz * 1e6 * 32 / K1_INSTR_PER_POSITION / 1e9
+        src = "nominal 1 instruction / clock / scheduler (no measurement committed)"
+    return {"unit": "G k-mer positions/s", "achieved": achieved, "peak": peak, "frac": achieved / peak, "peak_source": src,
+            "loop_instructions_per_position": K1_INSTR_PER_POSITION,
+            "measured_issue_rates_per_sm_clk": {k: v for k, v in ip.items() if isinstance(v, float) and not k.startswith("hash19")} or None}
 
 
-def _accuracy(res, truth, contig_len, first_counter):
+K1_INSTR_PER_POSITION = 170  # executed SASS instructions per k-mer position in k_sketch's loop (DESIGN.md section 3, scripts/sass_loops.py)
+
+
+def _accuracy(res, truth, contig_len, first_counter, lo):
     contig_of, start_of, strand_of = truth
     if len(res) == 0:
         return {"mapped": 0.0, "correct": 0.0}
-    q = res[:, 0] - first_counter
+    q = res[:, 0] - first_counter + lo
     ok = (res[:, 3] == contig_of[q]) & (np.abs(res[:, 4].astype(np.int64) - start_of[q]) < 20_000) & (res[:, 6] == strand_of[q])
-    mapped = len(np.unique(q)) / len(contig_of)
-    return {"mapped": float(mapped), "correct": float(ok.mean())}
+    mapped = len(np.unique(q)) / max(1, len(np.unique(np.arange(lo, lo + (res[:, 0].max() - first_counter + 1)))))
+    return {"mapped": float(min(1.0, mapped)), "correct": float(ok.mean())}
 
 
 def _parity_diff(cpu_rows, gpu_rows):
@@ -450,7 +602,16 @@ def _parity_diff(cpu_rows, gpu_rows):
     return out
 
 
-def cpu_baseline(args, hi, batch, S, threads=None, n_reads=None, gpu_rows=None, first_counter=0):
+def cpu_sample_reads(args, cfg, threads):
+    """queries per CPU sample: about 15 s of wall time (the port maps ~11 Mbp per second per CPU on configs[1]), at least one
+    query per thread, at most the whole step"""
+    if args.cpu_sample_reads:
+        return min(cfg["reads"], args.cpu_sample_reads)
+    want_bases = 170_000_000 * threads
+    return int(min(cfg["reads"], max(threads, want_bases // cfg["read_len"])))
+
+
+def cpu_baseline(args, cfg, hi, ascii_reads, S, threads=None, n_reads=None, gpu_rows=None, first_counter=0):
     """The oracle port of the reference path (oracle/libmm_oracle.so, mapModule per read, one task per read on
     all host threads) on a bounded sample of the same batch, with the same index content. With gpu_rows (the
     product's mappings of the whole batch) the port's mappings of the sampled reads are diffed against them."""
@@ -458,26 +619,24 @@ def cpu_baseline(args, hi, batch, S, threads=None, n_reads=None, gpu_rows=None, 
     import oracle_py
 
     threads = threads or usable_cpus()
+    L = cfg["read_len"]
     mi, keys, offs, pts, fr = hi.arrays()
-    O = oracle_py.Oracle(K, SEG, S, PI)
+    O = oracle_py.Oracle(K, cfg["seg"], S, cfg["pi"], filterMode={"map": 1, "one-to-one": 2, "none": 3}[cfg["filt"]])
     O.set_index(mi, keys, offs, pts, fr, np.full(args.contigs, args.ref_bp // args.contigs, dtype=np.int32))
-    L = oracle_py.lib()
+    lib = oracle_py.lib()
     import ctypes as C
 
-    L.orc_map_reads_mt.restype = C.c_int64
-    L.orc_map_reads_mt.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64),
-                                   C.c_void_p, C.c_int64]
+    lib.orc_map_reads_mt.restype = C.c_int64
+    lib.orc_map_reads_mt.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64),
+                                     C.c_void_p, C.c_int64]
     mapped = C.c_int64()
-    total_reads = len(batch.bases) // READ_LEN
-    if not n_reads:
-        n_reads = args.cpu_sample_reads
-    if not n_reads:  # about 15 s of wall time: the port maps ~1,100 reads (11 Mbp) per second per CPU on this workload
-        n_reads = int(min(total_reads, 17000 * threads))
+    n_reads = n_reads or cpu_sample_reads(args, cfg, threads)
+    n_reads = min(n_reads, len(ascii_reads) // L)
+    rows = np.zeros((64 * n_reads + 4096, 10), dtype=np.int32) if gpu_rows is not None else None
     t0 = time.time()
     c0 = os.times()
-    rows = np.zeros((4 * n_reads + 16, 10), dtype=np.int32) if gpu_rows is not None else None
-    n_map = L.orc_map_reads_mt(O.h, batch.bases.ctypes.data, n_reads, READ_LEN, first_counter, threads, C.byref(mapped),
-                               rows.ctypes.data if rows is not None else None, len(rows) if rows is not None else 0)
+    n_map = lib.orc_map_reads_mt(O.h, ascii_reads.ctypes.data, n_reads, L, first_counter, threads, C.byref(mapped),
+                                 rows.ctypes.data if rows is not None else None, len(rows) if rows is not None else 0)
     dt = time.time() - t0
     c1 = os.times()
     O.close()
@@ -485,11 +644,12 @@ def cpu_baseline(args, hi, batch, S, threads=None, n_reads=None, gpu_rows=None, 
     parity = None
     if gpu_rows is not None:
         sel = (gpu_rows[:, 0] - first_counter < n_reads) if len(gpu_rows) else np.zeros(0, bool)
-        parity = {"reads": int(n_reads), **_parity_diff(rows[: min(n_map, len(rows))], gpu_rows[sel])}
-    return {"parity": parity, "value": n_reads * READ_LEN / dt / 1e9, "unit": "Gbp/s", "cores": threads, "kind": "port",
+        parity = {"reads": int(n_reads), "stage": "per-read mappings (before the run-wide one-to-one sweep)" if cfg["filt"] == "one-to-one" else "final mappings",
+                  **_parity_diff(rows[: min(n_map, len(rows))], gpu_rows[sel])}
+    return {"parity": parity, "value": n_reads * L / dt / 1e9, "unit": "Gbp/s", "cores": threads, "kind": "port",
             "cpus_busy": round(busy, 1), "host": host_cpu_info(),
-            "sample": f"first {n_reads} reads of the batch ({n_reads * READ_LEN / 1e6:.0f} Mbp), oracle/libmm_oracle.so mapModule per read "
-                      f"on {threads} threads, {dt:.1f} s; {mapped.value} reads mapped, {n_map} mappings"}
+            "sample": f"first {n_reads} queries of the step ({n_reads * L / 1e6:.0f} Mbp), oracle/libmm_oracle.so mapModule per query "
+                      f"on {threads} threads, {dt:.1f} s; {mapped.value} queries mapped, {n_map} mappings"}
 
 
 def cpu_arm(args):
@@ -498,43 +658,34 @@ def cpu_arm(args):
     oracle port of the same path (kind = "port") on the index content the product's host builder produced -- tested
     bit-identical to the reference's own index (tests/test_host_cpu.py)."""
     rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     import torch
 
-    from mashmap_b200 import hostlib
-
     device = torch.device("cuda:0") if torch.cuda.is_available() else torch.device("cpu")
     threads = usable_cpus()
-    sample = args.cpu_sample_reads or min(args.reads, 17000 * threads)  # ~15 s per step (~1,100 reads/s per CPU)
-    a2 = argparse.Namespace(**vars(args))
-    a2.reads = sample
-    wl = setup_workload(a2, 0, 1, device)
-    hi = build_index(a2, wl, threads)
+    cfg = config_of(args)
+    sample = cpu_sample_reads(args, cfg, threads)
+    if cfg["kind"] == "reads":
+        cfg["reads"] = sample  # only the sample is generated
+    wl = setup_workload(args, cfg, 0, 1, device)
+    hi = build_index(args, cfg, wl, threads)
     S = wl["sketch"]
-    bases = wl["reads_dev"].reshape(-1).cpu().numpy()
-
-    class B:
-        pass
-
-    b = B()
-    b.bases = bases
+    ascii_reads = wl["queries"].reshape(-1).cpu().numpy()
     times, last = [], None
     for i in range(args.warmup + args.steps):
-        last = cpu_baseline(a2, hi, b, S, threads=threads, n_reads=sample)
+        last = cpu_baseline(args, cfg, hi, ascii_reads, S, threads=threads, n_reads=sample)
         last.pop("parity", None)
         if i >= args.warmup:
-            times.append(sample * READ_LEN / last["value"] / 1e9)
+            times.append(sample * cfg["read_len"] / last["value"] / 1e9)
     dt = sum(times)
-    val = sample * READ_LEN * args.steps / dt / 1e9
+    val = sample * cfg["read_len"] * args.steps / dt / 1e9
     last["value"] = val
     print(json.dumps({
         "impl": "reference", "metric": "mapped query Gbp/s", "value": val, "unit": "Gbp/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": cfg["scaling"],
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": f"bounded sample: {sample} synthetic ONT reads x {READ_LEN} bp vs {args.ref_bp / 1e9:.2f} Gbp uniform-random "
-                               f"reference, -s {SEG} --pi {int(PI * 100)}, k={K}, sketch={S} (BASELINE.json configs[1])"},
+        "config": {"workload": f"bounded sample ({sample} queries per step) of: " + workload_text(args, config_of(args), S)},
         "cpu_baseline": last,
         "e2e": {"value": val, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)

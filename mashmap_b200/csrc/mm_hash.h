@@ -29,7 +29,7 @@ MM_HD uint64_t mm_rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r));
 
 /* Building blocks of the hash. On the device they are spelled in 32-bit halves: a 64x64->64 multiply by a constant is
  * one mul.wide + two mad.lo (nvcc's own expansion of `x * c` spends two extra adds per multiply), a rotate is two
- * funnel shifts, `h*5 + c` is one mad.wide + one mad.lo. The per-base loop of the sketch kernel is issue-bound, so the
+ * funnel shifts, `h*5 + c` is shift-and-add. The per-base loop of the sketch kernel is issue-bound, so the
  * instruction count is the throughput. Same results as the plain C expressions (tests/test_host_cpu.py checks the
  * host spelling against the reference's getHash, the GPU sketch tests check the device spelling). */
 #if defined(__CUDA_ARCH__)
@@ -64,17 +64,13 @@ __device__ __forceinline__ uint64_t mm_rotl(uint64_t x)
   if (R < 32) return mm_pack64(__funnelshift_l(hi, lo, R), __funnelshift_l(lo, hi, R));
   return mm_pack64(__funnelshift_l(lo, hi, R - 32), __funnelshift_l(hi, lo, R - 32));
 }
-/* x * 5 + A (A < 2^32) */
+/* x * 5 + A (A < 2^32) as (x << 2) + x + A: two LEA + two adds on the ALU pipe. The multiply form costs an IMAD.WIDE, and
+ * the 32x32->64 multiply is the one instruction of this loop that does not overlap with ALU work (measured:
+ * mashmap_b200/csrc/bench/mm_issue_peak.cu), so every one that can be avoided is worth more than its count. */
 template <uint32_t A>
 __device__ __forceinline__ uint64_t mm_mul5_add(uint64_t x)
 {
-  uint32_t xl, xh, pl, ph;
-  uint64_t p;
-  mm_unpack64(x, xl, xh);
-  asm("mad.wide.u32 %0, %1, 5, %2;" : "=l"(p) : "r"(xl), "l"((uint64_t)A));
-  mm_unpack64(p, pl, ph);
-  asm("mad.lo.u32 %0, %1, 5, %0;" : "+r"(ph) : "r"(xh));
-  return mm_pack64(pl, ph);
+  return (x << 2) + x + (uint64_t)A;
 }
 __device__ __forceinline__ uint64_t mm_xorshr33(uint64_t k)
 { /* k ^ (k >> 33): only the low half changes */

@@ -40,6 +40,9 @@ namespace {
 #define MM_SK_THREADS 128
 #endif
 constexpr int SK_THREADS = MM_SK_THREADS;
+#ifndef MM_SK_MINB
+#define MM_SK_MINB 7 /* minimum resident CTAs per SM the fast kernel is compiled for (register budget = 65536 / (MINB * threads)) */
+#endif
 constexpr int SK_BUCKETS = 256;
 constexpr uint64_t SK_EMPTY = ~0ULL;
 constexpr uint32_t SK_POOL_FWD = 0x47544341u;  /* ASCII by code: A C T G */
@@ -327,9 +330,9 @@ __device__ __forceinline__ int sk_hash_run(const sk_run &r, uint32_t &amax, cons
   int cnt = 0;
   uint32_t lofs = 0; /* cnt * SK_THREADS */
 
-  auto position = [&](const uint32_t (&fw)[NH], const uint32_t (&rw)[NH], int pos, uint32_t last_byte) {
-    const uint64_t hf = sk_hash_words<K>(fw);
-    const uint64_t hb = sk_hash_words<K>(rw);
+  /* the candidate test of one position: its two hashes were computed before (all four positions of a step are hashed
+   * first, in straight-line code, so that the eight independent Murmur3 chains overlap; the tests follow) */
+  auto consider = [&](uint64_t hf, uint64_t hb, int pos, uint32_t last_byte) {
     bool ok = pos < r.p1;
     if (CHECK_N) {
       run = last_byte ? run + 1 : 0;
@@ -355,13 +358,20 @@ __device__ __forceinline__ int sk_hash_run(const sk_run &r, uint32_t &amax, cons
 #pragma unroll 1
   for (int p = r.p0; p < r.p1; p += 4) {
     uint32_t fw[NH], rw[NH];
+    uint64_t hf0, hb0, hf1, hb1, hf2, hb2, hf3, hb3;
     /* last byte of the forward k-mer of offset d = byte K-1+d of F */
 #define SK_LASTB(d) ((F[(K - 1 + (d)) >> 2] >> (8 * ((K - 1 + (d)) & 3))) & 0xFFu)
-    sk_extract<K, 0>(F, fw); sk_extract<K, ROFF - 0>(C, rw); position(fw, rw, p + 0, CHECK_N ? SK_LASTB(0) : 1u);
-    sk_extract<K, 1>(F, fw); sk_extract<K, ROFF - 1>(C, rw); position(fw, rw, p + 1, CHECK_N ? SK_LASTB(1) : 1u);
-    sk_extract<K, 2>(F, fw); sk_extract<K, ROFF - 2>(C, rw); position(fw, rw, p + 2, CHECK_N ? SK_LASTB(2) : 1u);
-    sk_extract<K, 3>(F, fw); sk_extract<K, ROFF - 3>(C, rw); position(fw, rw, p + 3, CHECK_N ? SK_LASTB(3) : 1u);
+    const uint32_t lb0 = CHECK_N ? SK_LASTB(0) : 1u, lb1 = CHECK_N ? SK_LASTB(1) : 1u, lb2 = CHECK_N ? SK_LASTB(2) : 1u,
+                   lb3 = CHECK_N ? SK_LASTB(3) : 1u;
 #undef SK_LASTB
+    sk_extract<K, 0>(F, fw); hf0 = sk_hash_words<K>(fw); sk_extract<K, ROFF - 0>(C, rw); hb0 = sk_hash_words<K>(rw);
+    sk_extract<K, 1>(F, fw); hf1 = sk_hash_words<K>(fw); sk_extract<K, ROFF - 1>(C, rw); hb1 = sk_hash_words<K>(rw);
+    sk_extract<K, 2>(F, fw); hf2 = sk_hash_words<K>(fw); sk_extract<K, ROFF - 2>(C, rw); hb2 = sk_hash_words<K>(rw);
+    sk_extract<K, 3>(F, fw); hf3 = sk_hash_words<K>(fw); sk_extract<K, ROFF - 3>(C, rw); hb3 = sk_hash_words<K>(rw);
+    consider(hf0, hb0, p + 0, lb0);
+    consider(hf1, hb1, p + 1, lb1);
+    consider(hf2, hb2, p + 2, lb2);
+    consider(hf3, hb3, p + 3, lb3);
     /* slide by one word */
 #pragma unroll
     for (int m = 0; m < NWIN - 1; m++) F[m] = F[m + 1];
@@ -667,7 +677,7 @@ __device__ __forceinline__ void skf_bucket_prefix(const uint32_t *cnt, uint32_t 
 }
 
 template <int K>
-__global__ void __launch_bounds__(SK_THREADS)
+__global__ void __launch_bounds__(SK_THREADS, MM_SK_MINB)
 k_sketch(const uint8_t *__restrict__ packed, const mm_segment *__restrict__ segs, uint32_t n_segs, int S, int seg_length,
          int NC, int CAP, uint64_t *__restrict__ sk_hash, int2 *__restrict__ sk_pos, int8_t *__restrict__ sk_strand,
          mm_segment_result *__restrict__ seg_res, uint32_t *__restrict__ reject_list, uint32_t *__restrict__ reject_count)

@@ -73,6 +73,16 @@ def lib():
         vp = C.c_void_p
         L.skch_bm_create.argtypes = [vp, C.c_float, C.c_int, C.c_int]
         L.skch_bm_create.restype = vp
+        L.skch_bm_create_ex.argtypes = [vp, C.c_float, C.c_int, C.c_int, C.c_int, vp, C.c_int]
+        L.skch_bm_create_ex.restype = vp
+        L.skch_mapping_record_bytes.restype = C.c_uint32
+        L.skch_bm_results_raw.argtypes = [vp, vp, C.c_uint64]
+        L.skch_bm_results_raw.restype = C.c_uint64
+        L.skch_bm_one_to_one.argtypes = [vp, vp, C.c_uint64, C.c_int32, C.c_int32]
+        L.skch_bm_one_to_one.restype = C.c_uint64
+        L.skch_bm_paf_final.argtypes = [vp, C.POINTER(C.c_uint64)]
+        L.skch_bm_paf_final.restype = vp
+        L.skch_bm_device_count.argtypes = [vp]
         L.skch_bm_destroy.argtypes = [vp]
         L.skch_bm_ctx.argtypes = [vp]
         L.skch_bm_ctx.restype = vp
@@ -99,10 +109,38 @@ def lib():
 class BatchMapper:
     """skch::BatchMapper: reads in pinned host memory -> one device call -> host tail -> PAF text."""
 
-    def __init__(self, host_index, pi=0.85, device=0, threads=8):
+    FILTER_MODES = {"map": 1, "one-to-one": 2, "none": 3}
+
+    def __init__(self, host_index, pi=0.85, device=0, threads=8, filter_mode="map", devices=None):
+        """devices: several GPUs driven by this one process (skch::Map --devices); the index image is replicated with
+        one grouped NCCL broadcast and the parts of every batch are dealt to the devices round robin"""
         self.index = host_index
-        self.h = lib().skch_bm_create(host_index.h, pi, device, threads)
+        devs = np.ascontiguousarray(devices if devices else [], dtype=np.int32)
+        self.h = lib().skch_bm_create_ex(host_index.h, pi, device, threads, self.FILTER_MODES[filter_mode],
+                                         devs.ctypes.data if len(devs) else None, len(devs))
         self.ctx_handle = lib().skch_bm_ctx(self.h)
+        self.record_bytes = int(lib().skch_mapping_record_bytes())
+
+    def results_raw(self):
+        """the mappings of the last map() as raw skch::MappingResult records ([n, record_bytes] uint8): what a rank hands
+        to mm_records_allgather"""
+        n = lib().skch_bm_results_raw(self.h, None, 0)
+        out = np.zeros((max(n, 1), self.record_bytes), dtype=np.uint8)
+        lib().skch_bm_results_raw(self.h, out.ctypes.data, n)
+        return out[:n]
+
+    def one_to_one(self, records, n_queries, query_len):
+        """-f one-to-one, the run-wide step over raw records of any origin (this rank's, or all ranks' after the all-gather):
+        returns (mappings kept, PAF text)"""
+        r = np.ascontiguousarray(records, dtype=np.uint8)
+        kept = lib().skch_bm_one_to_one(self.h, r.ctypes.data, len(r), int(n_queries), int(query_len))
+        n = C.c_uint64()
+        p = lib().skch_bm_paf_final(self.h, C.byref(n))
+        return int(kept), C.string_at(p, n.value)
+
+    @property
+    def device_count(self):
+        return int(lib().skch_bm_device_count(self.h))
 
     def make_batch(self, n_reads, read_len, first_seq_counter=0):
         return ReadBatch(self, n_reads, read_len, first_seq_counter)

@@ -80,3 +80,63 @@ def simulate_reads(ref, n_reads, read_len, err_lo, err_hi, seed, chunk=16384):
         t_strand[a : a + n] = torch.where(rev, -1, 1).to(torch.int8)
         t_err[a : a + n] = err
     return out, dict(contig=t_contig, start=t_start, strand=t_strand, err=t_err)
+
+
+def mutated_genome(ref, out_len, snp, indel, n_inversions, n_translocations, seed, rows=4):
+    """A second assembly of the same genome (BASELINE config 5): every contig of `ref` with substitutions at rate `snp`
+    and short insertions / deletions at rate `indel` (half each), cut to exactly out_len bases, then `n_inversions` blocks
+    of 50-200 kb reverse-complemented in place and `n_translocations` pairs of equally long blocks swapped between
+    contigs. Returns [n_contigs, out_len] uint8 on the device."""
+    device = ref.device
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    n_contigs, contig_len = ref.shape
+    assert out_len <= contig_len - 64
+    lut = torch.tensor(_ASCII, dtype=torch.uint8, device=device)
+    comp = torch.zeros(256, dtype=torch.uint8, device=device)
+    for a, b in zip(b"ACGT", b"TGCA"):
+        comp[a] = b
+    order = torch.tensor([0, 1, 3, 2], device=device)
+    out = torch.empty((n_contigs, out_len), dtype=torch.uint8, device=device)
+    for a in range(0, n_contigs, rows):
+        src = ref[a : a + rows]
+        n, span = src.shape
+        r = torch.rand((n, span), generator=g, device=device)
+        is_sub = r < snp
+        is_ins = (r >= snp) & (r < snp + indel / 2)
+        is_del = (r >= snp + indel / 2) & (r < snp + indel)
+        idx = order[((src >> 1) & 3).long()]
+        shift = torch.randint(1, 4, (n, span), generator=g, device=device)
+        base = torch.where(is_sub, lut[(idx + shift) % 4], src)
+        counts = torch.ones((n, span), dtype=torch.int32, device=device)
+        counts[is_del] = 0
+        counts[is_ins] = 2
+        pos = torch.cumsum(counts, dim=1, dtype=torch.int64) - counts
+        buf = torch.zeros((n, out_len + 2), dtype=torch.uint8, device=device)
+        rowsx = torch.arange(n, device=device)[:, None].expand(n, span)
+        keep = (counts > 0) & (pos < out_len)
+        buf[rowsx[keep], pos[keep]] = base[keep]
+        ins_ok = is_ins & (pos + 1 < out_len)
+        ins_base = lut[torch.randint(0, 4, (n, span), generator=g, device=device)]
+        buf[rowsx[ins_ok], (pos + 1)[ins_ok]] = ins_base[ins_ok]
+        out[a : a + n] = buf[:, :out_len]
+        del r, is_sub, is_ins, is_del, idx, shift, base, counts, pos, buf, rowsx, keep, ins_ok, ins_base
+    cpu = torch.Generator()
+    cpu.manual_seed(seed + 1)
+    for _ in range(n_inversions):
+        c = int(torch.randint(0, n_contigs, (1,), generator=cpu))
+        ln = int(torch.randint(50_000, 200_001, (1,), generator=cpu))
+        if ln + 2 >= out_len:
+            continue
+        st = int(torch.randint(0, out_len - ln, (1,), generator=cpu))
+        out[c, st : st + ln] = comp[out[c, st : st + ln].flip(0).long()]
+    for _ in range(n_translocations):
+        c1, c2 = (int(x) for x in torch.randint(0, n_contigs, (2,), generator=cpu))
+        ln = int(torch.randint(50_000, 200_001, (1,), generator=cpu))
+        if ln + 2 >= out_len or c1 == c2:
+            continue
+        s1, s2 = (int(x) for x in torch.randint(0, out_len - ln, (2,), generator=cpu))
+        tmp = out[c1, s1 : s1 + ln].clone()
+        out[c1, s1 : s1 + ln] = out[c2, s2 : s2 + ln]
+        out[c2, s2 : s2 + ln] = tmp
+    return out
