@@ -58,6 +58,19 @@ struct IndexHandle {
 };
 
 /* index + frequency filter over an existing minmer list */
+/* the chunked + stitched scan (what the GPU builder does per chunk) on the host; *rescans = chunks scanned from the previous
+ * chunk's exact state instead of a warm-up */
+int64_t skch_add_minmers_chunked(const char *seq, int64_t len, int k, int w, int s, int seqId, int64_t chunk, int64_t warm,
+                                 mm_minmer *out, int64_t cap, int32_t *rescans)
+{
+  std::string buf(seq, (size_t)len);
+  std::vector<MinmerInfo> v;
+  const int r = CommonFunc::addMinmersChunked(v, &buf[0], (offset_t)len, k, w, s, seqId, (offset_t)chunk, (offset_t)warm);
+  if (rescans) *rescans = r;
+  for (size_t i = 0; i < v.size() && (int64_t)i < cap; i++) out[i] = v[i];
+  return (int64_t)v.size();
+}
+
 void *skch_index_from_minmers(const mm_minmer *mi, uint64_t n, int n_contigs, float kmer_pct_threshold)
 {
   IndexHandle *h = new IndexHandle();

@@ -19,6 +19,7 @@
 #include <unordered_set>
 
 #include "../mm_hash.h"
+#include "../mm_winmachine.h"
 #include "skch_seqio.hpp"
 
 namespace skch {
@@ -69,13 +70,6 @@ inline void normalise(char *seq, offset_t len)
   }
 }
 
-struct KmerOcc {  // base_types.hpp:139-145 (KmerInfo)
-  hash_t hash;
-  seqno_t seqId;
-  offset_t pos;
-  strand_t strand;
-};
-
 inline MinmerInfo make_mi(hash_t h, offset_t a, offset_t b, seqno_t s, strand_t st)
 {
   MinmerInfo m;
@@ -83,173 +77,177 @@ inline MinmerInfo make_mi(hash_t h, offset_t a, offset_t b, seqno_t s, strand_t 
   return m;
 }
 
+/* storage of one window machine on the host */
+struct HostMachine {
+  wm_machine m;
+  std::vector<wm_kmer> ring, heap;
+  std::vector<wm_member> mem;
+  std::vector<wm_node> nodes;
+  std::vector<wm_record> out;
+  HostMachine(int k, int w, int s, size_t out_cap)
+      : ring((size_t)wm_ring_cap(w)), heap((size_t)wm_heap_cap(w)), mem((size_t)wm_mem_cap(s)), nodes((size_t)wm_node_cap(w)), out(out_cap)
+  {
+    m.ring = ring.data(); m.ring_cap = (int32_t)ring.size();
+    m.heap = heap.data(); m.heap_cap = (int32_t)heap.size();
+    m.mem = mem.data(); m.mem_cap = (int32_t)mem.size();
+    m.nodes = nodes.data(); m.node_cap = (int32_t)nodes.size();
+    m.out = out.data(); m.out_cap = out.size();
+    wm_init(m, k, w, s);
+  }
+};
+
+/* both hashes of the k-mer at position i of the normalised sequence (commonFunc.hpp:357-363) */
+inline void kmer_hashes(const char *seq, offset_t i, int k, char *rc, uint64_t &hf, uint64_t &hb)
+{
+  hf = HostKmerHasher::murmur((const unsigned char *)seq + i, k);
+  for (int j = 0; j < k; j++) {  // reverseComplement (commonFunc.hpp:50-73)
+    char b = seq[i + j];
+    b = b == 'A' ? 'T' : b == 'C' ? 'G' : b == 'G' ? 'C' : b == 'T' ? 'A' : b;
+    rc[k - j - 1] = b;
+  }
+  hb = HostKmerHasher::murmur((const unsigned char *)rc, k);
+}
+
 }  // namespace
 
 namespace CommonFunc {
 
+/* the post-processing of addMinmers (commonFunc.hpp:522-568) on the records a window machine emitted, in emission order:
+ * malformed-record removal, strand collapse (:534), chunking to <= windowSize (:535-555), sort on (wpos, wpos_end)
+ * (:558; std::sort, as the reference: the order of exact ties is libstdc++'s), adjacent (wpos, hash) de-duplication. */
+void finishMinmers(std::vector<MinmerInfo> &out, int windowSize)
+{
+  out.erase(std::remove_if(out.begin(), out.end(),
+                           [](MinmerInfo &mi) { return mi.wpos < 0 || mi.wpos_end < 0 || mi.wpos == mi.wpos_end; }),
+            out.end());
+  std::vector<MinmerInfo> chunked;
+  for (MinmerInfo &mi : out) {
+    mi.strand = mi.strand < 0 ? strnd::REV : strnd::FWD;  // :534 (its AMBIG branch cannot be reached)
+    if (mi.wpos_end > mi.wpos + windowSize) {
+      const int n = (int)std::ceil(float(mi.wpos_end - mi.wpos) / float(windowSize));
+      for (int c = 0; c < n; c++)
+        chunked.push_back(make_mi(mi.hash, mi.wpos + c * windowSize, std::min(mi.wpos + c * windowSize + windowSize, mi.wpos_end),
+                                  mi.seqId, mi.strand));
+    }
+  }
+  out.erase(std::remove_if(out.begin(), out.end(), [windowSize](MinmerInfo &mi) { return mi.wpos_end - mi.wpos > windowSize; }),
+            out.end());
+  out.insert(out.end(), chunked.begin(), chunked.end());
+  std::sort(out.begin(), out.end(),
+            [](MinmerInfo &l, MinmerInfo &r) { return std::tie(l.wpos, l.wpos_end) < std::tie(r.wpos, r.wpos_end); });
+  out.erase(std::unique(out.begin(), out.end(),
+                        [](MinmerInfo &l, MinmerInfo &r) { return (l.wpos == r.wpos) && (l.hash == r.hash); }),
+            out.end());
+}
+
 /*
- * Sliding-window minmer intervals of one contig -- commonFunc.hpp:301-570, followed step by step:
- * the same containers (ordered map of the sketch, binary heap of waiting k-mers, deque of the window),
- * the same order of the per-base steps, the same post-processing (malformed-record removal :523-528,
- * strand collapse :534, chunking to <= windowSize :535-555, std::sort on (wpos,wpos_end) :558, adjacent
- * (wpos,hash) de-duplication :563-568). Record boundaries are L2 evaluation points, so none of the
- * reference's quirks is "fixed" here.
+ * Sliding-window minmer intervals of one contig (commonFunc.hpp:301-570) on the host: the window machine of
+ * mm_winmachine.h (the code the GPU builder runs per chunk) driven over the whole contig, then finishMinmers.
  */
 void addMinmers(std::vector<MinmerInfo> &out, char *seq, offset_t len, int kmerSize, int windowSize, int alphabetSize,
                 int sketchSize, seqno_t seqCounter)
 {
-  typedef std::pair<MinmerInfo, std::deque<KmerOcc>> Tracked;  // a sketch member and its occurrences in the window
-  std::deque<std::tuple<hash_t, strand_t, offset_t>> window;   // every valid k-mer of the current window
-  std::map<hash_t, Tracked> sketch;                            // the <= s smallest distinct hashes
-  std::vector<KmerOcc> waiting;                                // min-heap on (hash,pos) of the other k-mers
-  auto heap_after = [](const KmerOcc &a, const KmerOcc &b) { return std::tie(a.hash, a.pos) > std::tie(b.hash, b.pos); };
-
   normalise(seq, len);
+  const offset_t npos = len - kmerSize + 1;
+  if (npos <= 0) return;
+  HostMachine hm(kmerSize, windowSize, sketchSize, (size_t)npos * 2 + (size_t)sketchSize + 64);
   std::unique_ptr<char[]> rc(new char[kmerSize]);
-  int ambig = 0;
-
-  for (offset_t i = 0; i < len - kmerSize + 1; i++) {
-    const offset_t wid = i + kmerSize - windowSize;  // window that ends with this k-mer
-
-    if (waiting.size() > (size_t)(2 * windowSize)) {  // :344-354 occasional purge of expired entries
-      waiting.erase(std::remove_if(waiting.begin(), waiting.end(), [wid](KmerOcc &ki) { return ki.pos < wid; }),
-                    waiting.end());
-      std::make_heap(waiting.begin(), waiting.end(), heap_after);
-    }
-
-    const hash_t hashFwd = HostKmerHasher::murmur((const unsigned char *)seq + i, kmerSize);
-    hash_t hashBwd;
-    if (alphabetSize == 4) {
-      for (int j = 0; j < kmerSize; j++) {  // reverseComplement (commonFunc.hpp:50-73)
-        char b = seq[i + j];
-        b = b == 'A' ? 'T' : b == 'C' ? 'G' : b == 'G' ? 'C' : b == 'T' ? 'A' : b;
-        rc[kmerSize - j - 1] = b;
-      }
-      hashBwd = HostKmerHasher::murmur((const unsigned char *)rc.get(), kmerSize);
-    } else {
-      hashBwd = std::numeric_limits<hash_t>::max();
-    }
-    const hash_t cur = std::min(hashFwd, hashBwd);
-    const strand_t curStrand = hashFwd < hashBwd ? strnd::FWD : strnd::REV;
-
-    // :376-410 the k-mer that just left the window
-    if (!window.empty() && std::get<2>(window.front()) < wid) {
-      const hash_t lh = std::get<0>(window.front());
-      const strand_t ls = std::get<1>(window.front());
-      if (sketch.size() > 0 && lh <= std::prev(sketch.end())->first) {
-        Tracked &tr = sketch.find(lh)->second;
-        if (tr.second.size() == 1) {
-          tr.first.wpos_end = wid;
-          out.push_back(tr.first);
-          sketch.erase(lh);
-        } else {
-          if (tr.first.strand - ls == 0 || tr.first.strand == 0) {
-            tr.first.wpos_end = wid;
-            out.push_back(tr.first);
-            tr.first.wpos = wid;
-            tr.first.wpos_end = -1;
-          }
-          tr.first.strand -= ls;
-          tr.second.pop_front();
-        }
-      }
-      window.pop_front();
-    }
-
-    if (seq[i + kmerSize - 1] == 'N') ambig = kmerSize;
-    if (hashBwd != hashFwd && ambig == 0) {  // :417-445 the arriving k-mer
-      window.push_back(std::make_tuple(cur, curStrand, i));
-      auto it = sketch.find(cur);
-      if (it != sketch.end()) {
-        Tracked &tr = it->second;
-        tr.second.emplace_back(KmerOcc{cur, seqCounter, i, curStrand});
-        if (tr.first.strand + curStrand == 0 || tr.first.strand == 0) {
-          tr.first.wpos_end = wid;
-          out.push_back(tr.first);
-          tr.first.wpos = wid;
-          tr.first.wpos_end = -1;
-        }
-        tr.first.strand += curStrand;
-      } else {
-        waiting.emplace_back(KmerOcc{cur, seqCounter, i, curStrand});
-        std::push_heap(waiting.begin(), waiting.end(), heap_after);
-      }
-    }
-    if (ambig > 0) ambig--;
-
-    if (wid >= 0) {  // :455-505 refill the sketch from the waiting heap
-      while (!waiting.empty() && waiting.front().pos < wid) {
-        std::pop_heap(waiting.begin(), waiting.end(), heap_after);
-        waiting.pop_back();
-      }
-      if (sketch.size() > 0 && waiting.size() > 0 && sketch.size() == (size_t)sketchSize &&
-          (waiting.front().hash < std::prev(sketch.end())->first)) {
-        Tracked &largest = std::prev(sketch.end())->second;
-        largest.first.wpos_end = wid;
-        out.push_back(largest.first);
-        for (KmerOcc &km : largest.second) {
-          if (km.pos > wid) {
-            waiting.push_back(km);
-            std::push_heap(waiting.begin(), waiting.end(), heap_after);
-          }
-        }
-        sketch.erase(largest.first.hash);
-      }
-      while (!waiting.empty() && sketch.size() < (size_t)sketchSize) {
-        if (waiting.front().pos < wid) {
-          std::pop_heap(waiting.begin(), waiting.end(), heap_after);
-          waiting.pop_back();
-        }
-        // the reference reads front() even if that pop emptied the heap (:495); the vector's storage still
-        // holds the popped element there, which is what data()[0] returns
-        const KmerOcc nk = waiting.data()[0];
-        sketch[nk.hash].first = make_mi(nk.hash, wid, -1, seqCounter, 0);
-        while (!waiting.empty() && waiting.front().hash == nk.hash) {
-          sketch[nk.hash].second.push_back(waiting.front());
-          sketch[nk.hash].first.strand += waiting.front().strand;
-          std::pop_heap(waiting.begin(), waiting.end(), heap_after);
-          waiting.pop_back();
-        }
-      }
-    }
+  for (offset_t i = 0; i < npos; i++) {
+    uint64_t hf, hb;
+    kmer_hashes(seq, i, kmerSize, rc.get(), hf, hb);
+    if (alphabetSize != 4) hb = std::numeric_limits<hash_t>::max();
+    wm_step(hm.m, i, hf, hb, seq[i + kmerSize - 1] == 'N');
   }
-
-  // :508-520 close the windows still open at the end of the contig
-  uint64_t rank = 1;
-  auto iter = sketch.begin();
-  while (iter != sketch.end() && rank <= (uint64_t)sketchSize) {
-    if (iter->second.first.wpos != -1) {
-      iter->second.first.wpos_end = len - kmerSize + 1;
-      out.push_back(iter->second.first);
-    }
-    std::advance(iter, 1);
-    rank += 1;
+  wm_flush(hm.m, npos);
+  if (hm.m.fail) {
+    std::cerr << "[mashmap-b200] ERROR: window machine capacity exceeded on sequence " << seqCounter << std::endl;
+    exit(1);
   }
+  const size_t base = out.size();
+  out.reserve(base + hm.m.out_n);
+  std::vector<MinmerInfo> mine;
+  mine.reserve(hm.m.out_n);
+  for (uint64_t r = 0; r < hm.m.out_n; r++) {
+    const wm_record &x = hm.m.out[r];
+    mine.push_back(make_mi(x.hash, x.wpos, x.wpos_end, seqCounter, (strand_t)x.votes));
+  }
+  finishMinmers(mine, windowSize);
+  out.insert(out.end(), mine.begin(), mine.end());
+}
 
-  out.erase(std::remove_if(out.begin(), out.end(),
-                           [](MinmerInfo &mi) { return mi.wpos < 0 || mi.wpos_end < 0 || mi.wpos == mi.wpos_end; }),
-            out.end());
-
-  std::vector<MinmerInfo> chunked;
-  std::for_each(out.begin(), out.end(), [&chunked, windowSize](MinmerInfo &mi) {
-    mi.strand = mi.strand < 0 ? (mi.strand == 0 ? strnd::AMBIG : strnd::REV) : strnd::FWD;  // :534
-    if (mi.wpos_end > mi.wpos + windowSize) {
-      for (int chunk = 0; chunk < std::ceil(float(mi.wpos_end - mi.wpos) / float(windowSize)); chunk++) {
-        chunked.push_back(make_mi(mi.hash, mi.wpos + chunk * windowSize,
-                                  std::min(mi.wpos + chunk * windowSize + windowSize, mi.wpos_end), mi.seqId, mi.strand));
+/*
+ * The same contig cut into chunks of `chunk` positions, each scanned by its own machine that starts `warm` positions
+ * early from an empty state, and stitched exactly as the GPU builder does (mm_index_build.cu; the scanning routine wm_scan
+ * is the very code its kernel runs): a chunk's records that were open at its start take their wpos from the previous
+ * chunk's machine; a chunk whose state digest at its start differs from the previous chunk's at its end, or whose refill
+ * ever took an expired heap entry, is re-scanned from the previous machine's exact state. Exists so that the stitching
+ * logic is tested on the CPU against the unchunked scan. Returns the number of chunks that had to be re-scanned.
+ */
+template <int K>
+static int addMinmersChunkedK(std::vector<MinmerInfo> &out, const uint8_t *seq, offset_t len, int windowSize, int sketchSize,
+                              seqno_t seqCounter, offset_t chunk, offset_t warm)
+{
+  const offset_t npos = len - K + 1;
+  if (npos <= 0) return 0;
+  std::vector<MinmerInfo> mine;
+  const size_t cap = (size_t)(chunk + warm) * 2 + (size_t)sketchSize + 64;
+  std::unique_ptr<HostMachine> prev;  // the machine whose state at its end is exact
+  wm_kmer_bytes<K> prev_win, cur_win;
+  int rescans = 0;
+  for (offset_t a = 0; a < npos; a += chunk) {
+    const offset_t b = std::min<offset_t>(npos, a + chunk);
+    std::unique_ptr<HostMachine> cur(new HostMachine(K, windowSize, sketchSize, cap));
+    bool ok = true;
+    if (a > 0) {
+      const offset_t from = std::max<offset_t>(0, a - warm);
+      cur->m.emit_from = a;
+      wm_scan<K>(cur->m, cur_win, seq, from, a, true);
+      const int32_t wid = a - 1 + K - windowSize;  // the last scanned position's window id
+      ok = !cur->m.drained && !cur->m.fail && wm_digest(cur->m, wid) == wm_digest(prev->m, wid);
+      cur->m.drained = 0;
+      if (ok) {  // inherit the open records' starts
+        for (int32_t j = 0; j < cur->m.mem_n; j++) {
+          const int32_t pj = wm_find(prev->m, cur->m.mem[j].hash);
+          cur->m.mem[j].wpos = pj >= 0 ? prev->m.mem[pj].wpos : cur->m.mem[j].wpos;
+        }
       }
     }
-  });
-  out.erase(std::remove_if(out.begin(), out.end(), [windowSize](MinmerInfo &mi) { return mi.wpos_end - mi.wpos > windowSize; }),
-            out.end());
-  out.insert(out.end(), chunked.begin(), chunked.end());
+    if (ok) {
+      wm_scan<K>(cur->m, cur_win, seq, a, b, a == 0);
+      if (cur->m.drained && a > 0) ok = false;  // the warm machine's own range touched expired heap entries: not trustworthy
+    }
+    if (!ok) {  // continue the previous (exact) machine through this chunk instead
+      rescans++;
+      prev->m.out_n = 0;
+      cur = std::move(prev);
+      cur_win = prev_win;
+      wm_scan<K>(cur->m, cur_win, seq, a, b, false);
+    }
+    if (b == npos) wm_flush(cur->m, npos);
+    if (cur->m.fail) { std::cerr << "[mashmap-b200] ERROR: window machine capacity exceeded" << std::endl; exit(1); }
+    for (uint64_t r = 0; r < cur->m.out_n; r++) {
+      const wm_record &x = cur->m.out[r];
+      mine.push_back(make_mi(x.hash, x.wpos, x.wpos_end, seqCounter, (strand_t)x.votes));
+    }
+    cur->m.out_n = 0;
+    prev = std::move(cur);
+    prev_win = cur_win;
+  }
+  finishMinmers(mine, windowSize);
+  out.insert(out.end(), mine.begin(), mine.end());
+  return rescans;
+}
 
-  std::sort(out.begin(), out.end(),
-            [](MinmerInfo &l, MinmerInfo &r) { return std::tie(l.wpos, l.wpos_end) < std::tie(r.wpos, r.wpos_end); });
-
-  out.erase(std::unique(out.begin(), out.end(),
-                        [](MinmerInfo &l, MinmerInfo &r) { return (l.wpos == r.wpos) && (l.hash == r.hash); }),
-            out.end());
+int addMinmersChunked(std::vector<MinmerInfo> &out, char *seq, offset_t len, int kmerSize, int windowSize, int sketchSize,
+                      seqno_t seqCounter, offset_t chunk, offset_t warm)
+{
+  switch (kmerSize) {
+#define X(KK) case KK: return addMinmersChunkedK<KK>(out, (const uint8_t *)seq, len, windowSize, sketchSize, seqCounter, chunk, warm);
+    X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16) X(17) X(18) X(19) X(20) X(21) X(22) X(23) X(24) X(25) X(26) X(27)
+    X(28) X(29) X(30) X(31) X(32)
+#undef X
+    default: std::cerr << "[mashmap-b200] ERROR: k-mer size " << kmerSize << " is outside 8..32" << std::endl; exit(1);
+  }
 }
 
 uint64_t getReferenceSize(const std::vector<std::string> &refSequences)

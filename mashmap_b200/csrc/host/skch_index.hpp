@@ -40,6 +40,11 @@ namespace CommonFunc {
 /* commonFunc.hpp:301-570 */
 void addMinmers(std::vector<MinmerInfo> &minmerIndex, char *seq, offset_t len, int kmerSize, int windowSize,
                 int alphabetSize, int sketchSize, seqno_t seqCounter);
+/* the post-processing of addMinmers (commonFunc.hpp:522-568) over records in emission order */
+void finishMinmers(std::vector<MinmerInfo> &out, int windowSize);
+/* the chunked + stitched scan the GPU builder performs, on the host (tests): returns the number of re-scanned chunks */
+int addMinmersChunked(std::vector<MinmerInfo> &out, char *seq, offset_t len, int kmerSize, int windowSize, int sketchSize,
+                      seqno_t seqCounter, offset_t chunk, offset_t warm);
 /* commonFunc.hpp:591-603 */
 uint64_t getReferenceSize(const std::vector<std::string> &refSequences);
 }  // namespace CommonFunc

@@ -284,6 +284,21 @@ def lookup_from_minmers(minmers, n_contigs, kmer_pct_threshold=0.001):
     return out
 
 
+def add_minmers_chunked(seq, k, w, s, chunk, warm, seq_id=0):
+    """CommonFunc::addMinmersChunked: the chunked + stitched window scan of the GPU index builder, run on the host.
+    Returns (records, number of chunks that were re-scanned from the previous chunk's exact state)"""
+    b = seq.tobytes() if isinstance(seq, np.ndarray) else bytes(seq)
+    L = lib()
+    L.skch_add_minmers_chunked.restype = C.c_int64
+    L.skch_add_minmers_chunked.argtypes = [C.c_char_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64,
+                                           C.c_void_p, C.c_int64, C.POINTER(C.c_int32)]
+    cap = 2 * len(b) + 1024
+    out = np.zeros(cap, dtype=capi.minmer_dtype)
+    r = C.c_int32()
+    n = L.skch_add_minmers_chunked(b, len(b), k, w, s, seq_id, chunk, warm, out.ctypes.data, cap, C.byref(r))
+    return out[:n].copy(), int(r.value)
+
+
 def min_hits_table(sketch_size, k, pi):
     L = lib()
     return np.array([0] + [L.skch_min_hits(s, k, pi) for s in range(1, sketch_size + 1)], dtype=np.int32)

@@ -129,7 +129,10 @@ def _cases_for_index():
     low = np.frombuffer(b"ACACACACACGTGTGTGTGT" * 1500, np.uint8).copy()
     pal = np.concatenate([g[:9000], synth.revcomp(g[:9000])])
     names, panel = synth.panel_genome(3, 1, 40_000, seed=4)
-    return {"random": g, "tandem": rep, "with_n": withn, "low_complexity": low, "palindrome": pal,
+    nstart = g[:20000].copy()
+    nstart[3] = ord("N"); nstart[11] = ord("n"); nstart[17] = ord("R")  # N inside the first k-1 bases: hashed as the letter N
+    nstart[6000:6030] = ord("N")
+    return {"random": g, "tandem": rep, "with_n": withn, "n_at_start": nstart, "low_complexity": low, "palindrome": pal,
             "panel": np.concatenate(panel), "short": g[:150], "tiny": g[:19]}
 
 
@@ -142,6 +145,24 @@ def test_host_index_builder_matches_reference_addMinmers(w, s, k):
         assert len(ref) == len(got), (name, len(ref), len(got))
         for f in ("hash", "wpos", "wpos_end", "seqId", "strand"):
             assert np.array_equal(ref[f], got[f]), (name, f)
+
+
+@needs_ref
+@pytest.mark.parametrize("w,s,k,chunk,warm", [(1000, 20, 19, 3000, 2000), (5000, 130, 19, 7000, 10000), (500, 10, 16, 1000, 1000),
+                                              (2000, 64, 21, 2500, 4000), (100, 3, 19, 333, 200)])
+def test_chunked_window_scan_equals_the_whole_contig_scan(w, s, k, chunk, warm):
+    """the GPU index builder cuts a contig into chunks, scans each with its own window machine after a warm-up and
+    stitches them (inherited record starts, state digests, re-scan of chunks whose warm state cannot be trusted): same
+    records as one machine over the whole contig == the reference's addMinmers, on every kind of input"""
+    rescanned = 0
+    for name, seq in _cases_for_index().items():
+        ref = refh.add_minmers(seq, k, w, s, seq_id=3)
+        got, r = hostlib.add_minmers_chunked(seq, k, w, s, chunk, warm, seq_id=3)
+        rescanned += r
+        assert len(ref) == len(got), (name, len(ref), len(got), r)
+        for f in ("hash", "wpos", "wpos_end", "seqId", "strand"):
+            assert np.array_equal(ref[f], got[f]), (name, f, r)
+    print("chunks re-scanned from exact state:", rescanned)
 
 
 def _tail_params(R):
