@@ -306,11 +306,14 @@ int skch_bm_map(void *hv, void *bv, uint64_t *paf_bytes, uint64_t *n_mapped_read
   BmBatch *b = (BmBatch *)bv;
   const double d0 = h->bm->secondsDevice, t0 = h->bm->secondsHostTail;
   const auto tm0 = std::chrono::steady_clock::now();
-  h->bm->mapBatch(b->batch, h->results, &h->text, nullptr);
+  /* -f one-to-one: the per-read mappings are not final (the run-wide sweep follows, skch_bm_one_to_one): no text yet */
+  const bool report_now = h->ih->p.filterMode != filter::ONETOONE;
+  if (!report_now) h->text.clear();
+  h->bm->mapBatch(b->batch, h->results, report_now ? &h->text : nullptr, nullptr);
   const auto tm1 = std::chrono::steady_clock::now();
   uint64_t bytes = 0, mapped = 0, maps = 0;
   for (size_t r = 0; r < h->results.size(); r++) {
-    bytes += h->text[r].size();
+    if (report_now) bytes += h->text[r].size();
     mapped += h->results[r].empty() ? 0 : 1;
     maps += h->results[r].size();
   }
