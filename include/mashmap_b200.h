@@ -145,6 +145,33 @@ int mm_index_upload(mm_ctx *ctx,
                     const int32_t *contig_len, const int32_t *contig_name_id,
                     const int32_t *contig_group, int32_t n_contigs);
 
+/* The same index BUILT ON THE DEVICE from the reference sequence: replaces the work of skch::Sketch's constructor --
+ * build() / CommonFunc::addMinmers for every contig (winSketch.hpp:147-254, commonFunc.hpp:301-570), index() (:379-404),
+ * computeFreqHist / computeFreqSeedSet / dropFreqSeedSet (:410-453, :488-504) -- and leaves the context as
+ * mm_index_upload would (threshold tables still come from mm_tables_upload). seqs: the contigs as text, back to back
+ * (contig i = [contig_offsets[i], contig_offsets[i+1])), in host memory or (seqs_on_device != 0) in device memory.
+ * Lower case and IUPAC codes are normalised as the reference does. Records are the reference's; where its std::sort on
+ * (wpos, wpos_end) leaves exact ties in an unspecified order, this builder keeps emission order.
+ * keep_lookup != 0 keeps the flat lookup arrays on the device for mm_index_download. */
+typedef struct mm_index_stats {
+  uint64_t n_minmers;                /* minmerIndex.size() after dropFreqSeedSet                     */
+  uint64_t n_minmers_before_filter;  /* "minmer windows picked from reference" (winSketch.hpp:228)  */
+  uint64_t n_keys;                   /* "unique minmers" (:403)                                      */
+  uint64_t n_points;                 /* interval points of all keys                                  */
+  int32_t freq_threshold;            /* Sketch::getFreqThreshold(); INT32_MAX = consider all         */
+  uint32_t n_chunks, n_fixed_chunks, fix_rounds; /* window scan: chunks, chunks re-scanned exactly, rounds */
+  uint32_t hist_min_count, hist_max_count;       /* frequency histogram end points (:418-420)   */
+  uint64_t hist_min_keys, hist_max_keys;
+  float ms_scan, ms_post, ms_lookup, ms_total;
+} mm_index_stats;
+int mm_index_build(mm_ctx *ctx, const char *seqs, int seqs_on_device, const uint64_t *contig_offsets, int32_t n_contigs,
+                   const int32_t *contig_name_id, const int32_t *contig_group, float kmer_pct_threshold, int keep_lookup,
+                   mm_index_stats *stats);
+/* Host copies of the index mm_index_build left on the device, in mm_index_upload's argument formats (any pointer may be
+ * NULL; the lookup arrays need keep_lookup). Sizes: mm_index_stats. */
+int mm_index_download(mm_ctx *ctx, mm_minmer *minmer_index, uint64_t *keys, uint64_t *offsets, mm_ipoint *points,
+                      uint8_t *key_is_freq);
+
 /* sketchCutoffs (Map::setProbs, computeMap.hpp:178-258) and
  * min_hits[s] = Stat::estimateMinimumHitsRelaxed(s, k, pi, 0.95) for s in [0, n_min_hits)
  * (map_stats.hpp:144-169; the reference recomputes it per fragment, computeMap.hpp:1144). */

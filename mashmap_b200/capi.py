@@ -57,6 +57,17 @@ class MashmapError(RuntimeError):
         self.code = code
 
 
+class IndexStats(C.Structure):
+    """mm_index_stats"""
+    _fields_ = [("n_minmers", C.c_uint64), ("n_minmers_before_filter", C.c_uint64), ("n_keys", C.c_uint64), ("n_points", C.c_uint64),
+                ("freq_threshold", C.c_int32), ("n_chunks", C.c_uint32), ("n_fixed_chunks", C.c_uint32), ("fix_rounds", C.c_uint32),
+                ("hist_min_count", C.c_uint32), ("hist_max_count", C.c_uint32), ("hist_min_keys", C.c_uint64), ("hist_max_keys", C.c_uint64),
+                ("ms_scan", C.c_float), ("ms_post", C.c_float), ("ms_lookup", C.c_float), ("ms_total", C.c_float)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
 _lib = None
 
 
@@ -81,6 +92,8 @@ def lib():
         L.mm_ctx_diag.argtypes = [vp, C.POINTER(u64 * 8)]
         L.mm_index_upload.argtypes = [vp, vp, u64, vp, vp, u64, vp, u64, vp, vp, vp, vp, i32]
         L.mm_tables_upload.argtypes = [vp, vp, i32, vp, i32]
+        L.mm_index_build.argtypes = [vp, vp, C.c_int, vp, i32, vp, vp, C.c_float, C.c_int, C.POINTER(IndexStats)]
+        L.mm_index_download.argtypes = [vp, vp, vp, vp, vp, vp]
         L.mm_index_blob.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
         L.mm_index_blob_alloc.argtypes = [vp, u64, C.POINTER(vp)]
         L.mm_index_adopt_blob.argtypes = [vp]
@@ -103,7 +116,7 @@ def lib():
 
 EXPORTED_SYMBOLS = [
     "mm_ctx_create", "mm_ctx_destroy", "mm_ctx_device", "mm_last_error", "mm_kernel_launches", "mm_ctx_diag", "mm_index_upload",
-    "mm_tables_upload", "mm_index_blob", "mm_index_blob_alloc", "mm_index_adopt_blob", "mm_ctx_share_index", "mm_sketch_segments",
+    "mm_tables_upload", "mm_index_build", "mm_index_download", "mm_index_blob", "mm_index_blob_alloc", "mm_index_adopt_blob", "mm_ctx_share_index", "mm_sketch_segments",
     "mm_map_segments", "mm_map_segments_packed", "mm_batch_upload", "mm_batch_upload_packed", "mm_last_pack_ms", "mm_map_resident", "mm_batch_fetch", "mm_batch_fetch_sketch",
     "mm_last_stage_ms", "mm_ctx_set_phase_hook", "mm_host_alloc", "mm_host_free",
 ]
@@ -222,6 +235,37 @@ class Context:
         self._check(self._L.mm_index_upload(self._h, _ptr(minmers), len(minmers), _ptr(keys), _ptr(offsets), len(keys),
                                             _ptr(points), len(points), _ptr(key_is_freq), _ptr(contig_len), _ptr(cn),
                                             _ptr(cg), len(contig_len)))
+
+    def index_build(self, seqs, contig_offsets, contig_name_id=None, contig_group=None, kmer_pct_threshold=0.001, keep_lookup=False,
+                    device_ptr=None):
+        """mm_index_build: the reference index built on the device. seqs: uint8 array (contigs back to back) on the host, or
+        pass device_ptr (int) for text that is already in device memory. Returns the statistics as a dict."""
+        offs = _c(contig_offsets, np.uint64)
+        n = len(offs) - 1
+        cn = None if contig_name_id is None else _c(contig_name_id, np.int32)
+        cg = None if contig_group is None else _c(contig_group, np.int32)
+        st = IndexStats()
+        if device_ptr is not None:
+            rc = self._L.mm_index_build(self._h, C.c_void_p(int(device_ptr)), 1, _ptr(offs), n, _ptr(cn), _ptr(cg), kmer_pct_threshold,
+                                        1 if keep_lookup else 0, C.byref(st))
+        else:
+            a = np.ascontiguousarray(seqs, dtype=np.uint8)
+            rc = self._L.mm_index_build(self._h, _ptr(a), 0, _ptr(offs), n, _ptr(cn), _ptr(cg), kmer_pct_threshold,
+                                        1 if keep_lookup else 0, C.byref(st))
+        self._check(rc)
+        self._index_stats = st.as_dict()
+        return self._index_stats
+
+    def index_download(self):
+        """host copies of the device-built index (needs keep_lookup=True): (minmers, keys, offsets, points, is_freq)"""
+        st = self._index_stats
+        mi = np.zeros(st["n_minmers"], dtype=minmer_dtype)
+        keys = np.zeros(st["n_keys"], dtype=np.uint64)
+        offs = np.zeros(st["n_keys"] + 1, dtype=np.uint64)
+        pts = np.zeros(st["n_points"], dtype=ipoint_dtype)
+        fr = np.zeros(st["n_keys"], dtype=np.uint8)
+        self._check(self._L.mm_index_download(self._h, _ptr(mi), _ptr(keys), _ptr(offs), _ptr(pts), _ptr(fr)))
+        return mi, keys, offs, pts, fr
 
     def tables_upload(self, sketch_cutoffs, min_hits):
         a = _c(sketch_cutoffs, np.int32)

@@ -14,6 +14,7 @@
 #include <string>
 #include <vector>
 
+#include "mm_index_build.h"
 #include "mm_internal.h"
 #include <chrono>
 
@@ -40,6 +41,8 @@ struct mm_ctx {
   /* batch */
   uint8_t *d_bases = nullptr; uint64_t bases_cap = 0; uint64_t n_bases = 0;
   uint8_t *d_packed = nullptr; uint64_t packed_cap = 0; /* nibbles, bytes */
+  mm_built_index built{}; /* lookup arrays of an index built on the device, kept for mm_index_download (keep_lookup) */
+  bool built_kept = false;
   bool batch_is_ascii = false; /* the resident batch came in as text: K0 (pack) runs in front of K1 */
   cudaEvent_t ev_pack = nullptr;
   float pack_ms = 0;
@@ -605,6 +608,7 @@ int mm_ctx_destroy(mm_ctx *c)
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   if (c->blob && c->blob_owned) cudaFree(c->blob);
+  mm_built_index_free(&c->built);
   cudaFree(c->d_bases); cudaFree(c->d_packed); cudaFree(c->d_sk_reject); cudaFree(c->d_segs); cudaFree(c->d_sk_hash); cudaFree(c->d_sk_val); cudaFree(c->d_sk_pos); cudaFree(c->d_sk_strand);
   cudaFree(c->d_seg_res); cudaFree(c->d_cands); cudaFree(c->d_loci); cudaFree(c->d_counters); cudaFree(c->d_scratch);
   cudaFree(c->d_l1_slow); cudaFree(c->d_l2_order); cudaFree(c->d_l2_ranges); cudaFree(c->d_l2_rec_off); cudaFree(c->d_l2_recs); cudaFree(c->d_scan_tmp);
@@ -952,5 +956,186 @@ int mm_host_alloc(void **ptr, uint64_t bytes)
   return cudaHostAlloc(ptr, bytes, cudaHostAllocPortable) == cudaSuccess ? MM_OK : MM_ENOMEM; /* pinned for every device of the process */
 }
 int mm_host_free(void *ptr) { return cudaFreeHost(ptr) == cudaSuccess ? MM_OK : MM_ECUDA; }
+
+} // extern "C"
+
+namespace {
+__global__ void k_count_seq(uint64_t n, const int32_t *__restrict__ seq, unsigned long long *cnt)
+{
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) atomicAdd(&cnt[seq[i]], 1ULL);
+}
+__global__ void k_unpack_points(uint64_t n, const uint64_t *__restrict__ pts, const uint64_t *__restrict__ keys, const uint64_t *__restrict__ offs,
+                                uint64_t n_keys, mm_ipoint *out)
+{ /* packed point -> skch::IntervalPoint (the hash comes from the key whose list the point is in) */
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t lo = 0, hi = n_keys; /* last key with offs <= i */
+  while (lo + 1 < hi) { const uint64_t mid = (lo + hi) >> 1; if (offs[mid] <= i) lo = mid; else hi = mid; }
+  mm_ipoint p;
+  memset(&p, 0, sizeof p);
+  p.pos = mm_point_pos(pts[i]); p.hash = keys[lo]; p.seqId = mm_point_seq(pts[i]); p.side = mm_point_open(pts[i]) ? 1 : -1;
+  out[i] = p;
+}
+} // namespace
+
+extern "C" {
+
+/* skch::Sketch's build + index + computeFreqHist + dropFreqSeedSet on the device (mm_index_build.cu) */
+int mm_index_build(mm_ctx *c, const char *seqs, int seqs_on_device, const uint64_t *contig_offsets, int32_t n_contigs,
+                   const int32_t *contig_name_id, const int32_t *contig_group, float kmer_pct_threshold, int keep_lookup,
+                   mm_index_stats *stats)
+{
+  if (!c) return MM_EINVAL;
+  if (n_contigs < 1 || !contig_offsets || !seqs) return fail(c, MM_EINVAL, "no contigs");
+  CU(c, cudaSetDevice(c->device));
+  const auto t0 = std::chrono::steady_clock::now();
+  if (c->blob && c->blob_owned) { cudaFree(c->blob); }
+  c->blob = nullptr; c->blob_ready = false;
+  mm_built_index_free(&c->built);
+  c->built_kept = false;
+  const uint64_t total = contig_offsets[n_contigs];
+  uint8_t *d_seq = (uint8_t *)seqs;
+  uint8_t *staged = nullptr;
+  if (!seqs_on_device) {
+    CU(c, cudaMalloc((void **)&staged, total + 64));
+    CU(c, cudaMemcpyAsync(staged, seqs, total, cudaMemcpyHostToDevice, c->stream));
+    d_seq = staged;
+  }
+  mm_built_index B;
+  std::string err;
+  int rc = mm_build_index_device(c->params, d_seq, contig_offsets, n_contigs, kmer_pct_threshold, c->stream, c->sm_count, &B, err);
+  if (staged) cudaFree(staged);
+  if (rc != MM_OK) { mm_built_index_free(&B); return fail(c, rc, "index build: %s", err.c_str()); }
+  c->launches += 12;
+
+  const uint64_t n_mi = B.n_minmers, n_keys = B.n_keys, n_points = B.n_points;
+  if (n_mi >= (1ULL << 32)) { mm_built_index_free(&B); return fail(c, MM_EINVAL, "more than 2^32 minmers"); }
+  /* contig_start from the seqId column */
+  std::vector<uint64_t> cstart((size_t)n_contigs + 1, 0);
+  if (n_mi) {
+    unsigned long long *d_cnt = nullptr;
+    CU(c, cudaMalloc((void **)&d_cnt, ((size_t)n_contigs + 1) * 8));
+    CU(c, cudaMemsetAsync(d_cnt, 0, ((size_t)n_contigs + 1) * 8, c->stream));
+    k_count_seq<<<(uint32_t)((n_mi + 255) / 256), 256, 0, c->stream>>>(n_mi, B.seq, d_cnt);
+    std::vector<unsigned long long> cnt((size_t)n_contigs + 1);
+    CU(c, cudaMemcpyAsync(cnt.data(), d_cnt, ((size_t)n_contigs + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    cudaFree(d_cnt);
+    for (int32_t q = 0; q < n_contigs; q++) cstart[(size_t)q + 1] = cstart[(size_t)q] + cnt[(size_t)q];
+  }
+  int tab_log2 = 4;
+  while ((1ULL << tab_log2) < 2 * n_keys + 2) tab_log2++;
+  const uint64_t tab_slots = 1ULL << tab_log2;
+  mm_blob_header h{};
+  h.magic = MM_BLOB_MAGIC;
+  h.n_minmers = n_mi; h.n_keys = n_keys; h.n_points = n_points;
+  h.n_contigs = n_contigs; h.tab_log2 = tab_log2;
+  uint64_t o = align_up(sizeof(mm_blob_header), 256);
+  auto place = [&](uint64_t bytes) { uint64_t at = o; o = align_up(o + bytes, 256); return at; };
+  h.off_idx_hash = place((n_mi + 1) * 8);
+  h.off_idx_wpos = place((n_mi + 1) * 4);
+  h.off_idx_wend = place((n_mi + 1) * 4);
+  h.off_idx_strand = place(n_mi + 1);
+  h.off_contig_start = place(((uint64_t)n_contigs + 1) * 8);
+  h.off_idx2_hash = place((n_mi + 1) * 8);
+  h.off_idx2_wend = place((n_mi + 1) * 4);
+  h.off_tab = place(tab_slots * sizeof(mm_tab_slot));
+  h.off_pts = place((n_points + 1) * 8);
+  h.off_contig_len = place((uint64_t)n_contigs * 4);
+  h.off_contig_name_id = place((uint64_t)n_contigs * 4);
+  h.off_contig_group = place((uint64_t)n_contigs * 4);
+  h.off_cutoffs = place(TABLE_REGION_BYTES);
+  h.off_min_hits = place(TABLE_REGION_BYTES);
+  h.total_bytes = o;
+  if (cudaMalloc((void **)&c->blob, o) != cudaSuccess) { cudaGetLastError(); mm_built_index_free(&B); return fail(c, MM_ENOMEM, "cannot allocate the index image (%llu bytes)", (unsigned long long)o); }
+  c->blob_bytes = o; c->blob_owned = true; c->hdr = h; c->share_src = nullptr;
+  if (n_mi) {
+    CU(c, cudaMemcpyAsync(c->blob + h.off_idx_hash, B.hash, n_mi * 8, cudaMemcpyDeviceToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(c->blob + h.off_idx_wpos, B.wpos, n_mi * 4, cudaMemcpyDeviceToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(c->blob + h.off_idx_wend, B.wend, n_mi * 4, cudaMemcpyDeviceToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(c->blob + h.off_idx_strand, B.strand, n_mi, cudaMemcpyDeviceToDevice, c->stream));
+  }
+  CU(c, cudaMemcpyAsync(c->blob + h.off_contig_start, cstart.data(), cstart.size() * 8, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  cudaFree(B.hash); cudaFree(B.wpos); cudaFree(B.wend); cudaFree(B.seq); cudaFree(B.strand);
+  B.hash = nullptr; B.wpos = nullptr; B.wend = nullptr; B.seq = nullptr; B.strand = nullptr;
+  CU(c, mm_build_death_order((const uint64_t *)(c->blob + h.off_idx_hash), (const int32_t *)(c->blob + h.off_idx_wend),
+                             (const uint64_t *)(c->blob + h.off_contig_start), n_contigs, n_mi,
+                             (uint64_t *)(c->blob + h.off_idx2_hash), (int32_t *)(c->blob + h.off_idx2_wend), c->stream));
+  if (n_points) CU(c, cudaMemcpyAsync(c->blob + h.off_pts, B.pts, n_points * 8, cudaMemcpyDeviceToDevice, c->stream));
+  CU(c, cudaMemsetAsync(c->blob + h.off_tab, 0, tab_slots * sizeof(mm_tab_slot), c->stream));
+  if (n_keys) {
+    uint32_t *d_err = nullptr;
+    CU(c, cudaMalloc((void **)&d_err, 4));
+    CU(c, cudaMemsetAsync(d_err, 0, 4, c->stream));
+    CU(c, mm_upload_build_table(B.keys, B.offs, B.is_freq, n_keys, (mm_tab_slot *)(c->blob + h.off_tab), tab_log2, d_err, c->stream));
+    uint32_t e = 0;
+    CU(c, cudaMemcpyAsync(&e, d_err, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    cudaFree(d_err);
+    if (e) { mm_built_index_free(&B); return fail(c, MM_EINVAL, "lookup table build failed (code %u)", e); }
+  }
+  std::vector<int32_t> clen((size_t)n_contigs), tmp((size_t)n_contigs, -1);
+  for (int32_t q = 0; q < n_contigs; q++) clen[(size_t)q] = (int32_t)(contig_offsets[q + 1] - contig_offsets[q]);
+  CU(c, cudaMemcpyAsync(c->blob + h.off_contig_len, clen.data(), (size_t)n_contigs * 4, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemcpyAsync(c->blob + h.off_contig_name_id, contig_name_id ? contig_name_id : tmp.data(), (size_t)n_contigs * 4, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  std::fill(tmp.begin(), tmp.end(), 0);
+  CU(c, cudaMemcpyAsync(c->blob + h.off_contig_group, contig_group ? contig_group : tmp.data(), (size_t)n_contigs * 4, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemcpyAsync(c->blob, &c->hdr, sizeof(c->hdr), cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  resolve_index(c);
+  c->blob_ready = true;
+  if (stats) {
+    memset(stats, 0, sizeof *stats);
+    stats->n_minmers = n_mi; stats->n_minmers_before_filter = B.n_minmers_before_filter; stats->n_keys = n_keys; stats->n_points = n_points;
+    stats->freq_threshold = B.freq_threshold; stats->n_chunks = B.n_chunks; stats->n_fixed_chunks = B.n_fixed_chunks; stats->fix_rounds = B.fix_rounds;
+    stats->hist_min_count = B.hist_min_count; stats->hist_max_count = B.hist_max_count; stats->hist_min_keys = B.hist_min_keys;
+    stats->hist_max_keys = B.hist_max_keys; stats->ms_scan = B.ms_scan; stats->ms_post = B.ms_post; stats->ms_lookup = B.ms_lookup;
+    stats->ms_total = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  }
+  if (keep_lookup) { c->built = B; c->built_kept = true; }
+  else mm_built_index_free(&B);
+  return write_tables(c);
+}
+
+/* host copies of what mm_index_build left on the device (needs keep_lookup); any output may be NULL */
+int mm_index_download(mm_ctx *c, mm_minmer *mi, uint64_t *keys, uint64_t *offsets, mm_ipoint *points, uint8_t *is_freq)
+{
+  if (!c || !c->blob_ready) return fail(c, MM_ESTATE, "no index");
+  if ((keys || offsets || points || is_freq) && !c->built_kept) return fail(c, MM_ESTATE, "the lookup arrays were not kept (keep_lookup)");
+  CU(c, cudaSetDevice(c->device));
+  const mm_blob_header &h = c->hdr;
+  if (mi && h.n_minmers) {
+    const uint64_t n = h.n_minmers;
+    std::vector<uint64_t> hh(n), cs((size_t)h.n_contigs + 1);
+    std::vector<int32_t> a(n), b(n);
+    std::vector<int8_t> st(n);
+    CU(c, cudaMemcpy(hh.data(), c->blob + h.off_idx_hash, n * 8, cudaMemcpyDeviceToHost));
+    CU(c, cudaMemcpy(a.data(), c->blob + h.off_idx_wpos, n * 4, cudaMemcpyDeviceToHost));
+    CU(c, cudaMemcpy(b.data(), c->blob + h.off_idx_wend, n * 4, cudaMemcpyDeviceToHost));
+    CU(c, cudaMemcpy(st.data(), c->blob + h.off_idx_strand, n, cudaMemcpyDeviceToHost));
+    CU(c, cudaMemcpy(cs.data(), c->blob + h.off_contig_start, cs.size() * 8, cudaMemcpyDeviceToHost));
+    int32_t q = 0;
+    for (uint64_t i = 0; i < n; i++) {
+      while (i >= cs[(size_t)q + 1]) q++;
+      mi[i].hash = hh[i]; mi[i].wpos = a[i]; mi[i].wpos_end = b[i]; mi[i].seqId = q; mi[i].strand = st[i]; mi[i]._pad = 0;
+    }
+  }
+  const mm_built_index &B = c->built;
+  if (keys && B.n_keys) CU(c, cudaMemcpy(keys, B.keys, B.n_keys * 8, cudaMemcpyDeviceToHost));
+  if (offsets) CU(c, cudaMemcpy(offsets, B.offs, (B.n_keys + 1) * 8, cudaMemcpyDeviceToHost));
+  if (is_freq && B.n_keys) CU(c, cudaMemcpy(is_freq, B.is_freq, B.n_keys, cudaMemcpyDeviceToHost));
+  if (points && B.n_points) {
+    mm_ipoint *d = nullptr;
+    CU(c, cudaMalloc((void **)&d, B.n_points * sizeof(mm_ipoint)));
+    k_unpack_points<<<(uint32_t)((B.n_points + 255) / 256), 256, 0, c->stream>>>(B.n_points, (const uint64_t *)(c->blob + h.off_pts), B.keys, B.offs, B.n_keys, d);
+    CU(c, cudaMemcpyAsync(points, d, B.n_points * sizeof(mm_ipoint), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    cudaFree(d);
+  }
+  return MM_OK;
+}
 
 } // extern "C"

@@ -408,7 +408,8 @@ __global__ void k_build_table(const uint64_t *keys, const uint64_t *offs, const 
 {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_keys) return;
-  const uint64_t cnt = offs[i + 1] - offs[i];
+  uint64_t cnt = offs[i + 1] - offs[i];
+  if (is_freq[i] && cnt > MM_VAL_CNT_MASK) cnt = MM_VAL_CNT_MASK; /* a frequent seed's list is never gathered: only the flag is read */
   if (cnt == 0 || cnt > MM_VAL_CNT_MASK || offs[i] >= (1ULL << (64 - MM_VAL_OFF_SHIFT))) { atomicOr(err, 2u); return; }
   const uint64_t val = (offs[i] << MM_VAL_OFF_SHIFT) | (cnt << 1) | (is_freq[i] ? 1ULL : 0ULL);
   const uint32_t mask = (1u << tab_log2) - 1u;
