@@ -41,11 +41,17 @@ int skch_sketch_cutoffs(int sketchSize, int k, float aniDiff, float aniDiffConf,
   return (int)c.size();
 }
 
+int64_t skch_add_minmers_ex(const char *seq, int64_t len, int k, int w, int s, int seqId, mm_minmer *out, int64_t cap, int stable_ties);
 int64_t skch_add_minmers(const char *seq, int64_t len, int k, int w, int s, int seqId, mm_minmer *out, int64_t cap)
+{
+  return skch_add_minmers_ex(seq, len, k, w, s, seqId, out, cap, 0);
+}
+/* stable_ties: records with equal (wpos, wpos_end) stay in emission order (the GPU builder's order) instead of std::sort's */
+int64_t skch_add_minmers_ex(const char *seq, int64_t len, int k, int w, int s, int seqId, mm_minmer *out, int64_t cap, int stable_ties)
 {
   std::string buf(seq, (size_t)len);
   std::vector<MinmerInfo> v;
-  CommonFunc::addMinmers(v, &buf[0], (offset_t)len, k, w, 4, s, seqId);
+  CommonFunc::addMinmers(v, &buf[0], (offset_t)len, k, w, 4, s, seqId, stable_ties != 0);
   if ((int64_t)v.size() > cap) return -(int64_t)v.size();
   if (!v.empty()) memcpy(out, v.data(), v.size() * sizeof(mm_minmer));
   return (int64_t)v.size();

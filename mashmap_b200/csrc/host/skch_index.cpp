@@ -114,8 +114,9 @@ namespace CommonFunc {
 
 /* the post-processing of addMinmers (commonFunc.hpp:522-568) on the records a window machine emitted, in emission order:
  * malformed-record removal, strand collapse (:534), chunking to <= windowSize (:535-555), sort on (wpos, wpos_end)
- * (:558; std::sort, as the reference: the order of exact ties is libstdc++'s), adjacent (wpos, hash) de-duplication. */
-void finishMinmers(std::vector<MinmerInfo> &out, int windowSize)
+ * (:558; std::sort, as the reference: the order of exact ties is libstdc++'s -- or, stable_ties, emission order as the GPU
+ * builder keeps it), adjacent (wpos, hash) de-duplication. */
+void finishMinmers(std::vector<MinmerInfo> &out, int windowSize, bool stable_ties)
 {
   out.erase(std::remove_if(out.begin(), out.end(),
                            [](MinmerInfo &mi) { return mi.wpos < 0 || mi.wpos_end < 0 || mi.wpos == mi.wpos_end; }),
@@ -133,8 +134,9 @@ void finishMinmers(std::vector<MinmerInfo> &out, int windowSize)
   out.erase(std::remove_if(out.begin(), out.end(), [windowSize](MinmerInfo &mi) { return mi.wpos_end - mi.wpos > windowSize; }),
             out.end());
   out.insert(out.end(), chunked.begin(), chunked.end());
-  std::sort(out.begin(), out.end(),
-            [](MinmerInfo &l, MinmerInfo &r) { return std::tie(l.wpos, l.wpos_end) < std::tie(r.wpos, r.wpos_end); });
+  auto before = [](const MinmerInfo &l, const MinmerInfo &r) { return std::tie(l.wpos, l.wpos_end) < std::tie(r.wpos, r.wpos_end); };
+  if (stable_ties) std::stable_sort(out.begin(), out.end(), before);  // the device builder's order: exact ties stay in emission order
+  else std::sort(out.begin(), out.end(), before);                     // the reference's call; tie order is libstdc++'s
   out.erase(std::unique(out.begin(), out.end(),
                         [](MinmerInfo &l, MinmerInfo &r) { return (l.wpos == r.wpos) && (l.hash == r.hash); }),
             out.end());
@@ -145,7 +147,7 @@ void finishMinmers(std::vector<MinmerInfo> &out, int windowSize)
  * mm_winmachine.h (the code the GPU builder runs per chunk) driven over the whole contig, then finishMinmers.
  */
 void addMinmers(std::vector<MinmerInfo> &out, char *seq, offset_t len, int kmerSize, int windowSize, int alphabetSize,
-                int sketchSize, seqno_t seqCounter)
+                int sketchSize, seqno_t seqCounter, bool stable_ties)
 {
   normalise(seq, len);
   const offset_t npos = len - kmerSize + 1;
@@ -171,7 +173,7 @@ void addMinmers(std::vector<MinmerInfo> &out, char *seq, offset_t len, int kmerS
     const wm_record &x = hm.m.out[r];
     mine.push_back(make_mi(x.hash, x.wpos, x.wpos_end, seqCounter, (strand_t)x.votes));
   }
-  finishMinmers(mine, windowSize);
+  finishMinmers(mine, windowSize, stable_ties);
   out.insert(out.end(), mine.begin(), mine.end());
 }
 
@@ -233,7 +235,7 @@ static int addMinmersChunkedK(std::vector<MinmerInfo> &out, const uint8_t *seq, 
     prev = std::move(cur);
     prev_win = cur_win;
   }
-  finishMinmers(mine, windowSize);
+  finishMinmers(mine, windowSize, false);
   out.insert(out.end(), mine.begin(), mine.end());
   return rescans;
 }

@@ -39,9 +39,9 @@ template <class T> using BigVec = std::vector<T, default_init_allocator<T>>;
 namespace CommonFunc {
 /* commonFunc.hpp:301-570 */
 void addMinmers(std::vector<MinmerInfo> &minmerIndex, char *seq, offset_t len, int kmerSize, int windowSize,
-                int alphabetSize, int sketchSize, seqno_t seqCounter);
+                int alphabetSize, int sketchSize, seqno_t seqCounter, bool stable_ties = false);
 /* the post-processing of addMinmers (commonFunc.hpp:522-568) over records in emission order */
-void finishMinmers(std::vector<MinmerInfo> &out, int windowSize);
+void finishMinmers(std::vector<MinmerInfo> &out, int windowSize, bool stable_ties = false);
 /* the chunked + stitched scan the GPU builder performs, on the host (tests): returns the number of re-scanned chunks */
 int addMinmersChunked(std::vector<MinmerInfo> &out, char *seq, offset_t len, int kmerSize, int windowSize, int sketchSize,
                       seqno_t seqCounter, offset_t chunk, offset_t warm);

@@ -51,7 +51,7 @@ struct wb_chunk_out {
 struct wb_open {
   uint64_t hash;
   int32_t wpos;
-  int32_t _pad;
+  uint32_t inherited; /* the record was already open at the chunk's start: wpos is the warm-up machine's, to be resolved */
 };
 struct wb_chain {
   uint32_t first, n;     /* rejected chunks [first, first + n) */
@@ -85,7 +85,7 @@ __device__ __forceinline__ void attach(wm_machine &m, unsigned char *slab, const
 __device__ __forceinline__ void export_open(const wm_machine &m, wb_open *ex, wb_chunk_out &o)
 {
   o.n_open = (uint32_t)m.mem_n;
-  for (int32_t j = 0; j < m.mem_n; j++) { ex[j].hash = m.mem[j].hash; ex[j].wpos = m.mem[j].wpos; ex[j]._pad = 0; }
+  for (int32_t j = 0; j < m.mem_n; j++) { ex[j].hash = m.mem[j].hash; ex[j].wpos = m.mem[j].wpos; ex[j].inherited = m.mem[j].inherited; }
 }
 __device__ __forceinline__ int32_t find_open(const wb_open *ex, uint32_t n, uint64_t h)
 {
@@ -193,6 +193,29 @@ k_window_fix(const uint8_t *__restrict__ seq, const uint64_t *__restrict__ conti
     else if (m.fail) o.flags |= 1u;
     o.n_rec = (uint32_t)m.out_n;
     outs[q] = o;
+  }
+}
+
+/* A record can stay open over several chunks: an exported entry that was itself inherited takes its start from the previous
+ * chunk's (already resolved) export. Sequential along the chunks of a contig, one block per contig, cheap (s entries per chunk). */
+__global__ void k_resolve_exports(const uint32_t *__restrict__ contig_first, const uint32_t *__restrict__ contig_n, uint32_t n_used,
+                                  const wb_chunk_out *__restrict__ outs, wb_open *exports, uint32_t export_stride, uint32_t *err)
+{
+  const uint32_t c = blockIdx.x;
+  if (c >= n_used) return;
+  const uint32_t first = contig_first[c], n = contig_n[c];
+  for (uint32_t q = first + 1; q < first + n; q++) {
+    const wb_open *pv = exports + (size_t)(q - 1) * export_stride;
+    wb_open *cur = exports + (size_t)q * export_stride;
+    const uint32_t np = outs[q - 1].n_open;
+    for (uint32_t e = threadIdx.x; e < outs[q].n_open; e += blockDim.x) {
+      if (!cur[e].inherited) continue;
+      const int32_t at = find_open(pv, np, cur[e].hash);
+      if (at < 0) { atomicOr(err, 2u); continue; }
+      cur[e].wpos = pv[at].wpos;
+      cur[e].inherited = 0;
+    }
+    __syncthreads();
   }
 }
 
@@ -512,6 +535,22 @@ int mm_build_index_device(const mm_params &p, const uint8_t *d_seq, const uint64
     CE(cudaMemcpyAsync(outs.data(), d_outs, (size_t)n_chunks * sizeof(wb_chunk_out), cudaMemcpyDeviceToHost, st));
     CE(cudaStreamSynchronize(st));
 
+    /* chunks of each contig (for the sequential resolution of inherited record starts) */
+    std::vector<uint32_t> cf, cnn;
+    for (uint32_t c = 0; c < n_chunks; c++) {
+      if (c == 0 || chunks[c].contig != chunks[c - 1].contig) { cf.push_back(c); cnn.push_back(0); }
+      cnn.back()++;
+    }
+    uint32_t *d_cf = nullptr, *d_cn = nullptr, *d_err = nullptr;
+    CE(dv.alloc(d_cf, cf.size())); CE(dv.alloc(d_cn, cf.size())); CE(dv.alloc(d_err, 1));
+    CE(cudaMemcpyAsync(d_cf, cf.data(), cf.size() * 4, cudaMemcpyHostToDevice, st));
+    CE(cudaMemcpyAsync(d_cn, cnn.data(), cf.size() * 4, cudaMemcpyHostToDevice, st));
+    CE(cudaMemsetAsync(d_err, 0, 4, st));
+    auto resolve = [&]() {
+      k_resolve_exports<<<(uint32_t)cf.size(), 128, 0, st>>>(d_cf, d_cn, (uint32_t)cf.size(), d_outs, d_ex, stride, d_err);
+      return cudaGetLastError();
+    };
+
     /* ---- acceptance chain, fix-up rounds ----
      * A chunk is good if it starts a contig and ran clean, or if its predecessor is good, it ran clean (no failure, no
      * expired heap entry taken) and its state digest at its start equals its predecessor's at its end. Runs of chunks that
@@ -570,6 +609,7 @@ int mm_build_index_device(const mm_params &p, const uint8_t *d_seq, const uint64
       for (auto &cn : chains)
         for (uint32_t q = 0; q < cn.n; q++) fix_off[cn.first + q] = cn.out_offset + (uint64_t)q * fix_cap;
       fix_used += need;
+      CE(resolve()); /* the re-scan takes record starts from the exports of the chunks before the chain */
       wb_chain *d_chains = nullptr;
       CE(dv.alloc(d_chains, chains.size()));
       CE(cudaMemcpyAsync(d_chains, chains.data(), chains.size() * sizeof(wb_chain), cudaMemcpyHostToDevice, st));
@@ -593,15 +633,13 @@ int mm_build_index_device(const mm_params &p, const uint8_t *d_seq, const uint64
       if (!ok[c]) { err = "chunk stitching did not converge"; return MM_ECUDA; }
     dv.free_now(slabs);
 
-    uint32_t *d_err = nullptr;
-    CE(dv.alloc(d_err, 1));
-    CE(cudaMemsetAsync(d_err, 0, 4, st));
+    CE(resolve());
     k_patch_starts<<<n_chunks, 128, 0, st>>>(d_chunks, d_outs, n_chunks, rec, rec_cap, d_ex, stride, d_err);
     CE(cudaGetLastError());
     uint32_t h_err = 0;
     CE(cudaMemcpyAsync(&h_err, d_err, 4, cudaMemcpyDeviceToHost, st));
     CE(cudaStreamSynchronize(st));
-    if (h_err) { err = "a record open at a chunk start is missing from the previous chunk's export"; return MM_ECUDA; }
+    if (h_err) { err = "a record open at a chunk start is missing from the previous chunk's export (code " + std::to_string(h_err) + ")"; return MM_ECUDA; }
     dv.free_now(d_ex);
 
     /* ---- raw records in emission order ---- */

@@ -310,12 +310,17 @@ def sketch_cutoffs(sketch_size, k, ani_diff=0.0, ani_diff_conf=0.999, enabled=Tr
     return out[:n].copy()
 
 
-def add_minmers(seq, k, w, s, seq_id=0):
+def add_minmers(seq, k, w, s, seq_id=0, stable_ties=False):
+    """CommonFunc::addMinmers of one contig on the host. stable_ties: records with equal (wpos, wpos_end) stay in emission
+    order (what the GPU builder does) instead of the order std::sort happens to leave them in (what the reference does)"""
     b = seq.tobytes() if isinstance(seq, np.ndarray) else bytes(seq)
     cap = max(1024, 4 * (len(b) // max(1, w) + 2) * (s + 2) + 4 * len(b) // 10)
+    L = lib()
+    L.skch_add_minmers_ex.restype = C.c_int64
+    L.skch_add_minmers_ex.argtypes = [C.c_char_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int]
     while True:
         out = np.zeros(cap, dtype=capi.minmer_dtype)
-        n = lib().skch_add_minmers(b, len(b), k, w, s, seq_id, out.ctypes.data, cap)
+        n = L.skch_add_minmers_ex(b, len(b), k, w, s, seq_id, out.ctypes.data, cap, 1 if stable_ties else 0)
         if n >= 0:
             return out[:n].copy()
         cap = -n + 16
