@@ -319,22 +319,32 @@ def setup_workload(args, cfg, rank, world, device):
         torch.cuda.synchronize()
     log(f"rank {rank}: reference {args.contigs} x {contig_len} bp and {cfg['reads']} queries x {cfg['read_len']} bp generated in "
         f"{time.time() - t0:.1f} s; sketch size {S}; this rank maps queries [{lo}, {hi})")
-    ref_host = ref.cpu().numpy().reshape(-1) if rank == 0 else None
     t = None
     if truth is not None:
         t = tuple(truth[k].cpu().numpy() for k in ("contig", "start", "strand"))
     all_q = q  # strong scaling keeps the whole set on rank 0 for the single-GPU comparison
-    del ref
-    return dict(ref_host=ref_host, contig_len=contig_len, sketch=S, queries=q[lo:hi], all_queries=all_q if (strong and rank == 0) else None,
+    return dict(ref_dev=ref if rank == 0 else None, contig_len=contig_len, sketch=S, queries=q[lo:hi], all_queries=all_q if (strong and rank == 0) else None,
                 truth=t, lo=lo, hi=hi, first_counter=first_counter)
 
 
-def build_index(args, cfg, wl, threads):
+def build_index_on_device(args, cfg, wl, ctx, keep_lookup):
+    """the reference index built on the GPU from the reference text that is already in device memory (mm_index_build)"""
+    t0 = time.time()
+    offs = np.arange(args.contigs + 1, dtype=np.uint64) * np.uint64(wl["contig_len"])
+    st = ctx.index_build(None, offs, device_ptr=wl["ref_dev"].data_ptr(), keep_lookup=keep_lookup)
+    log(f"device index: {st['n_minmers']} minmers ({st['n_minmers_before_filter']} before the frequent-seed filter), {st['n_keys']} keys, "
+        f"{st['n_points']} points, freq threshold {st['freq_threshold']} in {time.time() - t0:.2f} s (window scan {st['ms_scan'] / 1e3:.2f} s over "
+        f"{st['n_chunks']} chunks, {st['n_fixed_chunks']} re-scanned; records {st['ms_post'] / 1e3:.2f} s; lookup {st['ms_lookup'] / 1e3:.2f} s)")
+    return st
+
+
+def build_index_on_host(args, cfg, wl, threads):
+    """--impl reference without a GPU: the host builder (the same window machine, one task per contig)"""
     from mashmap_b200 import hostlib
 
     t0 = time.time()
     offs = np.arange(args.contigs + 1, dtype=np.uint64) * np.uint64(wl["contig_len"])
-    hi = hostlib.HostIndex.build(wl["ref_host"], offs, K, cfg["seg"], wl["sketch"], threads=threads)
+    hi = hostlib.HostIndex.build(wl["ref_dev"].cpu().numpy().reshape(-1), offs, K, cfg["seg"], wl["sketch"], threads=threads)
     log(f"host index: {hi.n_minmers} minmers, {hi.n_keys} keys, {hi.n_points} points, freq threshold {hi.freq_threshold} "
         f"in {time.time() - t0:.1f} s ({threads} threads)")
     return hi
@@ -379,18 +389,21 @@ def gpu_arm(args):
     # ---- index: built on the host by rank 0, uploaded; other ranks receive the device image with ONE NCCL broadcast ----
     comm = mnccl.create_with_torch(dist, rank, world, local_rank) if world > 1 else None  # the product's own communicator
     t_index = time.time()
-    if rank == 0:
-        hi = build_index(args, cfg, wl, usable_cpus())
-    else:
-        hi = hostlib.HostIndex.metadata_only(args.contigs, wl["contig_len"], K, SEG, S)  # the index arrives by broadcast
+    hi = hostlib.HostIndex.metadata_only(args.contigs, wl["contig_len"], K, SEG, S)  # contig names / lengths only: the index lives on the device
     bm = hostlib.BatchMapper(hi, pi=PI, device=local_rank, threads=host_threads, filter_mode=cfg["filt"])
     ctx = capi.Context.from_handle(bm.ctx_handle, S, device=local_rank)
+    want_cpu = (not args.no_cpu_baseline) and world == 1
+    ist = None
+    if rank == 0:  # rank 0 builds the index on its GPU; the other ranks receive the image
+        ist = build_index_on_device(args, cfg, wl, ctx, keep_lookup=want_cpu)
+    host_index_arrays = ctx.index_download() if (rank == 0 and want_cpu) else None
+    wl["ref_dev"] = None
+    torch.cuda.empty_cache()
     if comm is not None:
         t0 = time.time()
         n = comm.index_broadcast(bm.ctx_handle, root=0)  # mm_index_broadcast (include/mashmap_b200_nccl.h)
         log(f"rank {rank}: index image {n / 1e9:.2f} GB received/sent in {time.time() - t0:.2f} s (includes waiting for rank 0's build)")
     index_seconds = time.time() - t_index
-    wl["ref_host"] = None
 
     # ---- the batch: pinned host copy (e2e) and device-resident copy (value) ----
     n_local = wl["hi"] - wl["lo"]
@@ -513,7 +526,9 @@ def gpu_arm(args):
                                      "sharded by rank, mapping records by mm_records_allgather every e2e step"
                                      + ("; run-wide one-to-one sweep + sort on rank 0" if one_to_one else "")),
                        "wall_ms_per_step": wall_ms / args.steps, "index_build_seconds": index_seconds,
-                       "index": {"minmers": hi.n_minmers, "keys": hi.n_keys, "points": hi.n_points},
+                       "index": {"minmers": ist["n_minmers"], "keys": ist["n_keys"], "points": ist["n_points"], "built_on": "device (mm_index_build)",
+                                 "window_scan_s": ist["ms_scan"] / 1e3, "records_s": ist["ms_post"] / 1e3, "lookup_s": ist["ms_lookup"] / 1e3,
+                                 "chunks": ist["n_chunks"], "chunks_rescanned": ist["n_fixed_chunks"]},
                        "candidates": int(nc), "loci": int(nl), "host_threads": host_threads, "rare_paths": diag,
                        "mapped_read_fraction": None if acc is None else acc["mapped"],
                        "true_locus_fraction": None if acc is None else acc["correct"]},
@@ -536,7 +551,7 @@ def gpu_arm(args):
         if sharded_check is not None:
             out["sharded_check"] = sharded_check
         if not args.no_cpu_baseline and world == 1:
-            cb = cpu_baseline(args, cfg, hi, ascii_reads, S, gpu_rows=res, first_counter=wl["first_counter"])
+            cb = cpu_baseline(args, cfg, host_index_arrays, ascii_reads, S, gpu_rows=res, first_counter=wl["first_counter"])
             out["parity"] = cb.pop("parity")  # GPU mappings of the sampled reads == the CPU port's, at bench scale
             out["cpu_baseline"] = cb
         print(json.dumps(out), flush=True)
@@ -611,7 +626,7 @@ def cpu_sample_reads(args, cfg, threads):
     return int(min(cfg["reads"], max(threads, want_bases // cfg["read_len"])))
 
 
-def cpu_baseline(args, cfg, hi, ascii_reads, S, threads=None, n_reads=None, gpu_rows=None, first_counter=0):
+def cpu_baseline(args, cfg, index_arrays, ascii_reads, S, threads=None, n_reads=None, gpu_rows=None, first_counter=0):
     """The oracle port of the reference path (oracle/libmm_oracle.so, mapModule per read, one task per read on
     all host threads) on a bounded sample of the same batch, with the same index content. With gpu_rows (the
     product's mappings of the whole batch) the port's mappings of the sampled reads are diffed against them."""
@@ -620,7 +635,7 @@ def cpu_baseline(args, cfg, hi, ascii_reads, S, threads=None, n_reads=None, gpu_
 
     threads = threads or usable_cpus()
     L = cfg["read_len"]
-    mi, keys, offs, pts, fr = hi.arrays()
+    mi, keys, offs, pts, fr = index_arrays  # host copies of the index the GPU arm maps against
     O = oracle_py.Oracle(K, cfg["seg"], S, cfg["pi"], filterMode={"map": 1, "one-to-one": 2, "none": 3}[cfg["filt"]])
     O.set_index(mi, keys, offs, pts, fr, np.full(args.contigs, args.ref_bp // args.contigs, dtype=np.int32))
     lib = oracle_py.lib()
@@ -669,12 +684,21 @@ def cpu_arm(args):
     if cfg["kind"] == "reads":
         cfg["reads"] = sample  # only the sample is generated
     wl = setup_workload(args, cfg, 0, 1, device)
-    hi = build_index(args, cfg, wl, threads)
     S = wl["sketch"]
+    if device.type == "cuda":  # the index content is the same either way (tests/test_gpu_index_build.py); the GPU builds it in seconds
+        from mashmap_b200 import capi
+
+        ctx = capi.Context(device=0, kmer_size=K, seg_length=cfg["seg"], sketch_size=S)
+        build_index_on_device(args, cfg, wl, ctx, keep_lookup=True)
+        arrays = ctx.index_download()
+        ctx.close()
+    else:
+        arrays = build_index_on_host(args, cfg, wl, threads).arrays()
+    wl["ref_dev"] = None
     ascii_reads = wl["queries"].reshape(-1).cpu().numpy()
     times, last = [], None
     for i in range(args.warmup + args.steps):
-        last = cpu_baseline(args, cfg, hi, ascii_reads, S, threads=threads, n_reads=sample)
+        last = cpu_baseline(args, cfg, arrays, ascii_reads, S, threads=threads, n_reads=sample)
         last.pop("parity", None)
         if i >= args.warmup:
             times.append(sample * cfg["read_len"] / last["value"] / 1e9)

@@ -32,7 +32,7 @@ const OptDef kOptions[] = {
     {"sparsifyMappings", "x", true}, {"filter_mode", "f", true}, {"noMerge", "M", false}, {"legacy", nullptr, false},
     {"reportPercentage", nullptr, false},
     // B200-specific
-    {"device", nullptr, true}, {"devices", nullptr, true}, {"batchBases", nullptr, true}, {"subBatchBases", nullptr, true},
+    {"device", nullptr, true}, {"devices", nullptr, true}, {"hostIndex", nullptr, false}, {"batchBases", nullptr, true}, {"subBatchBases", nullptr, true},
 };
 
 [[noreturn]] void usage_error(const std::string &msg)
@@ -233,6 +233,7 @@ void parseandSave(int argc, char **argv, Parameters &parameters)
   parameters.outFileName = found("output") ? opt["output"] : "mashmap.out";
   parameters.legacy_output = found("legacy");
   parameters.report_ANI_percentage = found("reportPercentage");
+  parameters.host_index = found("hostIndex");
   if (found("device")) parameters.device = to<int>(opt["device"]);
   if (found("devices")) {  // "0-7", "0,2,5", "1": the GPUs this process drives; reads are sharded across them by batch parts
     parameters.devices.clear();

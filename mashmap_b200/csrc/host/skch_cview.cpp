@@ -116,6 +116,7 @@ void *skch_index_from_cli(int argc, const char **argv)
   std::vector<char *> av;
   for (auto &x : store) av.push_back(&x[0]);
   parseandSave((int)av.size(), av.data(), h->p);
+  h->p.host_index = true;  /* this view exposes the host arrays of the index: built on the host (the CLI builds it on the device) */
   h->sk = new Sketch(h->p);
   return h;
 }

@@ -267,7 +267,17 @@ uint64_t getReferenceSize(const std::vector<std::string> &refSequences)
 Sketch::Sketch(const Parameters &p) : param(p)
 {
   build();
-  finish();
+  if (!deviceBuildPending()) finish();
+}
+
+Sketch::~Sketch() { free(deviceText_); }
+
+void Sketch::deviceBuildDone(int freq_threshold) const
+{
+  free(deviceText_);
+  deviceText_ = nullptr;
+  deviceTextOffsets_.clear();
+  freqThreshold = freq_threshold;
 }
 
 Sketch::Sketch(const Parameters &p, const std::vector<ContigInfo> &contigs, const std::vector<const char *> &seqs)
@@ -350,16 +360,30 @@ void Sketch::build()
       exit(1);
     }
   }
+  // the device builds the index unless the host arrays are needed (index files) or asked for
+  const bool on_device = !param.host_index && param.loadIndexFilename.empty() && param.saveIndexFilename.empty() &&
+                         param.kmerSize >= 8 && param.kmerSize <= 32;
   // contigs are read by this thread and sketched by a pool; outputs are appended in input order
   struct Task { std::string seq; seqno_t id; };
   std::vector<std::unique_ptr<Task>> tasks;
   seqno_t seqCounter = 0;
+  uint64_t textBytes = 0, textCap = 0;
+  if (on_device) deviceTextOffsets_.push_back(0);
   for (const auto &fileName : param.refSequences) {
     bool ok = seqio::for_each_seq_in_file(fileName, allowed, param.target_prefix,
                                           [&](const std::string &name, const std::string &seq) {
                                             offset_t len = seq.length();
                                             metadata.push_back(ContigInfo{name, len});
-                                            if (len >= param.kmerSize && param.loadIndexFilename.empty()) {
+                                            if (on_device) {  // every contig, also the short ones: seqId = position in metadata
+                                              if (textBytes + seq.size() + 64 > textCap) {
+                                                textCap = std::max<uint64_t>(textCap * 2, textBytes + seq.size() + (64ULL << 20));
+                                                deviceText_ = (char *)realloc(deviceText_, textCap);
+                                                if (!deviceText_) { std::cerr << "[mashmap-b200] ERROR: out of memory reading the reference" << std::endl; exit(1); }
+                                              }
+                                              memcpy(deviceText_ + textBytes, seq.data(), seq.size());
+                                              textBytes += seq.size();
+                                              deviceTextOffsets_.push_back(textBytes);
+                                            } else if (len >= param.kmerSize && param.loadIndexFilename.empty()) {
                                               tasks.emplace_back(new Task{seq, seqCounter});
                                             }
                                             seqCounter++;
@@ -370,6 +394,10 @@ void Sketch::build()
   if (seqCounter == 0) {
     std::cerr << "[mashmap-b200::skch::Sketch::build] ERROR: No sequences indexed!" << std::endl;
     exit(1);
+  }
+  if (on_device) {
+    if (!deviceText_) deviceText_ = (char *)malloc(64);  // only empty contigs: still "pending", the device reports an empty index
+    return;
   }
   if (param.loadIndexFilename.empty()) {
     std::vector<MI_Type> outputs(tasks.size());

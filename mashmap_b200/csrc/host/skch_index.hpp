@@ -54,6 +54,7 @@ class Sketch {
   typedef std::vector<MinmerInfo> MI_Type;
 
   explicit Sketch(const Parameters &p);  // winSketch.hpp:122-138: build + index + frequency filter
+  ~Sketch();
   // same pipeline on sequences already in memory (seqs[i] has metadata[i].len bases); used by bench.py
   Sketch(const Parameters &p, const std::vector<ContigInfo> &contigs, const std::vector<const char *> &seqs);
   // index + frequency filter over an existing minmer list (winSketch.hpp:379-504 without build())
@@ -72,6 +73,14 @@ class Sketch {
   BigVec<IntervalPoint> lookupPoints;
   std::vector<uint8_t> lookupKeyIsFreq;      // frequentSeeds membership per key (winSketch.hpp:488-495)
 
+  /* The index is built ON THE DEVICE by default (mm_index_build, called by skch::BatchMapper which owns the device
+   * context): the constructor then only reads the contigs; minmerIndex and the lookup arrays stay empty on the host.
+   * --hostIndex, --saveIndex and --loadIndex keep everything on the host as before. */
+  bool deviceBuildPending() const { return deviceText_ != nullptr; }
+  const char *deviceText() const { return deviceText_; }
+  const std::vector<uint64_t> &deviceTextOffsets() const { return deviceTextOffsets_; }
+  void deviceBuildDone(int freq_threshold) const;  // releases the text, records the threshold
+
   int getFreqThreshold() const { return freqThreshold; }   // winSketch.hpp:483-486
   bool isFreqSeed(hash_t h) const;                         // winSketch.hpp:506-509
   bool isMinmerIndexEnd(MI_Type::const_iterator it) const { return it == minmerIndex.end(); }
@@ -84,8 +93,10 @@ class Sketch {
 
  private:
   const Parameters &param;
-  int freqThreshold = std::numeric_limits<int>::max();
+  mutable int freqThreshold = std::numeric_limits<int>::max();
   bool saving_ = false;
+  mutable char *deviceText_ = nullptr;           // contigs back to back (text), until the device has built the index
+  mutable std::vector<uint64_t> deviceTextOffsets_;
 
   void build();
   void buildFromMemory(const std::vector<const char *> &seqs);

@@ -174,11 +174,39 @@ BatchMapper::BatchMapper(const Parameters &p, const Sketch &refsketch) : param(p
   if (rc != MM_OK) die(std::string("mm_ctx_create: ") + mm_last_error(nullptr));
   std::vector<int32_t> clen(refSketch.metadata.size());
   for (size_t i = 0; i < clen.size(); i++) clen[i] = refSketch.metadata[i].len;
-  rc = mm_index_upload(ctx, refSketch.minmerIndex.data(), refSketch.minmerIndex.size(), refSketch.lookupKeys.data(),
-                       refSketch.lookupOffsets.data(), refSketch.lookupKeys.size(), refSketch.lookupPoints.data(),
-                       refSketch.lookupPoints.size(), refSketch.lookupKeyIsFreq.data(), clen.data(), contigNameId.data(),
-                       refIdGroup.data(), (int32_t)clen.size());
-  if (rc != MM_OK) die(std::string("mm_index_upload: ") + mm_last_error(ctx));
+  if (refSketch.deviceBuildPending()) {
+    // skch::Sketch's build / index / computeFreqHist / dropFreqSeedSet on the device (mm_index_build.cu); the log lines
+    // are the reference's (winSketch.hpp:228, :403, :418-449)
+    mm_index_stats st;
+    auto t0 = Clock::now();
+    rc = mm_index_build(ctx, refSketch.deviceText(), 0, refSketch.deviceTextOffsets().data(), (int32_t)clen.size(), contigNameId.data(),
+                        refIdGroup.data(), param.kmer_pct_threshold, 0, &st);
+    if (rc != MM_OK) die(std::string("mm_index_build: ") + mm_last_error(ctx) + " (--hostIndex builds the index on the host)");
+    std::cerr << "[mashmap-b200::skch::Sketch::build] minmer windows picked from reference = " << st.n_minmers_before_filter << std::endl;
+    std::cerr << "[mashmap-b200::skch::Sketch::index] unique minmers = " << st.n_keys << std::endl;
+    if (st.n_keys) {
+      std::cerr << "[mashmap-b200::skch::Sketch::computeFreqHist] Frequency histogram of minmer interval points = (" << st.hist_min_count << ", "
+                << st.hist_min_keys << ") ... (" << st.hist_max_count << ", " << st.hist_max_keys << ")" << std::endl;
+      if (st.freq_threshold != std::numeric_limits<int>::max())
+        std::cerr << "[mashmap-b200::skch::Sketch::computeFreqHist] With threshold " << param.kmer_pct_threshold
+                  << "%, ignore minmers occurring >= " << st.freq_threshold << " times during lookup." << std::endl;
+      else
+        std::cerr << "[mashmap-b200::skch::Sketch::computeFreqHist] With threshold " << param.kmer_pct_threshold
+                  << "%, consider all minmers during lookup." << std::endl;
+    } else {
+      std::cerr << "[mashmap-b200::skch::Sketch::computeFreqHist] No minmers." << std::endl;
+    }
+    std::cerr << "[mashmap-b200::skch::Sketch] index built on the device in " << since(t0) << " s (window scan " << st.ms_scan * 1e-3
+              << " s over " << st.n_chunks << " chunks, " << st.n_fixed_chunks << " re-scanned exactly; records " << st.ms_post * 1e-3
+              << " s; lookup + frequency filter " << st.ms_lookup * 1e-3 << " s)" << std::endl;
+    refSketch.deviceBuildDone(st.freq_threshold);
+  } else {
+    rc = mm_index_upload(ctx, refSketch.minmerIndex.data(), refSketch.minmerIndex.size(), refSketch.lookupKeys.data(),
+                         refSketch.lookupOffsets.data(), refSketch.lookupKeys.size(), refSketch.lookupPoints.data(),
+                         refSketch.lookupPoints.size(), refSketch.lookupKeyIsFreq.data(), clen.data(), contigNameId.data(),
+                         refIdGroup.data(), (int32_t)clen.size());
+    if (rc != MM_OK) die(std::string("mm_index_upload: ") + mm_last_error(ctx));
+  }
   rc = mm_tables_upload(ctx, sketchCutoffs.data(), (int32_t)sketchCutoffs.size(), minHits.data(), (int32_t)minHits.size());
   if (rc != MM_OK) die(std::string("mm_tables_upload: ") + mm_last_error(ctx));
   tail_ = new MapTail(param, refSketch.metadata, refIdGroup);
