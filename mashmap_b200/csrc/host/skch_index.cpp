@@ -82,14 +82,17 @@ struct HostMachine {
   wm_machine m;
   std::vector<wm_kmer> ring, heap;
   std::vector<wm_member> mem;
+  std::vector<uint64_t> mh;
+  std::vector<uint16_t> mslot, sfree;
   std::vector<wm_node> nodes;
   std::vector<wm_record> out;
   HostMachine(int k, int w, int s, size_t out_cap)
-      : ring((size_t)wm_ring_cap(w)), heap((size_t)wm_heap_cap(w)), mem((size_t)wm_mem_cap(s)), nodes((size_t)wm_node_cap(w)), out(out_cap)
+      : ring((size_t)wm_ring_cap(w)), heap((size_t)wm_heap_cap(w)), mem((size_t)wm_mem_cap(s)), mh((size_t)wm_mem_cap(s)),
+        mslot((size_t)wm_mem_cap(s)), sfree((size_t)wm_mem_cap(s)), nodes((size_t)wm_node_cap(w)), out(out_cap)
   {
     m.ring = ring.data(); m.ring_cap = (int32_t)ring.size();
     m.heap = heap.data(); m.heap_cap = (int32_t)heap.size();
-    m.mem = mem.data(); m.mem_cap = (int32_t)mem.size();
+    m.slots = mem.data(); m.mh = mh.data(); m.mslot = mslot.data(); m.sfree = sfree.data(); m.mem_cap = (int32_t)mem.size();
     m.nodes = nodes.data(); m.node_cap = (int32_t)nodes.size();
     m.out = out.data(); m.out_cap = out.size();
     wm_init(m, k, w, s);
@@ -209,8 +212,8 @@ static int addMinmersChunkedK(std::vector<MinmerInfo> &out, const uint8_t *seq, 
       cur->m.drained = 0;
       if (ok) {  // inherit the open records' starts
         for (int32_t j = 0; j < cur->m.mem_n; j++) {
-          const int32_t pj = wm_find(prev->m, cur->m.mem[j].hash);
-          cur->m.mem[j].wpos = pj >= 0 ? prev->m.mem[pj].wpos : cur->m.mem[j].wpos;
+          const int32_t pj = wm_find(prev->m, cur->m.mh[j]);
+          if (pj >= 0) wm_at(cur->m, j).wpos = wm_at(prev->m, pj).wpos;
         }
       }
     }

@@ -59,7 +59,7 @@ struct wb_chain {
 };
 
 struct wb_slab_layout {
-  size_t off_ring, off_heap, off_nodes, off_mem, bytes;
+  size_t off_ring, off_heap, off_nodes, off_mem, off_mh, off_mslot, off_sfree, bytes;
   int32_t ring_cap, heap_cap, node_cap, mem_cap;
 };
 wb_slab_layout slab_layout(int w, int s)
@@ -72,6 +72,9 @@ wb_slab_layout slab_layout(int w, int s)
   L.off_nodes = o; o += (size_t)L.node_cap * sizeof(wm_node);
   o = (o + 15) & ~(size_t)15;
   L.off_mem = o; o += (size_t)L.mem_cap * sizeof(wm_member);
+  L.off_mh = o; o += (size_t)L.mem_cap * 8;
+  L.off_mslot = o; o += (size_t)L.mem_cap * 2;
+  L.off_sfree = o; o += (size_t)L.mem_cap * 2;
   L.bytes = (o + 255) & ~(size_t)255;
   return L;
 }
@@ -80,12 +83,13 @@ __device__ __forceinline__ void attach(wm_machine &m, unsigned char *slab, const
   m.ring = (wm_kmer *)(slab + L.off_ring); m.ring_cap = L.ring_cap;
   m.heap = (wm_kmer *)(slab + L.off_heap); m.heap_cap = L.heap_cap;
   m.nodes = (wm_node *)(slab + L.off_nodes); m.node_cap = L.node_cap;
-  m.mem = (wm_member *)(slab + L.off_mem); m.mem_cap = L.mem_cap;
+  m.slots = (wm_member *)(slab + L.off_mem); m.mem_cap = L.mem_cap;
+  m.mh = (uint64_t *)(slab + L.off_mh); m.mslot = (uint16_t *)(slab + L.off_mslot); m.sfree = (uint16_t *)(slab + L.off_sfree);
 }
 __device__ __forceinline__ void export_open(const wm_machine &m, wb_open *ex, wb_chunk_out &o)
 {
   o.n_open = (uint32_t)m.mem_n;
-  for (int32_t j = 0; j < m.mem_n; j++) { ex[j].hash = m.mem[j].hash; ex[j].wpos = m.mem[j].wpos; ex[j].inherited = m.mem[j].inherited; }
+  for (int32_t j = 0; j < m.mem_n; j++) { const wm_member &e = wm_at(m, j); ex[j].hash = e.hash; ex[j].wpos = e.wpos; ex[j].inherited = e.inherited; }
 }
 __device__ __forceinline__ int32_t find_open(const wb_open *ex, uint32_t n, uint64_t h)
 {
@@ -123,7 +127,7 @@ k_window_scan(const uint8_t *__restrict__ seq, const uint64_t *__restrict__ cont
       o.d_start = wm_digest(m, ch.a - 1 + K - w);
       if (m.drained) o.flags |= 4u;
       m.drained = 0;
-      for (int32_t j = 0; j < m.mem_n; j++) m.mem[j].inherited = 1; /* their records started before a */
+      for (int32_t j = 0; j < m.mem_n; j++) wm_at(m, j).inherited = 1; /* their records started before a */
       wm_scan<K>(m, win, base, ch.a, ch.b, false);
     } else {
       wm_scan<K>(m, win, base, 0, ch.b, true);
@@ -168,8 +172,8 @@ k_window_fix(const uint8_t *__restrict__ seq, const uint64_t *__restrict__ conti
       const wb_open *ex = exports + (size_t)(cn.first - 2) * export_stride;
       const uint32_t nx = outs[cn.first - 2].n_open;
       for (int32_t j = 0; j < m.mem_n; j++) {
-        const int32_t at = find_open(ex, nx, m.mem[j].hash);
-        if (at >= 0) m.mem[j].wpos = ex[at].wpos;
+        const int32_t at = find_open(ex, nx, m.mh[j]);
+        if (at >= 0) wm_at(m, j).wpos = ex[at].wpos;
       }
       wm_scan<K>(m, win, base, pv.a, pv.b, false);
     } else {
@@ -512,7 +516,9 @@ int mm_build_index_device(const mm_params &p, const uint8_t *d_seq, const uint64
     CE(dv.alloc(d_chunks, n_chunks));
     CE(cudaMemcpyAsync(d_chunks, chunks.data(), (size_t)n_chunks * sizeof(wb_chunk), cudaMemcpyHostToDevice, st));
     const wb_slab_layout L = slab_layout(w, s);
-    uint32_t threads = (uint32_t)sm_count * 128;
+    int tpsm = 128; /* machines per SM: the scan is latency-bound (dependent accesses to a per-thread slab), more threads hide more */
+    if (const char *e = getenv("MM_INDEX_TPSM")) tpsm = std::max(128, atoi(e) / 128 * 128);
+    uint32_t threads = (uint32_t)sm_count * (uint32_t)tpsm;
     if (threads > n_chunks) threads = (n_chunks + 127) / 128 * 128;
     const uint32_t grid = threads / 128;
     unsigned char *slabs = nullptr;

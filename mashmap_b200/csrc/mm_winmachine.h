@@ -58,7 +58,10 @@ struct wm_machine {
   int32_t k, w, s;
   /* storage (caller-provided) */
   wm_kmer *ring; int32_t ring_cap, ring_head, ring_n;
-  wm_member *mem; int32_t mem_n, mem_cap;
+  /* the members: hashes ascending in mh[], mslot[i] = payload slot of the i-th smallest (the payloads stay where they are:
+   * a member entering or leaving the sketch moves 10 bytes per larger member, not a whole record) */
+  uint64_t *mh; uint16_t *mslot; wm_member *slots; uint16_t *sfree; int32_t sfree_n;
+  int32_t mem_n, mem_cap;
   wm_node *nodes; int32_t node_cap, node_free;
   wm_kmer *heap; int32_t heap_n, heap_cap;
   wm_record *out; uint64_t out_n, out_cap;
@@ -125,20 +128,22 @@ WM_HD void wm_heap_purge(wm_machine &m, int32_t wid)
   }
 }
 
+/* the i-th smallest member */
+WM_HD wm_member &wm_at(const wm_machine &m, int32_t i) { return m.slots[m.mslot[i]]; }
 /* index of the first member with hash >= h */
 WM_HD int32_t wm_lower_bound(const wm_machine &m, uint64_t h)
 {
   int32_t lo = 0, hi = m.mem_n;
   while (lo < hi) {
     const int32_t mid = (lo + hi) >> 1;
-    if (m.mem[mid].hash < h) lo = mid + 1; else hi = mid;
+    if (m.mh[mid] < h) lo = mid + 1; else hi = mid;
   }
   return lo;
 }
 WM_HD int32_t wm_find(const wm_machine &m, uint64_t h)
 {
   const int32_t i = wm_lower_bound(m, h);
-  return (i < m.mem_n && m.mem[i].hash == h) ? i : -1;
+  return (i < m.mem_n && m.mh[i] == h) ? i : -1;
 }
 WM_HD void wm_list_push_back(wm_machine &m, wm_member &e, int32_t pos, int32_t strand)
 {
@@ -165,18 +170,21 @@ WM_HD void wm_list_free(wm_machine &m, wm_member &e)
 }
 WM_HD void wm_erase_member(wm_machine &m, int32_t idx)
 {
-  wm_list_free(m, m.mem[idx]);
-  for (int32_t i = idx; i + 1 < m.mem_n; i++) m.mem[i] = m.mem[i + 1];
+  wm_list_free(m, wm_at(m, idx));
+  m.sfree[m.sfree_n++] = m.mslot[idx];
+  for (int32_t i = idx; i + 1 < m.mem_n; i++) { m.mh[i] = m.mh[i + 1]; m.mslot[i] = m.mslot[i + 1]; }
   m.mem_n--;
 }
 /* a new member at its place in hash order; returns its index (or -1) */
 WM_HD int32_t wm_insert_member(wm_machine &m, uint64_t h)
 {
-  if (m.mem_n >= m.mem_cap) { m.fail = 1; return -1; }
+  if (m.mem_n >= m.mem_cap || m.sfree_n <= 0) { m.fail = 1; return -1; }
   const int32_t at = wm_lower_bound(m, h);
-  for (int32_t i = m.mem_n; i > at; i--) m.mem[i] = m.mem[i - 1];
+  for (int32_t i = m.mem_n; i > at; i--) { m.mh[i] = m.mh[i - 1]; m.mslot[i] = m.mslot[i - 1]; }
   m.mem_n++;
-  wm_member &e = m.mem[at];
+  m.mh[at] = h;
+  m.mslot[at] = m.sfree[--m.sfree_n];
+  wm_member &e = wm_at(m, at);
   e.hash = h; e.wpos = -1; e.votes = 0; e.head = -1; e.tail = -1; e.count = 0; e.inherited = 0;
   return at;
 }
@@ -197,6 +205,8 @@ WM_HD void wm_init(wm_machine &m, int32_t k, int32_t w, int32_t s)
   m.k = k; m.w = w; m.s = s;
   m.ring_head = 0; m.ring_n = 0; m.mem_n = 0; m.heap_n = 0; m.out_n = 0; m.ambig = 0; m.emit_from = 0;
   m.fail = 0; m.drained = 0;
+  for (int32_t i = 0; i < m.mem_cap; i++) m.sfree[i] = (uint16_t)(m.mem_cap - 1 - i);
+  m.sfree_n = m.mem_cap;
   for (int32_t i = 0; i < m.node_cap; i++) m.nodes[i].next = i + 1 < m.node_cap ? i + 1 : -1;
   m.node_free = m.node_cap > 0 ? 0 : -1;
   if (m.heap_cap > 0) { m.heap[0].hash = 0; m.heap[0].pos = 0; m.heap[0].strand = 0; }
@@ -224,12 +234,12 @@ WM_HD void wm_step(wm_machine &m, int32_t i, uint64_t hash_fwd, uint64_t hash_bw
   if (m.ring_n > 0 && m.ring[m.ring_head].pos < wid) {
     const uint64_t lh = m.ring[m.ring_head].hash;
     const int32_t ls = m.ring[m.ring_head].strand;
-    if (m.mem_n > 0 && lh <= m.mem[m.mem_n - 1].hash) {
+    if (m.mem_n > 0 && lh <= m.mh[m.mem_n - 1]) {
       const int32_t idx = wm_find(m, lh);
       if (idx < 0) {
         m.fail = 1; /* the reference dereferences end() here */
       } else {
-        wm_member &e = m.mem[idx];
+        wm_member &e = wm_at(m, idx);
         if (e.count == 1) {
           wm_emit(m, e, wid, i);
           wm_erase_member(m, idx);
@@ -258,7 +268,7 @@ WM_HD void wm_step(wm_machine &m, int32_t i, uint64_t hash_fwd, uint64_t hash_bw
     }
     const int32_t idx = wm_find(m, cur);
     if (idx >= 0) {
-      wm_member &e = m.mem[idx];
+      wm_member &e = wm_at(m, idx);
       wm_list_push_back(m, e, i, cur_strand);
       if (e.votes + cur_strand == 0 || e.votes == 0) {
         wm_emit(m, e, wid, i);
@@ -274,8 +284,8 @@ WM_HD void wm_step(wm_machine &m, int32_t i, uint64_t hash_fwd, uint64_t hash_bw
 
   if (wid >= 0) { /* refill from the waiting heap (:455-505) */
     while (m.heap_n > 0 && m.heap[0].pos < wid) wm_heap_pop(m);
-    if (m.mem_n > 0 && m.heap_n > 0 && m.mem_n == m.s && m.heap[0].hash < m.mem[m.mem_n - 1].hash) {
-      wm_member &big = m.mem[m.mem_n - 1];
+    if (m.mem_n > 0 && m.heap_n > 0 && m.mem_n == m.s && m.heap[0].hash < m.mh[m.mem_n - 1]) {
+      wm_member &big = wm_at(m, m.mem_n - 1);
       wm_emit(m, big, wid, i);
       for (int32_t n = big.head, c = 0; c < big.count; c++, n = m.nodes[n].next) {
         if (m.nodes[n].pos > wid) { /* `>`: an occurrence at the window start is dropped (:478) */
@@ -296,11 +306,11 @@ WM_HD void wm_step(wm_machine &m, int32_t i, uint64_t hash_fwd, uint64_t hash_bw
       if (idx < 0) idx = wm_insert_member(m, nk.hash);
       if (idx < 0) break;
       { /* sortedWindow[h].first = MinmerInfo{h, wid, -1, seq, 0}: resets an existing member's record, keeps its list */
-        wm_member &e = m.mem[idx];
+        wm_member &e = wm_at(m, idx);
         e.wpos = wid; e.votes = 0; e.inherited = 0;
       }
       while (m.heap_n > 0 && m.heap[0].hash == nk.hash) {
-        wm_member &e = m.mem[idx];
+        wm_member &e = wm_at(m, idx);
         wm_list_push_back(m, e, m.heap[0].pos, m.heap[0].strand);
         e.votes += m.heap[0].strand;
         wm_heap_pop(m);
@@ -313,7 +323,7 @@ WM_HD void wm_step(wm_machine &m, int32_t i, uint64_t hash_fwd, uint64_t hash_bw
 WM_HD void wm_flush(wm_machine &m, int32_t n_positions)
 {
   for (int32_t i = 0; i < m.mem_n && i < m.s; i++) {
-    wm_member &e = m.mem[i];
+    wm_member &e = wm_at(m, i);
     if (e.wpos != -1) wm_emit(m, e, n_positions, n_positions);
   }
 }
@@ -335,7 +345,7 @@ WM_HD uint64_t wm_digest(const wm_machine &m, int32_t wid)
     d += wm_mix(m.ring[at].hash ^ wm_mix(((uint64_t)(uint32_t)m.ring[at].pos << 2) | (uint64_t)(m.ring[at].strand & 3)));
   }
   for (int32_t j = 0; j < m.mem_n; j++) {
-    const wm_member &e = m.mem[j];
+    const wm_member &e = wm_at(m, j);
     uint64_t x = wm_mix(e.hash + 0x9e3779b97f4a7c15ULL) ^ wm_mix(((uint64_t)(uint32_t)e.votes << 32) | (uint32_t)e.count) ^ (e.wpos == -1 ? 77 : 0);
     uint64_t seq = 0;
     for (int32_t n = e.head, c = 0; c < e.count; c++, n = m.nodes[n].next)
