@@ -492,7 +492,7 @@ int mm_build_index_device(const mm_params &p, const uint8_t *d_seq, const uint64
 
   /* ---- chunks ---- */
   const int warm = w + 2 * K + 64;
-  int chunk_len = 49152;
+  int chunk_len = 16384;
   if (const char *e = getenv("MM_INDEX_CHUNK")) chunk_len = std::max(1024, atoi(e)); /* tests: small chunks */
   std::vector<wb_chunk> chunks;
   for (int32_t c = 0; c < n_contigs; c++) {
@@ -516,7 +516,7 @@ int mm_build_index_device(const mm_params &p, const uint8_t *d_seq, const uint64
     CE(dv.alloc(d_chunks, n_chunks));
     CE(cudaMemcpyAsync(d_chunks, chunks.data(), (size_t)n_chunks * sizeof(wb_chunk), cudaMemcpyHostToDevice, st));
     const wb_slab_layout L = slab_layout(w, s);
-    int tpsm = 128; /* machines per SM: the scan is latency-bound (dependent accesses to a per-thread slab), more threads hide more */
+    int tpsm = 768; /* machines per SM: the scan is latency-bound (dependent accesses to a per-thread slab), more threads hide more */
     if (const char *e = getenv("MM_INDEX_TPSM")) tpsm = std::max(128, atoi(e) / 128 * 128);
     uint32_t threads = (uint32_t)sm_count * (uint32_t)tpsm;
     if (threads > n_chunks) threads = (n_chunks + 127) / 128 * 128;

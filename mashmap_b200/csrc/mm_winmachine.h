@@ -214,8 +214,8 @@ WM_HD void wm_init(wm_machine &m, int32_t k, int32_t w, int32_t s)
 
 /* capacities a slab must provide for (w, s) */
 WM_HD int32_t wm_ring_cap(int32_t w) { return w + 8; }
-WM_HD int32_t wm_node_cap(int32_t w) { return 2 * w + 64; }
-WM_HD int32_t wm_heap_cap(int32_t w) { return 4 * w + 64; }
+WM_HD int32_t wm_node_cap(int32_t w) { return w + w / 2 + 64; } /* occurrences of members: at most the window, plus stale ones */
+WM_HD int32_t wm_heap_cap(int32_t w) { return 3 * w + 64; }      /* purged past 2w (:344); a position adds at most a few entries */
 WM_HD int32_t wm_mem_cap(int32_t s) { return s + 4; }
 
 /*
@@ -266,7 +266,8 @@ WM_HD void wm_step(wm_machine &m, int32_t i, uint64_t hash_fwd, uint64_t hash_bw
       m.ring[at].hash = cur; m.ring[at].pos = i; m.ring[at].strand = cur_strand;
       m.ring_n++;
     }
-    const int32_t idx = wm_find(m, cur);
+    /* a hash above the largest member cannot be one (19 of 20 arrivals on ordinary sequence): no search */
+    const int32_t idx = (m.mem_n > 0 && cur <= m.mh[m.mem_n - 1]) ? wm_find(m, cur) : -1;
     if (idx >= 0) {
       wm_member &e = wm_at(m, idx);
       wm_list_push_back(m, e, i, cur_strand);
