@@ -454,21 +454,33 @@ def gpu_arm(args):
     # ---- e2e: host buffers -> C ABI -> records -> host tail -> (all-gather, one-to-one sweep) -> PAF text ----
     n_q_global = cfg["reads"] if strong else cfg["reads"] * world
 
+    e2e_parts = {"map_s": 0.0, "records_s": 0.0, "allgather_s": 0.0, "one_to_one_s": 0.0}
+
     def e2e_step():
+        ta = time.time()
         info = bm.map(batch)
+        tb = time.time()
+        e2e_parts["map_s"] += tb - ta
         gathered, final = 0, None
         if comm is not None or one_to_one:
             raw = bm.results_raw()
+            tc = time.time()
+            e2e_parts["records_s"] += tc - tb
             if comm is not None:  # all ranks' mapping records on every rank: mm_records_allgather
                 raw, counts = comm.records_allgather(raw)
                 gathered = int(counts.sum())
+            td = time.time()
+            e2e_parts["allgather_s"] += td - tc
             if one_to_one and rank == 0:  # the run-wide reference-axis sweep + sort (computeMap.hpp:358-405) over ALL records
                 kept, paf = bm.one_to_one(raw, n_q_global, L)
                 final = (kept, paf)
+            e2e_parts["one_to_one_s"] += time.time() - td
         return info, gathered, final
 
     for _ in range(min(args.warmup, 1)):
         e2e_step()
+    for k_ in e2e_parts:
+        e2e_parts[k_] = 0.0
     barrier()
     t0 = time.time()
     e2e_info, gathered, final = None, 0, None
@@ -537,6 +549,7 @@ def gpu_arm(args):
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps,
                     "stage_seconds_last_step": {"device_call": e2e_info["sec_device"], "host_tail": e2e_info["sec_tail"]},
                     "paf_bytes_per_step": int(len(final[1]) if final else e2e_info["paf_bytes"]), "records_gathered": int(gathered),
+                    "rank0_seconds_per_step": {k_: v_ / args.steps for k_, v_ in e2e_parts.items()},
                     "efficiency_note": "e2e includes the all-gather" + (" and the run-wide one-to-one sweep" if one_to_one else "")},
             "gpu_launches": int(launches),
             "kernel_ms_per_step": {"pack": k_ms[3] / args.steps, "sketch": k_ms[0] / args.steps, "l1": k_ms[1] / args.steps,

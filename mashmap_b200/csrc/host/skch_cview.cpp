@@ -19,6 +19,7 @@
 #include "skch_map.hpp"
 #include "skch_seqio.hpp"
 #include "skch_stats.hpp"
+#include "skch_filter.hpp"
 #include "skch_tail.hpp"
 
 using namespace skch;
@@ -428,6 +429,69 @@ int64_t skch_fasta_readers_diff(const char *path, int threads, uint64_t *n_recor
     if (a != b) bad++;
   }
   return bad;
+}
+
+/* Self-test of the run-wide one-to-one step (MapTail::finalizeOneToOne: sorts through (key, index) pairs, reference-axis
+ * sweep per contig on `threads` threads, PAF text in slices) against the plain statement of computeMap.hpp:358-405 +
+ * filter.hpp:333-394 (std::sort on the records, one serial sweep, one stream) on n random mappings full of ties.
+ * Returns the number of differing bytes of PAF text (0 = identical; -1 = different lengths). */
+int64_t skch_one_to_one_selftest(int64_t n, uint64_t seed, int threads, int n_contigs, int n_queries, double *sec_fast, double *sec_plain)
+{
+  Parameters p;
+  p.filterMode = filter::ONETOONE; p.threads = threads; p.numMappingsForSegment = 1;
+  std::vector<ContigInfo> meta, qmeta;
+  std::vector<int> groups((size_t)n_contigs, 0);
+  for (int i = 0; i < n_contigs; i++) meta.push_back(ContigInfo{"ctg" + std::to_string(i), 1000000});
+  for (int i = 0; i < n_queries; i++) qmeta.push_back(ContigInfo{"read" + std::to_string(i), 20000});
+  uint64_t x = seed * 0x9E3779B97F4A7C15ULL + 1;
+  auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+  MappingResultsVector_t all((size_t)n);
+  const float ids[6] = {0.95f, 0.96f, 0.97f, 0.9712f, 0.99f, 1.0f};
+  for (auto &m : all) {
+    memset(&m, 0, sizeof m);
+    m.querySeqId = (seqno_t)(rnd() % (uint64_t)n_queries);
+    m.queryLen = 20000;
+    m.queryStartPos = (offset_t)((rnd() % 4) * 5000);
+    m.queryEndPos = m.queryStartPos + 5000;
+    m.refSeqId = (seqno_t)(rnd() % (uint64_t)n_contigs);
+    m.refStartPos = (offset_t)((rnd() % 4000) * 250);  /* coarse grid: many equal starts */
+    m.refEndPos = std::min<offset_t>(m.refStartPos + 4999 + (offset_t)(rnd() % 3) * 2500, 999999);
+    if (rnd() % 50 == 0) { m.refStartPos = 0; m.refEndPos = 999999; }  /* spans its contig: the linking case of the parallel sweep */
+    m.nucIdentity = ids[rnd() % 6]; m.nucIdentityUpperBound = m.nucIdentity;
+    m.blockLength = 5000; m.sketchSize = 20; m.conservedSketches = 15; m.strand = rnd() & 1 ? strnd::FWD : strnd::REV;
+    m.kmerComplexity = 0.9; m.n_merged = 1;
+  }
+  std::sort(all.begin(), all.end(), [](const MappingResult &a, const MappingResult &b) { return a.querySeqId < b.querySeqId; });  /* read order */
+  MapTail tail(p, meta, groups);
+  /* plain */
+  MappingResultsVector_t a = all;
+  std::string paf_plain;
+  auto t0 = std::chrono::steady_clock::now();
+  {
+    std::sort(a.begin(), a.end(), [](const MappingResult &l, const MappingResult &r) { return std::tie(l.refSeqId, l.refStartPos) < std::tie(r.refSeqId, r.refStartPos); });
+    std::sort(a.begin(), a.end(), [](const MappingResult &l, const MappingResult &r) {
+      return std::tie(l.queryStartPos, l.refSeqId, l.refStartPos) < std::tie(r.queryStartPos, r.refSeqId, r.refStartPos); });
+    Filter::ref::filterMappings(a, meta, 0);
+    std::sort(a.begin(), a.end(), [](const MappingResult &l, const MappingResult &r) {
+      return std::tie(l.queryStartPos, l.refSeqId, l.refStartPos) < std::tie(r.queryStartPos, r.refSeqId, r.refStartPos); });
+    std::sort(a.begin(), a.end(), [](const MappingResult &l, const MappingResult &r) {
+      return std::tie(l.querySeqId, l.queryStartPos, l.refSeqId, l.refStartPos) < std::tie(r.querySeqId, r.queryStartPos, r.refSeqId, r.refStartPos); });
+    std::ostringstream os;
+    MapTail t2(p, meta, groups);
+    t2.qmetadata = &qmeta;
+    t2.formatMappings(a, "", os);
+    paf_plain = os.str();
+  }
+  if (sec_plain) *sec_plain = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  MappingResultsVector_t b = all;
+  std::string paf_fast;
+  t0 = std::chrono::steady_clock::now();
+  tail.finalizeOneToOne(b, qmeta, paf_fast);
+  if (sec_fast) *sec_fast = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  if (paf_fast.size() != paf_plain.size()) return -1;
+  int64_t diff = 0;
+  for (size_t i = 0; i < paf_fast.size(); i++) diff += paf_fast[i] != paf_plain[i];
+  return diff + (a.size() != b.size());
 }
 
 /* ---- host tail on caller-provided records ---- */

@@ -233,7 +233,8 @@ BatchMapper::BatchMapper(const Parameters &p, const Sketch &refsketch) : param(p
   }
   const int G = (int)groups.size();
   for (DeviceGroup *g : groups) {
-    g->tailThreads = std::max(1, param.threads / G);
+    // of a device's share of the host threads, three drive its pipeline (upload / kernels / fetch); the rest run the per-read tail
+    g->tailThreads = std::max(1, param.threads / G - 3);
     g->tailPool = new WorkerPool(g->tailThreads);
     // further contexts share the device's index image: one lane per pipeline stage in flight (upload / kernels / fetch + tail)
     g->lanes[0].ctx = g->owner;
@@ -303,33 +304,8 @@ void BatchMapper::addRead(ReadBatch &b, const std::string &name, const char *seq
 }
 
 void BatchMapper::finalizeOneToOne(MappingResultsVector_t &allReadMappings, const std::vector<ContigInfo> &qmetadata, std::string &paf) const
-{  // computeMap.hpp:358-405
-  const int n_mappings = param.numMappingsForSegment - 1;
-  auto sb = allReadMappings.begin(), se = allReadMappings.begin();
-  MappingResultsVector_t tmp, filtered;
-  while (se != allReadMappings.end()) {
-    if (param.skip_prefix) {
-      const int g = getRefGroup(qmetadata[sb->querySeqId].name);
-      se = std::find_if_not(sb, allReadMappings.end(),
-                            [&](const MappingResult &c) { return g == getRefGroup(qmetadata[c.querySeqId].name); });
-    } else {
-      se = allReadMappings.end();
-    }
-    tmp.insert(tmp.end(), std::make_move_iterator(sb), std::make_move_iterator(se));
-    tail_->filterByGroup(tmp, filtered, n_mappings, true);
-    tmp.clear();
-    sb = se;
-  }
-  allReadMappings = std::move(filtered);
-  std::sort(allReadMappings.begin(), allReadMappings.end(), [](const MappingResult &a, const MappingResult &b) {
-    return std::tie(a.querySeqId, a.queryStartPos, a.refSeqId, a.refStartPos) <
-           std::tie(b.querySeqId, b.queryStartPos, b.refSeqId, b.refStartPos);
-  });
-  std::ostringstream os;
-  MapTail t(param, refSketch.metadata, refIdGroup);
-  t.qmetadata = &qmetadata;
-  t.formatMappings(allReadMappings, "", os);
-  paf = os.str();
+{
+  tail_->finalizeOneToOne(allReadMappings, qmetadata, paf);
 }
 
 /* The three stages of one part (reads [r0, r1) of the batch) on one lane (= one device context with its own stream

@@ -1,4 +1,8 @@
 #include "skch_tail.hpp"
+#include <thread>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 
 #include <algorithm>
 #include <cmath>
@@ -196,13 +200,41 @@ void MapTail::mergeMappingsInRange(MappingResultsVector_t &readMappings, int max
                      readMappings.end());
 }
 
+/* std::sort(v, key(a) < key(b)) with the records moved once instead of at every swap: the sort runs on (key, index) pairs
+ * and the records are permuted afterwards. libstdc++'s introsort decides every move from comparison results alone, so the
+ * pairs end up in exactly the arrangement the records would have (also among records with equal keys, whose order the
+ * later steps depend on). Worth it from a few thousand 96-byte records on. */
+template <class KeyFn>
+static void sortLikeStd(MappingResultsVector_t &v, KeyFn key)
+{
+  typedef decltype(key(v[0])) K;
+  if (v.size() < 2048) {
+    std::sort(v.begin(), v.end(), [&](const MappingResult &a, const MappingResult &b) { return key(a) < key(b); });
+    return;
+  }
+  struct P { K k; uint32_t i; };
+  std::vector<P> p(v.size());
+  for (size_t i = 0; i < v.size(); i++) { p[i].k = key(v[i]); p[i].i = (uint32_t)i; }
+  std::sort(p.begin(), p.end(), [](const P &a, const P &b) { return a.k < b.k; });
+  MappingResultsVector_t out(v.size());
+  for (size_t i = 0; i < v.size(); i++) out[i] = v[p[i].i];
+  v.swap(out);
+}
+
 /* ---- filterByGroup (computeMap.hpp:504-561) ---- */
 void MapTail::filterByGroup(MappingResultsVector_t &unfiltered, MappingResultsVector_t &filtered, int n_mappings, bool filter_ref) const
 {
   filtered.reserve(unfiltered.size());
-  std::sort(unfiltered.begin(), unfiltered.end(), [](const MappingResult &a, const MappingResult &b) {
-    return std::tie(a.refSeqId, a.refStartPos) < std::tie(b.refSeqId, b.refStartPos);
-  });
+  const bool trace = filter_ref && getenv("MM_TRACE") != nullptr;
+  auto tt0 = std::chrono::steady_clock::now();
+  auto lap = [&](const char *what) {
+    if (!trace) return;
+    auto t = std::chrono::steady_clock::now();
+    fprintf(stderr, "[trace]   filterByGroup %s: %.1f ms\n", what, std::chrono::duration<double, std::milli>(t - tt0).count());
+    tt0 = t;
+  };
+  sortLikeStd(unfiltered, [](const MappingResult &a) { return std::make_tuple(a.refSeqId, a.refStartPos); });
+  lap("sort 1");
   auto sb = unfiltered.begin(), se = unfiltered.begin();
   if (param.filterMode == filter::MAP || param.filterMode == filter::ONETOONE) {
     MappingResultsVector_t tmp;
@@ -214,19 +246,78 @@ void MapTail::filterByGroup(MappingResultsVector_t &unfiltered, MappingResultsVe
         se = unfiltered.end();
       }
       tmp.insert(tmp.end(), std::make_move_iterator(sb), std::make_move_iterator(se));
-      std::sort(tmp.begin(), tmp.end(), [](const MappingResult &a, const MappingResult &b) {
-        return std::tie(a.queryStartPos, a.refSeqId, a.refStartPos) < std::tie(b.queryStartPos, b.refSeqId, b.refStartPos);
-      });
+      sortLikeStd(tmp, [](const MappingResult &a) { return std::make_tuple(a.queryStartPos, a.refSeqId, a.refStartPos); });
+      lap("sort 2");
       if (filter_ref) Filter::ref::filterMappingsParallel(tmp, metadata, (uint16_t)n_mappings, param.threads);
       else Filter::query::filterMappings(tmp, (uint16_t)n_mappings);
+      lap("sweep");
       filtered.insert(filtered.end(), std::make_move_iterator(tmp.begin()), std::make_move_iterator(tmp.end()));
       tmp.clear();
       sb = se;
     }
   }
-  std::sort(filtered.begin(), filtered.end(), [](const MappingResult &a, const MappingResult &b) {
-    return std::tie(a.queryStartPos, a.refSeqId, a.refStartPos) < std::tie(b.queryStartPos, b.refSeqId, b.refStartPos);
-  });
+  sortLikeStd(filtered, [](const MappingResult &a) { return std::make_tuple(a.queryStartPos, a.refSeqId, a.refStartPos); });
+}
+
+int MapTail::getRefGroup(const std::string &seqName) const
+{  // computeMap.hpp:164-177
+  const auto queryPrefix = seqName.substr(0, seqName.find_last_of(param.prefix_delim));
+  for (size_t i = 0; i < metadata.size(); i++)
+    if (queryPrefix == metadata[i].name.substr(0, metadata[i].name.find_last_of(param.prefix_delim))) return refIdGroup[i];
+  return -1;
+}
+
+/* -f one-to-one, the run-wide step of mapQuery (computeMap.hpp:358-405) */
+void MapTail::finalizeOneToOne(MappingResultsVector_t &allReadMappings, const std::vector<ContigInfo> &qmeta, std::string &paf) const
+{
+  const bool trace = getenv("MM_TRACE") != nullptr;
+  auto tt0 = std::chrono::steady_clock::now();
+  auto lap = [&](const char *what) {
+    if (!trace) return;
+    auto t = std::chrono::steady_clock::now();
+    fprintf(stderr, "[trace] one-to-one %s: %.1f ms\n", what, std::chrono::duration<double, std::milli>(t - tt0).count());
+    tt0 = t;
+  };
+  const int n_mappings = param.numMappingsForSegment - 1;
+  auto sb = allReadMappings.begin(), se = allReadMappings.begin();
+  MappingResultsVector_t tmp, filtered;
+  while (se != allReadMappings.end()) {
+    if (param.skip_prefix) {
+      const int g = getRefGroup(qmeta[sb->querySeqId].name);
+      se = std::find_if_not(sb, allReadMappings.end(), [&](const MappingResult &c) { return g == getRefGroup(qmeta[c.querySeqId].name); });
+    } else {
+      se = allReadMappings.end();
+    }
+    tmp.insert(tmp.end(), std::make_move_iterator(sb), std::make_move_iterator(se));
+    filterByGroup(tmp, filtered, n_mappings, true);
+    tmp.clear();
+    sb = se;
+  }
+  allReadMappings = std::move(filtered);
+  lap("filterByGroup");
+  sortLikeStd(allReadMappings, [](const MappingResult &a) { return std::make_tuple(a.querySeqId, a.queryStartPos, a.refSeqId, a.refStartPos); });
+  lap("final sort");
+  /* the PAF text: formatted in slices by the host threads and joined in order (every slice starts from a stream in its
+   * default state, as the single stream of the reference is for every line) */
+  MapTail t(param, metadata, refIdGroup);
+  t.qmetadata = &qmeta;
+  const size_t n = allReadMappings.size();
+  const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(1, param.threads), n / 2048));
+  std::vector<std::string> part((size_t)T);
+  auto work = [&](int ti) {
+    const size_t lo = n * (size_t)ti / (size_t)T, hi = n * (size_t)(ti + 1) / (size_t)T;
+    MappingResultsVector_t slice(allReadMappings.begin() + lo, allReadMappings.begin() + hi);
+    std::ostringstream os;
+    t.formatMappings(slice, "", os);
+    part[(size_t)ti] = os.str();
+  };
+  std::vector<std::thread> pool;
+  for (int ti = 1; ti < T; ti++) pool.emplace_back(work, ti);
+  work(0);
+  for (auto &th : pool) th.join();
+  paf.clear();
+  for (auto &x : part) paf += x;
+  lap("text");
 }
 
 /* ---- mapModule for one read, given the device results of its fragments (computeMap.hpp:570-714) ---- */

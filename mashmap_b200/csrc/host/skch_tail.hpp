@@ -59,6 +59,9 @@ class MapTail {
   void mergeMappingsInRange(MappingResultsVector_t &readMappings, int max_dist) const;
   void filterByGroup(MappingResultsVector_t &unfiltered, MappingResultsVector_t &filtered, int n_mappings, bool filter_ref) const;
   void mapRead(const ReadRec &rd, IdentityCache &idc, MappingResultsVector_t &out) const;
+  int getRefGroup(const std::string &seqName) const;  // computeMap.hpp:164-177
+  /* -f one-to-one, the run-wide step (computeMap.hpp:358-405): reference-axis sweep over ALL mappings, final order, PAF text */
+  void finalizeOneToOne(MappingResultsVector_t &allReadMappings, const std::vector<ContigInfo> &qmeta, std::string &paf) const;
   void formatMappings(const MappingResultsVector_t &readMappings, const std::string &queryName, std::ostream &os) const;
 
  private:

@@ -269,3 +269,21 @@ def test_host_index_equals_reference_sketch(workdir, which, args, threads):
         hi.close()
     finally:
         R.close()
+
+
+@pytest.mark.parametrize("n,threads", [(1500, 1), (60_000, 4), (150_000, 8)])
+def test_run_wide_one_to_one_step_equals_its_plain_statement(n, threads):
+    """-f one-to-one, the step mapQuery runs over ALL mappings at the end (computeMap.hpp:358-405): the product sorts through
+    (key, index) pairs, sweeps the reference axis contig by contig on several threads and formats the PAF text in slices;
+    same bytes as std::sort on the records + one serial sweep (filter.hpp:333-394) + one stream, on random mappings with many
+    equal keys, equal identities and mappings that span a whole contig"""
+    import ctypes as C
+
+    L = hostlib.lib()
+    L.skch_one_to_one_selftest.restype = C.c_int64
+    L.skch_one_to_one_selftest.argtypes = [C.c_int64, C.c_uint64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    for seed in (1, 2, 3):
+        tf, tp = C.c_double(), C.c_double()
+        d = L.skch_one_to_one_selftest(n, seed, threads, 64, max(10, n // 2), C.byref(tf), C.byref(tp))
+        print(f"n={n} seed={seed}: fast {tf.value * 1e3:.1f} ms, plain {tp.value * 1e3:.1f} ms")
+        assert d == 0
