@@ -235,11 +235,13 @@ BatchMapper::BatchMapper(const Parameters &p, const Sketch &refsketch) : param(p
   for (DeviceGroup *g : groups) {
     // of a device's share of the host threads, three drive its pipeline (upload / kernels / fetch); the rest run the per-read tail
     g->tailThreads = std::max(1, param.threads / G - 3);
+    if (const char *e = getenv("MM_TAIL_THREADS")) g->tailThreads = std::max(1, atoi(e));  // experiment
     g->tailPool = new WorkerPool(g->tailThreads);
     // further contexts share the device's index image: one lane per pipeline stage in flight (upload / kernels / fetch + tail)
     g->lanes[0].ctx = g->owner;
     g->nLanes = 1;
-    for (int l = 1; l < MAX_LANES; l++) {
+    const int max_lanes = getenv("MM_LANES") ? std::max(1, std::min<int>(MAX_LANES, atoi(getenv("MM_LANES")))) : MAX_LANES;  // experiment
+    for (int l = 1; l < max_lanes; l++) {
       mm_ctx *c2 = nullptr;
       if (mm_ctx_create(g->device, &mp, &c2) != MM_OK) break;
       if (mm_ctx_share_index(c2, g->owner) != MM_OK) { mm_ctx_destroy(c2); break; }

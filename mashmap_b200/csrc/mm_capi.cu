@@ -7,6 +7,7 @@
  * fails with MM_ENODEVICE.
  */
 #include <algorithm>
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -228,18 +229,44 @@ int prepare_batch_buffers(mm_ctx *c, uint64_t n_bases, uint64_t n_segs)
   return MM_OK;
 }
 
+/* experiment (MM_UPLOAD_KERNEL=<CTAs>): the host -> device copy done by a few CTAs that read the pinned host buffer
+ * through its unified address (PCIe reads issued by SMs) instead of by the copy engine */
+__global__ void __launch_bounds__(256) k_copy_from_host(uint4 *dst, const uint4 *src, uint64_t n16)
+{
+  const uint64_t stride = (uint64_t)gridDim.x * 256ULL;
+  uint64_t i = (uint64_t)blockIdx.x * 256ULL + threadIdx.x;
+  for (; i + 3 * stride < n16; i += 4 * stride) {
+    const uint4 a = __ldcs(src + i), b = __ldcs(src + i + stride), c = __ldcs(src + i + 2 * stride), d = __ldcs(src + i + 3 * stride);
+    dst[i] = a; dst[i + stride] = b; dst[i + 2 * stride] = c; dst[i + 3 * stride] = d;
+  }
+  for (; i < n16; i += stride) dst[i] = __ldcs(src + i);
+}
+
 /* host -> device copy of `bytes` bytes, in <= 16 MiB pieces when a phase hook is installed (MM_PHASE_UPLOAD_CHUNK) */
 int copy_in(mm_ctx *c, uint8_t *dst, const void *src, uint64_t bytes)
 {
+  static const int skip_after = getenv("MM_SKIP_H2D") ? atoi(getenv("MM_SKIP_H2D")) : 0; /* experiment: timing without the copies */
+  static const int copy_ctas = getenv("MM_UPLOAD_KERNEL") ? atoi(getenv("MM_UPLOAD_KERNEL")) : 0;
+  static std::atomic<int> calls{0};
+  if (skip_after > 0 && calls.fetch_add(1) >= skip_after) return MM_OK;
+  auto one = [&](uint8_t *d, const uint8_t *s_, uint64_t n) -> cudaError_t {
+    if (copy_ctas > 0 && ((uintptr_t)d % 16 == 0) && ((uintptr_t)s_ % 16 == 0)) {
+      const uint64_t n16 = n / 16;
+      if (n16) k_copy_from_host<<<copy_ctas, 256, 0, c->stream>>>((uint4 *)d, (const uint4 *)s_, n16);
+      if (n % 16) return cudaMemcpyAsync(d + n16 * 16, s_ + n16 * 16, n % 16, cudaMemcpyHostToDevice, c->stream);
+      return cudaGetLastError();
+    }
+    return cudaMemcpyAsync(d, s_, n, cudaMemcpyHostToDevice, c->stream);
+  };
   if (!c->hook) {
-    CU(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    CU(c, one(dst, (const uint8_t *)src, bytes));
     return MM_OK;
   }
   const uint64_t CH = 16ULL << 20;
   for (uint64_t at = 0; at < bytes; at += CH) {
     const uint64_t n = std::min(CH, bytes - at);
     c->hook(c->hook_user, MM_PHASE_UPLOAD_CHUNK, 1);
-    cudaError_t e = cudaMemcpyAsync(dst + at, (const uint8_t *)src + at, n, cudaMemcpyHostToDevice, c->stream);
+    cudaError_t e = one(dst + at, (const uint8_t *)src + at, n);
     if (e == cudaSuccess) e = wait_stream(c);
     c->hook(c->hook_user, MM_PHASE_UPLOAD_CHUNK, 0);
     CU(c, e);
@@ -381,7 +408,7 @@ int run_l2_stream(mm_ctx *c, uint32_t *h_cnt)
   RD(c, c->d_l2_rec_off + nc, (uint32_t *)&total, 2);
   const auto tk1 = std::chrono::steady_clock::now();
   c->stage_ms[6] = std::chrono::duration<float, std::milli>(tk1 - tk0).count(); /* host view: ranges + scan + readback */
-  if (total + 16 > c->l2_recs_cap) {
+  if (total + 64 > c->l2_recs_cap) { /* the scan's record readers run up to 2 * RING_CHUNKS + 2 records past a stream's end */
     if (c->d_l2_recs) cudaFree(c->d_l2_recs);
     c->d_l2_recs = nullptr; c->l2_recs_cap = 0;
     const uint64_t want = total + total / 16 + 1024;
@@ -594,6 +621,7 @@ int mm_ctx_create(int device, const mm_params *params, mm_ctx **out)
     if (g[0] == '1' && cudaEventCreateWithFlags(&c->ev_wait, cudaEventBlockingSync | cudaEventDisableTiming) == cudaSuccess)
       c->blocking_wait = true;
   }
+  if (const char *g = getenv("MM_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g)); /* experiment: 32 / 64 / 128 */
   if (const char *g = getenv("MM_L2_GENERAL")) c->l2_mode = (g[0] == '1') ? 0 : 1; /* test hook: general kernel only */
   if (const char *g = getenv("MM_SKETCH_TABLE")) c->sk_mode = (g[0] == '1') ? 1 : 0; /* test hook: general sketch kernel only */
   if (const char *g = getenv("MM_L1_CTA")) c->l1_warp = (g[0] == '1') ? 0 : 1; /* test hook: general L1 path only */

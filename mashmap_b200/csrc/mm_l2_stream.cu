@@ -37,6 +37,9 @@ namespace {
 
 constexpr int L2S_WARPS = 4;
 constexpr int L2S_THREADS = L2S_WARPS * 32;
+constexpr int L2S_BUCKET_BITS = 9;
+constexpr int L2S_BUCKETS = 1 << L2S_BUCKET_BITS; /* k_l2_prep: first-level table over the query sketch */
+__host__ __device__ inline size_t l2_prep_tab_off(int S) { return (((size_t)L2S_WARPS * (size_t)(S + 2) * 9) + 15) & ~(size_t)15; }
 constexpr int L2C_WARPS = 2;              /* k_l2_scan: warps per CTA (each warp = 32 candidates) */
 constexpr int L2C_THREADS = L2C_WARPS * 32;
 /* per-slot state word (16 bits): num_before_inc bits 0..10, active bit 11, strand_vote bits 12..15 (signed) */
@@ -86,6 +89,7 @@ k_l2_prep(const mm_params prm, const mm_dev_index ix, const mm_dev_batch b, uint
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint64_t *qhash = (uint64_t *)smem_raw + (size_t)wid * (S + 2);
   int8_t *qstr = (int8_t *)((uint64_t *)smem_raw + (size_t)L2S_WARPS * (S + 2)) + (size_t)wid * (S + 2);
+  uint16_t *qtab = (uint16_t *)(smem_raw + l2_prep_tab_off(S)) + (size_t)wid * L2S_BUCKETS;
   const uint32_t FULL = 0xffffffffu;
 
   for (uint32_t c = blockIdx.x * L2S_WARPS + wid; c < n_cands; c += gridDim.x * L2S_WARPS) {
@@ -100,7 +104,27 @@ k_l2_prep(const mm_params prm, const mm_dev_index ix, const mm_dev_batch b, uint
       qhash[j + 1] = b.sk_hash[sbase + j];
       qstr[j + 1] = b.sk_strand[sbase + j];
     }
+    if (lane == 0) qhash[n + 1] = ~0ULL; /* sentinel: the forward walk below needs no bound test */
     __syncwarp();
+    /* first-level table of the lower_bound over q_1..q_n (slidingMap.hpp:128-131): the sketch holds the n smallest
+     * hashes of the segment, roughly uniform below q_n, so bucket = hash >> shift (shift puts q_n in the top half of the
+     * table) leaves less than one sketch entry per bucket on average; qtab[b] = first j whose bucket is >= b. */
+    const uint64_t qmax = n > 0 ? qhash[n] : 0ULL;
+    const int shift = max(0, 64 - __clzll((long long)qmax) - L2S_BUCKET_BITS);
+    for (int j = lane + 1; j <= n; j += 32) {
+      const int bj = (int)(qhash[j] >> shift);
+      const int bp = j == 1 ? -1 : (int)(qhash[j - 1] >> shift);
+      for (int x = bp + 1; x <= bj; x++) qtab[x] = (uint16_t)j;
+    }
+    for (int x = (n > 0 ? (int)(qmax >> shift) + 1 : 0) + lane; x < L2S_BUCKETS; x += 32) qtab[x] = (uint16_t)(n + 1);
+    __syncwarp();
+    auto q_lower_bound = [&](uint64_t h) -> int {
+      const uint64_t bk = h >> shift;
+      if (bk >= (uint64_t)L2S_BUCKETS) return n + 1;
+      int a = (int)qtab[bk];
+      while (qhash[a] < h) a++;
+      return a;
+    };
     uint2 *out = b.l2_recs + off;
     /* ---- insert stream ---- */
     uint32_t n_out = 0;
@@ -112,11 +136,7 @@ k_l2_prep(const mm_params prm, const mm_dev_index ix, const mm_dev_batch b, uint
         const uint64_t e = r.it0 + t;
         const uint64_t h = ix.idx_hash[e];
         const int wpos = ix.idx_wpos[e];
-        int a = 1, z = n + 1; /* lower_bound over q_1..q_n (slidingMap.hpp:128-131) */
-        while (a < z) {
-          const int mid = (a + z) >> 1;
-          if (qhash[mid] < h) a = mid + 1; else z = mid;
-        }
+        const int a = q_lower_bound(h);
         const bool match = a <= n && qhash[a] == h;
         uint32_t info = (uint32_t)a;
         if (match) {
@@ -146,11 +166,7 @@ k_l2_prep(const mm_params prm, const mm_dev_index ix, const mm_dev_batch b, uint
       if (t < r.nD) {
         const uint64_t e = r.d0 + t;
         const uint64_t h = ix.idx2_hash[e];
-        int a = 1, z = n + 1;
-        while (a < z) {
-          const int mid = (a + z) >> 1;
-          if (qhash[mid] < h) a = mid + 1; else z = mid;
-        }
+        const int a = q_lower_bound(h);
         keep = a <= n; /* hashes above every query hash never touch the state (slidingMap.hpp:133-136,179-182) */
         const bool match = keep && qhash[a] == h;
         rec = make_uint2((uint32_t)ix.idx2_wend[e], (uint32_t)a | (match ? MM_L2_MATCH : 0u));
@@ -178,41 +194,40 @@ __global__ void k_l2_order_keys(const mm_dev_batch b, uint32_t n_cands, uint32_t
   vals[c] = c;
 }
 
-/* One lane's sequential reader of 8-byte op records: the current 4 records and the next 4 live in registers (32-byte
- * aligned chunks, two 16-byte loads each), the line after those is prefetched into L2. The scan consumes a record every
- * few hundred cycles per lane and L1 is almost entirely given to shared memory, so a plain `rec = p[i]` per step would
- * expose the full DRAM/L2 latency on every step. Reads run up to 8 records past the stream's end (the buffer has slack). */
-struct rec_stream {
-  const uint4 *next; /* chunk after `n0,n1` */
-  uint4 c0, c1, n0, n1;
-  uint32_t k;        /* record inside the current chunk, 0..3 */
-  __device__ __forceinline__ void open(const uint2 *base, uint64_t first)
-  {
-    const uint4 *p = (const uint4 *)(base + (first & ~3ULL));
-    k = (uint32_t)(first & 3ULL);
-    c0 = p[0]; c1 = p[1]; n0 = p[2]; n1 = p[3];
-    next = p + 4;
+/* One lane's sequential reader of 8-byte op records. The scan consumes a record every few hundred cycles per lane and
+ * L1 is almost entirely given to shared memory, so a plain `rec = p[i]` per step would expose the full DRAM/L2 latency on
+ * every step. Each lane therefore owns a ring of RING_CHUNKS 16-byte cells (2 records each) per stream in shared memory,
+ * laid out [cell][lane]: cells are filled by cp.async straight from global memory (no register staging), a cell is
+ * re-issued for the chunk RING_CHUNKS ahead as soon as its second record has been fetched, and the line after that is
+ * prefetched into L2. Fetching a record is one LDS.64 at a computed address (an earlier version kept the chunks in
+ * registers and picked the record with select chains: ~40 % of the kernel's instructions).
+ * Completion: when a lane first reads chunk c+1, the cp.async groups it committed after chunk c+1's own group number at
+ * least RING_CHUNKS-1 (the re-issues of this stream's next cells; groups of the other stream only add to that), so
+ * `cp.async.wait_group RING_CHUNKS-1` is enough. Reads run up to 2*RING_CHUNKS+2 records past a stream's end (slack). */
+constexpr int RING_CHUNKS = 4;
+constexpr uint32_t RING_CELL_STRIDE = 32 * 16;                       /* one cell of every lane */
+constexpr uint32_t RING_STREAM_BYTES = RING_CHUNKS * RING_CELL_STRIDE; /* 2 KB per stream per warp */
+
+__device__ __forceinline__ void ring_issue(uint32_t sm, const uint4 *g, uint32_t chunk)
+{
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n\tcp.async.commit_group;" ::"r"(sm + (chunk % RING_CHUNKS) * RING_CELL_STRIDE),
+               "l"(g + chunk)
+               : "memory");
+}
+/* sm: shared address of this lane's cell 0 of the stream; g: global address of chunk 0; ptr: next record, counted from chunk 0 */
+__device__ __forceinline__ uint2 ring_fetch(uint32_t sm, const uint4 *g, uint32_t &ptr)
+{
+  const uint32_t chunk = ptr >> 1, within = ptr & 1u;
+  if (within == 0) asm volatile("cp.async.wait_group %0;" ::"n"(RING_CHUNKS - 1) : "memory");
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(sm + (chunk % RING_CHUNKS) * RING_CELL_STRIDE + within * 8u) : "memory");
+  ptr++;
+  if (within) {
+    ring_issue(sm, g, chunk + RING_CHUNKS);
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(g + chunk + RING_CHUNKS + 8));
   }
-  __device__ __forceinline__ uint2 at(uint32_t kk) const /* kk in 0..4: record kk of the current chunk / first of the next */
-  {
-    uint2 r;
-    r.x = kk == 0 ? c0.x : kk == 1 ? c0.z : kk == 2 ? c1.x : kk == 3 ? c1.z : n0.x;
-    r.y = kk == 0 ? c0.y : kk == 1 ? c0.w : kk == 2 ? c1.y : kk == 3 ? c1.w : n0.y;
-    return r;
-  }
-  __device__ __forceinline__ uint2 cur() const { return at(k); }
-  __device__ __forceinline__ uint32_t peek_x() const { return at(k + 1).x; }
-  __device__ __forceinline__ void advance()
-  {
-    if (++k == 4) {
-      k = 0;
-      c0 = n0; c1 = n1;
-      n0 = next[0]; n1 = next[1];
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(next + 8));
-      next += 2;
-    }
-  }
-};
+  return v;
+}
 
 struct lane_locus {
   int start, end, mean, shared, strand;
@@ -224,7 +239,8 @@ k_l2_scan(const mm_params prm, const mm_dev_index ix, const mm_dev_batch b, uint
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int S = prm.sketch_size;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint16_t *words = (uint16_t *)smem_raw + (size_t)wid * (size_t)(S + 2) * 32; /* [slot][lane] */
+  uint16_t *words = (uint16_t *)(smem_raw + (size_t)L2C_WARPS * 2 * RING_STREAM_BYTES) + (size_t)wid * (size_t)(S + 2) * 32; /* [slot][lane] */
+  const uint32_t ring_sm = (uint32_t)__cvta_generic_to_shared(smem_raw) + (uint32_t)wid * 2u * RING_STREAM_BYTES;
   const uint32_t FULL = 0xffffffffu;
   const int LPC = (int)b.l2_loci_per_cand;
   const int segL = prm.seg_length;
@@ -275,12 +291,20 @@ k_l2_scan(const mm_params prm, const mm_dev_index ix, const mm_dev_batch b, uint
     };
 
     uint32_t i = 0, d = 0;
-    rec_stream is, ds;
-    is.open(b.l2_recs, valid ? b.l2_rec_off[c] : 0ULL);
-    ds.open(b.l2_recs, valid ? b.l2_rec_off[c] + r.nI : 0ULL);
+    /* record readers: insert stream (current + next record in registers: the next one's position is read at every
+     * evaluation point) and delete stream (current record) */
+    const uint32_t sm_i = ring_sm + (uint32_t)lane * 16u, sm_d = sm_i + RING_STREAM_BYTES;
+    const uint64_t first_i = valid ? b.l2_rec_off[c] : 0ULL, first_d = first_i + r.nI;
+    const uint4 *g_i = (const uint4 *)(b.l2_recs + (first_i & ~1ULL)), *g_d = (const uint4 *)(b.l2_recs + (first_d & ~1ULL));
+    uint32_t p_i = (uint32_t)(first_i & 1ULL), p_d = (uint32_t)(first_d & 1ULL);
+    asm volatile("cp.async.wait_all;" ::: "memory"); /* copies still in flight for the previous candidate's cells */
+    __syncwarp();
+#pragma unroll
+    for (int ch = 0; ch < RING_CHUNKS; ch++) { ring_issue(sm_i, g_i, ch); ring_issue(sm_d, g_d, ch); }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    uint2 irec = ring_fetch(sm_i, g_i, p_i), inext = ring_fetch(sm_i, g_i, p_i), drec = ring_fetch(sm_d, g_d, p_d);
     while (__any_sync(FULL, i < r.nI)) {
       if (i < r.nI) {
-        const uint2 irec = is.cur(), drec = ds.cur();
         const int ipos = (int)irec.x;
         const bool is_main = ipos >= cd.rangeStartPos;
         const bool do_del = is_main && d < r.nD && (int)drec.x <= ipos; /* evict while wpos_end <= wpos (:1344) */
@@ -315,11 +339,8 @@ k_l2_scan(const mm_params prm, const mm_dev_index ix, const mm_dev_batch b, uint
           pivot += mv;
           words[slot * 32 + lane] = (uint16_t)(match ? w_match : w_plain);
         }
-        if (do_del) {
-          d++;
-          ds.advance();
-        } else {
-          const int npos = (i + 1 < r.nI) ? (int)is.peek_x() : r.next_wpos;
+        if (!do_del) {
+          const int npos = (i + 1 < r.nI) ? (int)inext.x : r.next_wpos;
           if (is_main) { /* region tracking (computeMap.hpp:1373-1430) */
             if (shared > best) {
               n_loci = 0; has_back = false; /* l2_vec_out.clear() */
@@ -341,8 +362,12 @@ k_l2_scan(const mm_params prm, const mm_dev_index ix, const mm_dev_batch b, uint
               in_cand = false;
             }
           }
-          i++;
-          is.advance();
+        }
+        { /* consume the record: one fetch from whichever stream moved */
+          uint32_t p = do_del ? p_d : p_i;
+          const uint2 v = ring_fetch(do_del ? sm_d : sm_i, do_del ? g_d : g_i, p);
+          if (do_del) { p_d = p; drec = v; d++; }
+          else { p_i = p; irec = inext; inext = v; i++; }
         }
       }
     }
@@ -532,8 +557,8 @@ cudaError_t mm_launch_l2_order(const mm_dev_batch &b, uint32_t n_cands, void *wo
   return cub::DeviceRadixSort::SortPairsDescending(tmp, tmp_bytes, k0, k1, v0, v1, (int)n_cands, 0, 16, st);
 }
 
-static size_t l2_prep_smem(const mm_params &p) { return (size_t)L2S_WARPS * (size_t)(p.sketch_size + 2) * 9 + 16; }
-static size_t l2_scan_smem(const mm_params &p) { return (size_t)L2C_WARPS * (size_t)(p.sketch_size + 2) * 32 * 2; }
+static size_t l2_prep_smem(const mm_params &p) { return l2_prep_tab_off(p.sketch_size) + (size_t)L2S_WARPS * L2S_BUCKETS * 2; }
+static size_t l2_scan_smem(const mm_params &p) { return (size_t)L2C_WARPS * ((size_t)(p.sketch_size + 2) * 32 * 2 + 2 * RING_STREAM_BYTES); }
 
 cudaError_t mm_launch_l2_prep(const mm_params &p, const mm_dev_index &ix, const mm_dev_batch &b, uint32_t n_cands, cudaStream_t st,
                               int sm_count)
