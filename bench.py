@@ -67,6 +67,9 @@ def parse_args():
     ap.add_argument("--cpu-sample-reads", type=int, default=0, help="reads per CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sketch", type=int, default=0, help="sketch size override (0 = the reference's automatic choice)")
+    ap.add_argument("--ref-kind", default="auto", choices=["auto", "real", "port"], help="--impl reference: 'real' = the unmodified reference "
+                    "(oracle/_ref/libmm_ref.so: its own index build from FASTA, its own mapModule); 'port' = the oracle restatement on the "
+                    "product's index content; 'auto' = real when the library is there")
     ap.add_argument("--as-rank", type=int, default=-1, help="debug: generate the reads rank R of a multi-GPU run would get (read seed 2 + R)")
     return ap.parse_args()
 
@@ -630,6 +633,30 @@ def _parity_diff(cpu_rows, gpu_rows):
     return out
 
 
+def _port_vs_reference(port_rows, ref_rows, seg):
+    """the oracle port's mappings of a sample against the unmodified reference's. One known difference is classified, not
+    hidden: a split read whose only mapping is a single fragment reaches filterWeakMappings with MappingResult::n_merged never
+    written (computeMap.hpp:1227 / :429-430, undefined behaviour: the reference drops or keeps it depending on stack garbage);
+    the port and the product define n_merged = 1 there and keep it."""
+    def keyset(r):
+        return {tuple(x) for x in r[:, :9].tolist()}
+
+    a, b = keyset(port_rows), keyset(ref_rows)
+    only_port, only_ref = a - b, b - a
+    per_read = {}
+    for x in port_rows[:, 0].tolist():
+        per_read[x] = per_read.get(x, 0) + 1
+    ub = {x for x in only_port if x[8] == seg and per_read.get(x[0], 0) == 1}
+    ident = 0.0
+    if len(port_rows) and len(ref_rows):
+        common = {tuple(x[:9]): x[9] for x in ref_rows.tolist()}
+        d = [abs(x[9] - common[tuple(x[:9])]) for x in port_rows.tolist() if tuple(x[:9]) in common]
+        ident = max(d) / 1e6 if d else 0.0
+    return {"mappings_port": int(len(port_rows)), "mappings_reference": int(len(ref_rows)),
+            "single_fragment_mappings_dropped_by_the_reference_uninitialised_n_merged": len(ub),
+            "other_differences": len(only_port - ub) + len(only_ref), "max_identity_diff": ident}
+
+
 def cpu_sample_reads(args, cfg, threads):
     """queries per CPU sample: about 15 s of wall time (the port maps ~11 Mbp per second per CPU on configs[1]), at least one
     query per thread, at most the whole step"""
@@ -639,7 +666,7 @@ def cpu_sample_reads(args, cfg, threads):
     return int(min(cfg["reads"], max(threads, want_bases // cfg["read_len"])))
 
 
-def cpu_baseline(args, cfg, index_arrays, ascii_reads, S, threads=None, n_reads=None, gpu_rows=None, first_counter=0):
+def cpu_baseline(args, cfg, index_arrays, ascii_reads, S, threads=None, n_reads=None, gpu_rows=None, first_counter=0, want_rows=False):
     """The oracle port of the reference path (oracle/libmm_oracle.so, mapModule per read, one task per read on
     all host threads) on a bounded sample of the same batch, with the same index content. With gpu_rows (the
     product's mappings of the whole batch) the port's mappings of the sampled reads are diffed against them."""
@@ -674,17 +701,85 @@ def cpu_baseline(args, cfg, index_arrays, ascii_reads, S, threads=None, n_reads=
         sel = (gpu_rows[:, 0] - first_counter < n_reads) if len(gpu_rows) else np.zeros(0, bool)
         parity = {"reads": int(n_reads), "stage": "per-read mappings (before the run-wide one-to-one sweep)" if cfg["filt"] == "one-to-one" else "final mappings",
                   **_parity_diff(rows[: min(n_map, len(rows))], gpu_rows[sel])}
-    return {"parity": parity, "value": n_reads * L / dt / 1e9, "unit": "Gbp/s", "cores": threads, "kind": "port",
+    return {**({"rows": rows[: min(n_map, len(rows))]} if want_rows else {}),
+            "parity": parity, "value": n_reads * L / dt / 1e9, "unit": "Gbp/s", "cores": threads, "kind": "port",
             "cpus_busy": round(busy, 1), "host": host_cpu_info(),
             "sample": f"first {n_reads} queries of the step ({n_reads * L / 1e6:.0f} Mbp), oracle/libmm_oracle.so mapModule per query "
                       f"on {threads} threads, {dt:.1f} s; {mapped.value} queries mapped, {n_map} mappings"}
 
 
+def reference_library():
+    """oracle/_ref/libmm_ref.so (the unmodified reference behind oracle/ref_harness.cpp), or None"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    try:
+        import refh
+
+        return refh if refh.available() else None
+    except Exception:  # noqa: BLE001
+        return None
+
+
+def real_reference_session(args, cfg, wl, S, threads):
+    """The reference's own Sketch + Map on the bench's reference: the contigs are written as FASTA, the reference parses
+    them and builds its index itself (winSketch.hpp), exactly as `mashmap -r ref.fa` would. Returns (session, seconds)."""
+    import shutil
+    import tempfile
+
+    import refh
+
+    wd = tempfile.mkdtemp(prefix="mm_ref_arm_")
+    path = os.path.join(wd, "ref.fa")
+    t0 = time.time()
+    ref = wl["ref_dev"].cpu().numpy()
+    with open(path, "wb", buffering=1 << 24) as f:
+        for i in range(ref.shape[0]):
+            f.write(b">c%d\n" % i)
+            f.write(ref[i].tobytes())
+            f.write(b"\n")
+    del ref
+    t_fa = time.time() - t0
+    t0 = time.time()
+    try:
+        R = refh.RefSession(["-r", path, "-q", path, "-s", str(cfg["seg"]), "--pi", f"{cfg['pi'] * 100:g}", "-J", str(S), "-t", str(threads),
+                             "-f", cfg["filt"], "-k", str(K)])
+    finally:
+        shutil.rmtree(wd, ignore_errors=True)
+    t_ix = time.time() - t0
+    log(f"reference arm: FASTA written in {t_fa:.1f} s, the reference's own index built in {t_ix:.1f} s ({threads} threads)")
+    return R, t_fa + t_ix
+
+
+def real_reference_step(R, cfg, ascii_reads, n_reads, threads, first_counter=0, want_rows=False):
+    """one bounded sample through the reference's own mapModule (oracle/ref_harness.cpp: refh_map_reads_mt)"""
+    import ctypes as C
+
+    import refh
+
+    lib = refh.lib()
+    lib.refh_map_reads_mt.restype = C.c_int64
+    lib.refh_map_reads_mt.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64), C.c_void_p, C.c_int64]
+    L = cfg["read_len"]
+    mapped = C.c_int64()
+    rows = np.zeros((64 * n_reads + 4096, 10), dtype=np.int32) if want_rows else None
+    t0 = time.time()
+    c0 = os.times()
+    n_map = lib.refh_map_reads_mt(R.h, ascii_reads.ctypes.data, n_reads, L, first_counter, threads, C.byref(mapped),
+                                  rows.ctypes.data if rows is not None else None, len(rows) if rows is not None else 0)
+    dt = time.time() - t0
+    c1 = os.times()
+    busy = ((c1.user - c0.user) + (c1.system - c0.system)) / max(dt, 1e-9)
+    out = {"value": n_reads * L / dt / 1e9, "unit": "Gbp/s", "cores": threads, "kind": "reference", "cpus_busy": round(busy, 1), "host": host_cpu_info(),
+           "sample": f"first {n_reads} queries of the step ({n_reads * L / 1e6:.0f} Mbp), oracle/_ref/libmm_ref.so (the unmodified reference): "
+                     f"skch::Map::mapModule per query on {threads} threads, {dt:.1f} s; {mapped.value} queries mapped, {n_map} mappings"}
+    return out, (rows[: min(n_map, len(rows))] if rows is not None else None)
+
+
 def cpu_arm(args):
-    """--impl reference: the reference's CPU path on the host cores. oracle/_ref (the unmodified reference) builds its own
-    index from FASTA single-threaded per contig, which for a 3 Gbp reference takes minutes per run, so the arm times the
-    oracle port of the same path (kind = "port") on the index content the product's host builder produced -- tested
-    bit-identical to the reference's own index (tests/test_host_cpu.py)."""
+    """--impl reference: the reference's CPU path on the host cores, every step a bounded sample of the arm's workload.
+    kind "reference": the unmodified reference (oracle/_ref/libmm_ref.so) builds its own index from the FASTA of the bench's
+    reference (set-up, minutes at 3 Gbp, not timed) and maps each sample with its own mapModule on all host threads; the
+    oracle port runs the same sample once beside it (port_value, and the two sets of mappings are diffed).
+    kind "port" (--ref-kind port, or no library): the oracle port on the index content the product built."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -698,26 +793,43 @@ def cpu_arm(args):
         cfg["reads"] = sample  # only the sample is generated
     wl = setup_workload(args, cfg, 0, 1, device)
     S = wl["sketch"]
-    if device.type == "cuda":  # the index content is the same either way (tests/test_gpu_index_build.py); the GPU builds it in seconds
-        from mashmap_b200 import capi
+    real = args.ref_kind != "port" and reference_library() is not None
+    if args.ref_kind == "real" and not real:
+        raise SystemExit("--ref-kind real: oracle/_ref/libmm_ref.so is not there (make -C oracle)")
+    ascii_reads = np.ascontiguousarray(wl["queries"].reshape(-1).cpu().numpy())
+    R, setup_s, extra = None, None, {}
+    if real:
+        R, setup_s = real_reference_session(args, cfg, wl, S, threads)
+    if not real or cfg["kind"] == "reads":  # the port: the arm itself, or one sample beside the real reference
+        if device.type == "cuda":  # the index content is the same either way (tests/test_gpu_index_build.py); the GPU builds it in seconds
+            from mashmap_b200 import capi
 
-        ctx = capi.Context(device=0, kmer_size=K, seg_length=cfg["seg"], sketch_size=S)
-        build_index_on_device(args, cfg, wl, ctx, keep_lookup=True)
-        arrays = ctx.index_download()
-        ctx.close()
-    else:
-        arrays = build_index_on_host(args, cfg, wl, threads).arrays()
+            ctx = capi.Context(device=0, kmer_size=K, seg_length=cfg["seg"], sketch_size=S)
+            build_index_on_device(args, cfg, wl, ctx, keep_lookup=True)
+            arrays = ctx.index_download()
+            ctx.close()
+        else:
+            arrays = build_index_on_host(args, cfg, wl, threads).arrays()
     wl["ref_dev"] = None
-    ascii_reads = wl["queries"].reshape(-1).cpu().numpy()
     times, last = [], None
     for i in range(args.warmup + args.steps):
-        last = cpu_baseline(args, cfg, arrays, ascii_reads, S, threads=threads, n_reads=sample)
-        last.pop("parity", None)
+        if real:
+            last, _ = real_reference_step(R, cfg, ascii_reads, sample, threads)
+        else:
+            last = cpu_baseline(args, cfg, arrays, ascii_reads, S, threads=threads, n_reads=sample)
+            last.pop("parity", None)
         if i >= args.warmup:
             times.append(sample * cfg["read_len"] / last["value"] / 1e9)
+    if real and cfg["kind"] == "reads":  # the port on the same sample: speed beside the reference's, and the mappings diffed
+        _, ref_rows = real_reference_step(R, cfg, ascii_reads, sample, threads, want_rows=True)
+        port = cpu_baseline(args, cfg, arrays, ascii_reads, S, threads=threads, n_reads=sample, gpu_rows=ref_rows, want_rows=True)
+        extra = {"port_value": port["value"], "port_vs_reference": _port_vs_reference(port.pop("rows"), ref_rows, cfg["seg"]), "setup_seconds": round(setup_s, 1)}
+    if R is not None:
+        R.close()
     dt = sum(times)
     val = sample * cfg["read_len"] * args.steps / dt / 1e9
     last["value"] = val
+    last.update(extra)
     print(json.dumps({
         "impl": "reference", "metric": "mapped query Gbp/s", "value": val, "unit": "Gbp/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": cfg["scaling"],

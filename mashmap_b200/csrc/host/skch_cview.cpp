@@ -319,12 +319,7 @@ int skch_bm_map(void *hv, void *bv, uint64_t *paf_bytes, uint64_t *n_mapped_read
   if (!report_now) h->text.clear();
   h->bm->mapBatch(b->batch, h->results, report_now ? &h->text : nullptr, nullptr);
   const auto tm1 = std::chrono::steady_clock::now();
-  uint64_t bytes = 0, mapped = 0, maps = 0;
-  for (size_t r = 0; r < h->results.size(); r++) {
-    if (report_now) bytes += h->text[r].size();
-    mapped += h->results[r].empty() ? 0 : 1;
-    maps += h->results[r].size();
-  }
+  const uint64_t bytes = h->bm->lastTextBytes, mapped = h->bm->lastMappedReads, maps = h->bm->lastMappings; /* summed by the tail workers */
   if (getenv("MM_TRACE"))
     fprintf(stderr, "[trace] skch_bm_map: mapBatch %.1f ms, result summary %.1f ms\n",
             std::chrono::duration<double, std::milli>(tm1 - tm0).count(),

@@ -372,6 +372,7 @@ void BatchMapper::laneFinish(DeviceGroup &g, Lane &ln, const ReadBatch &b, std::
     IdentityCache idc;
     idc.k = param.kmerSize;
     std::ostringstream os;
+    uint64_t bytes = 0, mapped = 0, maps = 0;
     while (true) {
       const size_t lo = next.fetch_add(256);
       if (lo >= r1) break;
@@ -380,13 +381,18 @@ void BatchMapper::laneFinish(DeviceGroup &g, Lane &ln, const ReadBatch &b, std::
         results[r].clear();
         if (text) (*text)[r].clear();
         tail.mapRead(b.reads[r], idc, results[r]);
-        if (text && !results[r].empty()) {
+        if (results[r].empty()) continue;
+        mapped++;
+        maps += results[r].size();
+        if (text) {
           os.str(std::string());
           tail.formatMappings(results[r], b.reads[r].name, os);
           (*text)[r] = os.str();
+          bytes += (*text)[r].size();
         }
       }
     }
+    lastTextBytes += bytes; lastMappedReads += mapped; lastMappings += maps;
   };
   g.tailPool->run(nthreads, worker);
   ln.secTail += since(t0);
@@ -405,6 +411,7 @@ void BatchMapper::mapBatch(const ReadBatch &b, std::vector<MappingResultsVector_
   // would cost tens of milliseconds per batch), capacity is reused from the previous batch
   results.resize(nreads);
   if (text) text->resize(nreads);
+  lastTextBytes = 0; lastMappedReads = 0; lastMappings = 0;
   if (nreads == 0) return;
   double d0 = 0, t0 = 0;
   for (DeviceGroup *g : groups)

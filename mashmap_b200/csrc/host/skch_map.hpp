@@ -23,6 +23,7 @@
 #define SKCH_MAP_HPP
 
 #include <functional>
+#include <atomic>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -77,6 +78,8 @@ class BatchMapper {
   mm_ctx *context() const { return ctx; }
   int deviceCount() const { return (int)groups.size(); }
   double secondsDevice = 0, secondsHostTail = 0;
+  // totals of the last mapBatch, accumulated by the tail workers: text bytes, reads with a mapping, mappings
+  std::atomic<uint64_t> lastTextBytes{0}, lastMappedReads{0}, lastMappings{0};
   float lastStageMs[8] = {0};
 
  private:

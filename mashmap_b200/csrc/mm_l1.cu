@@ -589,11 +589,18 @@ __device__ bool l1_segment(const mm_params &prm, const mm_dev_index &ix, const m
   return true;
 }
 
-/* per-warp dynamic shared memory of k_l1_warp */
+/* per-warp dynamic shared memory of k_l1_warp: keys | head | copn | ginfo | (hit list, if it does not fit) | state.
+ * The hit list is dead once the points are gathered and copn / ginfo are first written by the scans after the sort, so
+ * the list lives in their space when it fits (S <= 256); head is the gather's owner array and stays apart. */
+__host__ __device__ inline size_t l1_warp_hits_extra(int S)
+{
+  const size_t need = (((size_t)S * sizeof(l1_hit) + 15) & ~(size_t)15);
+  return need <= (size_t)L1_WARP_POINTS * 8 ? 0 : need;
+}
 __host__ __device__ inline size_t l1_warp_smem(int S)
 {
-  size_t o = (((size_t)S * sizeof(l1_hit) + 15) & ~(size_t)15);
-  o += (size_t)L1_WARP_POINTS * (8 + 4 + 4 + 4); /* keys, copn, head, ginfo */
+  size_t o = (size_t)L1_WARP_POINTS * (8 + 4 + 4 + 4); /* keys, head, copn, ginfo */
+  o += l1_warp_hits_extra(S);
   o += (sizeof(l1_shared<32, L1_LOCAL_CANDS_WARP>) + 15) & ~(size_t)15;
   return (o + 15) & ~(size_t)15;
 }
@@ -606,11 +613,12 @@ k_l1_warp(const mm_params prm, const mm_dev_index ix, const mm_dev_batch b, uint
   const int S = prm.sketch_size;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned char *base = smem_raw + l1_warp_smem(S) * wid;
-  l1_hit *hits = (l1_hit *)base; base += (((size_t)S * sizeof(l1_hit) + 15) & ~(size_t)15);
   uint64_t *keys = (uint64_t *)base; base += (size_t)L1_WARP_POINTS * 8;
-  uint32_t *copn = (uint32_t *)base; base += (size_t)L1_WARP_POINTS * 4;
   uint32_t *head = (uint32_t *)base; base += (size_t)L1_WARP_POINTS * 4;
+  uint32_t *copn = (uint32_t *)base; base += (size_t)L1_WARP_POINTS * 4;
   uint32_t *ginfo = (uint32_t *)base; base += (size_t)L1_WARP_POINTS * 4;
+  l1_hit *hits = (l1_hit *)copn;
+  if (l1_warp_hits_extra(S)) { hits = (l1_hit *)base; base += l1_warp_hits_extra(S); }
   l1_shared<32, L1_LOCAL_CANDS_WARP> &sh = *(l1_shared<32, L1_LOCAL_CANDS_WARP> *)base;
 
   for (uint32_t seg = blockIdx.x * L1_WARPS_PER_CTA + wid; seg < b.n_segs; seg += gridDim.x * L1_WARPS_PER_CTA) {

@@ -309,6 +309,10 @@ k_l2_scan(const mm_params prm, const mm_dev_index ix, const mm_dev_batch b, uint
         const bool is_main = ipos >= cd.rangeStartPos;
         const bool do_del = is_main && d < r.nD && (int)drec.x <= ipos; /* evict while wpos_end <= wpos (:1344) */
         const uint32_t info = do_del ? drec.y : irec.y;
+        /* the record that replaces the consumed one, from whichever stream moves: fetched now, used at the end of the
+         * step, so that its shared-memory latency runs under the update */
+        uint32_t p = do_del ? p_d : p_i;
+        const uint2 v = ring_fetch(do_del ? sm_d : sm_i, do_del ? g_d : g_i, p);
         const int slot = (int)(info & MM_L2_SLOT_MASK);
         const bool match = (info & MM_L2_MATCH) != 0;
         const int prev_votes = votes; /* computeMap.hpp:1342 (only read after an insert) */
@@ -363,12 +367,9 @@ k_l2_scan(const mm_params prm, const mm_dev_index ix, const mm_dev_batch b, uint
             }
           }
         }
-        { /* consume the record: one fetch from whichever stream moved */
-          uint32_t p = do_del ? p_d : p_i;
-          const uint2 v = ring_fetch(do_del ? sm_d : sm_i, do_del ? g_d : g_i, p);
-          if (do_del) { p_d = p; drec = v; d++; }
-          else { p_i = p; irec = inext; inext = v; i++; }
-        }
+        /* consume the record */
+        if (do_del) { p_d = p; drec = v; d++; }
+        else { p_i = p; irec = inext; inext = v; i++; }
       }
     }
     if (valid) {

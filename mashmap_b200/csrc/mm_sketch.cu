@@ -382,6 +382,22 @@ __device__ __forceinline__ int sk_hash_run(const sk_run &r, uint32_t &amax, cons
   return cnt;
 }
 
+/* Does any base this thread's k-mers cover carry the N flag (nibble bit 3)? Exactly the bases [b0, b0 + positions + K - 1):
+ * the nibbles before and after them in the first / last word are masked off. (Scanning whole words, or a few bases too
+ * many, is not harmless: in a packed batch every read is padded with N nibbles up to a multiple of 32 bases, so the last
+ * thread of a read's last fragment would take the N-tracking variant of the hashing loop -- and its warp both variants.) */
+__device__ __forceinline__ bool sk_any_n(const uint32_t *nib, uint32_t b0, uint32_t n_bases)
+{
+  if (n_bases == 0) return false;
+  const uint32_t e = b0 + n_bases - 1u; /* last base */
+  const uint32_t w0 = b0 >> 3, w1 = e >> 3;
+  const uint32_t m0 = 0xFFFFFFFFu << ((b0 & 7u) * 4u), m1 = 0xFFFFFFFFu >> ((7u - (e & 7u)) * 4u);
+  if (w0 == w1) return (nib[w0] & m0 & m1 & 0x88888888u) != 0;
+  uint32_t acc = (nib[w0] & m0) | (nib[w1] & m1);
+  for (uint32_t w = w0 + 1; w < w1; w++) acc |= nib[w];
+  return (acc & 0x88888888u) != 0;
+}
+
 /* The general kernel: handles every input (any number of repeated k-mers, fewer than s distinct k-mers, thresholds that
  * have to be re-estimated). work_list == nullptr: all n_segs segments; else the segments listed there, *work_count of them
  * (the fast kernel's rejects; the count is read on the device, no host round trip). */
@@ -486,12 +502,7 @@ k_sketch_table(const uint8_t *__restrict__ packed, const mm_segment *__restrict_
       if (!waited) {
         mbar_wait(&bars[stage], (it >> 1) & 1);
         waited = true;
-        if (has_work) { /* any N (nibble bit 3) in the words this thread will read? (a few bases too many: harmless) */
-          const uint32_t w0 = r.b0 >> 3, w1 = (r.b0 + (uint32_t)(r.p1 - r.p0) + (uint32_t)K + 6u) >> 3;
-          uint32_t acc = 0;
-          for (uint32_t w = w0; w <= w1; w++) acc |= r.nib[w];
-          any_n = (acc & 0x88888888u) != 0;
-        }
+        if (has_work) any_n = sk_any_n(r.nib, r.b0, (uint32_t)(r.p1 - r.p0) + (uint32_t)K - 1u);
       }
       __syncthreads();
 
@@ -756,12 +767,9 @@ k_sketch(const uint8_t *__restrict__ packed, const mm_segment *__restrict__ segs
     mbar_wait(&bars[stage], (it >> 1) & 1);
     int cnt = 0;
     if (has_work) {
-      const uint32_t w0 = r.b0 >> 3, w1 = (r.b0 + (uint32_t)(r.p1 - r.p0) + (uint32_t)K + 6u) >> 3;
-      uint32_t acc = 0;
-      for (uint32_t w = w0; w <= w1; w++) acc |= r.nib[w];
       uint32_t amax = 0;
       const sk_spill_list spill{spill_h, spill_p, &ctrl->n_spill, SKF_SPILL};
-      if (acc & 0x88888888u) cnt = sk_hash_run<K, true, false>(r, amax, spill);
+      if (sk_any_n(r.nib, r.b0, (uint32_t)(r.p1 - r.p0) + (uint32_t)K - 1u)) cnt = sk_hash_run<K, true, false>(r, amax, spill);
       else cnt = sk_hash_run<K, false, false>(r, amax, spill);
     }
 

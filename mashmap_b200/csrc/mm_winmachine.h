@@ -168,11 +168,41 @@ WM_HD void wm_list_free(wm_machine &m, wm_member &e)
 {
   while (e.count > 0) wm_list_pop_front(m, e);
 }
+/* The sorted member arrays live in a per-machine slab (global memory on the device). An element-by-element shift is a
+ * chain of load -> store -> load on one cache line (the store invalidates the line the next load needs): moved 8 at a
+ * time, all loads of a batch first, the shift costs one memory round trip per 8 members instead of one per member (this
+ * loop was 64 % of the window-scan kernel's stall samples). */
+WM_HD void wm_members_shift_down(wm_machine &m, int32_t idx) /* [idx+1, mem_n) -> [idx, mem_n-1) */
+{
+  int32_t i = idx;
+  while (i + 8 < m.mem_n) {
+    uint64_t h[8]; uint16_t sl[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) { h[u] = m.mh[i + 1 + u]; sl[u] = m.mslot[i + 1 + u]; }
+#pragma unroll
+    for (int u = 0; u < 8; u++) { m.mh[i + u] = h[u]; m.mslot[i + u] = sl[u]; }
+    i += 8;
+  }
+  for (; i + 1 < m.mem_n; i++) { m.mh[i] = m.mh[i + 1]; m.mslot[i] = m.mslot[i + 1]; }
+}
+WM_HD void wm_members_shift_up(wm_machine &m, int32_t at) /* [at, mem_n) -> [at+1, mem_n] */
+{
+  int32_t i = m.mem_n;
+  while (i - at >= 8) {
+    uint64_t h[8]; uint16_t sl[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) { h[u] = m.mh[i - 1 - u]; sl[u] = m.mslot[i - 1 - u]; }
+#pragma unroll
+    for (int u = 0; u < 8; u++) { m.mh[i - u] = h[u]; m.mslot[i - u] = sl[u]; }
+    i -= 8;
+  }
+  for (; i > at; i--) { m.mh[i] = m.mh[i - 1]; m.mslot[i] = m.mslot[i - 1]; }
+}
 WM_HD void wm_erase_member(wm_machine &m, int32_t idx)
 {
   wm_list_free(m, wm_at(m, idx));
   m.sfree[m.sfree_n++] = m.mslot[idx];
-  for (int32_t i = idx; i + 1 < m.mem_n; i++) { m.mh[i] = m.mh[i + 1]; m.mslot[i] = m.mslot[i + 1]; }
+  wm_members_shift_down(m, idx);
   m.mem_n--;
 }
 /* a new member at its place in hash order; returns its index (or -1) */
@@ -180,7 +210,7 @@ WM_HD int32_t wm_insert_member(wm_machine &m, uint64_t h)
 {
   if (m.mem_n >= m.mem_cap || m.sfree_n <= 0) { m.fail = 1; return -1; }
   const int32_t at = wm_lower_bound(m, h);
-  for (int32_t i = m.mem_n; i > at; i--) { m.mh[i] = m.mh[i - 1]; m.mslot[i] = m.mslot[i - 1]; }
+  wm_members_shift_up(m, at);
   m.mem_n++;
   m.mh[at] = h;
   m.mslot[at] = m.sfree[--m.sfree_n];

@@ -332,5 +332,49 @@ int refh_map_read(void *hv, const char *name, const char *seq, int len, int seqC
   return n;
 }
 
+/* cpu_baseline / --impl reference driver around the reference's own mapModule: n_reads reads of read_len bases (back to
+ * back in `bases`), one read per task on `threads` threads like the reference's pool (computeMap.hpp:275,340).
+ * Same contract and row layout as orc_map_reads_mt of the port. */
+int64_t refh_map_reads_mt(void *hv, const char *bases, int64_t n_reads, int read_len, int first_seq_counter, int threads,
+                          int64_t *mapped_reads, int32_t *rows_out, int64_t cap_rows)
+{
+  Handle *h = (Handle *)hv;
+  std::atomic<int64_t> next{0}, total{0}, mapped{0};
+  std::vector<std::vector<skch::MappingResult>> keep(rows_out ? (size_t)n_reads : 0);
+  auto work = [&]() {
+    while (true) {
+      const int64_t i = next.fetch_add(1);
+      if (i >= n_reads) break;
+      std::string s(bases + i * (int64_t)read_len, (size_t)read_len);
+      const std::string name = "q" + std::to_string(first_seq_counter + i);
+      skch::InputSeqProgContainer *in = new skch::InputSeqProgContainer(s, name, first_seq_counter + (int)i, *h->progress);
+      skch::MapModuleOutput *o = h->map->mapModule(in);
+      delete in;
+      total += (int64_t)o->readMappings.size();
+      if (!o->readMappings.empty()) mapped++;
+      if (rows_out) keep[(size_t)i] = o->readMappings;
+      delete o;
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 0; t < std::max(1, threads); t++) pool.emplace_back(work);
+  for (auto &th : pool) th.join();
+  if (mapped_reads) *mapped_reads = mapped.load();
+  if (rows_out) {
+    int64_t n = 0;
+    for (auto &v : keep)
+      for (auto &m : v) {
+        if (n < cap_rows) {
+          int32_t *r = rows_out + n * 10;
+          r[0] = m.querySeqId; r[1] = m.queryStartPos; r[2] = m.queryEndPos; r[3] = m.refSeqId; r[4] = m.refStartPos;
+          r[5] = m.refEndPos; r[6] = m.strand; r[7] = m.conservedSketches; r[8] = m.blockLength;
+          r[9] = (int32_t)(m.nucIdentity * 1e6f);
+        }
+        n++;
+      }
+  }
+  return total.load();
+}
+
 } // extern "C"
 #pragma GCC visibility pop
