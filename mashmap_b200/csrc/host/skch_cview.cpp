@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <sstream>
+#include <random>
 #include <string>
 #include <vector>
 
@@ -550,6 +551,89 @@ const char *skch_tail_map_read(void *hv, const char *name, int32_t len, int32_t 
   h->text = os.str();
   if (n_out) *n_out = (int32_t)h->last.size();
   return h->text.c_str();
+}
+
+/* tail micro-benchmark (scripts/tail_perf.py): the host tail of n_reads reads, `iters` times over, on one thread.
+ * The reads' records are back to back: read r owns fragments [seg_first[r], seg_first[r+1]) and its candidate / locus
+ * indices are absolute. Returns seconds in mapRead and in formatMappings. */
+void skch_tail_bench(void *hv, int32_t n_reads, const int32_t *read_len, const uint64_t *seg_first, const mm_segment *segs,
+                     const mm_segment_result *segRes, const mm_l1_candidate *cands, const mm_l2_locus *loci, int iters,
+                     double *sec_map, double *sec_format, uint64_t *n_mappings)
+{
+  TailHandle *h = (TailHandle *)hv;
+  h->tail->segs = segs; h->tail->segRes = segRes; h->tail->cands = cands; h->tail->loci = loci;
+  std::vector<ReadRec> reads((size_t)n_reads);
+  for (int r = 0; r < n_reads; r++) {
+    reads[r].name = "read" + std::to_string(r); reads[r].len = read_len[r]; reads[r].seqCounter = r;
+    reads[r].first_seg = seg_first[r]; reads[r].n_seg = (uint32_t)(seg_first[r + 1] - seg_first[r]); reads[r].refGroup = -1;
+  }
+  IdentityCache idc;
+  idc.k = h->p.kmerSize;
+  std::vector<MappingResultsVector_t> res((size_t)n_reads);
+  std::ostringstream os;
+  double tm = 0, tf = 0;
+  uint64_t nm = 0;
+  for (int it = 0; it < iters; it++) {
+    auto t0 = std::chrono::steady_clock::now();
+    for (int r = 0; r < n_reads; r++) { res[r].clear(); h->tail->mapRead(reads[r], idc, res[r]); }
+    auto t1 = std::chrono::steady_clock::now();
+    for (int r = 0; r < n_reads; r++) {
+      if (res[r].empty()) continue;
+      h->text.clear();
+      h->tail->formatMappings(res[r], reads[r].name, h->text);
+      nm += res[r].size();
+    }
+    auto t2 = std::chrono::steady_clock::now();
+    tm += std::chrono::duration<double>(t1 - t0).count();
+    tf += std::chrono::duration<double>(t2 - t1).count();
+  }
+  if (sec_map) *sec_map = tm;
+  if (sec_format) *sec_format = tf;
+  if (n_mappings) *n_mappings = nm;
+}
+
+/* the string formatter of the PAF lines against the stream formatter (the reference's own statement) on n random mappings,
+ * in every output mode: returns the number of modes whose texts differ (0 = identical) */
+int skch_format_selftest(int64_t n, uint64_t seed)
+{
+  std::mt19937_64 rng(seed);
+  std::vector<ContigInfo> meta;
+  for (int i = 0; i < 7; i++) meta.push_back(ContigInfo{"contig_" + std::to_string(i), 1000000 + i});
+  std::vector<int> groups(meta.size(), 0);
+  MappingResultsVector_t v((size_t)n);
+  std::uniform_real_distribution<float> uf(0.0f, 1.0f);
+  for (auto &m : v) {
+    memset(&m, 0, sizeof(m));
+    m.queryLen = (offset_t)(rng() % 200000); m.queryStartPos = (offset_t)(rng() % 100000); m.queryEndPos = m.queryStartPos + (offset_t)(rng() % 100000);
+    m.refSeqId = (seqno_t)(rng() % meta.size()); m.refStartPos = (offset_t)(rng() % 1000000); m.refEndPos = m.refStartPos + (offset_t)(rng() % 100000);
+    m.strand = (rng() & 1) ? strnd::FWD : strnd::REV;
+    m.sketchSize = 1 + (int)(rng() % 1000); m.conservedSketches = (int)(rng() % (uint64_t)(m.sketchSize + 1)); m.blockLength = (int)(rng() % 100000);
+    switch (rng() % 6) { /* identities: arbitrary floats, dyadic values (exact decimal ties), the extremes */
+      case 0: m.nucIdentity = (float)(rng() % 129) / 128.0f; break;
+      case 1: m.nucIdentity = (float)(rng() % 1025) / 1024.0f; break;
+      case 2: m.nucIdentity = 1.0f; break;
+      case 3: m.nucIdentity = uf(rng) * 1e-4f; break;
+      default: m.nucIdentity = uf(rng);
+    }
+    switch (rng() % 4) {
+      case 0: m.kmerComplexity = (long double)((double)(rng() % 1000) / 999.0); break;
+      case 1: m.kmerComplexity = (long double)uf(rng); break;
+      case 2: m.kmerComplexity = (long double)(((double)uf(rng) + (double)uf(rng) + (double)uf(rng)) / 3.0); break;
+      default: m.kmerComplexity = 1.0L;
+    }
+  }
+  int bad = 0;
+  for (int mode = 0; mode < 8; mode++) {
+    Parameters p;
+    p.legacy_output = (mode & 1) != 0; p.report_ANI_percentage = (mode & 2) != 0; p.mergeMappings = (mode & 4) == 0;
+    MapTail t(p, meta, groups);
+    std::ostringstream os;
+    t.formatMappingsStream(v, "query_name", os);
+    std::string fast;
+    t.formatMappings(v, "query_name", fast);
+    if (os.str() != fast) bad++;
+  }
+  return bad;
 }
 
 }  // extern "C"

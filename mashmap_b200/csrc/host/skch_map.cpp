@@ -371,7 +371,6 @@ void BatchMapper::laneFinish(DeviceGroup &g, Lane &ln, const ReadBatch &b, std::
   auto worker = [&]() {
     IdentityCache idc;
     idc.k = param.kmerSize;
-    std::ostringstream os;
     uint64_t bytes = 0, mapped = 0, maps = 0;
     while (true) {
       const size_t lo = next.fetch_add(256);
@@ -385,9 +384,7 @@ void BatchMapper::laneFinish(DeviceGroup &g, Lane &ln, const ReadBatch &b, std::
         mapped++;
         maps += results[r].size();
         if (text) {
-          os.str(std::string());
-          tail.formatMappings(results[r], b.reads[r].name, os);
-          (*text)[r] = os.str();
+          tail.formatMappings(results[r], b.reads[r].name, (*text)[r]);
           bytes += (*text)[r].size();
         }
       }

@@ -5,6 +5,7 @@
 #include <cstdlib>
 
 #include <algorithm>
+#include <charconv>
 #include <cmath>
 #include <limits>
 #include <numeric>
@@ -307,9 +308,7 @@ void MapTail::finalizeOneToOne(MappingResultsVector_t &allReadMappings, const st
   auto work = [&](int ti) {
     const size_t lo = n * (size_t)ti / (size_t)T, hi = n * (size_t)(ti + 1) / (size_t)T;
     MappingResultsVector_t slice(allReadMappings.begin() + lo, allReadMappings.begin() + hi);
-    std::ostringstream os;
-    t.formatMappings(slice, "", os);
-    part[(size_t)ti] = os.str();
+    t.formatMappings(slice, "", part[(size_t)ti]);
   };
   std::vector<std::thread> pool;
   for (int ti = 1; ti < T; ti++) pool.emplace_back(work, ti);
@@ -395,7 +394,9 @@ void MapTail::mapRead(const ReadRec &rd, IdentityCache &idc, MappingResultsVecto
 }
 
 /* ---- reportReadMappings (computeMap.hpp:1758-1805): same stream formatting ---- */
-void MapTail::formatMappings(const MappingResultsVector_t &readMappings, const std::string &queryName, std::ostream &os) const
+/* reportReadMappings (computeMap.hpp:1758-1805) through an ostream, as the reference writes it: kept as the plain statement
+ * the fast formatter below is tested against (tests/test_host_cpu.py) */
+void MapTail::formatMappingsStream(const MappingResultsVector_t &readMappings, const std::string &queryName, std::ostream &os) const
 {
   for (auto &e : readMappings) {
     float fakeMapQ = e.nucIdentity == 1 ? 255 : std::round(-10.0 * std::log10(1 - (e.nucIdentity)));
@@ -413,6 +414,61 @@ void MapTail::formatMappings(const MappingResultsVector_t &readMappings, const s
     }
     os << "\n";
   }
+}
+
+namespace {
+/* what `os << v` writes for an integer / a floating-point value on a default-formatted stream: decimal digits, and
+ * printf's %g with precision 6 (std::to_chars(general, 6) is specified as exactly that conversion) */
+inline void put_int(std::string &out, long long v)
+{
+  char buf[24];
+  auto r = std::to_chars(buf, buf + sizeof(buf), v);
+  out.append(buf, r.ptr);
+}
+template <class F>
+inline void put_real(std::string &out, F v)
+{
+  char buf[64];
+  auto r = std::to_chars(buf, buf + sizeof(buf), v, std::chars_format::general, 6);
+  out.append(buf, r.ptr);
+}
+}  // namespace
+
+/* The same text appended to a string without a stream: the PAF lines were 3/4 of the host tail's time per read
+ * (scripts/tail_perf.py: 1.25 of 1.65 us), and at N GPUs on one host the tail is what the host CPUs are short of. */
+void MapTail::formatMappings(const MappingResultsVector_t &readMappings, const std::string &queryName, std::string &out) const
+{
+  const char sep = param.legacy_output ? ' ' : '\t';
+  for (auto &e : readMappings) {
+    const float fakeMapQ = e.nucIdentity == 1 ? 255 : std::round(-10.0 * std::log10(1 - (e.nucIdentity)));
+    out += (param.filterMode == filter::ONETOONE ? (*qmetadata)[e.querySeqId].name : queryName);
+    out += sep; put_int(out, e.queryLen);
+    out += sep; put_int(out, e.queryStartPos);
+    out += sep; put_int(out, e.queryEndPos - (param.legacy_output ? 1 : 0));
+    out += sep; out += (e.strand == strnd::FWD ? '+' : '-');
+    out += sep; out += metadata[e.refSeqId].name;
+    out += sep; put_int(out, metadata[e.refSeqId].len);
+    out += sep; put_int(out, e.refStartPos);
+    out += sep; put_int(out, e.refEndPos - (param.legacy_output ? 1 : 0));
+    if (!param.legacy_output) {
+      out += sep; put_int(out, e.conservedSketches);
+      out += sep; put_int(out, e.blockLength);
+      out += sep; put_real(out, fakeMapQ);
+      out += sep; out += "id:f:"; put_real(out, (param.report_ANI_percentage ? 100.0 : 1.0) * e.nucIdentity);
+      out += sep; out += "kc:f:"; put_real(out, e.kmerComplexity);
+      if (!param.mergeMappings) { out += sep; out += "jc:f:"; put_real(out, float(e.conservedSketches) / e.sketchSize); }
+    } else {
+      out += sep; put_real(out, e.nucIdentity * 100.0);
+    }
+    out += '\n';
+  }
+}
+
+void MapTail::formatMappings(const MappingResultsVector_t &readMappings, const std::string &queryName, std::ostream &os) const
+{
+  std::string text;
+  formatMappings(readMappings, queryName, text);
+  os << text;
 }
 
 

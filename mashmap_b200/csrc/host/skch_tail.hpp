@@ -63,6 +63,8 @@ class MapTail {
   /* -f one-to-one, the run-wide step (computeMap.hpp:358-405): reference-axis sweep over ALL mappings, final order, PAF text */
   void finalizeOneToOne(MappingResultsVector_t &allReadMappings, const std::vector<ContigInfo> &qmeta, std::string &paf) const;
   void formatMappings(const MappingResultsVector_t &readMappings, const std::string &queryName, std::ostream &os) const;
+  void formatMappings(const MappingResultsVector_t &readMappings, const std::string &queryName, std::string &out) const;  // appends
+  void formatMappingsStream(const MappingResultsVector_t &readMappings, const std::string &queryName, std::ostream &os) const;
 
  private:
   const Parameters &param;

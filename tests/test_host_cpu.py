@@ -287,3 +287,17 @@ def test_run_wide_one_to_one_step_equals_its_plain_statement(n, threads):
         d = L.skch_one_to_one_selftest(n, seed, threads, 64, max(10, n // 2), C.byref(tf), C.byref(tp))
         print(f"n={n} seed={seed}: fast {tf.value * 1e3:.1f} ms, plain {tp.value * 1e3:.1f} ms")
         assert d == 0
+
+
+def test_paf_text_without_a_stream_equals_the_stream_text():
+    """reportReadMappings (computeMap.hpp:1758-1805) writes every field through operator<<; the product appends the same
+    characters with std::to_chars (integers; %g with precision 6 for the mapping quality, identity, complexity and Jaccard
+    values). Same bytes on 200 k random mappings per seed -- arbitrary floats, dyadic identities (exact decimal ties),
+    0 and 1 -- in all eight output modes (legacy / percent identity / --noMerge)."""
+    import ctypes as C
+
+    L = hostlib.lib()
+    L.skch_format_selftest.restype = C.c_int
+    L.skch_format_selftest.argtypes = [C.c_int64, C.c_uint64]
+    for seed in (1, 2, 3):
+        assert L.skch_format_selftest(200_000, seed) == 0
