@@ -384,6 +384,8 @@ def gpu_arm(args):
 
     cfg = config_of(args)
     host_threads = max(1, usable_cpus() // max(1, world))  # sized to the CPU quota: more threads than CPUs only adds throttling
+    if os.environ.get("BENCH_HOST_THREADS"):  # experiments: what one of N ranks gets on a host with few CPUs
+        host_threads = max(1, int(os.environ["BENCH_HOST_THREADS"]))
     wl = setup_workload(args, cfg, rank, world, device)
     S, L, SEG, PI = wl["sketch"], cfg["read_len"], cfg["seg"], cfg["pi"]
     one_to_one = cfg["filt"] == "one-to-one"

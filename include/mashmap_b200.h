@@ -247,6 +247,12 @@ int mm_batch_fetch_sketch(mm_ctx *ctx, mm_minmer *out_sketch, int32_t *out_count
 typedef void (*mm_phase_hook)(void *user, int phase, int begin);
 int mm_ctx_set_phase_hook(mm_ctx *ctx, mm_phase_hook hook, void *user);
 
+/* How the calling thread waits for the device inside the library. 0 (default): it spins (cudaStreamSynchronize, lowest
+ * latency: right when the host has a CPU to spare per context). 1: it sleeps on a blocking event, which costs tens of
+ * microseconds per wait and frees the CPU: right when several contexts / processes share few host CPUs (one process per
+ * GPU on a host whose CPUs are outnumbered, skch::BatchMapper switches by itself). Nothing in the reference to replace. */
+int mm_ctx_set_wait_mode(mm_ctx *ctx, int blocking);
+
 /* CUDA-event time in milliseconds of each stage of the last mm_map_resident / mm_map_segments:
  * [0] sketch kernel  [1] L1 kernel  [2] L2 kernel  [3] H2D  [4] D2H
  * [5] first kernel launch -> last kernel end (events on the launching stream; includes the two counter

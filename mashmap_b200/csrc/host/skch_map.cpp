@@ -233,8 +233,12 @@ BatchMapper::BatchMapper(const Parameters &p, const Sketch &refsketch) : param(p
   }
   const int G = (int)groups.size();
   for (DeviceGroup *g : groups) {
-    // of a device's share of the host threads, three drive its pipeline (upload / kernels / fetch); the rest run the per-read tail
-    g->tailThreads = std::max(1, param.threads / G - 3);
+    // of a device's share of the host threads, three drive its pipeline (upload / kernels / fetch): with CPUs to spare they
+    // spin on the device (lowest latency) and the rest run the per-read tail; with four or fewer threads per device (one
+    // process per GPU on a host with few CPUs) they sleep on blocking events instead and every thread runs the tail
+    const int share = std::max(1, param.threads / G);
+    g->blockingWaits = getenv("MM_BLOCKING_WAIT") ? getenv("MM_BLOCKING_WAIT")[0] == '1' : share <= 4;
+    g->tailThreads = g->blockingWaits ? share : std::max(1, share - 3);
     if (const char *e = getenv("MM_TAIL_THREADS")) g->tailThreads = std::max(1, atoi(e));  // experiment
     g->tailPool = new WorkerPool(g->tailThreads);
     // further contexts share the device's index image: one lane per pipeline stage in flight (upload / kernels / fetch + tail)
@@ -248,6 +252,7 @@ BatchMapper::BatchMapper(const Parameters &p, const Sketch &refsketch) : param(p
       g->lanes[l].ctx = c2;
       g->nLanes = l + 1;
     }
+    for (int l = 0; l < g->nLanes; l++) mm_ctx_set_wait_mode(g->lanes[l].ctx, g->blockingWaits ? 1 : 0);
     if (g->nLanes > 1 && !getenv("MM_NO_GATE")) {
       g->gate = new Gate();
       for (int l = 0; l < g->nLanes; l++) mm_ctx_set_phase_hook(g->lanes[l].ctx, &BatchMapper::phaseHook, g->gate);
@@ -414,15 +419,17 @@ void BatchMapper::mapBatch(const ReadBatch &b, std::vector<MappingResultsVector_
   for (DeviceGroup *g : groups)
     for (auto &ln : g->lanes) { d0 += ln.secDevice; t0 += ln.secTail; }
   // parts of ~SUB bases (a read is never split across parts)
-  // A large batch ends with smaller parts: the last fetch + host tail has nothing left to hide behind. (Smaller FIRST
-  // parts were tried too and lost: the upload runs barely faster than the kernels, so a short first part only makes the
-  // compute thread wait for the second upload.)
+  // A large batch ends with smaller parts: the last fetch + host tail has nothing left to hide behind. It starts with a
+  // half-size part: the kernels wait for the first upload only, and an upload now takes about half as long as the
+  // kernels of the same part, so the second (full) part is on the device before the first one's kernels end. (When the
+  // upload was barely faster than the kernels, a short first part only made the compute thread wait for the second upload.)
   uint64_t SUB = std::max<uint64_t>(param.sub_batch_bases, 1);
   if (groups.size() > 1)  // several devices: enough parts for every device's three lanes
     SUB = std::max<uint64_t>(std::min<uint64_t>(SUB, b.used / (3 * groups.size()) + 1), (uint64_t)param.segLength);
   std::vector<uint64_t> targets;
   if (b.used >= 4 * SUB) {
     uint64_t left = b.used;
+    if (!getenv("MM_NO_RAMP")) { targets.push_back(SUB / 2); left -= SUB / 2; }
     while (left > SUB + SUB / 2 + SUB / 4) { targets.push_back(SUB); left -= SUB; }
     targets.push_back(std::max<uint64_t>(left * 4 / 7, 1));  // the rest in two parts, the last one the smaller
     targets.push_back(~0ULL);

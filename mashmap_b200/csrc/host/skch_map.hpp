@@ -119,6 +119,7 @@ class BatchMapper {
     int nLanes = 1;
     Gate *gate = nullptr;
     WorkerPool *tailPool = nullptr;  // persistent threads of the per-read host tail
+    bool blockingWaits = false;  // host waits sleep on events instead of spinning (few CPUs per device)
     int tailThreads = 1;
   };
   std::vector<DeviceGroup *> groups;

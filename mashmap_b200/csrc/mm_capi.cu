@@ -433,12 +433,13 @@ int run_l2_stream(mm_ctx *c, uint32_t *h_cnt)
       CU(c, cudaEventRecord(c->ev[8], c->stream));
       CU(c, mm_launch_l2_prep(c->params, c->ix, b, (uint32_t)nc, c->stream, c->sm_count));
       CU(c, cudaEventRecord(c->ev[9], c->stream));
+      if (guard.open && c->blocking_wait) CU(c, cudaEventRecord(c->ev_wait, c->stream));
       uint32_t *perm = nullptr;
       CU(c, mm_launch_l2_order(b, (uint32_t)nc, c->d_l2_order, c->l2_order_bytes, &perm, c->stream));
       b.l2_perm = perm;
       CU(c, mm_launch_l2_scan(c->params, c->ix, b, (uint32_t)nc, c->stream, c->sm_count));
       /* the scan is already queued behind it: waiting for the end of the preparation kernel costs no bubble */
-      if (guard.open) CU(c, cudaEventSynchronize(c->ev[9]));
+      if (guard.open) CU(c, cudaEventSynchronize(c->blocking_wait ? c->ev_wait : c->ev[9]));
     }
     c->launches += 4; /* own kernels: ranges, prep, order keys, scan (the prefix sum and the sort are library calls, not counted) */
     RD(c, c->d_counters, h_cnt, 16);
@@ -955,6 +956,20 @@ int mm_map_segments_packed(mm_ctx *c, const uint8_t *nibbles, uint64_t n_bases, 
                            mm_l2_locus *loci, uint64_t loci_cap, uint64_t *n_loci)
 {
   return map_segments_any(c, nibbles, n_bases, segs, n_segs, seg_results, cands, cand_cap, n_candidates, loci, loci_cap, n_loci, 1);
+}
+
+int mm_ctx_set_wait_mode(mm_ctx *c, int blocking)
+{
+  if (!c) return MM_EINVAL;
+  if (blocking && !c->ev_wait) {
+    cudaSetDevice(c->device);
+    if (cudaEventCreateWithFlags(&c->ev_wait, cudaEventBlockingSync | cudaEventDisableTiming) != cudaSuccess) {
+      c->ev_wait = nullptr;
+      return fail(c, MM_ECUDA, "cannot create the blocking event");
+    }
+  }
+  c->blocking_wait = blocking != 0;
+  return MM_OK;
 }
 
 int mm_ctx_set_phase_hook(mm_ctx *c, mm_phase_hook hook, void *user)

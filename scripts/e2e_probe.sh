@@ -21,6 +21,10 @@ PY
 for v in "$@"; do
   case $v in
     base) run base ;;
+    few2) run few2 BENCH_HOST_THREADS=2 ;;
+    few2spin) run few2spin BENCH_HOST_THREADS=2 MM_BLOCKING_WAIT=0 ;;
+    few4) run few4 BENCH_HOST_THREADS=4 ;;
+    noramp) run noramp MM_NO_RAMP=1 ;;
     skip) run skip MM_SKIP_H2D=12 ;;
     serial) run serial MM_LANES=1 ;;
     tail1) run tail1 MM_TAIL_THREADS=1 ;;
