@@ -706,6 +706,8 @@ def cpu_baseline(args, cfg, index_arrays, ascii_reads, S, threads=None, n_reads=
     return {**({"rows": rows[: min(n_map, len(rows))]} if want_rows else {}),
             "parity": parity, "value": n_reads * L / dt / 1e9, "unit": "Gbp/s", "cores": threads, "kind": "port",
             "cpus_busy": round(busy, 1), "host": host_cpu_info(),
+            "note": "the port is a plain restatement kept for checking, slower than the program it restates: the unmodified reference "
+                    "itself is timed by `bench.py --impl reference` (kind \"reference\")",
             "sample": f"first {n_reads} queries of the step ({n_reads * L / 1e6:.0f} Mbp), oracle/libmm_oracle.so mapModule per query "
                       f"on {threads} threads, {dt:.1f} s; {mapped.value} queries mapped, {n_map} mappings"}
 

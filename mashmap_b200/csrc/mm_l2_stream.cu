@@ -126,26 +126,41 @@ k_l2_prep(const mm_params prm, const mm_dev_index ix, const mm_dev_batch b, uint
       return a;
     };
     uint2 *out = b.l2_recs + off;
+    /* Both streams are read one 32-entry chunk ahead: the loads of chunk i+1 are issued before chunk i is looked up,
+     * compacted and stored (the stores keep the compiler from hoisting them by itself), so a warp always has a chunk of
+     * index entries in flight -- the kernel was bound by the latency of these loads (73 % long-scoreboard stalls). The
+     * wpos_end and strand of an insert entry are loaded with it, needed or not. */
     /* ---- insert stream ---- */
+    struct in_entry { uint64_t h; int32_t wpos, wend; int32_t strand; };
+    auto load_in = [&](uint32_t t) {
+      in_entry x; x.h = 0; x.wpos = 0; x.wend = 0; x.strand = 0;
+      if (t < r.nI) {
+        const uint64_t e = r.it0 + t;
+        x.h = ix.idx_hash[e]; x.wpos = ix.idx_wpos[e]; x.wend = ix.idx_wend[e]; x.strand = (int32_t)ix.idx_strand[e];
+      }
+      return x;
+    };
     uint32_t n_out = 0;
+    in_entry nxt = load_in((uint32_t)lane);
     for (uint32_t t0 = 0; t0 < r.nI; t0 += 32) {
       const uint32_t t = t0 + lane;
+      const in_entry en = nxt;
+      nxt = load_in(t + 32u);
       bool keep = false;
       uint2 rec = make_uint2(0, 0);
       if (t < r.nI) {
-        const uint64_t e = r.it0 + t;
-        const uint64_t h = ix.idx_hash[e];
-        const int wpos = ix.idx_wpos[e];
+        const uint64_t h = en.h;
+        const int wpos = en.wpos;
         const int a = q_lower_bound(h);
         const bool match = a <= n && qhash[a] == h;
         uint32_t info = (uint32_t)a;
         if (match) {
           info |= MM_L2_MATCH;
-          const int vote = (int)qstr[a] * (int)ix.idx_strand[e]; /* q_strand * mi.strand (slidingMap.hpp:141) */
-          info |= (uint32_t)(vote & 3) << 17;                    /* 2-bit two's complement: -1, 0, +1 */
+          const int vote = (int)qstr[a] * en.strand;   /* q_strand * mi.strand (slidingMap.hpp:141) */
+          info |= (uint32_t)(vote & 3) << 17;           /* 2-bit two's complement: -1, 0, +1 */
         }
         if (wpos < cd.rangeStartPos) { /* set-up entry (computeMap.hpp:1323-1338) */
-          keep = ix.idx_wend[e] > cd.rangeStartPos && a <= n;
+          keep = en.wend > cd.rangeStartPos && a <= n;
         } else {
           keep = true; /* every main entry is an evaluation point, even when it changes nothing */
         }
@@ -157,19 +172,26 @@ k_l2_prep(const mm_params prm, const mm_dev_index ix, const mm_dev_batch b, uint
     }
     const uint32_t nI2 = n_out;
     /* ---- delete stream ---- */
+    struct del_entry { uint64_t h; int32_t wend; };
+    auto load_del = [&](uint32_t t) {
+      del_entry x; x.h = 0; x.wend = 0;
+      if (t < r.nD) { const uint64_t e = r.d0 + t; x.h = ix.idx2_hash[e]; x.wend = ix.idx2_wend[e]; }
+      return x;
+    };
     uint2 *dout = out + nI2;
     uint32_t n_del = 0;
+    del_entry dnx = load_del((uint32_t)lane);
     for (uint32_t t0 = 0; t0 < r.nD; t0 += 32) {
       const uint32_t t = t0 + lane;
+      const del_entry en = dnx;
+      dnx = load_del(t + 32u);
       bool keep = false;
       uint2 rec = make_uint2(0, 0);
       if (t < r.nD) {
-        const uint64_t e = r.d0 + t;
-        const uint64_t h = ix.idx2_hash[e];
-        const int a = q_lower_bound(h);
+        const int a = q_lower_bound(en.h);
         keep = a <= n; /* hashes above every query hash never touch the state (slidingMap.hpp:133-136,179-182) */
-        const bool match = keep && qhash[a] == h;
-        rec = make_uint2((uint32_t)ix.idx2_wend[e], (uint32_t)a | (match ? MM_L2_MATCH : 0u));
+        const bool match = keep && qhash[a] == en.h;
+        rec = make_uint2((uint32_t)en.wend, (uint32_t)a | (match ? MM_L2_MATCH : 0u));
       }
       const uint32_t km = __ballot_sync(FULL, keep);
       if (keep) dout[n_del + __popc(km & ((1u << lane) - 1u))] = rec;
@@ -273,7 +295,8 @@ k_l2_scan(const mm_params prm, const mm_dev_index ix, const mm_dev_batch b, uint
     int pivot = n, pivRank = n, shared = 0, votes = 0;
     int best = 1; /* bestSketchSize (computeMap.hpp:1317) */
     bool in_cand = false, has_back = false;
-    lane_locus cur = {0, 0, 0, 0, 0}, back = {0, 0, 0, 0, 0};
+    int cur_start = 0, cur_end = 0; /* the open region */
+    lane_locus back = {0, 0, 0, 0, 0};
     int n_loci = 0;
     mm_l2_locus *lout = b.loci + (size_t)c * (size_t)LPC;
     auto store = [&](int k, const lane_locus &l) {
@@ -343,29 +366,25 @@ k_l2_scan(const mm_params prm, const mm_dev_index ix, const mm_dev_batch b, uint
           pivot += mv;
           words[slot * 32 + lane] = (uint16_t)(match ? w_match : w_plain);
         }
-        if (!do_del) {
+        { /* region tracking at every main insert (computeMap.hpp:1373-1430), as predicated updates: the branchy form
+           * (three cases, struct copies) cost a quarter of the step's instructions in moves and reconvergence points.
+           * While a region is open its sharedSketchSize equals `best`, so only its start and end are kept.
+           *   shared > best : l2_vec_out.clear(), a new region starts here           (:1375-1392)
+           *   shared == best: the open region goes on, or a new one starts here      (:1393-1406)
+           *   shared < best : an open region ends at the next position               (:1407-1427) -- the only branch */
+          const bool track = !do_del && is_main;
           const int npos = (i + 1 < r.nI) ? (int)inext.x : r.next_wpos;
-          if (is_main) { /* region tracking (computeMap.hpp:1373-1430) */
-            if (shared > best) {
-              n_loci = 0; has_back = false; /* l2_vec_out.clear() */
-              in_cand = true;
-              best = shared;
-              cur.shared = shared; cur.start = ipos; cur.end = npos;
-            } else if (shared == best) {
-              if (!in_cand) { cur.shared = shared; cur.start = ipos; }
-              in_cand = true;
-              cur.end = npos;
-            } else {
-              if (in_cand) {
-                cur.end = npos;
-                cur.mean = (cur.start + cur.end) / 2;
-                cur.strand = prev_votes >= 0 ? 1 : -1;
-                push_or_merge(cur);
-                cur.start = cur.end = cur.mean = cur.shared = cur.strand = 0;
-              }
-              in_cand = false;
-            }
+          const bool gt = track && shared > best, ge = track && shared >= best;
+          if (track && !ge && in_cand) {
+            lane_locus l;
+            l.start = cur_start; l.end = npos; l.mean = (cur_start + npos) / 2; l.shared = best;
+            l.strand = prev_votes >= 0 ? 1 : -1;
+            push_or_merge(l);
           }
+          if (gt) { n_loci = 0; has_back = false; best = shared; }
+          if (ge && (gt || !in_cand)) cur_start = ipos;
+          if (ge) cur_end = npos;
+          if (track) in_cand = ge;
         }
         /* consume the record */
         if (do_del) { p_d = p; drec = v; d++; }
@@ -374,9 +393,10 @@ k_l2_scan(const mm_params prm, const mm_dev_index ix, const mm_dev_batch b, uint
     }
     if (valid) {
       if (in_cand) { /* computeMap.hpp:1435-1450 */
-        cur.mean = (cur.start + cur.end) / 2;
-        cur.strand = votes >= 0 ? 1 : -1;
-        push_or_merge(cur);
+        lane_locus l;
+        l.start = cur_start; l.end = cur_end; l.mean = (cur_start + cur_end) / 2; l.shared = best;
+        l.strand = votes >= 0 ? 1 : -1;
+        push_or_merge(l);
       }
       if (has_back) { store(n_loci, back); n_loci++; }
       if (n_loci > LPC) {
