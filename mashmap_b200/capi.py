@@ -118,7 +118,7 @@ EXPORTED_SYMBOLS = [
     "mm_ctx_create", "mm_ctx_destroy", "mm_ctx_device", "mm_last_error", "mm_kernel_launches", "mm_ctx_diag", "mm_index_upload",
     "mm_tables_upload", "mm_index_build", "mm_index_download", "mm_index_blob", "mm_index_blob_alloc", "mm_index_adopt_blob", "mm_ctx_share_index", "mm_sketch_segments",
     "mm_map_segments", "mm_map_segments_packed", "mm_batch_upload", "mm_batch_upload_packed", "mm_last_pack_ms", "mm_map_resident", "mm_batch_fetch", "mm_batch_fetch_sketch",
-    "mm_last_stage_ms", "mm_ctx_set_phase_hook", "mm_ctx_set_wait_mode", "mm_host_alloc", "mm_host_free",
+    "mm_last_stage_ms", "mm_ctx_set_phase_hook", "mm_ctx_set_wait_mode", "mm_params_check", "mm_host_alloc", "mm_host_free",
 ]
 
 

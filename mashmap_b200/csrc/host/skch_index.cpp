@@ -267,8 +267,22 @@ uint64_t getReferenceSize(const std::vector<std::string> &refSequences)
 
 }  // namespace CommonFunc
 
+/* The limits of the B200 path, checked BEFORE the reference is read and indexed (the reference itself accepts these
+ * inputs; failing after a 3 Gbp index has been built would waste minutes): see README.md, "Limits". */
+static void checkPathLimits(const Parameters &p)
+{
+  auto die = [](const std::string &m) { std::cerr << "[mashmap-b200] ERROR: " << m << std::endl; exit(1); };
+  if (!p.split) die("--noSplit is not supported by the B200 path (fragments longer than the segment length)");
+  mm_params mp{};
+  mp.kmer_size = p.kmerSize; mp.seg_length = p.segLength; mp.sketch_size = std::max(1, p.sketchSize);
+  if (mm_params_check(&mp) != MM_OK) die(mm_last_error(nullptr));
+  if (p.sketchSize > 1000)
+    std::cerr << "[mashmap-b200] NOTE: sketch size " << p.sketchSize << " > 1000: the L2 stage uses its general kernel (about 4x slower)" << std::endl;
+}
+
 Sketch::Sketch(const Parameters &p) : param(p)
 {
+  checkPathLimits(param);
   build();
   if (!deviceBuildPending()) finish();
 }

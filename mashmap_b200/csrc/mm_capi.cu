@@ -584,6 +584,19 @@ int run_pipeline(mm_ctx *c)
 
 extern "C" {
 
+int mm_params_check(const mm_params *params)
+{
+  if (!params) return fail(nullptr, MM_EINVAL, "null params");
+  if (!mm_sketch_kmer_supported(params->kmer_size))
+    return fail(nullptr, MM_EINVAL, "k-mer size %d is not compiled in (8..32)", params->kmer_size);
+  if (params->sketch_size < 1 || params->seg_length < params->kmer_size)
+    return fail(nullptr, MM_EINVAL, "bad sketch_size / seg_length");
+  if (mm_sketch_smem_bytes(params->seg_length, params->sketch_size, params->kmer_size, nullptr, nullptr) == 0)
+    return fail(nullptr, MM_EINVAL, "seg_length %d / sketch_size %d exceed the shared-memory budget of the sketch kernel",
+                params->seg_length, params->sketch_size);
+  return MM_OK;
+}
+
 int mm_ctx_create(int device, const mm_params *params, mm_ctx **out)
 {
   if (!params || !out) return fail(nullptr, MM_EINVAL, "null argument");
@@ -596,13 +609,7 @@ int mm_ctx_create(int device, const mm_params *params, mm_ctx **out)
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(nullptr, MM_ENODEVICE, "cannot query device");
   if (prop.major != 10) return fail(nullptr, MM_ENODEVICE, "device %d is sm_%d%d; this build is sm_100a only", device, prop.major, prop.minor);
-  if (!mm_sketch_kmer_supported(params->kmer_size))
-    return fail(nullptr, MM_EINVAL, "k-mer size %d is not compiled in", params->kmer_size);
-  if (params->sketch_size < 1 || params->seg_length < params->kmer_size)
-    return fail(nullptr, MM_EINVAL, "bad sketch_size / seg_length");
-  if (mm_sketch_smem_bytes(params->seg_length, params->sketch_size, params->kmer_size, nullptr, nullptr) == 0)
-    return fail(nullptr, MM_EINVAL, "seg_length %d / sketch_size %d exceed the shared-memory budget of the sketch kernel",
-                params->seg_length, params->sketch_size);
+  if (int rc = mm_params_check(params)) return rc;
   mm_ctx *c = new mm_ctx();
   c->device = device;
   c->params = *params;

@@ -293,6 +293,7 @@ k_l2_scan(const mm_params prm, const mm_dev_index ix, const mm_dev_batch b, uint
     }
     __syncwarp();
     int pivot = n, pivRank = n, shared = 0, votes = 0;
+    bool sv_overflow = false;
     int best = 1; /* bestSketchSize (computeMap.hpp:1317) */
     bool in_cand = false, has_back = false;
     int cur_start = 0, cur_end = 0; /* the open region */
@@ -352,6 +353,7 @@ k_l2_scan(const mm_params prm, const mm_dev_index ix, const mm_dev_batch b, uint
           int vote = (int)((info >> 17) & 3u);
           vote = vote == 3 ? -1 : vote;
           const int sv2 = do_del ? 0 : svw + vote;
+          sv_overflow |= match && (sv2 > 7 || sv2 < -8); /* the 4-bit vote sum would wrap: the general kernel redoes the candidate */
           const uint32_t w_match = w_set_sv(do_del ? (w & ~W_ACT) : (w | W_ACT), sv2);
           const uint32_t w_plain = w + (uint32_t)sgn;
           const int pr = pivRank + (le ? sgn : 0);
@@ -399,7 +401,7 @@ k_l2_scan(const mm_params prm, const mm_dev_index ix, const mm_dev_batch b, uint
         push_or_merge(l);
       }
       if (has_back) { store(n_loci, back); n_loci++; }
-      if (n_loci > LPC) {
+      if (n_loci > LPC || sv_overflow) {
         atomicAdd(b.counters + 7, 1u); /* redo by the general kernel */
         b.cands[c].first_locus = 0;
         b.cands[c].n_loci = 0xFFFFFFFFu;

@@ -382,6 +382,21 @@ __device__ __forceinline__ int sk_hash_run(const sk_run &r, uint32_t &amax, cons
   return cnt;
 }
 
+/* initial threshold for a segment of n k-mer positions: expect c*S distinct survivors, c = 1.1 + 6/sqrt(S). The canonical hash
+ * is the MIN of two uniform hashes, so P(canonical <= t) = 1 - (1-t)^2: solve that for the wanted fraction f = c*S/n.
+ * Double-precision sqrt and divide: a few hundred instructions, so the kernels evaluate it once for the usual length
+ * (seg_length) and again only for the segments that differ. */
+__device__ __forceinline__ uint64_t sk_threshold(int S, int n)
+{
+  uint64_t T = SK_EMPTY;
+  if (n > 0) {
+    const double c = 1.1 + 6.0 / sqrt((double)S);
+    const double f = c * (double)S / (double)n;
+    if (f < 1.0) T = (uint64_t)((1.0 - sqrt(1.0 - f)) * 18446744073709551616.0);
+  }
+  return T;
+}
+
 /* Does any base this thread's k-mers cover carry the N flag (nibble bit 3)? Exactly the bases [b0, b0 + positions + K - 1):
  * the nibbles before and after them in the first / last word are masked off. (Scanning whole words, or a few bases too
  * many, is not harmless: in a packed batch every read is padded with N nibbles up to a multiple of 32 bases, so the last
@@ -445,6 +460,8 @@ k_sketch_table(const uint8_t *__restrict__ packed, const mm_segment *__restrict_
     bulk_g2s(smem + (size_t)stage * L.stage_bytes, packed + g0, bytes, &bars[stage]);
   };
 
+  const int n_usual = seg_length - K + 1;
+  const uint64_t T_usual = sk_threshold(S, n_usual);
   uint32_t it = 0;
   if (tid == 0 && blockIdx.x < n_segs) issue(work_list ? work_list[blockIdx.x] : blockIdx.x, 0);
 
@@ -471,14 +488,7 @@ k_sketch_table(const uint8_t *__restrict__ packed, const mm_segment *__restrict_
     r.list_h = list_h; r.list_p = list_p; r.cap = CAP;
     const bool has_work = r.p0 < r.p1;
 
-    /* initial threshold: expect c*S distinct survivors, c = 1.1 + 6/sqrt(S). The canonical hash is the MIN of two
-     * uniform hashes, so P(canonical <= t) = 1 - (1-t)^2: solve that for the wanted fraction f = c*S/n. */
-    uint64_t T = SK_EMPTY;
-    if (n > 0) {
-      const double c = 1.1 + 6.0 / sqrt((double)S);
-      const double f = c * (double)S / (double)n;
-      if (f < 1.0) T = (uint64_t)((1.0 - sqrt(1.0 - f)) * 18446744073709551616.0);
-    }
+    uint64_t T = n == n_usual ? T_usual : sk_threshold(S, n);
     uint64_t lo = 0, hi = 0;
     bool have_lo = false, have_hi = false;
     bool waited = false;
@@ -731,6 +741,8 @@ k_sketch(const uint8_t *__restrict__ packed, const mm_segment *__restrict__ segs
     bulk_g2s(smem + (size_t)stage * L.stage_bytes, packed + g0, bytes, &bars[stage]);
   };
 
+  const int n_usual = seg_length - K + 1;
+  const uint64_t T_usual = sk_threshold(S, n_usual);
   uint32_t it = 0;
   if (tid == 0 && blockIdx.x < n_segs) issue(blockIdx.x, 0);
 
@@ -756,12 +768,7 @@ k_sketch(const uint8_t *__restrict__ packed, const mm_segment *__restrict__ segs
     r.b0 = skew + (uint32_t)r.p0;
     r.list_h = list_h; r.list_p = list_p; r.cap = CAP;
     const bool has_work = r.p0 < r.p1;
-    uint64_t T = SK_EMPTY;
-    if (n > 0) {
-      const double c = 1.1 + 6.0 / sqrt((double)S);
-      const double f = c * (double)S / (double)n;
-      if (f < 1.0) T = (uint64_t)((1.0 - sqrt(1.0 - f)) * 18446744073709551616.0);
-    }
+    const uint64_t T = n == n_usual ? T_usual : sk_threshold(S, n);
     r.T_hi = (uint32_t)(T >> 32);
 
     mbar_wait(&bars[stage], (it >> 1) & 1);

@@ -301,3 +301,25 @@ def test_paf_text_without_a_stream_equals_the_stream_text():
     L.skch_format_selftest.argtypes = [C.c_int64, C.c_uint64]
     for seed in (1, 2, 3):
         assert L.skch_format_selftest(200_000, seed) == 0
+
+
+def test_path_limits_are_checked_without_a_device():
+    """mm_params_check: the limits of the device path (k, shared-memory budget of the sketch kernel) answered before any
+    reference is read -- skch::Sketch calls it first -- and without a GPU"""
+    import ctypes as C
+
+    L = capi.lib()
+    L.mm_params_check.restype = C.c_int
+    L.mm_params_check.argtypes = [C.c_void_p]
+    L.mm_last_error.restype = C.c_char_p
+    L.mm_last_error.argtypes = [C.c_void_p]
+
+    def check(k, seg, s):
+        p = capi.Params(kmer_size=k, seg_length=seg, sketch_size=s)
+        return L.mm_params_check(C.byref(p))
+
+    assert check(19, 5000, 220) == 0
+    assert check(16, 1000, 40) == 0
+    assert check(19, 10000, 1000) == 0
+    assert check(40, 5000, 220) != 0 and b"k-mer size" in L.mm_last_error(None)
+    assert check(19, 400000, 220) != 0 and b"shared-memory" in L.mm_last_error(None)
