@@ -264,6 +264,7 @@ BatchMapper::~BatchMapper()
 {
   for (DeviceGroup *g : groups) {
     delete g->tailPool;
+    for (int l = 0; l < MAX_LANES; l++) { g->lanes[l].segRes.release(); g->lanes[l].cands.release(); g->lanes[l].loci.release(); }
     for (int l = g->nLanes - 1; l >= 1; l--) mm_ctx_destroy(g->lanes[l].ctx);
     if (g->owner && g->owner != ctx) mm_ctx_destroy(g->owner);
     delete g->gate;
@@ -354,9 +355,9 @@ void BatchMapper::laneFinish(DeviceGroup &g, Lane &ln, const ReadBatch &b, std::
   const int tail_threads = g.tailThreads;
   auto t0 = Clock::now();
   const size_t r0 = ln.r0, r1 = ln.r1;
-  if (ln.segRes.size() < ln.nseg) ln.segRes.resize(ln.nseg);
-  if (ln.cands.size() < ln.nc) ln.cands.resize(ln.nc + ln.nc / 8 + 1024);
-  if (ln.loci.size() < ln.nl) ln.loci.resize(ln.nl + ln.nl / 8 + 1024);
+  if (ln.segRes.size() < ln.nseg) ln.segRes.reserve(ln.nseg + ln.nseg / 8 + 1024);
+  if (ln.cands.size() < ln.nc) ln.cands.reserve(ln.nc + ln.nc / 8 + 1024);
+  if (ln.loci.size() < ln.nl) ln.loci.reserve(ln.nl + ln.nl / 8 + 1024);
   int rc = mm_batch_fetch(ln.ctx, ln.segRes.data(), ln.cands.data(), ln.cands.size(), ln.loci.data(), ln.loci.size());
   if (rc != MM_OK) die(std::string("mm_batch_fetch: ") + mm_last_error(ln.ctx));
   mm_last_stage_ms(ln.ctx, ln.stageMs);

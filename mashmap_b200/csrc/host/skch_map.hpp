@@ -24,6 +24,7 @@
 
 #include <functional>
 #include <atomic>
+#include <iostream>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -96,9 +97,28 @@ class BatchMapper {
   struct Lane {  // per pipeline lane: device context (own stream + buffers) and its host-side record buffers
     mm_ctx *ctx = nullptr;
     std::vector<mm_segment> segs;
-    std::vector<mm_segment_result> segRes;
-    std::vector<mm_l1_candidate> cands;
-    std::vector<mm_l2_locus> loci;
+    /* the records mm_batch_fetch copies back live in pinned memory: a device->host copy into pageable memory goes through
+     * the driver's staging buffer at ~8 GB/s and costs host CPU time on top (1.8 ms per 134 k-fragment part) */
+    template <class T>
+    struct PinnedArray {
+      T *p = nullptr;
+      size_t cap = 0;
+      T *data() const { return p; }
+      size_t size() const { return cap; }
+      void reserve(size_t n)
+      {
+        if (n <= cap) return;
+        if (p) mm_host_free(p);
+        p = nullptr; cap = 0;
+        void *q = nullptr;
+        if (mm_host_alloc(&q, n * sizeof(T)) != MM_OK) { std::cerr << "[mashmap-b200] ERROR: cannot pin " << n * sizeof(T) << " bytes" << std::endl; exit(1); }
+        p = (T *)q; cap = n;
+      }
+      void release() { if (p) mm_host_free(p); p = nullptr; cap = 0; }
+    };
+    PinnedArray<mm_segment_result> segRes;
+    PinnedArray<mm_l1_candidate> cands;
+    PinnedArray<mm_l2_locus> loci;
     size_t r0 = 0, r1 = 0, s0 = 0, nseg = 0;  // the part in flight on this lane
     uint64_t nc = 0, nl = 0;
     double secDevice = 0, secTail = 0, msUpload = 0, msCompute = 0;

@@ -322,8 +322,9 @@ void MapTail::finalizeOneToOne(MappingResultsVector_t &allReadMappings, const st
 /* ---- mapModule for one read, given the device results of its fragments (computeMap.hpp:570-714) ---- */
 void MapTail::mapRead(const ReadRec &rd, IdentityCache &idc, MappingResultsVector_t &out) const
 {
-  MappingResultsVector_t unfiltered, l2Mappings;
-  std::vector<mm_l1_candidate> work;
+  MappingResultsVector_t &unfiltered = idc.unfiltered, &l2Mappings = idc.l2Mappings;
+  std::vector<mm_l1_candidate> &work = idc.work;
+  unfiltered.clear(); l2Mappings.clear(); work.clear();
   bool split_mapping = true;
   if (rd.len <= param.segLength) {  // :587-607 (param.split is always true here)
     fragmentMappings(segs[rd.first_seg], segRes[rd.first_seg], rd, idc, work, l2Mappings);
@@ -360,11 +361,12 @@ void MapTail::mapRead(const ReadRec &rd, IdentityCache &idc, MappingResultsVecto
                      unfiltered.end());
   }
   if (param.filterMode == filter::MAP || param.filterMode == filter::ONETOONE) {
-    MappingResultsVector_t tmp;
+    MappingResultsVector_t &tmp = idc.filtered;
+    tmp.clear();
     filterByGroup(unfiltered, tmp, n_mappings, false);
-    unfiltered = std::move(tmp);
+    unfiltered.swap(tmp);
   }
-  out.swap(unfiltered);
+  out.assign(unfiltered.begin(), unfiltered.end());  // `out` keeps the capacity it had for the previous batch's read
   if (param.filterLengthMismatches) {  // filterFalseHighIdentity :441-454
     out.erase(std::remove_if(out.begin(), out.end(),
                              [&](MappingResult &e) {

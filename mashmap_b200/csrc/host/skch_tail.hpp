@@ -40,6 +40,9 @@ struct IdentityCache {
   int k = 19;
   std::unordered_map<uint64_t, std::pair<float, float>> memo;
   std::pair<float, float> get(int shared, int qs);
+  // per-worker scratch of MapTail::mapRead (cleared, never shrunk: no allocation per read once warm)
+  MappingResultsVector_t unfiltered, l2Mappings, filtered;
+  std::vector<mm_l1_candidate> work;
 };
 
 class MapTail {
