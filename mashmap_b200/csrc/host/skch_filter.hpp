@@ -10,6 +10,9 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <set>
 #include <thread>
 #include <tuple>
@@ -144,6 +147,9 @@ inline void filterMappingsParallel(MappingResultsVector_t &readMappings, const s
   const size_t n = readMappings.size();
   if (n <= 1) return;
   if (threads <= 1 || n < 4096) { filterMappings(readMappings, metadata, secondaryToKeep); return; }
+  const bool trace_ = getenv("MM_TRACE") != nullptr;
+  auto tt_ = std::chrono::steady_clock::now();
+  auto lap_ = [&](const char *w) { if (!trace_) return; auto t = std::chrono::steady_clock::now(); fprintf(stderr, "[trace]     sweep %s: %.1f ms\n", w, std::chrono::duration<double, std::milli>(t - tt_).count()); tt_ = t; };
   for (auto &e : readMappings) e.discard = 1;
   /* mappings by contig (counting sort keeps id order inside a contig) */
   const size_t nc = metadata.size();
@@ -167,6 +173,7 @@ inline void filterMappingsParallel(MappingResultsVector_t &readMappings, const s
     if (link && !units.empty() && units.back().second == c - 1) units.back().second = c;
     else units.emplace_back(c, c);
   }
+  lap_("prepare");
   std::atomic<size_t> next{0};
   auto work = [&]() {
     Order ord{&readMappings};
@@ -214,8 +221,10 @@ inline void filterMappingsParallel(MappingResultsVector_t &readMappings, const s
   for (int t = 1; t < threads; t++) pool.emplace_back(work);
   work();
   for (auto &th : pool) th.join();
+  lap_("units");
   readMappings.erase(std::remove_if(readMappings.begin(), readMappings.end(), [](MappingResult &e) { return e.discard == 1; }),
                      readMappings.end());
+  lap_("erase");
 }
 
 }  // namespace ref

@@ -206,7 +206,7 @@ void MapTail::mergeMappingsInRange(MappingResultsVector_t &readMappings, int max
  * pairs end up in exactly the arrangement the records would have (also among records with equal keys, whose order the
  * later steps depend on). Worth it from a few thousand 96-byte records on. */
 template <class KeyFn>
-static void sortLikeStd(MappingResultsVector_t &v, KeyFn key)
+static void sortLikeStd(MappingResultsVector_t &v, KeyFn key, int threads = 1)
 {
   typedef decltype(key(v[0])) K;
   if (v.size() < 2048) {
@@ -214,11 +214,24 @@ static void sortLikeStd(MappingResultsVector_t &v, KeyFn key)
     return;
   }
   struct P { K k; uint32_t i; };
-  std::vector<P> p(v.size());
-  for (size_t i = 0; i < v.size(); i++) { p[i].k = key(v[i]); p[i].i = (uint32_t)i; }
-  std::sort(p.begin(), p.end(), [](const P &a, const P &b) { return a.k < b.k; });
-  MappingResultsVector_t out(v.size());
-  for (size_t i = 0; i < v.size(); i++) out[i] = v[p[i].i];
+  const size_t n = v.size();
+  const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(1, threads), n / 16384));
+  auto in_slices = [&](auto fn) {  // fn(lo, hi) over [0, n) on T threads
+    std::vector<std::thread> pool;
+    for (int t = 1; t < T; t++) pool.emplace_back([&, t] { fn(n * (size_t)t / (size_t)T, n * (size_t)(t + 1) / (size_t)T); });
+    fn(0, n / (size_t)T);
+    for (auto &th : pool) th.join();
+  };
+  static thread_local std::vector<P> p;                    // scratch kept between calls: no 14 MB of fresh pages per sort
+  static thread_local MappingResultsVector_t out;
+  p.resize(n);
+  out.resize(n);
+  P *pp = p.data();  // the helper threads must see THIS thread's scratch, not their own (empty) thread_local copies
+  MappingResult *oo = out.data();
+  const MappingResult *vv = v.data();
+  in_slices([&](size_t lo, size_t hi) { for (size_t i = lo; i < hi; i++) { pp[i].k = key(vv[i]); pp[i].i = (uint32_t)i; } });
+  std::sort(p.begin(), p.end(), [](const P &a, const P &b) { return a.k < b.k; });  // serial: its permutation IS the specification
+  in_slices([&](size_t lo, size_t hi) { for (size_t i = lo; i < hi; i++) oo[i] = vv[pp[i].i]; });
   v.swap(out);
 }
 
@@ -234,7 +247,8 @@ void MapTail::filterByGroup(MappingResultsVector_t &unfiltered, MappingResultsVe
     fprintf(stderr, "[trace]   filterByGroup %s: %.1f ms\n", what, std::chrono::duration<double, std::milli>(t - tt0).count());
     tt0 = t;
   };
-  sortLikeStd(unfiltered, [](const MappingResult &a) { return std::make_tuple(a.refSeqId, a.refStartPos); });
+  const int sort_threads = filter_ref ? param.threads : 1;  // the run-wide step only: the per-read calls are far below the threshold
+  sortLikeStd(unfiltered, [](const MappingResult &a) { return std::make_tuple(a.refSeqId, a.refStartPos); }, sort_threads);
   lap("sort 1");
   auto sb = unfiltered.begin(), se = unfiltered.begin();
   if (param.filterMode == filter::MAP || param.filterMode == filter::ONETOONE) {
@@ -247,7 +261,7 @@ void MapTail::filterByGroup(MappingResultsVector_t &unfiltered, MappingResultsVe
         se = unfiltered.end();
       }
       tmp.insert(tmp.end(), std::make_move_iterator(sb), std::make_move_iterator(se));
-      sortLikeStd(tmp, [](const MappingResult &a) { return std::make_tuple(a.queryStartPos, a.refSeqId, a.refStartPos); });
+      sortLikeStd(tmp, [](const MappingResult &a) { return std::make_tuple(a.queryStartPos, a.refSeqId, a.refStartPos); }, sort_threads);
       lap("sort 2");
       if (filter_ref) Filter::ref::filterMappingsParallel(tmp, metadata, (uint16_t)n_mappings, param.threads);
       else Filter::query::filterMappings(tmp, (uint16_t)n_mappings);
@@ -257,7 +271,7 @@ void MapTail::filterByGroup(MappingResultsVector_t &unfiltered, MappingResultsVe
       sb = se;
     }
   }
-  sortLikeStd(filtered, [](const MappingResult &a) { return std::make_tuple(a.queryStartPos, a.refSeqId, a.refStartPos); });
+  sortLikeStd(filtered, [](const MappingResult &a) { return std::make_tuple(a.queryStartPos, a.refSeqId, a.refStartPos); }, sort_threads);
 }
 
 int MapTail::getRefGroup(const std::string &seqName) const
@@ -296,7 +310,7 @@ void MapTail::finalizeOneToOne(MappingResultsVector_t &allReadMappings, const st
   }
   allReadMappings = std::move(filtered);
   lap("filterByGroup");
-  sortLikeStd(allReadMappings, [](const MappingResult &a) { return std::make_tuple(a.querySeqId, a.queryStartPos, a.refSeqId, a.refStartPos); });
+  sortLikeStd(allReadMappings, [](const MappingResult &a) { return std::make_tuple(a.querySeqId, a.queryStartPos, a.refSeqId, a.refStartPos); }, param.threads);
   lap("final sort");
   /* the PAF text: formatted in slices by the host threads and joined in order (every slice starts from a stream in its
    * default state, as the single stream of the reference is for every line) */
