@@ -66,6 +66,10 @@ def parse_args():
     ap.add_argument("--contigs", type=int, default=256)
     ap.add_argument("--cpu-sample-reads", type=int, default=0, help="reads per CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-kind", default="auto", choices=["auto", "reference", "port"], help="cpu_baseline leg of the b200 arm: 'reference' = the "
+                    "unmodified reference (oracle/_ref/libmm_ref.so builds its own index from the FASTA of the bench's reference: + 1.5 min "
+                    "of set-up at 3 Gbp); 'port' = the oracle restatement on the product's index content; 'auto' = reference when the "
+                    "library is there")
     ap.add_argument("--sketch", type=int, default=0, help="sketch size override (0 = the reference's automatic choice)")
     ap.add_argument("--ref-kind", default="auto", choices=["auto", "real", "port"], help="--impl reference: 'real' = the unmodified reference "
                     "(oracle/_ref/libmm_ref.so: its own index build from FASTA, its own mapModule); 'port' = the oracle restatement on the "
@@ -398,10 +402,17 @@ def gpu_arm(args):
     bm = hostlib.BatchMapper(hi, pi=PI, device=local_rank, threads=host_threads, filter_mode=cfg["filt"])
     ctx = capi.Context.from_handle(bm.ctx_handle, S, device=local_rank)
     want_cpu = (not args.no_cpu_baseline) and world == 1
+    cpu_real = want_cpu and args.cpu_kind != "port" and reference_library() is not None
+    if want_cpu and args.cpu_kind == "reference" and not cpu_real:
+        raise SystemExit("--cpu-kind reference: oracle/_ref/libmm_ref.so is not there (make -C oracle)")
+    ref_session = None
+    if cpu_real:  # the reference indexes the same contigs itself, from FASTA, while they are still at hand (not timed)
+        ref_session, _ = real_reference_session(args, cfg, wl, S, usable_cpus())
+    want_port = want_cpu and not cpu_real
     ist = None
     if rank == 0:  # rank 0 builds the index on its GPU; the other ranks receive the image
-        ist = build_index_on_device(args, cfg, wl, ctx, keep_lookup=want_cpu)
-    host_index_arrays = ctx.index_download() if (rank == 0 and want_cpu) else None
+        ist = build_index_on_device(args, cfg, wl, ctx, keep_lookup=want_port)
+    host_index_arrays = ctx.index_download() if (rank == 0 and want_port) else None
     wl["ref_dev"] = None
     torch.cuda.empty_cache()
     if comm is not None:
@@ -569,7 +580,23 @@ def gpu_arm(args):
         }
         if sharded_check is not None:
             out["sharded_check"] = sharded_check
-        if not args.no_cpu_baseline and world == 1:
+        if want_cpu and cpu_real:
+            # the unmodified reference on a bounded sample of the step, on all host threads; its mappings of those reads are
+            # diffed against the product's (the timed result): parity against the reference itself at bench scale
+            threads = usable_cpus()
+            n_cpu = min(cpu_sample_reads(args, cfg, threads), n_local)
+            cb, ref_rows = real_reference_step(ref_session, cfg, ascii_reads, n_cpu, threads, first_counter=wl["first_counter"], want_rows=True)
+            ref_session.close()
+            sel = (res[:, 0] - wl["first_counter"] < n_cpu) if len(res) else np.zeros(0, bool)
+            d = _port_vs_reference(res[sel], ref_rows, cfg["seg"])
+            out["parity"] = {"reads": int(n_cpu), "against": "the unmodified reference (oracle/_ref/libmm_ref.so, its own index)",
+                             "stage": "per-read mappings (before the run-wide one-to-one sweep)" if one_to_one else "final mappings",
+                             "mappings_gpu": d["mappings_port"], "mappings_reference": d["mappings_reference"],
+                             "single_fragment_mappings_dropped_by_the_reference_uninitialised_n_merged":
+                                 d["single_fragment_mappings_dropped_by_the_reference_uninitialised_n_merged"],
+                             "mismatches": d["other_differences"], "max_identity_diff": d["max_identity_diff"]}
+            out["cpu_baseline"] = cb
+        elif want_cpu:
             cb = cpu_baseline(args, cfg, host_index_arrays, ascii_reads, S, gpu_rows=res, first_counter=wl["first_counter"])
             out["parity"] = cb.pop("parity")  # GPU mappings of the sampled reads == the CPU port's, at bench scale
             out["cpu_baseline"] = cb

@@ -125,7 +125,11 @@ class BatchMapper:
         """the mappings of the last map() as raw skch::MappingResult records ([n, record_bytes] uint8): what a rank hands
         to mm_records_allgather"""
         n = lib().skch_bm_results_raw(self.h, None, 0)
-        out = np.zeros((max(n, 1), self.record_bytes), dtype=np.uint8)
+        need = max(n, 1) * self.record_bytes
+        buf = getattr(self, "_raw_pin", None)
+        if buf is None or buf.nbytes < need:  # a pinned buffer kept between calls: the records go to the device next
+            self._raw_pin = buf = capi.PinnedBuffer(need + need // 4)
+        out = buf.array[:need].reshape(max(n, 1), self.record_bytes)
         lib().skch_bm_results_raw(self.h, out.ctypes.data, n)
         return out[:n]
 

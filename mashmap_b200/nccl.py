@@ -78,9 +78,14 @@ class Comm:
         r = np.ascontiguousarray(records)
         row_bytes = int(r.dtype.itemsize * (np.prod(r.shape[1:]) if r.ndim > 1 else 1))
         counts = np.zeros(self.n_ranks, dtype=np.uint64)
-        cap = max(int(len(r)) * self.n_ranks * 2, 1024)
+        cap = max(int(len(r)) * self.n_ranks + int(len(r)) // 2, 1024)
         while True:
-            out = np.zeros((cap,) + r.shape[1:], dtype=r.dtype)
+            # the gathered rows land in a pinned buffer kept between calls (a fresh pageable array per call costs page
+            # faults on hundreds of MB and a staged device->host copy at a fraction of the PCIe rate)
+            need = cap * row_bytes
+            if getattr(self, "_pin", None) is None or self._pin.nbytes < need:
+                self._pin = capi.PinnedBuffer(need)
+            out = self._pin.array[:need].view(r.dtype).reshape((cap,) + r.shape[1:])
             rc = self._L.mm_records_allgather(self._h, r.ctypes.data, len(r), row_bytes, out.ctypes.data, cap, counts.ctypes.data)
             if rc == capi.MM_ECAPACITY:
                 cap = int(counts.sum()) + 16
