@@ -408,6 +408,7 @@ def gpu_arm(args):
     ref_session = None
     if cpu_real:  # the reference indexes the same contigs itself, from FASTA, while they are still at hand (not timed)
         ref_session, _ = real_reference_session(args, cfg, wl, S, usable_cpus())
+        t_index = time.time()  # index_build_seconds is the product's side only
     want_port = want_cpu and not cpu_real
     ist = None
     if rank == 0:  # rank 0 builds the index on its GPU; the other ranks receive the image

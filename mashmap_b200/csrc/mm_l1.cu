@@ -345,18 +345,14 @@ __device__ int l1_process_range(const mm_params &prm, const mm_dev_index &ix, co
 }
 
 /* probe the lookup table for one hash: 0 = absent, else offset<<25 | count<<1 | isFreqSeed */
-__device__ __forceinline__ uint64_t l1_probe(const mm_dev_index &ix, uint64_t h, int l2_hint = 0)
+__device__ __forceinline__ uint64_t l1_probe(const mm_dev_index &ix, uint64_t h)
 {
   uint32_t slot = mm_tab_slot_of(h, ix.tab_log2);
   const uint32_t tmask = (1u << ix.tab_log2) - 1u;
   while (true) {
-    mm_tab_slot t;
-    if (l2_hint == 64) /* experiment (MM_PROBE_L2=64|128): the L2 fetch size around the slot (ncu: 128 B of DRAM per probe by default) */
-      asm("ld.global.L2::64B.v2.u64 {%0, %1}, [%2];" : "=l"(t.key), "=l"(t.val) : "l"(ix.tab + slot));
-    else if (l2_hint == 128)
-      asm("ld.global.L2::128B.v2.u64 {%0, %1}, [%2];" : "=l"(t.key), "=l"(t.val) : "l"(ix.tab + slot));
-    else
-      t = ix.tab[slot];
+    /* (128 B of DRAM traffic per probe, ncu; neither cudaLimitMaxL2FetchGranularity = 32 nor ld.global.L2::64B / ::128B changes
+     * the kernel's time) */
+    const mm_tab_slot t = ix.tab[slot];
     if (t.val == MM_TAB_EMPTY_VAL) return 0;
     if (t.key == h) return t.val;
     slot = (slot + 1) & tmask;
@@ -365,14 +361,14 @@ __device__ __forceinline__ uint64_t l1_probe(const mm_dev_index &ix, uint64_t h,
 
 /* K2a: one thread per sketch entry -- the random table probes of the whole batch with full memory-level parallelism
  * (the per-segment kernels below are latency-bound when they probe themselves: 7 dependent DRAM round trips per lane). */
-__global__ void __launch_bounds__(256) k_l1_probe(const mm_dev_index ix, const mm_dev_batch b, int S, int l2_hint)
+__global__ void __launch_bounds__(256) k_l1_probe(const mm_dev_index ix, const mm_dev_batch b, int S)
 {
   const uint64_t total = (uint64_t)b.n_segs * (uint64_t)S;
   for (uint64_t e = (uint64_t)blockIdx.x * 256ULL + threadIdx.x; e < total; e += (uint64_t)gridDim.x * 256ULL) {
     const uint32_t seg = (uint32_t)(e / (uint32_t)S);
     const int j = (int)(e - (uint64_t)seg * (uint32_t)S);
     if (j >= b.seg_res[seg].sketch_raw_count) continue;
-    b.sk_val[e] = l1_probe(ix, b.sk_hash[e], l2_hint);
+    b.sk_val[e] = l1_probe(ix, b.sk_hash[e]);
   }
 }
 
@@ -682,8 +678,7 @@ cudaError_t mm_launch_l1(const mm_params &p, const mm_dev_index &ix, const mm_de
   {
     const uint64_t total = (uint64_t)b.n_segs * (uint64_t)p.sketch_size;
     const uint64_t blocks = (total + 255) / 256;
-    static const int l2_hint = getenv("MM_PROBE_L2") ? atoi(getenv("MM_PROBE_L2")) : 0;
-    k_l1_probe<<<(uint32_t)std::min<uint64_t>(blocks, 1u << 30), 256, 0, st>>>(ix, b, p.sketch_size, l2_hint);
+    k_l1_probe<<<(uint32_t)std::min<uint64_t>(blocks, 1u << 30), 256, 0, st>>>(ix, b, p.sketch_size);
     cudaError_t e0 = cudaGetLastError();
     if (e0 != cudaSuccess) return e0;
   }

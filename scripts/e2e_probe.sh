@@ -21,8 +21,8 @@ PY
 for v in "$@"; do
   case $v in
     base) run base ;;
-    probe64) run probe64 MM_PROBE_L2=64 ;;
-    probe128) run probe128 MM_PROBE_L2=128 ;;
+    few8) run few8 BENCH_HOST_THREADS=8 ;;
+    few8block) run few8block BENCH_HOST_THREADS=8 MM_BLOCKING_WAIT=1 ;;
     few2) run few2 BENCH_HOST_THREADS=2 ;;
     few2spin) run few2spin BENCH_HOST_THREADS=2 MM_BLOCKING_WAIT=0 ;;
     few4) run few4 BENCH_HOST_THREADS=4 ;;
