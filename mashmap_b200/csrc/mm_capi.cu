@@ -677,6 +677,16 @@ int mm_index_upload(mm_ctx *c, const mm_minmer *mi, uint64_t n_mi, const uint64_
   CU(c, cudaSetDevice(c->device));
   if (c->blob && c->blob_owned) { cudaFree(c->blob); }
   c->blob = nullptr; c->blob_ready = false;
+  /* every early return below releases the temporaries (dev_tmp) and the half-built image (blob_guard) */
+  struct dev_tmp {
+    void *p = nullptr;
+    ~dev_tmp() { if (p) cudaFree(p); }
+  };
+  struct blob_guard {
+    mm_ctx *c;
+    bool done = false;
+    ~blob_guard() { if (!done && c->blob && c->blob_owned) { cudaFree(c->blob); c->blob = nullptr; c->blob_bytes = 0; c->blob_ready = false; } }
+  } guard{c};
 
   /* contig_start: first index entry of each contig; the index must be ordered by (seqId, wpos) */
   std::vector<uint64_t> cstart((size_t)n_contigs + 1, 0);
@@ -724,8 +734,9 @@ int mm_index_upload(mm_ctx *c, const mm_minmer *mi, uint64_t n_mi, const uint64_
   /* AoS records go up in chunks and are re-laid out on the device (SoA index, packed points, hash table) */
   {
     const uint64_t CH = 1ULL << 24;
-    void *stage = nullptr;
-    CU(c, cudaMalloc(&stage, CH * 24));
+    dev_tmp stage_buf;
+    CU(c, cudaMalloc(&stage_buf.p, CH * 24));
+    void *stage = stage_buf.p;
     for (uint64_t at = 0; at < n_mi; at += CH) {
       const uint64_t n = std::min(CH, n_mi - at);
       CU(c, cudaMemcpyAsync(stage, mi + at, n * sizeof(mm_minmer), cudaMemcpyHostToDevice, c->stream));
@@ -739,8 +750,9 @@ int mm_index_upload(mm_ctx *c, const mm_minmer *mi, uint64_t n_mi, const uint64_
     CU(c, mm_build_death_order((const uint64_t *)(c->blob + h.off_idx_hash), (const int32_t *)(c->blob + h.off_idx_wend),
                                (const uint64_t *)(c->blob + h.off_contig_start), n_contigs, n_mi,
                                (uint64_t *)(c->blob + h.off_idx2_hash), (int32_t *)(c->blob + h.off_idx2_wend), c->stream));
-    uint32_t *d_err = nullptr;
-    CU(c, cudaMalloc((void **)&d_err, 4));
+    dev_tmp err_buf;
+    CU(c, cudaMalloc(&err_buf.p, 4));
+    uint32_t *d_err = (uint32_t *)err_buf.p;
     CU(c, cudaMemsetAsync(d_err, 0, 4, c->stream));
     for (uint64_t at = 0; at < n_points; at += CH) {
       const uint64_t n = std::min(CH, n_points - at);
@@ -748,26 +760,25 @@ int mm_index_upload(mm_ctx *c, const mm_minmer *mi, uint64_t n_mi, const uint64_
       CU(c, mm_upload_pack_points((const mm_ipoint *)stage, n, n_contigs, (uint64_t *)(c->blob + h.off_pts) + at, d_err, c->stream));
       CU(c, cudaStreamSynchronize(c->stream));
     }
-    cudaFree(stage);
+    cudaFree(stage_buf.p); stage_buf.p = nullptr;
     /* open-addressing table, filled on the device */
     CU(c, cudaMemsetAsync(c->blob + h.off_tab, 0, tab_slots * sizeof(mm_tab_slot), c->stream));
     if (n_keys) {
-      uint64_t *d_keys = nullptr, *d_offs = nullptr;
-      uint8_t *d_freq = nullptr;
-      CU(c, cudaMalloc((void **)&d_keys, n_keys * 8));
-      CU(c, cudaMalloc((void **)&d_offs, (n_keys + 1) * 8));
-      CU(c, cudaMalloc((void **)&d_freq, n_keys));
+      dev_tmp keys_buf, offs_buf, freq_buf;
+      CU(c, cudaMalloc(&keys_buf.p, n_keys * 8));
+      CU(c, cudaMalloc(&offs_buf.p, (n_keys + 1) * 8));
+      CU(c, cudaMalloc(&freq_buf.p, n_keys));
+      uint64_t *d_keys = (uint64_t *)keys_buf.p, *d_offs = (uint64_t *)offs_buf.p;
+      uint8_t *d_freq = (uint8_t *)freq_buf.p;
       CU(c, cudaMemcpyAsync(d_keys, keys, n_keys * 8, cudaMemcpyHostToDevice, c->stream));
       CU(c, cudaMemcpyAsync(d_offs, offsets, (n_keys + 1) * 8, cudaMemcpyHostToDevice, c->stream));
       CU(c, cudaMemcpyAsync(d_freq, key_is_freq, n_keys, cudaMemcpyHostToDevice, c->stream));
       CU(c, mm_upload_build_table(d_keys, d_offs, d_freq, n_keys, (mm_tab_slot *)(c->blob + h.off_tab), tab_log2, d_err, c->stream));
       CU(c, cudaStreamSynchronize(c->stream));
-      cudaFree(d_keys); cudaFree(d_offs); cudaFree(d_freq);
     }
     uint32_t err = 0;
     CU(c, cudaMemcpyAsync(&err, d_err, 4, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
-    cudaFree(d_err);
     if (err & 1) return fail(c, MM_EINVAL, "an interval point has a bad seqId or a negative position");
     if (err & 2) return fail(c, MM_EINVAL, "a key has no or too many (>= 2^24) interval points, or offsets overflow");
     if (err & 4) return fail(c, MM_EINVAL, "duplicate key in the lookup index");
@@ -782,6 +793,7 @@ int mm_index_upload(mm_ctx *c, const mm_minmer *mi, uint64_t n_mi, const uint64_
   CU(c, cudaStreamSynchronize(c->stream));
   resolve_index(c);
   c->blob_ready = true;
+  guard.done = true;
   return write_tables(c);
 }
 
