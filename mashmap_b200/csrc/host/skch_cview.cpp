@@ -214,6 +214,8 @@ struct BmHandle {
   std::vector<MappingResultsVector_t> results;
   std::vector<std::string> text;
   std::string paf;
+  std::vector<ContigInfo> one_to_one_queries;  // skch_bm_one_to_one's query names, kept between calls
+  int32_t one_to_one_query_len = -1;
 };
 struct BmBatch {
   BmHandle *owner;
@@ -355,8 +357,12 @@ uint64_t skch_bm_one_to_one(void *hv, const void *recs, uint64_t n, int32_t n_qu
 {
   BmHandle *h = (BmHandle *)hv;
   MappingResultsVector_t all((const MappingResult *)recs, (const MappingResult *)recs + n);
-  std::vector<ContigInfo> q((size_t)n_queries);
-  for (int32_t i = 0; i < n_queries; i++) q[(size_t)i] = ContigInfo{"read" + std::to_string(i), query_len};
+  std::vector<ContigInfo> &q = h->one_to_one_queries;
+  if ((int32_t)q.size() != n_queries || h->one_to_one_query_len != query_len) {
+    q.resize((size_t)n_queries);
+    for (int32_t i = 0; i < n_queries; i++) q[(size_t)i] = ContigInfo{"read" + std::to_string(i), query_len};
+    h->one_to_one_query_len = query_len;
+  }
   h->paf.clear();
   h->bm->finalizeOneToOne(all, q, h->paf);
   return all.size();
@@ -430,8 +436,9 @@ int64_t skch_fasta_readers_diff(const char *path, int threads, uint64_t *n_recor
 /* Self-test of the run-wide one-to-one step (MapTail::finalizeOneToOne: sorts through (key, index) pairs, reference-axis
  * sweep per contig on `threads` threads, PAF text in slices) against the plain statement of computeMap.hpp:358-405 +
  * filter.hpp:333-394 (std::sort on the records, one serial sweep, one stream) on n random mappings full of ties.
+ * One mapping in `span_every` covers its whole contig (0 = none: every contig is a sweep unit of its own, as with reads).
  * Returns the number of differing bytes of PAF text (0 = identical; -1 = different lengths). */
-int64_t skch_one_to_one_selftest(int64_t n, uint64_t seed, int threads, int n_contigs, int n_queries, double *sec_fast, double *sec_plain)
+int64_t skch_one_to_one_selftest(int64_t n, uint64_t seed, int threads, int n_contigs, int n_queries, int span_every, double *sec_fast, double *sec_plain)
 {
   Parameters p;
   p.filterMode = filter::ONETOONE; p.threads = threads; p.numMappingsForSegment = 1;
@@ -452,7 +459,7 @@ int64_t skch_one_to_one_selftest(int64_t n, uint64_t seed, int threads, int n_co
     m.refSeqId = (seqno_t)(rnd() % (uint64_t)n_contigs);
     m.refStartPos = (offset_t)((rnd() % 4000) * 250);  /* coarse grid: many equal starts */
     m.refEndPos = std::min<offset_t>(m.refStartPos + 4999 + (offset_t)(rnd() % 3) * 2500, 999999);
-    if (rnd() % 50 == 0) { m.refStartPos = 0; m.refEndPos = 999999; }  /* spans its contig: the linking case of the parallel sweep */
+    if (span_every > 0 && rnd() % (uint64_t)span_every == 0) { m.refStartPos = 0; m.refEndPos = 999999; }  /* spans its contig: the linking case of the parallel sweep */
     m.nucIdentity = ids[rnd() % 6]; m.nucIdentityUpperBound = m.nucIdentity;
     m.blockLength = 5000; m.sketchSize = 20; m.conservedSketches = 15; m.strand = rnd() & 1 ? strnd::FWD : strnd::REV;
     m.kmerComplexity = 0.9; m.n_merged = 1;

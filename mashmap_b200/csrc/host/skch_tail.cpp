@@ -6,6 +6,9 @@
 
 #include <algorithm>
 #include <charconv>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <cmath>
 #include <limits>
 #include <numeric>
@@ -201,10 +204,146 @@ void MapTail::mergeMappingsInRange(MappingResultsVector_t &readMappings, int max
                      readMappings.end());
 }
 
-/* std::sort(v, key(a) < key(b)) with the records moved once instead of at every swap: the sort runs on (key, index) pairs
- * and the records are permuted afterwards. libstdc++'s introsort decides every move from comparison results alone, so the
- * pairs end up in exactly the arrangement the records would have (also among records with equal keys, whose order the
- * later steps depend on). Worth it from a few thousand 96-byte records on. */
+/* ---- std::sort's permutation, computed faster ----
+ * The run-wide one-to-one step sorts ALL mappings four times with std::sort, and what it writes depends on how std::sort
+ * leaves records with EQUAL keys (the reference-axis sweep refuses a mapping equivalent to one already in its status, and
+ * which of two equivalent mappings comes first is decided by these sorts). So the product must end up with exactly the
+ * arrangement libstdc++'s introsort gives the reference. Three things make that cheap without changing it:
+ *  (1) the sort runs on (key, index) pairs and the 96-byte records are permuted once afterwards -- introsort decides every
+ *      move from comparison results alone, so the pairs end up arranged as the records would;
+ *  (2) the key tuple is packed into unsigned words whose order is the tuple's lexicographic order (int32 fields biased by
+ *      2^31): same comparison results, fewer instructions and no branches per comparison;
+ *  (3) the quicksort phase runs on several threads. __introsort_loop partitions a range and then treats the two sides
+ *      independently; everything left of a cut is <= everything right of it, so the final insertion pass never moves a
+ *      record across a cut either. Handing the right-hand side of a cut to another thread therefore changes nothing but
+ *      the order in which disjoint ranges are processed. The code below calls libstdc++'s own partition / loop / heap /
+ *      insertion routines (bits/stl_algo.h), it does not restate them; other standard libraries take the serial std::sort. */
+namespace {
+
+inline uint32_t biased(int32_t x) { return (uint32_t)x ^ 0x80000000u; }
+inline uint64_t pack2(int32_t a, int32_t b) { return ((uint64_t)biased(a) << 32) | biased(b); }
+
+struct Key2 {  // (a, b)
+  uint64_t k;
+  bool operator<(const Key2 &o) const { return k < o.k; }
+};
+struct Key3 {  // (a, b, c)
+  uint64_t hi;
+  uint32_t lo;
+  bool operator<(const Key3 &o) const { return hi < o.hi || (hi == o.hi && lo < o.lo); }
+} __attribute__((packed));
+struct Key4 {  // (a, b, c, d)
+  uint64_t hi, lo;
+  bool operator<(const Key4 &o) const { return hi < o.hi || (hi == o.hi && lo < o.lo); }
+};
+inline Key2 key_ref(const MappingResult &m) { return Key2{pack2(m.refSeqId, m.refStartPos)}; }
+inline Key3 key_query_ref(const MappingResult &m) { return Key3{pack2(m.queryStartPos, m.refSeqId), biased(m.refStartPos)}; }
+inline Key4 key_read_query_ref(const MappingResult &m)
+{
+  return Key4{pack2(m.querySeqId, m.queryStartPos), pack2(m.refSeqId, m.refStartPos)};
+}
+
+/* a handful of helper threads for one call; jobs may enqueue jobs */
+class JobPool {
+ public:
+  explicit JobPool(int threads) : threads_(threads) {}
+  void add(std::function<void()> fn)
+  {
+    {
+      std::lock_guard<std::mutex> g(m_);
+      q_.push_back(std::move(fn));
+      pending_++;
+    }
+    cv_.notify_one();
+  }
+  void finish()  // helpers start now (the first jobs are queued); the caller works too, until every job (and the jobs they added) is done
+  {
+    for (int t = 1; t < threads_; t++) pool_.emplace_back([this] { run(); });
+    run();
+    for (auto &th : pool_) th.join();
+    pool_.clear();
+  }
+
+ private:
+  void run()
+  {
+    std::unique_lock<std::mutex> g(m_);
+    while (true) {
+      if (!q_.empty()) {
+        auto fn = std::move(q_.back());
+        q_.pop_back();
+        g.unlock();
+        fn();
+        g.lock();
+        if (--pending_ == 0) cv_.notify_all();
+      } else if (pending_ == 0) {
+        return;
+      } else {
+        cv_.wait(g);
+      }
+    }
+  }
+  std::mutex m_;
+  std::condition_variable cv_;
+  std::vector<std::function<void()>> q_;
+  size_t pending_ = 0;
+  int threads_;
+  std::vector<std::thread> pool_;
+};
+
+#if defined(__GLIBCXX__)
+template <class P, class Cmp>
+void introsortJob(P *first, P *last, long depth, Cmp cmp, JobPool &pool, long grain)
+{  // std::__introsort_loop(first, last, depth, cmp) with the recursive call given away, then the insertion pass of what is left
+  while (last - first > 16) {  // _S_threshold
+    if (last - first <= grain) {
+      std::__introsort_loop(first, last, depth, cmp);
+      break;
+    }
+    if (depth == 0) {
+      std::__partial_sort(first, last, last, cmp);
+      break;
+    }
+    --depth;
+    P *cut = std::__unguarded_partition_pivot(first, last, cmp);
+    P *rlast = last;
+    pool.add([=, &pool] { introsortJob(cut, rlast, depth, cmp, pool, grain); });
+    last = cut;
+  }
+  std::__insertion_sort(first, last, cmp);
+}
+#endif
+
+/* p[0..n) arranged as std::sort(p, p + n, less) arranges it */
+template <class P, class Less>
+void sortExactlyLikeStd(P *p, size_t n, Less less, int threads)
+{
+#if defined(__GLIBCXX__)
+  if (threads > 1 && n >= 32768) {
+    auto cmp = __gnu_cxx::__ops::__iter_comp_iter(less);
+    JobPool pool(threads);
+    const long grain = (long)std::max<size_t>(4096, n / ((size_t)threads * 8));
+    const long depth = std::__lg((long)n) * 2;
+    pool.add([=, &pool] { introsortJob(p, p + n, depth, cmp, pool, grain); });
+    pool.finish();
+    return;
+  }
+#endif
+  std::sort(p, p + n, less);
+}
+
+template <class Fn>
+void inSlices(size_t n, int T, Fn fn)  // fn(lo, hi) over [0, n) on T threads
+{
+  std::vector<std::thread> pool;
+  for (int t = 1; t < T; t++) pool.emplace_back([&, t] { fn(n * (size_t)t / (size_t)T, n * (size_t)(t + 1) / (size_t)T); });
+  fn(0, n / (size_t)T);
+  for (auto &th : pool) th.join();
+}
+
+}  // namespace
+
+/* std::sort(v, key(a) < key(b)): see above. `key` returns one of the packed keys. */
 template <class KeyFn>
 static void sortLikeStd(MappingResultsVector_t &v, KeyFn key, int threads = 1)
 {
@@ -213,15 +352,9 @@ static void sortLikeStd(MappingResultsVector_t &v, KeyFn key, int threads = 1)
     std::sort(v.begin(), v.end(), [&](const MappingResult &a, const MappingResult &b) { return key(a) < key(b); });
     return;
   }
-  struct P { K k; uint32_t i; };
+  struct P { K k; uint32_t i; } __attribute__((packed));
   const size_t n = v.size();
   const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(1, threads), n / 16384));
-  auto in_slices = [&](auto fn) {  // fn(lo, hi) over [0, n) on T threads
-    std::vector<std::thread> pool;
-    for (int t = 1; t < T; t++) pool.emplace_back([&, t] { fn(n * (size_t)t / (size_t)T, n * (size_t)(t + 1) / (size_t)T); });
-    fn(0, n / (size_t)T);
-    for (auto &th : pool) th.join();
-  };
   static thread_local std::vector<P> p;                    // scratch kept between calls: no 14 MB of fresh pages per sort
   static thread_local MappingResultsVector_t out;
   p.resize(n);
@@ -229,9 +362,9 @@ static void sortLikeStd(MappingResultsVector_t &v, KeyFn key, int threads = 1)
   P *pp = p.data();  // the helper threads must see THIS thread's scratch, not their own (empty) thread_local copies
   MappingResult *oo = out.data();
   const MappingResult *vv = v.data();
-  in_slices([&](size_t lo, size_t hi) { for (size_t i = lo; i < hi; i++) { pp[i].k = key(vv[i]); pp[i].i = (uint32_t)i; } });
-  std::sort(p.begin(), p.end(), [](const P &a, const P &b) { return a.k < b.k; });  // serial: its permutation IS the specification
-  in_slices([&](size_t lo, size_t hi) { for (size_t i = lo; i < hi; i++) oo[i] = vv[pp[i].i]; });
+  inSlices(n, T, [&](size_t lo, size_t hi) { for (size_t i = lo; i < hi; i++) { pp[i].k = key(vv[i]); pp[i].i = (uint32_t)i; } });
+  sortExactlyLikeStd(pp, n, [](const P &a, const P &b) { return a.k < b.k; }, T);
+  inSlices(n, T, [&](size_t lo, size_t hi) { for (size_t i = lo; i < hi; i++) oo[i] = vv[pp[i].i]; });
   v.swap(out);
 }
 
@@ -248,7 +381,7 @@ void MapTail::filterByGroup(MappingResultsVector_t &unfiltered, MappingResultsVe
     tt0 = t;
   };
   const int sort_threads = filter_ref ? param.threads : 1;  // the run-wide step only: the per-read calls are far below the threshold
-  sortLikeStd(unfiltered, [](const MappingResult &a) { return std::make_tuple(a.refSeqId, a.refStartPos); }, sort_threads);
+  sortLikeStd(unfiltered, key_ref, sort_threads);
   lap("sort 1");
   auto sb = unfiltered.begin(), se = unfiltered.begin();
   if (param.filterMode == filter::MAP || param.filterMode == filter::ONETOONE) {
@@ -261,7 +394,7 @@ void MapTail::filterByGroup(MappingResultsVector_t &unfiltered, MappingResultsVe
         se = unfiltered.end();
       }
       tmp.insert(tmp.end(), std::make_move_iterator(sb), std::make_move_iterator(se));
-      sortLikeStd(tmp, [](const MappingResult &a) { return std::make_tuple(a.queryStartPos, a.refSeqId, a.refStartPos); }, sort_threads);
+      sortLikeStd(tmp, key_query_ref, sort_threads);
       lap("sort 2");
       if (filter_ref) Filter::ref::filterMappingsParallel(tmp, metadata, (uint16_t)n_mappings, param.threads);
       else Filter::query::filterMappings(tmp, (uint16_t)n_mappings);
@@ -271,7 +404,7 @@ void MapTail::filterByGroup(MappingResultsVector_t &unfiltered, MappingResultsVe
       sb = se;
     }
   }
-  sortLikeStd(filtered, [](const MappingResult &a) { return std::make_tuple(a.queryStartPos, a.refSeqId, a.refStartPos); }, sort_threads);
+  sortLikeStd(filtered, key_query_ref, sort_threads);
 }
 
 int MapTail::getRefGroup(const std::string &seqName) const
@@ -310,7 +443,7 @@ void MapTail::finalizeOneToOne(MappingResultsVector_t &allReadMappings, const st
   }
   allReadMappings = std::move(filtered);
   lap("filterByGroup");
-  sortLikeStd(allReadMappings, [](const MappingResult &a) { return std::make_tuple(a.querySeqId, a.queryStartPos, a.refSeqId, a.refStartPos); }, param.threads);
+  sortLikeStd(allReadMappings, key_read_query_ref, param.threads);
   lap("final sort");
   /* the PAF text: formatted in slices by the host threads and joined in order (every slice starts from a stream in its
    * default state, as the single stream of the reference is for every line) */
@@ -321,14 +454,17 @@ void MapTail::finalizeOneToOne(MappingResultsVector_t &allReadMappings, const st
   std::vector<std::string> part((size_t)T);
   auto work = [&](int ti) {
     const size_t lo = n * (size_t)ti / (size_t)T, hi = n * (size_t)(ti + 1) / (size_t)T;
-    MappingResultsVector_t slice(allReadMappings.begin() + lo, allReadMappings.begin() + hi);
-    t.formatMappings(slice, "", part[(size_t)ti]);
+    part[(size_t)ti].reserve((hi - lo) * 112);
+    t.formatMappings(allReadMappings.data() + lo, hi - lo, "", part[(size_t)ti]);
   };
   std::vector<std::thread> pool;
   for (int ti = 1; ti < T; ti++) pool.emplace_back(work, ti);
   work(0);
   for (auto &th : pool) th.join();
   paf.clear();
+  size_t total = 0;
+  for (auto &x : part) total += x.size();
+  paf.reserve(total);
   for (auto &x : part) paf += x;
   lap("text");
 }
@@ -454,8 +590,14 @@ inline void put_real(std::string &out, F v)
  * (scripts/tail_perf.py: 1.25 of 1.65 us), and at N GPUs on one host the tail is what the host CPUs are short of. */
 void MapTail::formatMappings(const MappingResultsVector_t &readMappings, const std::string &queryName, std::string &out) const
 {
+  formatMappings(readMappings.data(), readMappings.size(), queryName, out);
+}
+
+void MapTail::formatMappings(const MappingResult *first, size_t n, const std::string &queryName, std::string &out) const
+{
   const char sep = param.legacy_output ? ' ' : '\t';
-  for (auto &e : readMappings) {
+  for (const MappingResult *it = first; it != first + n; ++it) {
+    const MappingResult &e = *it;
     const float fakeMapQ = e.nucIdentity == 1 ? 255 : std::round(-10.0 * std::log10(1 - (e.nucIdentity)));
     out += (param.filterMode == filter::ONETOONE ? (*qmetadata)[e.querySeqId].name : queryName);
     out += sep; put_int(out, e.queryLen);

@@ -67,6 +67,7 @@ class MapTail {
   void finalizeOneToOne(MappingResultsVector_t &allReadMappings, const std::vector<ContigInfo> &qmeta, std::string &paf) const;
   void formatMappings(const MappingResultsVector_t &readMappings, const std::string &queryName, std::ostream &os) const;
   void formatMappings(const MappingResultsVector_t &readMappings, const std::string &queryName, std::string &out) const;  // appends
+  void formatMappings(const MappingResult *first, size_t n, const std::string &queryName, std::string &out) const;     // appends
   void formatMappingsStream(const MappingResultsVector_t &readMappings, const std::string &queryName, std::ostream &os) const;
 
  private:

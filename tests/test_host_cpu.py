@@ -281,12 +281,13 @@ def test_run_wide_one_to_one_step_equals_its_plain_statement(n, threads):
 
     L = hostlib.lib()
     L.skch_one_to_one_selftest.restype = C.c_int64
-    L.skch_one_to_one_selftest.argtypes = [C.c_int64, C.c_uint64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.skch_one_to_one_selftest.argtypes = [C.c_int64, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     for seed in (1, 2, 3):
         tf, tp = C.c_double(), C.c_double()
-        d = L.skch_one_to_one_selftest(n, seed, threads, 64, max(10, n // 2), C.byref(tf), C.byref(tp))
-        print(f"n={n} seed={seed}: fast {tf.value * 1e3:.1f} ms, plain {tp.value * 1e3:.1f} ms")
-        assert d == 0
+        for span_every in (50, 0):  # contigs chained into few sweep units by spanning mappings / every contig on its own
+            d = L.skch_one_to_one_selftest(n, seed, threads, 64, max(10, n // 2), span_every, C.byref(tf), C.byref(tp))
+            print(f"n={n} seed={seed} span_every={span_every}: fast {tf.value * 1e3:.1f} ms, plain {tp.value * 1e3:.1f} ms")
+            assert d == 0
 
 
 def test_paf_text_without_a_stream_equals_the_stream_text():
