@@ -36,6 +36,14 @@ int64_t skch_recommended_sketch_size(int k, float pi, int64_t segLength, uint64_
 {
   return Stat::recommendedSketchSize(fixed::pval_cutoff, fixed::confidence_interval, k, 4, pi, segLength, refSize);
 }
+/* gsl_ran_hypergeometric_pdf(k, n1, n2, t) for k = 0..t as the product computes it (tests/test_stats_scipy_cpu.py) */
+int skch_hypergeometric_pmf_row(unsigned n1, unsigned n2, unsigned t, double *out, int cap)
+{
+  std::vector<double> row;
+  Stat::hypergeometric_pmf_row(n1, n2, t, row);
+  for (int i = 0; i < (int)row.size() && i < cap; i++) out[i] = row[(size_t)i];
+  return (int)row.size();
+}
 int skch_sketch_cutoffs(int sketchSize, int k, float aniDiff, float aniDiffConf, int enabled, int *out, int cap)
 {
   std::vector<int> c = Stat::sketchCutoffs(sketchSize, k, aniDiff, aniDiffConf, enabled != 0);

@@ -25,7 +25,9 @@ double binomial_Q(unsigned int k, double p, unsigned int n)
     t *= odds * (double)(n - i) / (double)(i + 1);
     total += t;
     if (i + 1 > k) upper += t;
-    if (t < total * 1e-19) break;
+    /* stop when nothing that follows can change either sum: a tail that starts far above the mode (k >> mode) is tiny
+     * against the total but is the whole of `upper`, so the walk goes on until it has been collected */
+    if (t < total * 1e-19 && i + 1 > k && t < upper * 1e-19) break;
   }
   t = 1.0;
   for (unsigned int i = mode; i > 0; i--) { /* i -> i-1 */
