@@ -227,25 +227,37 @@ def keep_rank_stderr(rank):
         print(f"[bench] rank {rank}: cannot keep a per-rank log: {e}", file=sys.stderr)
 
 
-def bind_to_gpu_numa_node(local_rank):
+def _gpu_numa_node(pynvml, index):
+    h = pynvml.nvmlDeviceGetHandleByIndex(index)
+    node = None
+    try:
+        node = pynvml.nvmlDeviceGetNumaNodeId(h)
+    except Exception:
+        pass
+    if node is None or node < 0:
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        node = int(open(f"/sys/bus/pci/devices/{bus[-12:].lower()}/numa_node").read())
+    return node
+
+
+def bind_to_gpu_numa_node(local_rank, world=1):
     """CPU affinity (and with it first-touch memory placement) of this rank = the NUMA node its GPU hangs off: the pinned
-    batch buffer and the host tail then stay on the socket whose PCIe root the copies use"""
+    batch buffer and the host tail then stay on the socket whose PCIe root the copies use. Returns (node, CPUs of the node
+    this process may use, ranks of this job whose GPU hangs off the same node) or None."""
     try:
         import pynvml
 
         pynvml.nvmlInit()
-        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
-        node = None
-        try:
-            node = pynvml.nvmlDeviceGetNumaNodeId(h)
-        except Exception:
-            pass
-        if node is None or node < 0:
-            bus = pynvml.nvmlDeviceGetPciInfo(h).busId
-            bus = bus.decode() if isinstance(bus, bytes) else bus
-            node = int(open(f"/sys/bus/pci/devices/{bus[-12:].lower()}/numa_node").read())
+        node = _gpu_numa_node(pynvml, local_rank)
         if node < 0:
             return None
+        sharing = 0
+        for r in range(world):  # one rank per GPU, rank r on GPU r of this node (torchrun's LOCAL_RANK)
+            try:
+                sharing += _gpu_numa_node(pynvml, r) == node
+            except Exception:
+                pass
         cpus = []
         for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
             a, _, b = part.partition("-")
@@ -253,10 +265,24 @@ def bind_to_gpu_numa_node(local_rank):
         cpus = sorted(set(cpus) & os.sched_getaffinity(0))
         if cpus:
             os.sched_setaffinity(0, cpus)
-            return node, len(cpus)
+            return node, len(cpus), max(1, sharing)
     except Exception as e:
         log(f"NUMA binding skipped: {e}")
     return None
+
+
+def host_threads_for_rank(world, numa):
+    """host threads of one rank: its share of the CPUs it can really run on. Without a NUMA binding that is usable CPUs / ranks;
+    with one, the node's CPUs are shared by the ranks bound to that node only (8 GPUs on two nodes of 64 CPUs under a 96-CPU
+    quota: min(64 / 4, 96 / 8) = 12 per rank, not 64 / 8). More threads than CPUs only adds throttling."""
+    info = host_cpu_info()
+    share = usable_cpus() // max(1, world)
+    if numa is not None:
+        _, node_cpus, sharing = numa
+        share = node_cpus // sharing
+        if "cgroup_quota_cpus" in info:
+            share = min(share, int(info["cgroup_quota_cpus"]) // max(1, world))
+    return max(1, share)
 
 
 def config_of(args):
@@ -372,7 +398,7 @@ def gpu_arm(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         keep_rank_stderr(rank)
-    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
+    numa = bind_to_gpu_numa_node(local_rank, world) if world > 1 else None
     import torch
 
     log(f"rank {rank}/{world}: host memory {host_memory_info()}, cpus {host_cpu_info()}, bound to NUMA node {numa}")
@@ -387,7 +413,7 @@ def gpu_arm(args):
     from mashmap_b200 import nccl as mnccl
 
     cfg = config_of(args)
-    host_threads = max(1, usable_cpus() // max(1, world))  # sized to the CPU quota: more threads than CPUs only adds throttling
+    host_threads = host_threads_for_rank(world, numa)  # sized to the CPUs this rank can really use
     if os.environ.get("BENCH_HOST_THREADS"):  # experiments: what one of N ranks gets on a host with few CPUs
         host_threads = max(1, int(os.environ["BENCH_HOST_THREADS"]))
     wl = setup_workload(args, cfg, rank, world, device)

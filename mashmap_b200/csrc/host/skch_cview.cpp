@@ -349,13 +349,31 @@ uint32_t skch_mapping_record_bytes() { return (uint32_t)sizeof(MappingResult); }
 uint64_t skch_bm_results_raw(void *hv, void *out, uint64_t cap)
 {
   BmHandle *h = (BmHandle *)hv;
+  const size_t nr = h->results.size();
   uint64_t n = 0;
+  for (auto &v : h->results) n += v.size();
   MappingResult *o = (MappingResult *)out;
-  for (auto &v : h->results)
-    for (auto &m : v) {
-      if (o && n < cap) o[n] = m;
-      n++;
+  if (!o || n > cap) return n;
+  /* every read's mappings are a heap block of their own: the copy is a million cache misses, spread over the host threads */
+  const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(1, h->ih->p.threads), nr / 4096));
+  std::vector<uint64_t> first((size_t)T + 1, 0);
+  for (int t = 0; t < T; t++) {
+    uint64_t c = 0;
+    for (size_t r = nr * (size_t)t / (size_t)T; r < nr * (size_t)(t + 1) / (size_t)T; r++) c += h->results[r].size();
+    first[(size_t)t + 1] = first[(size_t)t] + c;
+  }
+  auto work = [&](int t) {
+    MappingResult *at = o + first[(size_t)t];
+    for (size_t r = nr * (size_t)t / (size_t)T; r < nr * (size_t)(t + 1) / (size_t)T; r++) {
+      const MappingResultsVector_t &v = h->results[r];
+      if (!v.empty()) memcpy((void *)at, (const void *)v.data(), v.size() * sizeof(MappingResult));
+      at += v.size();
     }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < T; t++) pool.emplace_back(work, t);
+  work(0);
+  for (auto &th : pool) th.join();
   return n;
 }
 /* -f one-to-one, the run-wide step (computeMap.hpp:358-405) over `n` raw records of any origin (one rank's, or all ranks'

@@ -64,3 +64,23 @@ def test_gather_and_broadcast_world2():
     assert ids0 == ids1 == [expect0, expect1]          # every rank sees every rank's records, untruncated, in rank order
     assert rk0[0] == [0] * len(expect0) and rk0[1] == [1] * len(expect1)
     assert blob0 == blob1 == list(range(256)) + [0]
+
+
+def test_host_threads_of_a_rank_follow_its_numa_node_and_the_quota(monkeypatch):
+    """bench.py sizes a rank's host threads to the CPUs it can really run on: the CPUs of its GPU's NUMA node shared by the
+    ranks bound to that node, and never more than the cgroup quota's share"""
+    import importlib.util
+    import sys
+
+    spec = importlib.util.spec_from_file_location("bench_for_test", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    sys.modules["bench_for_test"] = bench
+    spec.loader.exec_module(bench)
+    monkeypatch.setattr(bench, "host_cpu_info", lambda: {"visible": 128, "affinity": 64, "cgroup_quota_cpus": 96.0})
+    assert bench.host_threads_for_rank(8, (0, 64, 4)) == 12   # two nodes x 4 GPUs, 96-CPU quota
+    assert bench.host_threads_for_rank(4, (0, 64, 4)) == 16   # 4 GPUs on one node
+    assert bench.host_threads_for_rank(2, (0, 64, 2)) == 32
+    monkeypatch.setattr(bench, "host_cpu_info", lambda: {"visible": 128, "affinity": 128, "cgroup_quota_cpus": 16.0})
+    assert bench.host_threads_for_rank(8, (1, 64, 4)) == 2    # a 16-CPU quota: 2 per rank
+    assert bench.host_threads_for_rank(8, None) == 2          # no binding: usable CPUs / ranks
+    assert bench.host_threads_for_rank(1, None) == 16
