@@ -576,7 +576,7 @@ const char *skch_tail_map_read(void *hv, const char *name, int32_t len, int32_t 
   ReadRec rd;
   rd.name = name; rd.len = len; rd.seqCounter = seqCounter; rd.first_seg = 0; rd.n_seg = n_seg; rd.refGroup = refGroup;
   IdentityCache idc;
-  idc.k = h->p.kmerSize;
+  idc.k = h->p.kmerSize; idc.ANIDiff = h->p.ANIDiff;
   h->last.clear();
   h->tail->mapRead(rd, idc, h->last);
   std::ostringstream os;
@@ -601,7 +601,7 @@ void skch_tail_bench(void *hv, int32_t n_reads, const int32_t *read_len, const u
     reads[r].first_seg = seg_first[r]; reads[r].n_seg = (uint32_t)(seg_first[r + 1] - seg_first[r]); reads[r].refGroup = -1;
   }
   IdentityCache idc;
-  idc.k = h->p.kmerSize;
+  idc.k = h->p.kmerSize; idc.ANIDiff = h->p.ANIDiff;
   std::vector<MappingResultsVector_t> res((size_t)n_reads);
   std::ostringstream os;
   double tm = 0, tf = 0;
@@ -656,6 +656,7 @@ int skch_format_selftest(int64_t n, uint64_t seed)
     }
   }
   int bad = 0;
+  bad += (int)MapTail::realTextSelftest(n * 4, seed);  /* the number formatter alone, against snprintf("%g") */
   for (int mode = 0; mode < 8; mode++) {
     Parameters p;
     p.legacy_output = (mode & 1) != 0; p.report_ANI_percentage = (mode & 2) != 0; p.mergeMappings = (mode & 4) == 0;

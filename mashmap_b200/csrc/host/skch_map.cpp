@@ -377,7 +377,7 @@ void BatchMapper::laneFinish(DeviceGroup &g, Lane &ln, const ReadBatch &b, std::
   std::atomic<size_t> next{r0};
   auto worker = [&]() {
     IdentityCache idc;
-    idc.k = param.kmerSize;
+    idc.k = param.kmerSize; idc.ANIDiff = param.ANIDiff;
     uint64_t bytes = 0, mapped = 0, maps = 0;
     while (true) {
       const size_t lo = next.fetch_add(256);

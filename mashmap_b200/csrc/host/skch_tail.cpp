@@ -32,17 +32,43 @@ size_t MappingResult::hash() const
   return res;
 }
 
+IdentityCache::Table &IdentityCache::table(int qs)
+{
+  if (qs == last_qs) return *last;
+  Table &t = tables[qs];
+  if (t.identity.empty()) {
+    t.identity.assign((size_t)qs + 1, std::make_pair(-1.0f, 0.0f));
+    t.cutoff.assign((size_t)qs + 1, -1.0);
+  }
+  last = &t;  // references into an unordered_map stay valid when it grows
+  last_qs = qs;
+  return t;
+}
+
 std::pair<float, float> IdentityCache::get(int shared, int qs)
 {
-  const uint64_t key = ((uint64_t)(uint32_t)shared << 32) | (uint32_t)qs;
-  auto it = memo.find(key);
-  if (it != memo.end()) return it->second;
+  Table &t = table(qs);
+  const bool in_table = shared >= 0 && shared <= qs;
+  if (in_table && t.identity[(size_t)shared].first >= 0) return t.identity[(size_t)shared];
   float mash_dist = Stat::j2md(1.0 * shared / qs, k);
   float nucIdentity = (1 - mash_dist);
   float nucIdentityUpperBound = 1 - Stat::md_lower_bound(mash_dist, qs, k, fixed::confidence_interval);
   auto v = std::make_pair(nucIdentity, nucIdentityUpperBound);
-  memo.emplace(key, v);
+  if (in_table && nucIdentity >= 0) t.identity[(size_t)shared] = v;
   return v;
+}
+
+/* computeMap.hpp:1195-1200 for an integer-valued bestJaccardNumerator (it only ever holds 0 or a sharedSketchSize) */
+double IdentityCache::cutoffJaccard(int best, int qs)
+{
+  Table &t = table(qs);
+  const bool in_table = best >= 0 && best <= qs;
+  if (in_table && t.cutoff[(size_t)best] >= 0) return t.cutoff[(size_t)best];
+  const double bestJaccardNumerator = best;
+  double cutoff_ani = std::max(0.0, double((1 - Stat::j2md(bestJaccardNumerator / qs, k)) - ANIDiff));
+  double cutoff_j = Stat::md2j(1 - cutoff_ani, k);
+  if (in_table && cutoff_j >= 0) t.cutoff[(size_t)best] = cutoff_j;
+  return cutoff_j;
 }
 
 namespace {
@@ -50,8 +76,13 @@ namespace {
 /* union-find with the merge rule of dsets::DisjointSets (reference src/common/dset64.hpp:62-124):
  * the root of lower rank goes under the other; on equal rank the larger id goes under the smaller. */
 struct UnionFind {
-  std::vector<uint32_t> parent, rnk;
-  explicit UnionFind(size_t n) : parent(n), rnk(n, 0) { std::iota(parent.begin(), parent.end(), 0u); }
+  std::vector<uint32_t> &parent, &rnk;  // the caller's scratch (kept between reads)
+  UnionFind(size_t n, std::vector<uint32_t> &p, std::vector<uint32_t> &r) : parent(p), rnk(r)
+  {
+    parent.resize(n);
+    rnk.assign(n, 0);
+    std::iota(parent.begin(), parent.end(), 0u);
+  }
   uint32_t find(uint32_t x)
   {
     while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; }
@@ -99,8 +130,7 @@ void MapTail::fragmentMappings(const mm_segment &sg, const mm_segment_result &sr
     while (it != end) {
       const mm_l1_candidate &cd = work[it];
       if (param.stage1_topANI_filter) {
-        double cutoff_ani = std::max(0.0, double((1 - Stat::j2md(bestJaccardNumerator / qs, param.kmerSize)) - param.ANIDiff));
-        double cutoff_j = Stat::md2j(1 - cutoff_ani, param.kmerSize);
+        const double cutoff_j = idc.cutoffJaccard((int)bestJaccardNumerator, qs);
         if (double(cd.intersectionSize) / qs < cutoff_j) break;
       }
       for (uint32_t li = 0; li < cd.n_loci; li++) {
@@ -153,8 +183,9 @@ void MapTail::mergeMappingsInRange(MappingResultsVector_t &readMappings, int max
     return std::tie(a.refSeqId, a.refStartPos, a.queryStartPos) < std::tie(b.refSeqId, b.refStartPos, b.queryStartPos);
   });
   for (size_t i = 0; i < readMappings.size(); i++) { readMappings[i].splitMappingId = (offset_t)i; readMappings[i].discard = 0; }
-  UnionFind uf(readMappings.size());
-  std::vector<std::pair<double, uint64_t>> distances;
+  static thread_local std::vector<uint32_t> uf_parent, uf_rank;  // per-worker scratch: no allocation per read once warm
+  static thread_local std::vector<std::pair<double, uint64_t>> distances;
+  UnionFind uf(readMappings.size(), uf_parent, uf_rank);
   for (auto it = readMappings.begin(); it != readMappings.end(); it++) {
     distances.clear();
     for (auto it2 = std::next(it); it2 != readMappings.end(); it2++) {
@@ -577,10 +608,49 @@ inline void put_int(std::string &out, long long v)
   auto r = std::to_chars(buf, buf + sizeof(buf), v);
   out.append(buf, r.ptr);
 }
+/* printf's %g with precision 6 for 1e-3 <= v < 1e6 without the general-purpose conversion (three of these per PAF line
+ * were most of the formatting time): scale to six significant digits, round to nearest-even, strip trailing zeros. The
+ * scaling v * 10^(5-e) is checked to be EXACT (fma residue 0), so the rounding sees the true value -- ties of dyadic
+ * identities included -- and anything else (other magnitudes, inexact products, nan, inf, zero, negatives) takes
+ * std::to_chars. Returns the end of the text, or nullptr when it declines. */
+inline char *g6_fast(char *buf, double v)
+{
+  if (!(v >= 1e-3 && v < 1e6)) return nullptr;
+  static const double p10[9] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8};
+  int e = v >= 1e3 ? (v >= 1e5 ? 5 : v >= 1e4 ? 4 : 3)
+                   : v >= 1e0 ? (v >= 1e2 ? 2 : v >= 1e1 ? 1 : 0) : (v >= 1e-1 ? -1 : v >= 1e-2 ? -2 : -3);
+  const double scale = p10[5 - e];
+  const double p = v * scale;
+  if (std::fma(v, scale, -p) != 0.0) return nullptr;
+  long n = (long)std::nearbyint(p);  // round-half-even (default rounding mode) of an exact value
+  if (n < 100000 || n > 1000000) return nullptr;  // a threshold constant on the wrong side of its power of ten
+  if (n == 1000000) { n = 100000; e++; }
+  if (e > 5) return nullptr;  // rounds up to 1e+06
+  char d[6];
+  for (int i = 5; i >= 0; i--) { d[i] = (char)('0' + n % 10); n /= 10; }
+  int last = 5;
+  while (last > 0 && d[last] == '0') last--;  // %g drops trailing zeros (d[0] is never 0)
+  char *o = buf;
+  if (e >= 0) {
+    for (int i = 0; i <= e; i++) *o++ = d[i];
+    if (last > e) {
+      *o++ = '.';
+      for (int i = e + 1; i <= last; i++) *o++ = d[i];
+    }
+  } else {
+    *o++ = '0'; *o++ = '.';
+    for (int i = 0; i < -e - 1; i++) *o++ = '0';
+    for (int i = 0; i <= last; i++) *o++ = d[i];
+  }
+  return o;
+}
 template <class F>
 inline void put_real(std::string &out, F v)
 {
   char buf[64];
+  const double dv = (double)v;
+  if ((F)dv == v)  // always for float and double; a long double kmerComplexity holds a float or a mean computed in double
+    if (char *e = g6_fast(buf, dv)) { out.append(buf, e); return; }
   auto r = std::to_chars(buf, buf + sizeof(buf), v, std::chars_format::general, 6);
   out.append(buf, r.ptr);
 }
@@ -620,6 +690,48 @@ void MapTail::formatMappings(const MappingResult *first, size_t n, const std::st
     }
     out += '\n';
   }
+}
+
+int64_t MapTail::realTextSelftest(int64_t n, uint64_t seed)
+{
+  uint64_t x = seed * 0x9E3779B97F4A7C15ULL + 12345;
+  auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+  int64_t bad = 0;
+  auto check = [&](auto v) {
+    char want[64];
+    if (sizeof(v) > sizeof(double)) snprintf(want, sizeof want, "%Lg", (long double)v);
+    else snprintf(want, sizeof want, "%g", (double)v);
+    std::string got;
+    put_real(got, v);
+    if (got != want) bad++;
+  };
+  const double edges[] = {0.0, -0.0, 1.0, 0.1, 0.01, 0.001, 0.0001, 1e-5, 0.5, 0.25, 0.125, 999999.0, 999999.5, 999999.4999, 1e6, 1e7,
+                          99999.95, 99999.949, 0.9999995, 0.99999949, 0.00099999949, 0.0009999995, 0.001000001, 255.0, 13.0, 100.0,
+                          9.9999995, 123456.5, 12345.65, 1234.565, 0.1234565, 0.01234565, 1e-300, 1e300, -1.5, -0.0625};
+  for (double v : edges) {
+    check(v); check((float)v); check((long double)v);
+    check(std::nextafter(v, 2 * v + 1)); check(std::nextafter(v, -1.0));
+    check(std::nextafterf((float)v, 2 * (float)v + 1)); check(std::nextafterf((float)v, -1.0f));
+  }
+  check(std::numeric_limits<double>::infinity()); check(std::numeric_limits<double>::quiet_NaN());
+  for (int64_t i = 0; i < n; i++) {
+    const int kind = (int)(rnd() % 8);
+    const double u = (double)(rnd() >> 11) / 9007199254740992.0;  // [0, 1)
+    double v;
+    switch (kind) {
+      case 0: v = u; break;
+      case 1: v = (float)u; break;
+      case 2: v = (double)(rnd() % 4097) / 4096.0; break;                    // dyadic: exact decimal ties
+      case 3: v = (double)(rnd() % 2000001) / 2.0; break;                    // halves up to 1e6
+      case 4: v = std::pow(10.0, -6.0 + 14.0 * u); break;                    // every magnitude around the fast range
+      case 5: v = 100.0 * (double)(float)u; break;                           // identities as percentages
+      case 6: v = ((double)(float)u + (double)(float)((double)(rnd() >> 11) / 9007199254740992.0)) / 2.0; break;  // means of floats
+      default: v = (double)(rnd() % 1000000) / 100000.0 + ((rnd() & 1) ? 0.000005 : 0.0);  // decimal ties that are not exact in binary
+    }
+    check(v); check((float)v);
+    if ((i & 7) == 0) check((long double)v);
+  }
+  return bad;
 }
 
 void MapTail::formatMappings(const MappingResultsVector_t &readMappings, const std::string &queryName, std::ostream &os) const

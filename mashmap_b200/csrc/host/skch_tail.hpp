@@ -34,12 +34,23 @@ struct ReadRec {
   int refGroup;
 };
 
-/* (sharedSketchSize, Q.sketchSize) -> (nucIdentity, nucIdentityUpperBound), doL2Mapping :1211-1215.
- * Pure functions of two small integers; memoised per worker thread. */
+/* Pure functions of two small integers, memoised per worker thread in flat tables (one per query sketch size seen):
+ *   (sharedSketchSize, Q.sketchSize) -> (nucIdentity, nucIdentityUpperBound), doL2Mapping :1211-1215;
+ *   (best Jaccard numerator so far, Q.sketchSize) -> the Jaccard cut-off of the stage-1 top-ANI filter, :1195-1200
+ * (two pow() per candidate otherwise: most of the tail's time per read). */
 struct IdentityCache {
   int k = 19;
-  std::unordered_map<uint64_t, std::pair<float, float>> memo;
+  float ANIDiff = 0.0f;  // Parameters::ANIDiff, part of the cut-off
+  struct Table {
+    std::vector<std::pair<float, float>> identity;  // by shared count; first < 0 = not computed yet
+    std::vector<double> cutoff;                     // by best numerator; < 0 = not computed yet
+  };
+  std::unordered_map<int, Table> tables;
+  Table *last = nullptr;
+  int last_qs = -1;
+  Table &table(int qs);
   std::pair<float, float> get(int shared, int qs);
+  double cutoffJaccard(int best, int qs);
   // per-worker scratch of MapTail::mapRead (cleared, never shrunk: no allocation per read once warm)
   MappingResultsVector_t unfiltered, l2Mappings, filtered;
   std::vector<mm_l1_candidate> work;
@@ -69,6 +80,8 @@ class MapTail {
   void formatMappings(const MappingResultsVector_t &readMappings, const std::string &queryName, std::string &out) const;  // appends
   void formatMappings(const MappingResult *first, size_t n, const std::string &queryName, std::string &out) const;     // appends
   void formatMappingsStream(const MappingResultsVector_t &readMappings, const std::string &queryName, std::ostream &os) const;
+  /* the real-number text of formatMappings against snprintf("%g") on n values of every kind; returns the differences */
+  static int64_t realTextSelftest(int64_t n, uint64_t seed);
 
  private:
   const Parameters &param;
