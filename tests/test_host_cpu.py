@@ -211,6 +211,7 @@ def _paf_fields(m, qname, names, lens):
 @pytest.mark.parametrize("which,args", [("random", ["-s", "5000", "--pi", "85"]),
                                         ("panel", ["-s", "5000", "--pi", "85"]),
                                         ("panel", ["-s", "2000", "--pi", "90", "-J", "25", "--noHgFilter", "-n", "3"]),
+                                        ("panel", ["-s", "2000", "--pi", "90", "-J", "25", "--hgFilterAniDiff", "2", "--hgFilterConf", "99", "-n", "3"]),
                                         ("random", ["-s", "5000", "--pi", "85", "-f", "none"]),
                                         ("random", ["-s", "5000", "--pi", "85", "--noMerge"])])
 def test_host_tail_matches_reference_mapModule(workdir, which, args):
