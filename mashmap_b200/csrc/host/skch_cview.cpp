@@ -222,7 +222,8 @@ struct BmHandle {
   std::vector<MappingResultsVector_t> results;
   std::vector<std::string> text;
   std::string paf;
-  std::vector<ContigInfo> one_to_one_queries;  // skch_bm_one_to_one's query names, kept between calls
+  MappingResultsVector_t one_to_one_records;   // skch_bm_one_to_one's working copy of the records, kept between calls
+  std::vector<ContigInfo> one_to_one_queries;  // ... and its query names
   int32_t one_to_one_query_len = -1;
 };
 struct BmBatch {
@@ -382,7 +383,8 @@ uint64_t skch_bm_results_raw(void *hv, void *out, uint64_t cap)
 uint64_t skch_bm_one_to_one(void *hv, const void *recs, uint64_t n, int32_t n_queries, int32_t query_len)
 {
   BmHandle *h = (BmHandle *)hv;
-  MappingResultsVector_t all((const MappingResult *)recs, (const MappingResult *)recs + n);
+  MappingResultsVector_t &all = h->one_to_one_records;
+  all.assign((const MappingResult *)recs, (const MappingResult *)recs + n);
   std::vector<ContigInfo> &q = h->one_to_one_queries;
   if ((int32_t)q.size() != n_queries || h->one_to_one_query_len != query_len) {
     q.resize((size_t)n_queries);

@@ -142,35 +142,66 @@ inline void filterMappings(MappingResultsVector_t &readMappings, const std::vect
  * events of the reference only erase from an empty status and are not needed here.
  */
 inline void filterMappingsParallel(MappingResultsVector_t &readMappings, const std::vector<ContigInfo> &metadata, int secondaryToKeep,
-                                   int threads)
+                                   int threads, bool erase_discarded = true)
 {
   const size_t n = readMappings.size();
   if (n <= 1) return;
-  if (threads <= 1 || n < 4096) { filterMappings(readMappings, metadata, secondaryToKeep); return; }
+  if (threads <= 1 || n < 4096) {
+    filterMappings(readMappings, metadata, secondaryToKeep);  // erases
+    return;
+  }
   const bool trace_ = getenv("MM_TRACE") != nullptr;
   auto tt_ = std::chrono::steady_clock::now();
   auto lap_ = [&](const char *w) { if (!trace_) return; auto t = std::chrono::steady_clock::now(); fprintf(stderr, "[trace]     sweep %s: %.1f ms\n", w, std::chrono::duration<double, std::milli>(t - tt_).count()); tt_ = t; };
-  for (auto &e : readMappings) e.discard = 1;
-  /* mappings by contig (counting sort keeps id order inside a contig) */
+  const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)threads, n / 8192));
+  auto in_slices = [&](auto fn) {  // fn(t, lo, hi) over [0, n) on T threads
+    std::vector<std::thread> pool;
+    for (int t = 1; t < T; t++) pool.emplace_back([&, t] { fn(t, n * (size_t)t / (size_t)T, n * (size_t)(t + 1) / (size_t)T); });
+    fn(0, 0, n / (size_t)T);
+    for (auto &th : pool) th.join();
+  };
+  /* mappings by contig: a counting sort that keeps id order inside a contig (slice t's ids of contig c follow slice t-1's) */
   const size_t nc = metadata.size();
+  std::vector<std::vector<size_t>> cnt((size_t)T, std::vector<size_t>(nc, 0));
+  in_slices([&](int t, size_t lo, size_t hi) {
+    std::vector<size_t> &c = cnt[(size_t)t];
+    for (size_t i = lo; i < hi; i++) { readMappings[i].discard = 1; c[(size_t)readMappings[i].refSeqId]++; }
+  });
   std::vector<size_t> start(nc + 2, 0);
-  for (auto &e : readMappings) start[(size_t)e.refSeqId + 1]++;
-  for (size_t c = 0; c < nc; c++) start[c + 1] += start[c];
-  std::vector<int> ids(n);
-  {
-    std::vector<size_t> at(start.begin(), start.end() - 1);
-    for (size_t i = 0; i < n; i++) ids[at[(size_t)readMappings[i].refSeqId]++] = (int)i;
+  for (size_t c = 0; c < nc; c++) {
+    size_t at = start[c];
+    for (int t = 0; t < T; t++) { const size_t k = cnt[(size_t)t][c]; cnt[(size_t)t][c] = at; at += k; }  // count -> first slot
+    start[c + 1] = at;
   }
+  start[nc + 1] = start[nc];
+  std::vector<int> ids(n);
+  in_slices([&](int t, size_t lo, size_t hi) {
+    std::vector<size_t> &at = cnt[(size_t)t];
+    for (size_t i = lo; i < hi; i++) ids[at[(size_t)readMappings[i].refSeqId]++] = (int)i;
+  });
   /* sweep units: runs of contigs; contig c joins c-1 when c-1 has a mapping covering [0, len-1] */
+  std::vector<uint8_t> link(nc, 0);
+  {
+    std::atomic<size_t> next_c{1};
+    auto find_links = [&]() {
+      while (true) {
+        const size_t c = next_c.fetch_add(1);
+        if (c >= nc) break;
+        if (start[c + 1] == start[c]) continue;
+        for (size_t j = start[c - 1]; j < start[c]; j++) {
+          const MappingResult &m = readMappings[ids[j]];
+          if (m.refStartPos == 0 && m.refEndPos == metadata[c - 1].len - 1) { link[c] = 1; break; }
+        }
+      }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < T; t++) pool.emplace_back(find_links);
+    find_links();
+    for (auto &th : pool) th.join();
+  }
   std::vector<std::pair<size_t, size_t>> units;  // [first contig, last contig]
   for (size_t c = 0; c < nc; c++) {
-    bool link = false;
-    if (c > 0 && start[c + 1] > start[c])
-      for (size_t j = start[c - 1]; j < start[c] && !link; j++) {
-        const MappingResult &m = readMappings[ids[j]];
-        link = m.refStartPos == 0 && m.refEndPos == metadata[c - 1].len - 1;
-      }
-    if (link && !units.empty() && units.back().second == c - 1) units.back().second = c;
+    if (link[c] && !units.empty() && units.back().second == c - 1) units.back().second = c;
     else units.emplace_back(c, c);
   }
   lap_("prepare");
@@ -222,9 +253,11 @@ inline void filterMappingsParallel(MappingResultsVector_t &readMappings, const s
   work();
   for (auto &th : pool) th.join();
   lap_("units");
-  readMappings.erase(std::remove_if(readMappings.begin(), readMappings.end(), [](MappingResult &e) { return e.discard == 1; }),
-                     readMappings.end());
-  lap_("erase");
+  if (erase_discarded) {  // a caller that sorts next can drop the discarded records while it gathers (sortLikeStd)
+    readMappings.erase(std::remove_if(readMappings.begin(), readMappings.end(), [](MappingResult &e) { return e.discard == 1; }),
+                       readMappings.end());
+    lap_("erase");
+  }
 }
 
 }  // namespace ref

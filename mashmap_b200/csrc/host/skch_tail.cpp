@@ -3,6 +3,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include <algorithm>
 #include <charconv>
@@ -374,27 +375,35 @@ void inSlices(size_t n, int T, Fn fn)  // fn(lo, hi) over [0, n) on T threads
 
 }  // namespace
 
-/* std::sort(v, key(a) < key(b)): see above. `key` returns one of the packed keys. */
+/* std::sort(v, key(a) < key(b)): see above. `key` returns one of the packed keys. With drop_discarded, records whose
+ * `discard` flag is set are erased first (remove_if keeps the others in order, and so does leaving them out of the pairs). */
 template <class KeyFn>
-static void sortLikeStd(MappingResultsVector_t &v, KeyFn key, int threads = 1)
+static void sortLikeStd(MappingResultsVector_t &v, KeyFn key, int threads = 1, bool drop_discarded = false)
 {
   typedef decltype(key(v[0])) K;
   if (v.size() < 2048) {
+    if (drop_discarded) v.erase(std::remove_if(v.begin(), v.end(), [](const MappingResult &e) { return e.discard == 1; }), v.end());
     std::sort(v.begin(), v.end(), [&](const MappingResult &a, const MappingResult &b) { return key(a) < key(b); });
     return;
   }
   struct P { K k; uint32_t i; } __attribute__((packed));
-  const size_t n = v.size();
+  size_t n = v.size();
   const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(1, threads), n / 16384));
   static thread_local std::vector<P> p;                    // scratch kept between calls: no 14 MB of fresh pages per sort
   static thread_local MappingResultsVector_t out;
   p.resize(n);
-  out.resize(n);
   P *pp = p.data();  // the helper threads must see THIS thread's scratch, not their own (empty) thread_local copies
-  MappingResult *oo = out.data();
   const MappingResult *vv = v.data();
   inSlices(n, T, [&](size_t lo, size_t hi) { for (size_t i = lo; i < hi; i++) { pp[i].k = key(vv[i]); pp[i].i = (uint32_t)i; } });
+  if (drop_discarded) {
+    size_t m = 0;
+    for (size_t i = 0; i < n; i++)
+      if (!vv[i].discard) pp[m++] = pp[i];
+    n = m;
+  }
   sortExactlyLikeStd(pp, n, [](const P &a, const P &b) { return a.k < b.k; }, T);
+  out.resize(n);
+  MappingResult *oo = out.data();
   inSlices(n, T, [&](size_t lo, size_t hi) { for (size_t i = lo; i < hi; i++) oo[i] = vv[pp[i].i]; });
   v.swap(out);
 }
@@ -458,21 +467,32 @@ void MapTail::finalizeOneToOne(MappingResultsVector_t &allReadMappings, const st
     tt0 = t;
   };
   const int n_mappings = param.numMappingsForSegment - 1;
-  auto sb = allReadMappings.begin(), se = allReadMappings.begin();
-  MappingResultsVector_t tmp, filtered;
-  while (se != allReadMappings.end()) {
-    if (param.skip_prefix) {
+  if (!param.skip_prefix) {
+    /* one group of queries and one of references: filterByGroup's steps (:504-561) on the vector itself -- the general
+     * path below copies the ten megabytes of records of a 100 k-read run four times into freshly allocated vectors */
+    const bool tr2 = trace;
+    auto lap2 = [&](const char *what) { if (tr2) lap(what); };
+    sortLikeStd(allReadMappings, key_ref, param.threads);
+    lap2("  sort by reference position");
+    sortLikeStd(allReadMappings, key_query_ref, param.threads);
+    lap2("  sort by query start");
+    Filter::ref::filterMappingsParallel(allReadMappings, metadata, (uint16_t)n_mappings, param.threads, false);
+    lap2("  sweep");
+    sortLikeStd(allReadMappings, key_query_ref, param.threads, true);  // drops what the sweep discarded
+    lap2("  sort by query start again");
+  } else {
+    auto sb = allReadMappings.begin(), se = allReadMappings.begin();
+    MappingResultsVector_t tmp, filtered;
+    while (se != allReadMappings.end()) {
       const int g = getRefGroup(qmeta[sb->querySeqId].name);
       se = std::find_if_not(sb, allReadMappings.end(), [&](const MappingResult &c) { return g == getRefGroup(qmeta[c.querySeqId].name); });
-    } else {
-      se = allReadMappings.end();
+      tmp.insert(tmp.end(), std::make_move_iterator(sb), std::make_move_iterator(se));
+      filterByGroup(tmp, filtered, n_mappings, true);
+      tmp.clear();
+      sb = se;
     }
-    tmp.insert(tmp.end(), std::make_move_iterator(sb), std::make_move_iterator(se));
-    filterByGroup(tmp, filtered, n_mappings, true);
-    tmp.clear();
-    sb = se;
+    allReadMappings = std::move(filtered);
   }
-  allReadMappings = std::move(filtered);
   lap("filterByGroup");
   sortLikeStd(allReadMappings, key_read_query_ref, param.threads);
   lap("final sort");
@@ -481,22 +501,37 @@ void MapTail::finalizeOneToOne(MappingResultsVector_t &allReadMappings, const st
   MapTail t(param, metadata, refIdGroup);
   t.qmetadata = &qmeta;
   const size_t n = allReadMappings.size();
+  if (trace) fprintf(stderr, "[trace] one-to-one %zu mappings kept\n", n);
   const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(1, param.threads), n / 2048));
-  std::vector<std::string> part((size_t)T);
-  auto work = [&](int ti) {
+  std::vector<std::string> &part = textParts;  // kept between calls: no fresh pages for 10 MB of text every run
+  if (part.size() < (size_t)T) part.resize((size_t)T);
+  std::vector<size_t> at((size_t)T + 1, 0);
+  auto fmt = [&](int ti) {
     const size_t lo = n * (size_t)ti / (size_t)T, hi = n * (size_t)(ti + 1) / (size_t)T;
-    part[(size_t)ti].reserve((hi - lo) * 112);
-    t.formatMappings(allReadMappings.data() + lo, hi - lo, "", part[(size_t)ti]);
+    /* the string OBJECT a thread appends to lives on its own stack: the headers of part[0..T) sit next to each other in
+     * one vector and every append writes the length field (no false sharing between the formatting threads) */
+    std::string mine = std::move(part[(size_t)ti]);
+    mine.clear();
+    t.formatMappings(allReadMappings.data() + lo, hi - lo, "", mine);
+    part[(size_t)ti] = std::move(mine);
   };
-  std::vector<std::thread> pool;
-  for (int ti = 1; ti < T; ti++) pool.emplace_back(work, ti);
-  work(0);
-  for (auto &th : pool) th.join();
-  paf.clear();
-  size_t total = 0;
-  for (auto &x : part) total += x.size();
-  paf.reserve(total);
-  for (auto &x : part) paf += x;
+  {
+    std::vector<std::thread> pool;
+    for (int ti = 1; ti < T; ti++) pool.emplace_back(fmt, ti);
+    fmt(0);
+    for (auto &th : pool) th.join();
+  }
+  lap("text: format");
+  for (int ti = 0; ti < T; ti++) at[(size_t)ti + 1] = at[(size_t)ti] + part[(size_t)ti].size();
+  paf.resize(at[(size_t)T]);
+  char *dst = &paf[0];
+  auto join = [&](int ti) { memcpy(dst + at[(size_t)ti], part[(size_t)ti].data(), part[(size_t)ti].size()); };
+  {
+    std::vector<std::thread> pool;
+    for (int ti = 1; ti < T; ti++) pool.emplace_back(join, ti);
+    join(0);
+    for (auto &th : pool) th.join();
+  }
   lap("text");
 }
 
@@ -649,8 +684,15 @@ inline void put_real(std::string &out, F v)
 {
   char buf[64];
   const double dv = (double)v;
-  if ((F)dv == v)  // always for float and double; a long double kmerComplexity holds a float or a mean computed in double
+  if ((F)dv == v) {  // always for float and double; a long double kmerComplexity holds a float or a mean computed in double
     if (char *e = g6_fast(buf, dv)) { out.append(buf, e); return; }
+    /* same value, same text -- and the double conversion is lock-free, while libstdc++ prints a long double through
+     * snprintf under a freshly created "C" locale (newlocale / freelocale take a process-wide lock on every call: 16
+     * formatting threads ran at the speed of one) */
+    auto r = std::to_chars(buf, buf + sizeof(buf), dv, std::chars_format::general, 6);
+    out.append(buf, r.ptr);
+    return;
+  }
   auto r = std::to_chars(buf, buf + sizeof(buf), v, std::chars_format::general, 6);
   out.append(buf, r.ptr);
 }

@@ -87,6 +87,7 @@ class MapTail {
   const Parameters &param;
   const std::vector<ContigInfo> &metadata;
   const std::vector<int> &refIdGroup;
+  mutable std::vector<std::string> textParts;  // finalizeOneToOne's per-thread text, kept between calls (one caller at a time)
 };
 
 }  // namespace skch

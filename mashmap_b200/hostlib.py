@@ -133,14 +133,21 @@ class BatchMapper:
         lib().skch_bm_results_raw(self.h, out.ctypes.data, n)
         return out[:n]
 
-    def one_to_one(self, records, n_queries, query_len):
+    def one_to_one(self, records, n_queries, query_len, copy=True):
         """-f one-to-one, the run-wide step over raw records of any origin (this rank's, or all ranks' after the all-gather):
-        returns (mappings kept, PAF text)"""
+        returns (mappings kept, PAF text). copy=False hands back a view of the text where the library wrote it (valid until
+        the next call) instead of a Python copy of it"""
         r = np.ascontiguousarray(records, dtype=np.uint8)
         kept = lib().skch_bm_one_to_one(self.h, r.ctypes.data, len(r), int(n_queries), int(query_len))
+        return int(kept), self.paf_final(copy)
+
+    def paf_final(self, copy=True):
+        """the PAF text of the last one_to_one()"""
         n = C.c_uint64()
         p = lib().skch_bm_paf_final(self.h, C.byref(n))
-        return int(kept), C.string_at(p, n.value)
+        if copy:
+            return C.string_at(p, n.value)
+        return memoryview((C.c_char * n.value).from_address(C.cast(p, C.c_void_p).value)) if n.value else memoryview(b"")
 
     @property
     def device_count(self):
