@@ -50,8 +50,16 @@ with open(os.path.join(P, "r2_kernels_full.csv"), "w", newline="") as f:
     w.writerow([hdr[i] for i in idx]); w.writerow([units[i] for i in idx])
     for k, r in last.items():
         w.writerow([r[i] for i in idx])
-per = {k: {"ms": val(r, "gpu__time_duration.sum", T), "dram_read_bytes": val(r, "dram__bytes_read.sum", B),
-           "dram_write_bytes": val(r, "dram__bytes_write.sum", B)} for k, r in last.items()}
+def num(r, c, scale):
+    try:
+        v = val(r, c, scale)
+        return v if v == v else 0.0  # a launch too short to sample reports nan
+    except ValueError:
+        return 0.0
+
+
+per = {k: {"ms": num(r, "gpu__time_duration.sum", T), "dram_read_bytes": num(r, "dram__bytes_read.sum", B),
+           "dram_write_bytes": num(r, "dram__bytes_write.sum", B)} for k, r in last.items()}
 tp = os.path.join(P, "roofline_traffic.json")
 old = json.load(open(tp)) if os.path.exists(tp) else {}
 reduced = old.get("reduced_workload") or {k: old[k] for k in ("source", "segments_in_capture", "k_sketch_dram_bytes_per_segment", "per_kernel") if k in old}
