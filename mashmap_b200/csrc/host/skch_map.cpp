@@ -376,8 +376,10 @@ void BatchMapper::laneFinish(DeviceGroup &g, Lane &ln, const ReadBatch &b, std::
   const int nthreads = std::max(1, std::min<int>(tail_threads, (int)((nreads + 255) / 256)));
   std::atomic<size_t> next{r0};
   auto worker = [&]() {
-    IdentityCache idc;
-    idc.k = param.kmerSize; idc.ANIDiff = param.ANIDiff;
+    /* one cache per pool thread, kept across parts and batches: filling its tables costs a binomial search per distinct
+     * shared-sketch count (about a millisecond per worker), which every part used to pay again */
+    static thread_local IdentityCache idc;
+    idc.use(param.kmerSize, param.ANIDiff);
     uint64_t bytes = 0, mapped = 0, maps = 0;
     while (true) {
       const size_t lo = next.fetch_add(256);

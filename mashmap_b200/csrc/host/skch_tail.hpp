@@ -49,6 +49,11 @@ struct IdentityCache {
   Table *last = nullptr;
   int last_qs = -1;
   Table &table(int qs);
+  void use(int kmerSize, float aniDiff)  // (re)binds the cache to a parameter set; the tables survive while it stays the same
+  {
+    if (kmerSize != k || aniDiff != ANIDiff) { tables.clear(); last = nullptr; last_qs = -1; }
+    k = kmerSize; ANIDiff = aniDiff;
+  }
   std::pair<float, float> get(int shared, int qs);
   double cutoffJaccard(int best, int qs);
   // per-worker scratch of MapTail::mapRead (cleared, never shrunk: no allocation per read once warm)
