@@ -627,6 +627,11 @@ void skch_tail_bench(void *hv, int32_t n_reads, const int32_t *read_len, const u
   if (n_mappings) *n_mappings = nm;
 }
 
+int64_t skch_sort_selftest(int64_t n, uint64_t seed, int threads, int pattern, int64_t *heap_branches)
+{
+  return MapTail::sortSelftest(n, seed, threads, pattern, heap_branches);
+}
+
 /* the string formatter of the PAF lines against the stream formatter (the reference's own statement) on n random mappings,
  * in every output mode: returns the number of modes whose texts differ (0 = identical) */
 int skch_format_selftest(int64_t n, uint64_t seed)

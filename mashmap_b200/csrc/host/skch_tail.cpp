@@ -6,6 +6,7 @@
 #include <cstring>
 
 #include <algorithm>
+#include <atomic>
 #include <charconv>
 #include <condition_variable>
 #include <functional>
@@ -323,6 +324,8 @@ class JobPool {
   std::vector<std::thread> pool_;
 };
 
+std::atomic<long> g_heapSortBranch{0};  // how often the threaded sort took introsort's heap-sort branch (self-test evidence)
+
 #if defined(__GLIBCXX__)
 template <class P, class Cmp>
 void introsortJob(P *first, P *last, long depth, Cmp cmp, JobPool &pool, long grain)
@@ -333,6 +336,7 @@ void introsortJob(P *first, P *last, long depth, Cmp cmp, JobPool &pool, long gr
       break;
     }
     if (depth == 0) {
+      g_heapSortBranch.fetch_add(1, std::memory_order_relaxed);
       std::__partial_sort(first, last, last, cmp);
       break;
     }
@@ -406,6 +410,60 @@ static void sortLikeStd(MappingResultsVector_t &v, KeyFn key, int threads = 1, b
   MappingResult *oo = out.data();
   inSlices(n, T, [&](size_t lo, size_t hi) { for (size_t i = lo; i < hi; i++) oo[i] = vv[pp[i].i]; });
   v.swap(out);
+}
+
+/* Self-test of sortExactlyLikeStd against std::sort on (key, index) pairs, n elements, `threads` threads.
+ * pattern 0: random keys from a small range (many ties); 1: ascending; 2: descending; 3: organ pipe; 4: all equal;
+ * 5, 6: an adversarial input built with McIlroy's "antiqsort" construction against libstdc++'s own std::sort (keys are decided
+ *    while std::sort runs, so that every pivot it picks is nearly the smallest key left): quicksort degenerates, the depth
+ *    limit is reached and the heap-sort branch (__partial_sort) of the threaded version runs, on ranges of every size.
+ * Returns the number of positions at which the two arrangements differ; *heap_branches = how often the threaded sort took
+ * the heap-sort branch. */
+int64_t MapTail::sortSelftest(int64_t n64, uint64_t seed, int threads, int pattern, int64_t *heap_branches)
+{
+  struct P { uint64_t k; uint32_t i; } __attribute__((packed));
+  const long heap0 = g_heapSortBranch.load();
+  const size_t n = (size_t)n64;
+  uint64_t x = seed * 0x9E3779B97F4A7C15ULL + 777;
+  auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+  std::vector<uint64_t> key(n);
+  switch (pattern) {
+    case 0: for (auto &k : key) k = rnd() % 1000; break;
+    case 1: for (size_t i = 0; i < n; i++) key[i] = i / 3; break;
+    case 2: for (size_t i = 0; i < n; i++) key[i] = (n - i) / 3; break;
+    case 3: for (size_t i = 0; i < n; i++) key[i] = std::min(i, n - 1 - i) / 2; break;
+    case 4: for (auto &k : key) k = 42; break;
+    default: {
+      /* antiqsort: items start as "gas" (undecided, larger than every decided key); a comparison of two gas items freezes
+       * the one that was a recent pivot candidate to the next solid value */
+      const uint64_t gas = (uint64_t)n;
+      std::vector<uint64_t> val(n, gas);
+      std::vector<uint32_t> ptr(n);
+      for (size_t i = 0; i < n; i++) ptr[i] = (uint32_t)i;
+      uint64_t nsolid = 0;
+      uint32_t candidate = 0;
+      std::sort(ptr.begin(), ptr.end(), [&](uint32_t a, uint32_t b) {
+        if (val[a] == gas && val[b] == gas) {
+          if (a == candidate) val[a] = nsolid++;
+          else val[b] = nsolid++;
+        }
+        if (val[a] == gas) candidate = a;
+        else if (val[b] == gas) candidate = b;
+        return val[a] < val[b];
+      });
+      for (size_t i = 0; i < n; i++) key[i] = (val[i] == gas ? nsolid : val[i]) / (pattern == 6 ? 2 : 1);  // 6: halved, ties as well
+    }
+  }
+  std::vector<P> a(n), b(n);
+  for (size_t i = 0; i < n; i++) { a[i].k = key[i]; a[i].i = (uint32_t)i; }
+  b = a;
+  auto less = [](const P &l, const P &r) { return l.k < r.k; };
+  std::sort(a.begin(), a.end(), less);
+  sortExactlyLikeStd(b.data(), n, less, threads);
+  int64_t bad = 0;
+  for (size_t i = 0; i < n; i++) bad += a[i].i != b[i].i;
+  if (heap_branches) *heap_branches = g_heapSortBranch.load() - heap0;
+  return bad;
 }
 
 /* ---- filterByGroup (computeMap.hpp:504-561) ---- */

@@ -87,6 +87,8 @@ class MapTail {
   void formatMappingsStream(const MappingResultsVector_t &readMappings, const std::string &queryName, std::ostream &os) const;
   /* the real-number text of formatMappings against snprintf("%g") on n values of every kind; returns the differences */
   static int64_t realTextSelftest(int64_t n, uint64_t seed);
+  /* the threaded exact sort against std::sort on n (key, index) pairs of a given pattern; returns the differences */
+  static int64_t sortSelftest(int64_t n, uint64_t seed, int threads, int pattern, int64_t *heap_branches);
 
  private:
   const Parameters &param;

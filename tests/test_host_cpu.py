@@ -291,6 +291,26 @@ def test_run_wide_one_to_one_step_equals_its_plain_statement(n, threads):
             assert d == 0
 
 
+def test_threaded_exact_sort_equals_std_sort_on_every_pattern():
+    """sortExactlyLikeStd (libstdc++'s own partition / loop / heap / insertion routines with the recursive call handed to
+    other threads) leaves (key, index) pairs exactly where std::sort leaves them -- ties included -- on random keys with many
+    ties, sorted, reversed, organ-pipe and constant inputs, and on an antiqsort adversary built against std::sort itself,
+    which drives the quicksort phase to its depth limit so that the heap-sort branch of the threaded version runs"""
+    import ctypes as C
+
+    L = hostlib.lib()
+    L.skch_sort_selftest.restype = C.c_int64
+    L.skch_sort_selftest.argtypes = [C.c_int64, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_int64)]
+    heap_hits = 0
+    for pattern in range(7):
+        for n, threads in ((33_000, 2), (70_001, 5), (250_000, 8)):
+            hb = C.c_int64()
+            assert L.skch_sort_selftest(n, 11 + pattern, threads, pattern, C.byref(hb)) == 0, (pattern, n, threads)
+            if pattern >= 5:
+                heap_hits += hb.value
+    assert heap_hits > 0  # the adversary did reach introsort's depth limit in the threaded code
+
+
 def test_paf_text_without_a_stream_equals_the_stream_text():
     """reportReadMappings (computeMap.hpp:1758-1805) writes every field through operator<<; the product appends the same
     characters with std::to_chars (integers; %g with precision 6 for the mapping quality, identity, complexity and Jaccard
