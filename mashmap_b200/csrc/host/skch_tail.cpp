@@ -256,10 +256,11 @@ namespace {
 inline uint32_t biased(int32_t x) { return (uint32_t)x ^ 0x80000000u; }
 inline uint64_t pack2(int32_t a, int32_t b) { return ((uint64_t)biased(a) << 32) | biased(b); }
 
+/* packed (alignment 1): they live inside packed (key, index) pairs at any offset */
 struct Key2 {  // (a, b)
   uint64_t k;
   bool operator<(const Key2 &o) const { return k < o.k; }
-};
+} __attribute__((packed));
 struct Key3 {  // (a, b, c)
   uint64_t hi;
   uint32_t lo;
@@ -268,7 +269,7 @@ struct Key3 {  // (a, b, c)
 struct Key4 {  // (a, b, c, d)
   uint64_t hi, lo;
   bool operator<(const Key4 &o) const { return hi < o.hi || (hi == o.hi && lo < o.lo); }
-};
+} __attribute__((packed));
 inline Key2 key_ref(const MappingResult &m) { return Key2{pack2(m.refSeqId, m.refStartPos)}; }
 inline Key3 key_query_ref(const MappingResult &m) { return Key3{pack2(m.queryStartPos, m.refSeqId), biased(m.refStartPos)}; }
 inline Key4 key_read_query_ref(const MappingResult &m)
