@@ -562,6 +562,46 @@ void *skch_tail_create(const skch_tail_params *tp, int n_contigs, const char **n
   return h;
 }
 
+/* -f one-to-one, the run-wide step (MapTail::finalizeOneToOne) on caller-provided mappings in the flat record layout of the
+ * checkers (oracle/mm_oracle_types.h orc_mapping: the members of skch::MappingResult as int32 / float / double), on `threads`
+ * threads. No device involved: tests compare it with the reference's own statements of the step. Returns the mappings kept. */
+struct skch_flat_mapping {
+  int32_t queryLen, refStartPos, refEndPos, queryStartPos, queryEndPos, refSeqId, querySeqId, blockLength;
+  float nucIdentity, nucIdentityUpperBound;
+  int32_t sketchSize, conservedSketches, strand, approxMatches, n_merged, splitMappingId, discard, selfMapFilter;
+  double kmerComplexity;
+};
+int64_t skch_tail_one_to_one(void *hv, const skch_flat_mapping *in, int64_t n, skch_flat_mapping *out, int32_t n_queries, int threads)
+{
+  TailHandle *h = (TailHandle *)hv;
+  h->p.threads = threads;
+  MappingResultsVector_t all((size_t)n);
+  for (int64_t i = 0; i < n; i++) {
+    MappingResult &m = all[(size_t)i];
+    const skch_flat_mapping &o = in[i];
+    memset(&m, 0, sizeof m);
+    m.queryLen = o.queryLen; m.refStartPos = o.refStartPos; m.refEndPos = o.refEndPos; m.queryStartPos = o.queryStartPos;
+    m.queryEndPos = o.queryEndPos; m.refSeqId = o.refSeqId; m.querySeqId = o.querySeqId; m.blockLength = o.blockLength;
+    m.nucIdentity = o.nucIdentity; m.nucIdentityUpperBound = o.nucIdentityUpperBound; m.sketchSize = o.sketchSize;
+    m.conservedSketches = o.conservedSketches; m.strand = (strand_t)o.strand; m.approxMatches = o.approxMatches; m.n_merged = o.n_merged;
+    m.splitMappingId = o.splitMappingId; m.discard = (uint8_t)o.discard; m.selfMapFilter = o.selfMapFilter != 0;
+    m.kmerComplexity = o.kmerComplexity;
+  }
+  std::vector<ContigInfo> q((size_t)n_queries);
+  for (int32_t i = 0; i < n_queries; i++) q[(size_t)i] = ContigInfo{"q" + std::to_string(i), 0};
+  h->tail->finalizeOneToOne(all, q, h->text);
+  for (size_t i = 0; i < all.size(); i++) {
+    const MappingResult &m = all[i];
+    skch_flat_mapping &o = out[i];
+    o.queryLen = m.queryLen; o.refStartPos = m.refStartPos; o.refEndPos = m.refEndPos; o.queryStartPos = m.queryStartPos;
+    o.queryEndPos = m.queryEndPos; o.refSeqId = m.refSeqId; o.querySeqId = m.querySeqId; o.blockLength = m.blockLength;
+    o.nucIdentity = m.nucIdentity; o.nucIdentityUpperBound = m.nucIdentityUpperBound; o.sketchSize = m.sketchSize;
+    o.conservedSketches = m.conservedSketches; o.strand = m.strand; o.approxMatches = m.approxMatches; o.n_merged = m.n_merged;
+    o.splitMappingId = m.splitMappingId; o.discard = m.discard; o.selfMapFilter = m.selfMapFilter; o.kmerComplexity = (double)m.kmerComplexity;
+  }
+  return (int64_t)all.size();
+}
+
 void skch_tail_destroy(void *hv)
 {
   TailHandle *h = (TailHandle *)hv;

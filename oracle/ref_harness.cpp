@@ -332,6 +332,40 @@ int refh_map_read(void *hv, const char *name, const char *seq, int len, int seqC
   return n;
 }
 
+/* ---- -f one-to-one, the run-wide step of mapQuery (computeMap.hpp:358-405) on caller-provided mappings ----
+ * The step is not a function of its own in the reference (it sits at the end of mapQuery), so its statements are repeated
+ * here around the reference's OWN filterByGroup (:504-561, with Filter::ref::filterMappings and its std::sort calls inside)
+ * and the final std::sort with the reference's comparator, for sessions without -Y (one query group). Returns the number of
+ * mappings kept; out needs room for n. */
+int64_t refh_one_to_one(void *hv, const orc_mapping *in, int64_t n, orc_mapping *out)
+{
+  Handle *h = (Handle *)hv;
+  skch::Map &M = *h->map;
+  skch::MappingResultsVector_t allReadMappings((size_t)n);
+  for (int64_t i = 0; i < n; i++) {
+    skch::MappingResult &m = allReadMappings[(size_t)i];
+    const orc_mapping &o = in[i];
+    m.queryLen = o.queryLen; m.refStartPos = o.refStartPos; m.refEndPos = o.refEndPos;
+    m.queryStartPos = o.queryStartPos; m.queryEndPos = o.queryEndPos;
+    m.refSeqId = o.refSeqId; m.querySeqId = o.querySeqId; m.blockLength = o.blockLength;
+    m.nucIdentity = o.nucIdentity; m.nucIdentityUpperBound = o.nucIdentityUpperBound;
+    m.sketchSize = o.sketchSize; m.conservedSketches = o.conservedSketches;
+    m.strand = o.strand; m.approxMatches = o.approxMatches; m.n_merged = o.n_merged;
+    m.splitMappingId = o.splitMappingId; m.discard = o.discard; m.selfMapFilter = o.selfMapFilter;
+    m.kmerComplexity = o.kmerComplexity;
+  }
+  int n_mappings = M.param.numMappingsForSegment - 1;
+  skch::MappingResultsVector_t tmpMappings, filteredMappings;
+  tmpMappings.insert(tmpMappings.end(), std::make_move_iterator(allReadMappings.begin()), std::make_move_iterator(allReadMappings.end()));
+  M.filterByGroup(tmpMappings, filteredMappings, n_mappings, true);
+  allReadMappings = std::move(filteredMappings);
+  std::sort(allReadMappings.begin(), allReadMappings.end(), [](const skch::MappingResult &a, const skch::MappingResult &b) {
+    return std::tie(a.querySeqId, a.queryStartPos, a.refSeqId, a.refStartPos) < std::tie(b.querySeqId, b.queryStartPos, b.refSeqId, b.refStartPos);
+  });
+  for (size_t i = 0; i < allReadMappings.size(); i++) flatten(allReadMappings[i], out[i]);
+  return (int64_t)allReadMappings.size();
+}
+
 /* cpu_baseline / --impl reference driver around the reference's own mapModule: n_reads reads of read_len bases (back to
  * back in `bases`), one read per task on `threads` threads like the reference's pool (computeMap.hpp:275,340).
  * Same contract and row layout as orc_map_reads_mt of the port. */

@@ -244,3 +244,66 @@ def test_host_index_and_host_tail_equal_the_reference_on_random_configurations(w
         finally:
             R.close()
     assert n_reads > 200
+
+
+@needs_ref
+@pytest.mark.parametrize("n,threads,span_every", [(3000, 1, 40), (50_000, 4, 0), (120_000, 8, 60)])
+def test_run_wide_one_to_one_step_equals_the_reference_itself(workdir, n, threads, span_every):
+    """-f one-to-one's run-wide step (computeMap.hpp:358-405) on the SAME random mappings through the reference's own
+    filterByGroup / Filter::ref::filterMappings / std::sort calls (oracle/_ref, refh_one_to_one) and through the product's
+    MapTail::finalizeOneToOne on several threads: same mappings in the same order. The mappings are full of ties -- equal
+    sort keys, equal identities, equal start positions (the sweep refuses an equivalent mapping, and which one arrives first
+    is decided by std::sort's treatment of equal keys) -- and some cover a whole contig or end on its last base (the
+    position+1 wrap into the next contig of filter.hpp:311-324)."""
+    import ctypes as C
+
+    rng = np.random.default_rng(n + threads)
+    lens = [int(x) for x in rng.integers(200_000, 400_000, 24)]
+    unit = synth.random_sequence(1000, rng)  # only the contig LENGTHS matter to the step: one repeated unit keeps the session cheap
+    ref = os.path.join(workdir, f"o2o_{n}.fa")
+    synth.write_fasta(ref, [f"c{i}" for i in range(len(lens))], [np.resize(unit, ln) for ln in lens])
+    R = refh.RefSession(["-r", ref, "-q", ref, "-s", "5000", "--pi", "90", "-f", "one-to-one", "-t", "2"])
+    try:
+        assert [int(x) for x in R.contig_len] == lens
+        m = np.zeros(n, dtype=refh.mapping_dtype)
+        n_q = max(10, n // 2)
+        m["querySeqId"] = np.sort(rng.integers(0, n_q, n))  # read order, as mapQuery collects them
+        m["queryLen"] = 20000
+        m["queryStartPos"] = rng.integers(0, 4, n) * 5000
+        m["queryEndPos"] = m["queryStartPos"] + 5000
+        m["refSeqId"] = rng.integers(0, len(lens), n)
+        clen = np.array(lens)[m["refSeqId"]]
+        m["refStartPos"] = rng.integers(0, 800, n) * 250  # a coarse grid: many equal starts
+        m["refEndPos"] = np.minimum(m["refStartPos"] + 4999 + rng.integers(0, 3, n) * 2500, clen - 1)
+        if span_every:
+            whole = rng.integers(0, span_every, n) == 0
+            m["refStartPos"][whole] = 0
+            m["refEndPos"][whole] = clen[whole] - 1
+        tail_end = rng.integers(0, 50, n) == 0  # ends on the last base of its contig
+        m["refEndPos"][tail_end] = clen[tail_end] - 1
+        m["refStartPos"] = np.minimum(m["refStartPos"], m["refEndPos"])
+        m["nucIdentity"] = rng.choice(np.float32([0.95, 0.96, 0.97, 0.9712, 0.99, 1.0]), n)
+        m["nucIdentityUpperBound"] = m["nucIdentity"]
+        m["blockLength"], m["sketchSize"], m["conservedSketches"], m["n_merged"] = 5000, 20, 15, 1
+        m["strand"] = rng.choice([1, -1], n)
+        m["kmerComplexity"] = 0.9
+        want = np.zeros(n, dtype=refh.mapping_dtype)
+        L = refh.lib()
+        L.refh_one_to_one.restype = C.c_int64
+        L.refh_one_to_one.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        n_want = L.refh_one_to_one(R.h, m.ctypes.data, n, want.ctypes.data)
+        from test_host_cpu import _tail_params
+
+        tail = hostlib.HostTail(_tail_params(R), R.contig_names, R.contig_len)
+        H = hostlib.lib()
+        H.skch_tail_one_to_one.restype = C.c_int64
+        H.skch_tail_one_to_one.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int]
+        got = np.zeros(n, dtype=refh.mapping_dtype)
+        n_got = H.skch_tail_one_to_one(tail.h, m.ctypes.data, n, got.ctypes.data, n_q, threads)
+        tail.close()
+        assert 0 < n_want < n and n_got == n_want
+        for f in ("querySeqId", "queryStartPos", "queryEndPos", "refSeqId", "refStartPos", "refEndPos", "strand", "nucIdentity"):
+            assert np.array_equal(got[f][:n_got], want[f][:n_want]), f
+        print(f"n={n}: {n_want} mappings kept by both")
+    finally:
+        R.close()
