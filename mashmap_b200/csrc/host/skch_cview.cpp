@@ -461,6 +461,34 @@ int64_t skch_fasta_readers_diff(const char *path, int threads, uint64_t *n_recor
   return bad;
 }
 
+/* records, bases and an FNV-1a digest of every (name, sequence) pair of a file in order, through the line reader (bulk = 0)
+ * or the memory-mapped bulk reader (bulk = 1; returns -1 when it declines the file): compared with the same digest taken
+ * through the reference's own reader (oracle/_ref, refh_read_file_digest) */
+int skch_read_file_digest(const char *path, int bulk, int threads, uint64_t *n_records, uint64_t *n_bases, uint64_t *digest)
+{
+  uint64_t h = 1469598103934665603ULL, nr = 0, nb = 0;
+  auto eat = [&h](const std::string &s) {
+    for (unsigned char c : s) { h ^= c; h *= 1099511628211ULL; }
+    h ^= 0xFF; h *= 1099511628211ULL;
+  };
+  if (!bulk) {
+    if (!seqio::for_each_seq_in_file(path, {}, "", [&](const std::string &name, const std::string &seq) {
+          eat(name); eat(seq); nr++; nb += seq.size();
+        }))
+      return -2;
+  } else {
+    seqio::FastaFile ff;
+    if (!ff.open(path, threads)) return -1;
+    for (const auto &r : ff.records()) {
+      std::string seq(r.seq_len, '\0');
+      ff.copy_bases(r, &seq[0]);
+      eat(ff.name(r)); eat(seq); nr++; nb += seq.size();
+    }
+  }
+  *n_records = nr; *n_bases = nb; *digest = h;
+  return 0;
+}
+
 /* Self-test of the run-wide one-to-one step (MapTail::finalizeOneToOne: sorts through (key, index) pairs, reference-axis
  * sweep per contig on `threads` threads, PAF text in slices) against the plain statement of computeMap.hpp:358-405 +
  * filter.hpp:333-394 (std::sort on the records, one serial sweep, one stream) on n random mappings full of ties.

@@ -332,6 +332,22 @@ int refh_map_read(void *hv, const char *name, const char *seq, int len, int seqC
   return n;
 }
 
+/* ---- input: the reference's own reader (common/seqiter.hpp:20-111) over a file: records, bases and an FNV-1a digest of
+ * every (name, sequence) pair in order, for the product's two readers to be compared with ---- */
+int refh_read_file_digest(const char *path, uint64_t *n_records, uint64_t *n_bases, uint64_t *digest)
+{
+  uint64_t h = 1469598103934665603ULL, nr = 0, nb = 0;
+  auto eat = [&h](const std::string &s) {
+    for (unsigned char c : s) { h ^= c; h *= 1099511628211ULL; }
+    h ^= 0xFF; h *= 1099511628211ULL;
+  };
+  seqiter::for_each_seq_in_file(path, {}, "", [&](const std::string &name, const std::string &seq) {
+    eat(name); eat(seq); nr++; nb += seq.size();
+  });
+  *n_records = nr; *n_bases = nb; *digest = h;
+  return 0;
+}
+
 /* ---- -f one-to-one, the run-wide step of mapQuery (computeMap.hpp:358-405) on caller-provided mappings ----
  * The step is not a function of its own in the reference (it sits at the end of mapQuery), so its statements are repeated
  * here around the reference's OWN filterByGroup (:504-561, with Filter::ref::filterMappings and its std::sort calls inside)

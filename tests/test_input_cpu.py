@@ -75,3 +75,66 @@ def test_host_packer_matches_the_format_statement():
         if len(seq) & 1:  # the unused high nibble of the last byte is an N in both
             assert want[-1] >> 4 == 8 and got[-1] >> 4 == 8
         assert np.array_equal(want, got), len(seq)
+
+
+def _digest(lib_fn, *args):
+    import ctypes as C
+
+    n, b, d = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    rc = lib_fn(*args, C.byref(n), C.byref(b), C.byref(d))
+    return rc, n.value, b.value, d.value
+
+
+def test_both_readers_equal_the_reference_reader(tmp_path):
+    """the reference's own reader (common/seqiter.hpp:20-111, run through oracle/_ref) against the product's line reader
+    and its memory-mapped bulk reader on the same files: same records, same names, same bases (an FNV-1a digest over every
+    name and sequence in order). Multi-line FASTA with blank lines, descriptions, '>' inside a header, CRLF ends (the '\\r'
+    stays in the sequence in the reference, and in both readers), no newline at the end, a record without sequence, lower
+    case and IUPAC letters; gzip and FASTQ for the line reader (the bulk reader declines them)."""
+    import ctypes as C
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import refh
+
+    if not refh.available():
+        pytest.skip("oracle/_ref/libmm_ref.so not built")
+    R, H = refh.lib(), hostlib.lib()
+    R.refh_read_file_digest.argtypes = [C.c_char_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    H.skch_read_file_digest.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    rng = np.random.default_rng(11)
+    files = {}
+    for v in range(12):
+        recs = []
+        for i in range(int(rng.integers(1, 60))):
+            n = int(rng.choice([0, 1, 17, 59, 60, 61, 1000, 7001]))
+            name = f"s{v}_{i}" + (" desc with\ttab" if rng.random() < 0.5 else "") + (" >inner" if rng.random() < 0.2 else "")
+            recs.append((name, random_bases(rng, n)))
+        width = int(rng.choice([0, 60, 80, 7]))
+        data = b""
+        for name, s in recs:
+            data += b">" + name.encode() + b"\n"
+            if width == 0:
+                data += s + b"\n"
+            else:
+                for o in range(0, len(s), width):
+                    data += s[o : o + width] + b"\n"
+                if rng.random() < 0.2:
+                    data += b"\n"
+        if rng.random() < 0.3:
+            data = data.rstrip(b"\n")
+        if rng.random() < 0.25:
+            data = data.replace(b"\n", b"\r\n")
+        files[f"v{v}.fa"] = data
+    files["fq.fq"] = b"".join(b"@r%d extra\n" % i + random_bases(rng, int(rng.integers(1, 300))) + b"\n+\n" + b"I" * 3 + b"\n" for i in range(40))
+    for name, data in files.items():
+        p = write(str(tmp_path / name), data)
+        want = _digest(R.refh_read_file_digest, p.encode())
+        assert _digest(H.skch_read_file_digest, p.encode(), 0, 1) == want, name
+        bulk = _digest(H.skch_read_file_digest, p.encode(), 1, 3)
+        assert bulk == want or (bulk[0] == -1 and name.endswith(".fq")), name
+        gz = str(tmp_path / (name + ".gz"))
+        with gzip.open(gz, "wb") as f:
+            f.write(data)
+        assert _digest(R.refh_read_file_digest, gz.encode()) == want, name
+        assert _digest(H.skch_read_file_digest, gz.encode(), 0, 1) == want, name
