@@ -599,22 +599,22 @@ struct skch_flat_mapping {
   int32_t sketchSize, conservedSketches, strand, approxMatches, n_merged, splitMappingId, discard, selfMapFilter;
   double kmerComplexity;
 };
+static void unflatten(const skch_flat_mapping &o, MappingResult &m)
+{
+  memset(&m, 0, sizeof m);
+  m.queryLen = o.queryLen; m.refStartPos = o.refStartPos; m.refEndPos = o.refEndPos; m.queryStartPos = o.queryStartPos;
+  m.queryEndPos = o.queryEndPos; m.refSeqId = o.refSeqId; m.querySeqId = o.querySeqId; m.blockLength = o.blockLength;
+  m.nucIdentity = o.nucIdentity; m.nucIdentityUpperBound = o.nucIdentityUpperBound; m.sketchSize = o.sketchSize;
+  m.conservedSketches = o.conservedSketches; m.strand = (strand_t)o.strand; m.approxMatches = o.approxMatches; m.n_merged = o.n_merged;
+  m.splitMappingId = o.splitMappingId; m.discard = (uint8_t)o.discard; m.selfMapFilter = o.selfMapFilter != 0;
+  m.kmerComplexity = o.kmerComplexity;
+}
 int64_t skch_tail_one_to_one(void *hv, const skch_flat_mapping *in, int64_t n, skch_flat_mapping *out, int32_t n_queries, int threads)
 {
   TailHandle *h = (TailHandle *)hv;
   h->p.threads = threads;
   MappingResultsVector_t all((size_t)n);
-  for (int64_t i = 0; i < n; i++) {
-    MappingResult &m = all[(size_t)i];
-    const skch_flat_mapping &o = in[i];
-    memset(&m, 0, sizeof m);
-    m.queryLen = o.queryLen; m.refStartPos = o.refStartPos; m.refEndPos = o.refEndPos; m.queryStartPos = o.queryStartPos;
-    m.queryEndPos = o.queryEndPos; m.refSeqId = o.refSeqId; m.querySeqId = o.querySeqId; m.blockLength = o.blockLength;
-    m.nucIdentity = o.nucIdentity; m.nucIdentityUpperBound = o.nucIdentityUpperBound; m.sketchSize = o.sketchSize;
-    m.conservedSketches = o.conservedSketches; m.strand = (strand_t)o.strand; m.approxMatches = o.approxMatches; m.n_merged = o.n_merged;
-    m.splitMappingId = o.splitMappingId; m.discard = (uint8_t)o.discard; m.selfMapFilter = o.selfMapFilter != 0;
-    m.kmerComplexity = o.kmerComplexity;
-  }
+  for (int64_t i = 0; i < n; i++) unflatten(in[i], all[(size_t)i]);
   std::vector<ContigInfo> q((size_t)n_queries);
   for (int32_t i = 0; i < n_queries; i++) q[(size_t)i] = ContigInfo{"q" + std::to_string(i), 0};
   h->tail->finalizeOneToOne(all, q, h->text);
@@ -628,6 +628,18 @@ int64_t skch_tail_one_to_one(void *hv, const skch_flat_mapping *in, int64_t n, s
     o.splitMappingId = m.splitMappingId; o.discard = m.discard; o.selfMapFilter = m.selfMapFilter; o.kmerComplexity = (double)m.kmerComplexity;
   }
   return (int64_t)all.size();
+}
+/* the PAF text of caller-provided mappings of one read (MapTail::formatMappings, the stream-free formatter the product
+ * writes with), for comparison with the reference's own reportReadMappings (oracle/_ref, refh_report_mappings) */
+const char *skch_tail_format(void *hv, const skch_flat_mapping *in, int64_t n, const char *queryName, uint64_t *n_bytes)
+{
+  TailHandle *h = (TailHandle *)hv;
+  MappingResultsVector_t v((size_t)n);
+  for (int64_t i = 0; i < n; i++) unflatten(in[i], v[(size_t)i]);
+  h->text.clear();
+  h->tail->formatMappings(v, queryName, h->text);
+  if (n_bytes) *n_bytes = h->text.size();
+  return h->text.c_str();
 }
 
 void skch_tail_destroy(void *hv)

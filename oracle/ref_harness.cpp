@@ -78,6 +78,17 @@ void flatten(const skch::MappingResult &m, orc_mapping &o) {
   o.kmerComplexity = (double)m.kmerComplexity;
 }
 
+void unflatten(const orc_mapping &o, skch::MappingResult &m) {
+  m.queryLen = o.queryLen; m.refStartPos = o.refStartPos; m.refEndPos = o.refEndPos;
+  m.queryStartPos = o.queryStartPos; m.queryEndPos = o.queryEndPos;
+  m.refSeqId = o.refSeqId; m.querySeqId = o.querySeqId; m.blockLength = o.blockLength;
+  m.nucIdentity = o.nucIdentity; m.nucIdentityUpperBound = o.nucIdentityUpperBound;
+  m.sketchSize = o.sketchSize; m.conservedSketches = o.conservedSketches;
+  m.strand = o.strand; m.approxMatches = o.approxMatches; m.n_merged = o.n_merged;
+  m.splitMappingId = o.splitMappingId; m.discard = o.discard; m.selfMapFilter = o.selfMapFilter;
+  m.kmerComplexity = o.kmerComplexity;
+}
+
 void copy_minmers(const std::vector<skch::MinmerInfo> &v, orc_minmer *out) {
   for (size_t i = 0; i < v.size(); i++) {
     out[i].hash = v[i].hash; out[i].wpos = v[i].wpos; out[i].wpos_end = v[i].wpos_end;
@@ -332,6 +343,18 @@ int refh_map_read(void *hv, const char *name, const char *seq, int len, int seqC
   return n;
 }
 
+/* ---- output: the reference's own reportReadMappings (computeMap.hpp:1758-1805) on caller-provided mappings, written to
+ * `path` through a std::ofstream as the reference does (per-read mode: every line starts with queryName) ---- */
+int refh_report_mappings(void *hv, const orc_mapping *in, int64_t n, const char *queryName, const char *path)
+{
+  Handle *h = (Handle *)hv;
+  skch::MappingResultsVector_t v((size_t)n);
+  for (int64_t i = 0; i < n; i++) unflatten(in[i], v[(size_t)i]);
+  std::ofstream os(path);
+  h->map->reportReadMappings(v, queryName, os);
+  return os.good() ? 0 : 1;
+}
+
 /* ---- input: the reference's own reader (common/seqiter.hpp:20-111) over a file: records, bases and an FNV-1a digest of
  * every (name, sequence) pair in order, for the product's two readers to be compared with ---- */
 int refh_read_file_digest(const char *path, uint64_t *n_records, uint64_t *n_bases, uint64_t *digest)
@@ -358,18 +381,7 @@ int64_t refh_one_to_one(void *hv, const orc_mapping *in, int64_t n, orc_mapping 
   Handle *h = (Handle *)hv;
   skch::Map &M = *h->map;
   skch::MappingResultsVector_t allReadMappings((size_t)n);
-  for (int64_t i = 0; i < n; i++) {
-    skch::MappingResult &m = allReadMappings[(size_t)i];
-    const orc_mapping &o = in[i];
-    m.queryLen = o.queryLen; m.refStartPos = o.refStartPos; m.refEndPos = o.refEndPos;
-    m.queryStartPos = o.queryStartPos; m.queryEndPos = o.queryEndPos;
-    m.refSeqId = o.refSeqId; m.querySeqId = o.querySeqId; m.blockLength = o.blockLength;
-    m.nucIdentity = o.nucIdentity; m.nucIdentityUpperBound = o.nucIdentityUpperBound;
-    m.sketchSize = o.sketchSize; m.conservedSketches = o.conservedSketches;
-    m.strand = o.strand; m.approxMatches = o.approxMatches; m.n_merged = o.n_merged;
-    m.splitMappingId = o.splitMappingId; m.discard = o.discard; m.selfMapFilter = o.selfMapFilter;
-    m.kmerComplexity = o.kmerComplexity;
-  }
+  for (int64_t i = 0; i < n; i++) unflatten(in[i], allReadMappings[(size_t)i]);
   int n_mappings = M.param.numMappingsForSegment - 1;
   skch::MappingResultsVector_t tmpMappings, filteredMappings;
   tmpMappings.insert(tmpMappings.end(), std::make_move_iterator(allReadMappings.begin()), std::make_move_iterator(allReadMappings.end()));

@@ -307,3 +307,61 @@ def test_run_wide_one_to_one_step_equals_the_reference_itself(workdir, n, thread
         print(f"n={n}: {n_want} mappings kept by both")
     finally:
         R.close()
+
+
+@needs_ref
+@pytest.mark.parametrize("extra", [[], ["--legacy"], ["--reportPercentage"], ["--noMerge"], ["--noMerge", "--reportPercentage"]])
+def test_paf_text_equals_the_reference_s_own_report(workdir, extra):
+    """reportReadMappings (computeMap.hpp:1758-1805) of the reference ITSELF, through its std::ofstream, against the product's
+    stream-free formatter on the same 20,000 random mappings: same bytes. Identities and complexities of every kind (floats,
+    means of two to four floats computed in double, dyadic values, 0, 1, tiny values), in every output mode."""
+    import ctypes as C
+
+    from test_host_cpu import _tail_params
+
+    rng = np.random.default_rng(len(extra) * 7 + 3)
+    genome = [synth.random_sequence(int(n), rng) for n in (30_000, 45_000, 31_000)]
+    ref = os.path.join(workdir, "paf_text.fa")
+    synth.write_fasta(ref, ["chrA", "chrB some description", "c"], genome)
+    R = refh.RefSession(["-r", ref, "-q", ref, "-s", "2000", "--pi", "90", "-t", "1"] + extra)
+    try:
+        n = 20_000
+        m = np.zeros(n, dtype=refh.mapping_dtype)
+        m["queryLen"] = rng.integers(1, 300_000, n)
+        m["queryStartPos"] = rng.integers(0, 100_000, n)
+        m["queryEndPos"] = m["queryStartPos"] + rng.integers(0, 100_000, n)
+        m["refSeqId"] = rng.integers(0, 3, n)
+        m["refStartPos"] = rng.integers(0, 30_000, n)
+        m["refEndPos"] = m["refStartPos"] + rng.integers(0, 10_000, n)
+        m["strand"] = rng.choice([1, -1], n)
+        m["sketchSize"] = rng.integers(1, 1000, n)
+        m["conservedSketches"] = (rng.random(n) * (m["sketchSize"] + 1)).astype(np.int32)
+        m["blockLength"] = rng.integers(0, 100_000, n)
+        f32 = rng.random(n).astype(np.float32)
+        kind = rng.integers(0, 6, n)
+        ident = np.where(kind == 0, (rng.integers(0, 129, n) / 128).astype(np.float32),
+                 np.where(kind == 1, np.float32(1.0), np.where(kind == 2, f32 * np.float32(1e-4), np.where(kind == 3, np.float32(0.0), f32))))
+        m["nucIdentity"] = ident
+        a, b, c, d = (rng.random(n).astype(np.float32).astype(np.float64) for _ in range(4))
+        kk = rng.integers(0, 5, n)
+        m["kmerComplexity"] = np.where(kk == 0, a, np.where(kk == 1, (a + b) / 2, np.where(kk == 2, ((a + b) + c) / 3, np.where(kk == 3, (((a + b) + c) + d) / 4, 1.0))))
+        path = os.path.join(workdir, "paf_text.out")
+        L = refh.lib()
+        L.refh_report_mappings.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_char_p, C.c_char_p]
+        assert L.refh_report_mappings(R.h, m.ctypes.data, n, b"read_17 x", path.encode()) == 0
+        want = open(path, "rb").read()
+        tail = hostlib.HostTail(_tail_params(R), R.contig_names, R.contig_len)
+        H = hostlib.lib()
+        H.skch_tail_format.restype = C.c_void_p
+        H.skch_tail_format.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_char_p, C.POINTER(C.c_uint64)]
+        nb = C.c_uint64()
+        p = H.skch_tail_format(tail.h, m.ctypes.data, n, b"read_17 x", C.byref(nb))
+        got = C.string_at(p, nb.value)
+        tail.close()
+        if got != want:
+            gl, wl = got.split(b"\n"), want.split(b"\n")
+            bad = [(g, w) for g, w in zip(gl, wl) if g != w][:3]
+            raise AssertionError(f"{len(gl)} vs {len(wl)} lines; first differences: {bad}")
+        assert want.count(b"\n") == n
+    finally:
+        R.close()
