@@ -611,6 +611,8 @@ def gpu_arm(args):
                          "instruction_roofline": _instruction_roofline(n_segs, SEG, k1_ms, clocks, sm_count),
                          "note": "bit-exact Murmur3 makes K1 INT-ALU bound (SURVEY 8(d)); see DESIGN.md for the instruction roofline"},
         }
+        if world == 1:
+            out["roofline"]["other_kernels"] = l1_l2_rooflines(ctx, seg_res, cands, loci, SEG, k_ms[1] / args.steps, k_ms[2] / args.steps, peak)
         if sharded_check is not None:
             out["sharded_check"] = sharded_check
         if want_cpu and cpu_real:
@@ -639,6 +641,49 @@ def gpu_arm(args):
         if comm is not None:
             comm.close()
         dist.destroy_process_group()
+
+
+def algorithmic_bytes_l1_l2(seg_res, cands, loci, idx_seq, idx_wpos, seg_len):
+    """SURVEY 8(d)'s algorithmic bytes of the L1 and L2 stages for one step, counted on the step's own records:
+      B2 = 32 s_q (table probes) + 24 m (interval points) + 16 c (candidates out)           summed over the fragments
+      B3 = 24 n_scan + 24 s_q + 24 c_out                                                     summed over the L1 candidates
+    m = interval points of a fragment (segment result), c = its candidates, c_out = loci of a candidate, and n_scan = the
+    minmerIndex entries between lower_bound((seqId, rangeStart - L - 1)) and the last entry with wpos <= rangeEnd
+    (computeMap.hpp:1290-1340), counted against the index records themselves (idx_seq / idx_wpos, sorted by (seqId, wpos))."""
+    s_q = seg_res["sketch_size"].astype(np.int64)
+    b2 = 32 * int(s_q.sum()) + 24 * int(seg_res["n_points"].astype(np.int64).sum()) + 16 * int(len(cands))
+    key = (idx_seq.astype(np.uint64) << np.uint64(32)) | idx_wpos.astype(np.uint32).astype(np.uint64)
+    cseq = cands["seqId"].astype(np.uint64) << np.uint64(32)
+    lo = np.maximum(cands["rangeStartPos"].astype(np.int64) - seg_len - 1, 0).astype(np.uint64)
+    hi = np.maximum(cands["rangeEndPos"].astype(np.int64), 0).astype(np.uint64)
+    first = np.searchsorted(key, cseq | lo, side="left")
+    last = np.searchsorted(key, cseq | hi, side="right")
+    n_scan = int(np.maximum(last.astype(np.int64) - first.astype(np.int64), 0).sum())
+    b3 = 24 * n_scan + 24 * int(s_q[cands["segment"]].sum()) + 24 * int(len(loci))
+    return {"B2_bytes": b2, "B3_bytes": b3, "interval_points": int(seg_res["n_points"].astype(np.int64).sum()), "candidates": int(len(cands)),
+            "index_entries_scanned": n_scan, "loci": int(len(loci))}
+
+
+def l1_l2_rooflines(ctx, seg_res, cands, loci, seg_len, k2_ms, k3_ms, peak):
+    """roofline entries of K2 and K3: algorithmic bytes counted on the real configuration / stage time.
+    Needs a host copy of the index records (6 GB at 3 Gbp, a few seconds, outside every timed region); any failure only
+    drops the entries."""
+    try:
+        t0 = time.time()
+        mi = ctx.index_minmers()
+        counts = algorithmic_bytes_l1_l2(seg_res, cands, loci, mi["seqId"], mi["wpos"], seg_len)
+        del mi
+        n = max(1, len(seg_res))
+        out = {}
+        for name, b, ms in (("K2 (k_l1_probe + k_l1_warp + k_l1_cta)", counts["B2_bytes"], k2_ms), ("K3 (k_l2_ranges + k_l2_prep + k_l2_scan)", counts["B3_bytes"], k3_ms)):
+            ach = b / (ms * 1e-3) / 1e9
+            out[name] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "algorithmic_bytes_per_segment": b / n}
+        out["counts_per_step"] = counts
+        out["counted_in_seconds"] = round(time.time() - t0, 1)
+        return out
+    except Exception as e:  # never fatal: the contract's roofline is K1's
+        log(f"K2 / K3 roofline entries skipped: {type(e).__name__}: {e}")
+        return None
 
 
 def _instruction_roofline(n_segs, seg, k1_ms, clocks, sm_count):

@@ -267,6 +267,15 @@ class Context:
         self._check(self._L.mm_index_download(self._h, _ptr(mi), _ptr(keys), _ptr(offs), _ptr(pts), _ptr(fr)))
         return mi, keys, offs, pts, fr
 
+    def index_minmers(self):
+        """host copy of the device index's minmerIndex records only (needs no keep_lookup)"""
+        n = int(self._index_stats["n_minmers"]) if getattr(self, "_index_stats", None) else 0
+        if n == 0:
+            raise MashmapError(MM_ESTATE, "no device-built index statistics in this context")
+        mi = np.zeros(n, dtype=minmer_dtype)
+        self._check(self._L.mm_index_download(self._h, _ptr(mi), None, None, None, None))
+        return mi
+
     def tables_upload(self, sketch_cutoffs, min_hits):
         a = _c(sketch_cutoffs, np.int32)
         b = _c(min_hits, np.int32)

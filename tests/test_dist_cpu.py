@@ -84,3 +84,35 @@ def test_host_threads_of_a_rank_follow_its_numa_node_and_the_quota(monkeypatch):
     assert bench.host_threads_for_rank(8, (1, 64, 4)) == 2    # a 16-CPU quota: 2 per rank
     assert bench.host_threads_for_rank(8, None) == 2          # no binding: usable CPUs / ranks
     assert bench.host_threads_for_rank(1, None) == 16
+
+
+def test_algorithmic_bytes_of_l1_and_l2_are_counted_on_the_records():
+    """bench.py's K2 / K3 roofline entries: SURVEY 8(d)'s B2 and B3 counted on a step's own records and the index records
+    (n_scan = index entries from lower_bound((seqId, rangeStart - L - 1)) to the last one with wpos <= rangeEnd)"""
+    import importlib.util
+    import sys
+
+    from mashmap_b200 import capi
+
+    spec = importlib.util.spec_from_file_location("bench_for_test2", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    sys.modules["bench_for_test2"] = bench
+    spec.loader.exec_module(bench)
+    # index: contig 0 has entries at wpos 0, 10, ..., 990; contig 1 at 5, 15, ..., 495
+    idx_seq = np.concatenate([np.zeros(100, np.int32), np.ones(50, np.int32)])
+    idx_wpos = np.concatenate([np.arange(100, dtype=np.int32) * 10, np.arange(50, dtype=np.int32) * 10 + 5])
+    seg_res = np.zeros(3, dtype=capi.segres_dtype)
+    seg_res["sketch_size"] = [20, 20, 7]
+    seg_res["n_points"] = [40, 12, 0]
+    cands = np.zeros(3, dtype=capi.l1_dtype)
+    cands["seqId"] = [0, 1, 0]
+    cands["rangeStartPos"] = [300, 20, 50]
+    cands["rangeEndPos"] = [400, 60, 55]
+    cands["segment"] = [0, 0, 1]
+    loci = np.zeros(4, dtype=capi.l2_dtype)
+    r = bench.algorithmic_bytes_l1_l2(seg_res, cands, loci, idx_seq, idx_wpos, seg_len=100)
+    # candidate 0: wpos in [199, 400] on contig 0 -> 200..400 = 21 entries; candidate 1: [-81 -> 0, 60] on contig 1 -> 5..55 = 6;
+    # candidate 2: [-51 -> 0, 55] on contig 0 -> 0..50 = 6
+    assert r["index_entries_scanned"] == 21 + 6 + 6
+    assert r["B2_bytes"] == 32 * 47 + 24 * 52 + 16 * 3
+    assert r["B3_bytes"] == 24 * 33 + 24 * (20 + 20 + 20) + 24 * 4
