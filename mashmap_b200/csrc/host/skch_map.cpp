@@ -153,7 +153,8 @@ void BatchMapper::phaseHook(void *user, int phase, int begin)
 
 BatchMapper::BatchMapper(const Parameters &p, const Sketch &refsketch) : param(p), refSketch(refsketch)
 {
-  if (!param.split) die("--noSplit is not supported by the B200 path (fragments longer than the segment length)");
+  // --noSplit (param.split == false): a query no longer than a segment is one fragment with or without the option
+  // (computeMap.hpp:587-607), so it is accepted; addRead stops the run at the first longer query.
   // Map::Map (computeMap.hpp:123-139): setProbs, setRefGroups; plus the per-sketch-size minimum-hit table
   sketchCutoffs = Stat::sketchCutoffs(param.sketchSize, param.kmerSize, param.ANIDiff, param.ANIDiffConf, param.stage1_topANI_filter);
   setRefGroups();
@@ -301,7 +302,11 @@ void BatchMapper::addRead(ReadBatch &b, const std::string &name, const char *seq
     s.offset = b.used + (uint64_t)start; s.length = flen; s.seq_counter = seqCounter; s.name_id = name_id; s.ref_group = rd.refGroup;
     b.segs.push_back(s);
   };
-  if (len <= param.segLength) push(0, len);  // computeMap.hpp:587-607
+  if (!param.split && len > param.segLength)
+    die("--noSplit: query '" + name + "' (" + std::to_string(len) + " bp) is longer than the segment length (" + std::to_string(param.segLength) +
+        " bp): the B200 path maps unsplit queries up to the segment length only (fragments longer than a segment -- windowLen > 0, "
+        "computeMap.hpp:933,1306 -- are not implemented on the device); raise -s or drop --noSplit");
+  if (len <= param.segLength) push(0, len);  // computeMap.hpp:587-607 (with or without --noSplit)
   else {
     const int n = len / param.segLength;  // :610-641
     for (int i = 0; i < n; i++) push(i * param.segLength, param.segLength);
