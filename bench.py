@@ -680,7 +680,7 @@ def l1_l2_rooflines(ctx, seg_res, cands, loci, seg_len, k2_ms, k3_ms, peak):
             out[name] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "algorithmic_bytes_per_segment": b / n}
         out["counts_per_step"] = counts
         out["counted_in_seconds"] = round(time.time() - t0, 1)
-        return out
+        return json.loads(json.dumps(out))  # plain Python numbers only: the JSON line must never fail on this extra
     except Exception as e:  # never fatal: the contract's roofline is K1's
         log(f"K2 / K3 roofline entries skipped: {type(e).__name__}: {e}")
         return None
